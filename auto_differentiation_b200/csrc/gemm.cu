@@ -1,0 +1,69 @@
+// Public GEMM entry: validation + dispatch between the fp32 SIMT kernel and the tcgen05/TMA kernels.
+// Reference calls replaced: np.matmul Matmul.result tgrad.py:535-539 / get_grad :530-533, tensordot's
+// GEMMs :304,:222-228, np.dot TimeAffine layers.py:280,307,308, LSTM :632,:666-669, FeedForward
+// :1252,:1263,:1266, MultiHeadAttention :1347-1360.
+#include "common.cuh"
+#include "gemm_internal.cuh"
+
+using namespace b200ad;
+
+static int fill_args(const b200ad_gemm_desc* d, const float* a, const float* b, float* c, const float* bias,
+                     GemmArgs* g) {
+  B200AD_REQUIRE(d, "gemm: null descriptor");
+  B200AD_REQUIRE(d->m >= 0 && d->n >= 0 && d->k >= 0, "gemm: negative dimension");
+  B200AD_REQUIRE(d->batch0 >= 1 && d->batch1 >= 1, "gemm: batch extents must be >= 1");
+  B200AD_REQUIRE(d->act >= 0 && d->act <= 3, "gemm: bad activation %d", d->act);
+  B200AD_REQUIRE(d->precision >= 0 && d->precision <= 4, "gemm: bad precision %d", d->precision);
+  const int64_t a_inner = d->trans_a ? d->m : d->k, b_inner = d->trans_b ? d->k : d->n;
+  B200AD_REQUIRE(d->lda >= a_inner && d->ldb >= b_inner && d->ldc >= d->n,
+                 "gemm: leading dimension smaller than the row (lda=%lld ldb=%lld ldc=%lld)", (long long)d->lda,
+                 (long long)d->ldb, (long long)d->ldc);
+  g->a = a; g->b = b; g->c = c; g->bias = bias;
+  g->m = d->m; g->n = d->n; g->k = d->k;
+  g->lda = d->lda; g->ldb = d->ldb; g->ldc = d->ldc;
+  g->batch0 = d->batch0; g->batch1 = d->batch1;
+  g->a_stride0 = d->a_stride0; g->a_stride1 = d->a_stride1;
+  g->b_stride0 = d->b_stride0; g->b_stride1 = d->b_stride1;
+  g->c_stride0 = d->c_stride0; g->c_stride1 = d->c_stride1;
+  g->alpha = d->alpha; g->beta = d->beta;
+  g->trans_a = d->trans_a != 0; g->trans_b = d->trans_b != 0; g->act = d->act;
+  return B200AD_OK;
+}
+
+extern "C" {
+
+int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float* b, const float* c) {
+  GemmArgs g;
+  if (fill_args(d, a, b, const_cast<float*>(c), nullptr, &g)) return 0;
+  if (d->precision == B200AD_GEMM_FP32 || d->precision == B200AD_GEMM_AUTO) return 1;
+  const char* why = nullptr;
+  return gemm_tc_supported(g, d->precision, &why) ? 1 : 0;
+}
+
+int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d) {
+  GemmArgs g;
+  if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
+  if (d->precision == B200AD_GEMM_FP32) return 0;
+  const int prec = d->precision == B200AD_GEMM_AUTO ? B200AD_GEMM_TF32X3 : d->precision;
+  return gemm_tc_workspace_bytes(g, prec);
+}
+
+int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float* c, const float* bias,
+                void* workspace, int64_t workspace_bytes, void* stream) {
+  GemmArgs g;
+  int rc = fill_args(d, a, b, c, bias, &g);
+  if (rc) return rc;
+  if (g.m == 0 || g.n == 0) return B200AD_OK;
+  B200AD_REQUIRE(c && (g.k == 0 || (a && b)), "gemm: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int prec = d->precision;
+  if (prec == B200AD_GEMM_AUTO) {
+    const char* why = nullptr;
+    prec = gemm_tc_supported(g, B200AD_GEMM_TF32X3, &why) ? B200AD_GEMM_TF32X3 : B200AD_GEMM_FP32;
+  }
+  if (prec == B200AD_GEMM_FP32 || g.k == 0) return gemm_simt_launch(g, s);
+  const char* why = "unsupported";
+  if (!gemm_tc_supported(g, prec, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): %s", why);
+  return gemm_tc_launch(g, prec, workspace, workspace_bytes, s);
+}
+}

@@ -1,0 +1,552 @@
+"""Hand-written layers with the surface of the reference's ``layers/layers.py`` (forward/backward pairs
+plus ``weights``/``grads`` lists mutated in place), computed on a B200 through libb200ad.so.
+
+Where the reference loops in Python over time steps and launches ~20 CuPy temporaries per step, the
+B200 path restructures the math (same results): all input projections, weight gradients and input
+gradients of a recurrent layer are single large GEMMs over N*T rows; only the truly sequential part
+(h_{t-1} @ Wh, and dh = dA_t @ Wh^T) stays in the loop, each step being one GEMM plus one fused
+gate kernel working in place on time-major buffers.
+
+Arrays: layers accept host (NumPy) arrays or DeviceArrays and return DeviceArrays (`np.asarray(out)`
+copies to the host); weights handed to a constructor are moved to the device once and then updated in
+place by the optimizers (identity is preserved for `remove_duplicate` and Adam's positional m/v).
+"""
+import math
+
+import numpy as np
+
+from .. import _lib as L
+from .. import device as D
+from ..device import DeviceArray, asarray
+from ..optim_host import AdamCore, SGDCore, clip_grads, remove_duplicate  # noqa: F401
+from ..auto_grad import tgrad as ad
+
+np.random.seed(42)  # the reference reseeds the global RNG at import (layers.py:15)
+
+
+def _dev(x):
+    return x if isinstance(x, DeviceArray) else asarray(x)
+
+
+def softmax(x, dims):
+    """Stable softmax (reference layers.py:38-43)."""
+    x = _dev(x)
+    ax = dims % x.ndim
+    if ax != x.ndim - 1:
+        perm = [i for i in range(x.ndim) if i != ax] + [ax]
+        y = D.softmax_lastaxis(x.transpose(*perm).contiguous())
+        return y.transpose(*np.argsort(perm).tolist()).contiguous()
+    return D.softmax_lastaxis(x)
+
+
+class Adam(AdamCore):
+    """Adam (reference layers.py:46-73 == utils/optimizer.py:4-29): one fused multi-tensor kernel."""
+
+
+class SGD(SGDCore):
+    """SGD (reference layers.py:821-831)."""
+
+
+class Sum:
+    def forward(self, x):
+        return D.sum_axis(_dev(x), 0, True)
+
+    def backward(self, dy, collums):
+        return D.repeat_axis(_dev(dy), collums, 0)
+
+
+class MatMul:
+    """Weight-only matmul layer (reference: RNN_Implementation.ipynb:293-315)."""
+
+    def __init__(self, W):
+        W = _dev(W)
+        self.weights = [W]
+        self.X = None
+        self.gradients = [D.zeros_like(W)]
+        self.grads = self.gradients
+
+    def forward(self, forward_input):
+        W, = self.weights
+        self.X = _dev(forward_input)
+        return D.matmul(self.X, W)
+
+    def backward(self, d_backward_input):
+        W = self.weights[0]
+        d = _dev(d_backward_input)
+        dX = D.matmul(d, W, trans_b=True)
+        D.matmul(self.X, d, trans_a=True, out=self.gradients[0])
+        return dX
+
+
+# --------------------------------------------------------------------------------------------------
+# affine / feed-forward / relu
+# --------------------------------------------------------------------------------------------------
+class TimeAffine:
+    """(N,T,D) @ W + b (reference layers.py:244-314): one GEMM with the bias fused in the epilogue;
+    backward = column-sum + two GEMMs written straight into `grads`."""
+
+    def __init__(self, w, b):
+        w, b = _dev(w), _dev(b)
+        self.weights = [w, b]
+        self.x = None
+        self.forward_shape = None
+        self.grads = [D.zeros(w.shape), D.zeros(b.shape)]
+        self.accumulate = False
+
+    def forward(self, x_sequence):
+        x = _dev(x_sequence)
+        N, T, Dm = x.shape
+        W, b = self.weights
+        rx = x.reshape(N * T, Dm)
+        out = D.matmul(rx, W, bias=b.reshape(-1))
+        self.x = rx
+        out = out.reshape(N, T, W.shape[1])
+        self.forward_shape = out.shape
+        self._xshape = (N, T, Dm)
+        return out
+
+    def backward(self, d_sequence):
+        N, T, Dm = self._xshape
+        W, b = self.weights
+        dout = _dev(d_sequence).reshape(N * T, W.shape[1]).contiguous()
+        beta = 1.0 if self.accumulate else 0.0
+        db = D.reduce_mid(dout, 1, N * T, W.shape[1])                      # np.sum(dout, axis=0)   :306
+        D.axpby_(db, self.grads[1].reshape(-1), 1.0, beta)
+        D.matmul(self.x, dout, trans_a=True, out=self.grads[0], beta=beta)  # rx.T @ dout           :307
+        dx = D.matmul(dout, W, trans_b=True)                                # dout @ W.T            :308
+        return dx.reshape(N, T, Dm)
+
+
+class ReLU:
+    def __init__(self):
+        self.cache = None
+
+    def forward(self, x):
+        x = _dev(x)
+        out = D.unary(L.U_RELU, x)
+        self.cache = out   # (out > 0) == (x > 0)
+        return out
+
+    def backward(self, dout):
+        return D.unary_bwd(L.U_RELU, _dev(dout), y=self.cache)
+
+
+class FeedForward:
+    """relu(x @ w + b) (reference layers.py:1242-1266).  The reference's backward stores dW/db into
+    `self.weights` (a bug, :1263-1264); this follows the math and fills `self.grads`."""
+
+    def __init__(self, w, b, dtype=np.float32):
+        w, b = _dev(w), _dev(b)
+        self.weights = [w, b]
+        self.grads = [D.zeros(w.shape), D.zeros(b.shape)]
+        self.cache = None
+        self.accumulate = False
+
+    def forward(self, x):
+        w, b = self.weights
+        x = _dev(x)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        out = D.matmul(x2, w, bias=b.reshape(-1), act=L.ACT_RELU)
+        self.cache = (x2, out, x.shape)
+        return out.reshape(x.shape[:-1] + (w.shape[1],))
+
+    def backward(self, dx):
+        w, b = self.weights
+        x2, out, xshape = self.cache
+        g = _dev(dx).reshape(out.shape).contiguous()
+        dz = D.act_bwd(g, out, L.ACT_RELU)
+        beta = 1.0 if self.accumulate else 0.0
+        D.matmul(x2, dz, trans_a=True, out=self.grads[0], beta=beta)
+        db = D.reduce_mid(dz, 1, dz.shape[0], dz.shape[1])
+        D.axpby_(db, self.grads[1].reshape(-1), 1.0, beta)
+        return D.matmul(dz, w, trans_b=True).reshape(xshape)
+
+
+class SkipConnection:
+    def __init__(self):
+        self.weights, self.grads = [], []
+
+    def forward(self, x, y):
+        return _dev(x) + _dev(y)
+
+    def backward(self, dout):
+        dout = _dev(dout)
+        return dout, dout.copy()
+
+
+# --------------------------------------------------------------------------------------------------
+# recurrent cells
+# --------------------------------------------------------------------------------------------------
+def _cell_call(fn, *args):
+    L.check(fn(*args, D.stream_ptr()))
+
+
+def _last_contig(a):
+    """`a` itself when its last axis is contiguous (time slices are then addressable in place)."""
+    return a if (a.shape[-1] == 1 or a.t.stride(-1) == 1) else a.contiguous()
+
+
+def _row_view(a):
+    """(ptr, ld) of a 2-D view with contiguous rows."""
+    p, ld, _, _ = D._rows_ld(a)
+    return p, ld
+
+
+class RNN:
+    """tanh cell h' = tanh(x@Wx + h@Wh + b) (reference layers.py:144-182).  The shipped backward is
+    broken (passes the summed db into both MatMul.backward, never fills grads); this
+    implements the intended math, which equals what the reference TAPE yields for the same expression."""
+
+    def __init__(self, w_input, w_prev, b):
+        w_input, w_prev, b = _dev(w_input), _dev(w_prev), _dev(b)
+        self.weights = [w_input, w_prev, b]
+        self.grads = [D.zeros(w_input.shape), D.zeros(w_prev.shape), D.zeros(b.shape)]
+        self.cache = None
+
+    def forward(self, word_vector, h_prev):
+        w_input, w_prev, b = self.weights
+        x, h_prev = _dev(word_vector), _dev(h_prev)
+        pre = D.matmul(x, w_input, bias=b.reshape(-1))
+        D.matmul(h_prev, w_prev, out=pre, beta=1.0)
+        h_next = D.bias_act(pre, None, L.ACT_TANH)
+        self.cache = (x, h_prev, h_next)
+        return h_next
+
+    def backward(self, dh_next):
+        w_input, w_prev, b = self.weights
+        x, h_prev, h_next = self.cache
+        dt = D.act_bwd(_dev(dh_next).contiguous(), h_next, L.ACT_TANH)   # dh*(1-h'^2)       :176
+        D.copy_into_(D.reduce_mid(dt, 1, dt.shape[0], dt.shape[1]).reshape(b.shape), self.grads[2])  # db :177
+        D.matmul(x, dt, trans_a=True, out=self.grads[0])
+        D.matmul(h_prev, dt, trans_a=True, out=self.grads[1])
+        dx = D.matmul(dt, w_input, trans_b=True)
+        dh_prev = D.matmul(dt, w_prev, trans_b=True)
+        return dh_prev, dx
+
+
+class _TimeRecurrent:
+    """Shared time-major machinery of TimeRNN / TimeLSTM."""
+    _gate_mult = 1
+
+    def _setup(self, wx, wh, b, stateful):
+        wx, wh, b = _dev(wx), _dev(wh), _dev(b)
+        self.weights = [wx, wh, b]
+        self.grads = [D.zeros(wx.shape), D.zeros(wh.shape), D.zeros(b.shape)]
+        self.stateful = stateful
+        self.h, self.dh, self.c = None, None, None
+        self.accumulate = False
+        self.layers = []
+
+    def _project_inputs(self, xs):
+        """xs (N,T,D) -> time-major copy (T,N,D) and pre-activations (T,N,G) = x@Wx + b in ONE GEMM."""
+        wx, wh, b = self.weights
+        N, T, Dm = xs.shape
+        G = wx.shape[1]
+        xs_tm = xs.transpose(1, 0, 2).contiguous()
+        pre = D.matmul(xs_tm.reshape(T * N, Dm), wx, bias=b.reshape(-1)).reshape(T, N, G)
+        return xs_tm, pre
+
+    def _weight_grads(self, xs_tm, hprev_tm, dA_tm):
+        """dWx, dWh, db and dxs as four large GEMMs / one column-sum over all T*N rows."""
+        wx, wh, b = self.weights
+        T, N, Dm = xs_tm.shape
+        G = dA_tm.shape[2]
+        H = wh.shape[0]
+        beta = 1.0 if self.accumulate else 0.0
+        dA2 = dA_tm.reshape(T * N, G)
+        D.matmul(xs_tm.reshape(T * N, Dm), dA2, trans_a=True, out=self.grads[0], beta=beta)
+        D.matmul(hprev_tm.reshape(T * N, H), dA2, trans_a=True, out=self.grads[1], beta=beta)
+        db = D.reduce_mid(dA2, 1, T * N, G)
+        D.axpby_(db, self.grads[2].reshape(-1), 1.0, beta)
+        dxs_tm = D.matmul(dA2, wx, trans_b=True).reshape(T, N, Dm)
+        return dxs_tm.transpose(1, 0, 2)
+
+    def set_state(self, h, c=None):
+        self.h = None if h is None else _dev(h)
+        self.c = None if c is None else _dev(c)
+
+    def reset_state(self):
+        self.h, self.c = None, None
+
+
+class TimeRNN(_TimeRecurrent):
+    """Unrolled tanh RNN (reference layers.py:185-225; forward semantics kept, backward as intended)."""
+
+    def __init__(self, w_input, w_prev, b, stateful=False):
+        self._setup(w_input, w_prev, b, stateful)
+
+    def forward(self, x_sequence):
+        wx, wh, b = self.weights
+        xs = _dev(x_sequence)
+        N, T, Dm = xs.shape
+        H = wh.shape[0]
+        if not self.stateful or self.h is None:
+            self.h = D.zeros((N, H))
+        xs_tm, pre = self._project_inputs(xs)
+        hs_ext = D.empty((T + 1, N, H))       # hs_ext[t] = h_{t-1}; hs_ext[0] = initial state
+        D.copy_into_(self.h, hs_ext[0])
+        for t in range(T):
+            D.matmul(hs_ext[t], wh, out=pre[t], beta=1.0)        # pre_t += h_{t-1} @ Wh
+            D.bias_act(pre[t], None, L.ACT_TANH, out=hs_ext[t + 1])
+        self.h = hs_ext[T]
+        self._cache = (xs_tm, hs_ext)
+        return hs_ext[1:].transpose(1, 0, 2)
+
+    def backward(self, dhs):
+        wx, wh, b = self.weights
+        xs_tm, hs_ext = self._cache
+        T, N, Dm = xs_tm.shape
+        H = wh.shape[0]
+        dhs = _last_contig(_dev(dhs))
+        dA = D.empty((T, N, H))
+        dh = None
+        lib = L.load()
+        for t in reversed(range(T)):
+            pa, lda = _row_view(dhs[:, t, :])
+            pb, ldb = _row_view(dh) if dh is not None else (None, 0)
+            ph, ldh = _row_view(hs_ext[t + 1])
+            pd, ldd = _row_view(dA[t])
+            _cell_call(lib.b200ad_rnn_cell_bwd, pa, lda, pb, ldb, ph, ldh, pd, ldd, N, H)
+            dh = D.matmul(dA[t], wh, trans_b=True)
+        self.dh = dh
+        return self._weight_grads(xs_tm, hs_ext[:T], dA)
+
+
+class LSTM:
+    """One LSTM step (reference layers.py:616-676): gates [f,g,i,o]; returns (c', h')."""
+
+    def __init__(self, wx, wh, b, dtype=np.float32):
+        wx, wh, b = _dev(wx), _dev(wh), _dev(b)
+        self.weights = [wx, wh, b]
+        self.grads = [D.zeros(wx.shape), D.zeros(wh.shape), D.zeros(b.shape)]
+        self._var = None
+
+    def forward(self, x, h, c):
+        wx, wh, b = self.weights
+        x, h, c = _dev(x), _dev(h).contiguous(), _dev(c).contiguous()
+        N, H = h.shape
+        a = D.matmul(x, wx, bias=b.reshape(-1))          # x@wx + b
+        D.matmul(h, wh, out=a, beta=1.0)                 # + h@wh              :632
+        gates, ct, ht = D.empty((N, 4 * H)), D.empty((N, H)), D.empty((N, H))
+        _cell_call(L.load().b200ad_lstm_cell_fwd, a.ptr, 4 * H, c.ptr, H, gates.ptr, 4 * H, ct.ptr, H, ht.ptr, H,
+                   N, H)
+        self._var = (ct, ht, h, c, x, gates)
+        return ct, ht
+
+    def backward(self, dh_next, dc_next):
+        wx, wh, b = self.weights
+        ct, ht, h, c, x, gates = self._var
+        N, H = h.shape
+        dh_next, dc_next = _dev(dh_next).contiguous(), _dev(dc_next).contiguous()
+        db = D.empty((N, 4 * H))                         # np.hstack((stack0..3))   :663
+        dc = D.empty((N, H))
+        _cell_call(L.load().b200ad_lstm_cell_bwd, dh_next.ptr, H, None, 0, dc_next.ptr, gates.ptr, 4 * H, c.ptr, H,
+                   ct.ptr, H, ht.ptr, H, db.ptr, 4 * H, dc.ptr, N, H)
+        D.matmul(x, db, trans_a=True, out=self.grads[0])  # dWx = x.T @ db            :666
+        D.matmul(h, db, trans_a=True, out=self.grads[1])  # dWh = h.T @ db            :667
+        dx = D.matmul(db, wx, trans_b=True)               # :668
+        dh = D.matmul(db, wh, trans_b=True)               # :669
+        D.copy_into_(D.reduce_mid(db, 1, N, 4 * H).reshape(b.shape), self.grads[2])  # :674
+        return dx, dh, dc
+
+
+class TimeLSTM(_TimeRecurrent):
+    """Unrolled LSTM (reference layers.py:552-604)."""
+
+    def __init__(self, wx, wh, b, stateful=False):
+        self._setup(wx, wh, b, stateful)
+        self.forward_shape = None
+
+    def forward(self, xs):
+        wx, wh, b = self.weights
+        xs = _dev(xs)
+        N, T, Dm = xs.shape
+        H = wh.shape[0]
+        if not self.stateful or self.h is None:
+            self.h = D.zeros((N, H))
+        if not self.stateful or self.c is None:
+            self.c = D.zeros((N, H))
+        xs_tm, pre = self._project_inputs(xs)          # pre: (T,N,4H)
+        hs_ext = D.empty((T + 1, N, H))
+        cs_ext = D.empty((T + 1, N, H))
+        gates = D.empty((T, N, 4 * H))
+        D.copy_into_(self.h, hs_ext[0])
+        D.copy_into_(self.c, cs_ext[0])
+        lib = L.load()
+        for t in range(T):
+            D.matmul(hs_ext[t], wh, out=pre[t], beta=1.0)   # A_t = x_t@wx + b + h_{t-1}@wh     :632
+            _cell_call(lib.b200ad_lstm_cell_fwd, pre[t].ptr, 4 * H, cs_ext[t].ptr, H, gates[t].ptr, 4 * H,
+                       cs_ext[t + 1].ptr, H, hs_ext[t + 1].ptr, H, N, H)
+        self.h, self.c = hs_ext[T], cs_ext[T]
+        self._cache = (xs_tm, hs_ext, cs_ext, gates)
+        out = hs_ext[1:].transpose(1, 0, 2)
+        self.forward_shape = out.shape
+        return out
+
+    def backward(self, dhs):
+        wx, wh, b = self.weights
+        xs_tm, hs_ext, cs_ext, gates = self._cache
+        T, N, Dm = xs_tm.shape
+        H = wh.shape[0]
+        dhs = _last_contig(_dev(dhs))
+        dA = D.empty((T, N, 4 * H))
+        dc_bufs = (D.empty((N, H)), D.empty((N, H)))
+        dh, dc = None, None
+        lib = L.load()
+        for t in reversed(range(T)):
+            pa, lda = _row_view(dhs[:, t, :])
+            pb, ldb = (dh.ptr, H) if dh is not None else (None, 0)
+            dc_out = dc_bufs[t & 1]
+            _cell_call(lib.b200ad_lstm_cell_bwd, pa, lda, pb, ldb, dc.ptr if dc is not None else None,
+                       gates[t].ptr, 4 * H, cs_ext[t].ptr, H, cs_ext[t + 1].ptr, H, hs_ext[t + 1].ptr, H,
+                       dA[t].ptr, 4 * H, dc_out.ptr, N, H)
+            dc = dc_out
+            dh = D.matmul(dA[t], wh, trans_b=True)          # dh = db @ wh.T                     :669
+        self.dh = dh
+        return self._weight_grads(xs_tm, hs_ext[:T], dA)
+
+
+# --------------------------------------------------------------------------------------------------
+# embedding / loss
+# --------------------------------------------------------------------------------------------------
+class Embedding:
+    def __init__(self, W):
+        W = _dev(W)
+        self.params = [W]
+        self.weights = self.params
+        self.grads = [D.zeros(W.shape)]
+        self.idx = None
+
+    def forward(self, idx):
+        W, = self.params
+        self.idx = D.as_index(idx)
+        return D.embedding_gather(W, self.idx)
+
+    def backward(self, dout):
+        dW, = self.grads
+        D.embedding_scatter_add_(_dev(dout), self.idx, dW)   # dW[...] = 0; np.add.at(dW, idx, dout)
+        return None
+
+
+class TimeEmbedding:
+    """(N,T) ids -> (N,T,D) (reference layers.py:461-507): one gather / one deterministic scatter-add
+    over all N*T positions instead of a Python loop over T."""
+
+    def __init__(self, w):
+        w = _dev(w)
+        self.weights = [w]
+        self.grads = [D.zeros(w.shape)]
+        self.layers = []
+        self.idx = None
+
+    def forward(self, xs):
+        self.idx = D.as_index(xs)
+        return D.embedding_gather(self.weights[0], self.idx)
+
+    def backward(self, d_sequence):
+        D.embedding_scatter_add_(_dev(d_sequence), self.idx, self.grads[0])
+        return None
+
+
+class TimeSoftmaxWithLoss:
+    """Masked mean cross-entropy over (N,T,V) logits (reference layers.py:510-549).  `forward`
+    returns the loss as a 0-d DeviceArray (float(loss) syncs; arithmetic on it stays on the device)."""
+
+    def __init__(self):
+        self.weights, self.grads = [], []
+        self.cache = None
+        self.ignore_label = -1
+
+    def forward(self, xs, ts):
+        xs = _dev(xs)
+        N, T, V = xs.shape
+        if getattr(ts, "ndim", 0) == 3:            # one-hot labels -> argmax(axis=2)   :519-520
+            ts = D.argmax_rows(_dev(ts).reshape(N * T, V))
+        else:
+            ts = D.as_index(ts).reshape(N * T)
+        lc, ys = D.xent_fwd(xs.reshape(N * T, V), ts, self.ignore_label, 0.0, 0)
+        self.cache = (ts, ys, lc, (N, T, V))
+        return lc[0]
+
+    def backward(self, dout=1):
+        ts, ys, lc, (N, T, V) = self.cache
+        dx = D.xent_bwd(ys, ts, lc, float(dout), self.ignore_label, out=ys)   # in place on the cached probs :541
+        return dx.reshape(N, T, V)
+
+
+# --------------------------------------------------------------------------------------------------
+# multi-head attention
+# --------------------------------------------------------------------------------------------------
+class MultiHeadAttention:
+    """Reference forward layers.py:1331-1375 (backward there is `pass`); the backward implemented here
+    yields the gradients of the tape twin Test/MultiHeadAttentionTest.py:49-91.
+
+    softmax(QK^T/sqrt(d_k)) is evaluated in the stable form — equal to the reference's naive
+    exp/sum (:1356) whenever that is finite.  Head split/merge are strided views consumed directly
+    by the batched GEMMs (no permute copies)."""
+
+    def __init__(self, wordvec_size, hidden_size, num_heads, weights=None):
+        self.num_heads = num_heads
+        self.d_k = wordvec_size // num_heads
+        assert isinstance(self.d_k, int), f"{self.d_k} is not int"
+        if weights is None:
+            weights = [np.random.randn(wordvec_size, hidden_size) for _ in range(4)]
+        self.weights = [_dev(w) for w in weights]
+        self.grads = [D.zeros(w.shape) for w in self.weights]
+        self.cache = None
+        self.accumulate = False
+
+    def forward(self, query, key, value):
+        query, key, value = _dev(query), _dev(key), _dev(value)
+        B, S, Dm = query.shape
+        h = self.num_heads
+        wq, wk, wv, wo = self.weights
+        Hd = wq.shape[1]
+        dk = Hd // h
+        q2, k2, v2 = (a.reshape(B * S, Dm) for a in (query, key, value))
+        Q, K, V = D.matmul(q2, wq), D.matmul(k2, wk), D.matmul(v2, wv)          # :1347-1349
+        Qh, Kh, Vh = (a.reshape(B, S, h, dk).transpose(0, 2, 1, 3) for a in (Q, K, V))
+        scores = D.matmul(Qh, Kh, trans_b=True)                                  # :1355 (scale folded into softmax)
+        P = D.softmax_lastaxis(scores, in_scale=1.0 / math.sqrt(dk))             # :1356
+        O = D.empty((B, S, h, dk))
+        D.matmul(P, Vh, out=O.transpose(0, 2, 1, 3))                             # :1357 written in merged layout
+        O2 = O.reshape(B * S, h * dk)
+        out = D.matmul(O2, wo).reshape(B, S, wo.shape[1])                        # :1360
+        self.cache = (q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk))
+        return out
+
+    def backward(self, dout=None):
+        if dout is None:
+            return None   # the reference's backward is a stub (layers.py:1366-1367)
+        wq, wk, wv, wo = self.weights
+        q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk) = self.cache
+        beta = 1.0 if self.accumulate else 0.0
+        d2 = _dev(dout).reshape(B * S, wo.shape[1]).contiguous()
+        D.matmul(O2, d2, trans_a=True, out=self.grads[3], beta=beta)             # dwo
+        dO = D.matmul(d2, wo, trans_b=True).reshape(B, S, h, dk)
+        dOh = dO.transpose(0, 2, 1, 3)
+        dP = D.matmul(dOh, Vh, trans_b=True)                                     # (B,h,S,S)
+        dV = D.empty((B, S, h, dk))
+        D.matmul(P, dOh, trans_a=True, out=dV.transpose(0, 2, 1, 3))
+        dS = D.softmax_bwd_lastaxis(dP, P, out_scale=1.0 / math.sqrt(dk), out=dP)
+        dQ, dK = D.empty((B, S, h, dk)), D.empty((B, S, h, dk))
+        D.matmul(dS, Kh, out=dQ.transpose(0, 2, 1, 3))
+        D.matmul(dS, Qh, trans_a=True, out=dK.transpose(0, 2, 1, 3))
+        dQ2, dK2, dV2 = (a.reshape(B * S, h * dk) for a in (dQ, dK, dV))
+        D.matmul(q2, dQ2, trans_a=True, out=self.grads[0], beta=beta)
+        D.matmul(k2, dK2, trans_a=True, out=self.grads[1], beta=beta)
+        D.matmul(v2, dV2, trans_a=True, out=self.grads[2], beta=beta)
+        dquery = D.matmul(dQ2, wq, trans_b=True).reshape(B, S, Dm)
+        dkey = D.matmul(dK2, wk, trans_b=True).reshape(B, S, Dm)
+        dvalue = D.matmul(dV2, wv, trans_b=True).reshape(B, S, Dm)
+        return dquery, dkey, dvalue
+
+    def split_heads(self, x):
+        x = _dev(x)
+        batch_size, sequence_length, _ = x.shape
+        return x.reshape(batch_size, sequence_length, self.num_heads, self.d_k).transpose(0, 2, 1, 3)
+
+    def combine_heads(self, x):
+        x = _dev(x)
+        batch_size, _, sequence_length, _ = x.shape
+        return x.transpose(0, 2, 1, 3).reshape(batch_size, sequence_length, -1)
