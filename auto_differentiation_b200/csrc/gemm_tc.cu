@@ -1,15 +1,714 @@
-// tcgen05 / TMA GEMM — placeholder until the tensor-core kernel lands (reports "unsupported" so that
-// B200AD_GEMM_AUTO resolves to the fp32 SIMT kernel).
+// tcgen05 / TMEM / TMA GEMM for sm_100a — the dense-contraction hot kernel.
+//
+//   C[b0,b1] = alpha * op(A) @ op(B) + beta * C (+ bias[n], activation), fp32 in HBM, fp32 accumulate in TMEM.
+//
+// Precisions
+//   TF32    one tcgen05.mma.kind::tf32 pass (10-bit mantissa operands)        — diagnostic / roofline probe
+//   TF32X3  error-compensated split: A = Ah + Al, B = Bh + Bl (each exactly representable in tf32),
+//           D = Ah*Bh + Ah*Bl + Al*Bh  (the dropped Al*Bl term is ~2^-22 relative) — fp32-faithful, the default
+// The hi/lo split is done IN SHARED MEMORY by four "splitter" warps on the tile TMA just delivered (an
+// elementwise rewrite, so it is independent of the swizzled layout): no extra HBM traffic, no pre-pass.
+//
+// Structure (persistent, warp-specialised, one CTA per SM, static tile scheduler):
+//   warp 0      TMA producer: cp.async.bulk.tensor (4-D maps: inner, rows, batch1, batch0; 128B swizzle)
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma 128 x BN x 8, accumulators in TMEM (double buffered)
+//   warps 2-5   splitter (TF32X3 only): raw tile -> masked hi (in place) + lo tile, fence.proxy.async
+//   warps 6-9   epilogue: tcgen05.ld TMEM -> registers -> alpha/beta/bias/activation -> global
+// Pipelines: raw_full / conv_full / empty mbarriers over a ring of smem stages, tmem_full / tmem_empty over
+// the two accumulator buffers, so the epilogue of tile i overlaps the main loop of tile i+1.
+// Both operand majors are fed natively: a row-major (rows x K) operand is K-major, a (K x cols) row-major
+// operand is MN-major (UMMA descriptor major bit), so NN / NT / TN / TT need no transposes.
+// Skinny problems (weight gradients: M,N ~ 512, K ~ 1e5) use split-K with a deterministic two-pass reduce.
 #include "common.cuh"
 #include "gemm_internal.cuh"
+#include <cuda.h>
+#include <mutex>
 
 namespace b200ad {
-bool gemm_tc_supported(const GemmArgs&, int, const char** why) {
-  if (why) *why = "tcgen05 path not built";
-  return false;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // 32 fp32 = 128 B = one swizzle-128B row
+constexpr int TC_THREADS = 320;           // 10 warps
+constexpr uint32_t TC_SMEM_LIMIT = 232448;  // 227 KB
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int64_t gemm_tc_workspace_bytes(const GemmArgs&, int) { return 0; }
-int gemm_tc_launch(const GemmArgs&, int, void*, int64_t, cudaStream_t) {
-  return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): not built");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a launch failure (trap) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.commit: the mbarrier is arrived on when all previously issued MMAs of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// UMMA shared-memory matrix descriptor (sm100: version 1).  Offsets in bytes.
+// layout: 2 = SWIZZLE_128B (16 B atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32 B atoms, 4-row
+// period) — the ONLY layout tcgen05 accepts for MN-major tf32 operands.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
+struct TcParams {
+  float* c;
+  const float* c_in;       // beta source (== c)
+  const float* bias;
+  float* partial;          // split-K workspace [split][batch][M][N] or nullptr
+  int64_t m, n, k;
+  int64_t ldc, c_stride0, c_stride1;
+  int64_t batch1;
+  int32_t batches, m_tiles, n_tiles, splits, kblocks_total, kblocks_per_split;
+  int32_t a_mn_major, b_mn_major, x3, mask_hi, act;
+  int32_t chunk_kb, chunked;   // TMEM accumulation chunk (k-blocks); chunked: buffer 0 = chunk sum X, buffer 1 = running total Y
+  float alpha, beta;
+};
+
+template <int ACT>
+__device__ __forceinline__ float tc_act(float x) {
+  if constexpr (ACT == 1) return tanhf(x);
+  else if constexpr (ACT == 2) return 1.f / (1.f + expf(-x));
+  else if constexpr (ACT == 3) return (x > 0.f || x != x) ? x : 0.f;
+  else return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams p, const int stages) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16B aligned by the ABI: round up to 1024 (swizzle-128B atoms)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = (A_BYTES + B_BYTES) * (p.x3 ? 2 : 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* raw_full = bars;                  // [stages]  TMA -> splitter (or MMA)
+  uint64_t* conv_full = bars + stages;        // [stages]  splitter -> MMA
+  uint64_t* empty = bars + 2 * stages;        // [stages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 3 * stages;    // [2]       MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]       epilogue -> MMA
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&conv_full[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int total_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+        const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+        const int split = t % p.splits;
+        const int batch = t / p.splits;
+        const int b0 = (int)(batch / p.batch1), b1 = (int)(batch % p.batch1);
+        const int kb0 = split * p.kblocks_per_split;
+        int kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&raw_full[s], A_BYTES + B_BYTES);
+          const int k0 = kb * TC_BK;
+          if (!p.a_mn_major) {
+            tma_load_4d(&map_a, &raw_full[s], sa, k0, m_tile * TC_BM, b1, b0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 32; ++c)
+              tma_load_4d(&map_a, &raw_full[s], sa + c * 4096, m_tile * TC_BM + c * 32, k0, b1, b0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_4d(&map_b, &raw_full[s], sb, k0, n_tile * BN, b1, b0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c)
+              tma_load_4d(&map_b, &raw_full[s], sb + c * 4096, n_tile * BN + c * 32, k0, b1, b0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                           ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO), k-step = +32 B inside the atom.
+    // MN-major (SWIZZLE_128B_BASE32B): 32-element chunks 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO),
+    // k-step (8 rows) = +1024 B.
+    const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
+    const uint32_t a_sbo = p.a_mn_major ? 512u : 1024u, b_sbo = p.b_mn_major ? 512u : 1024u;
+    const uint32_t a_lay = p.a_mn_major ? 1u : 2u, b_lay = p.b_mn_major ? 1u : 2u;
+    const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
+    uint32_t it = 0, uit = 0;   // k-block counter (smem ring) and accumulation-unit counter (TMEM buffers)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile / (p.n_tiles * p.m_tiles);
+      const int split = t % p.splits;
+      const int kb0 = split * p.kblocks_per_split;
+      int kb1 = kb0 + p.kblocks_per_split;
+      if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+      for (int cb0 = kb0; cb0 < kb1; cb0 += p.chunk_kb, ++uit) {
+        int cb1 = cb0 + p.chunk_kb;
+        if (cb1 > kb1) cb1 = kb1;
+        const uint32_t buf = p.chunked ? 0u : (uit & 1);
+        const uint32_t buf_ph = p.chunked ? (uit & 1) : ((uit >> 1) & 1);
+        mbar_wait(&tmem_empty[buf], buf_ph ^ 1);          // epilogue has drained / folded this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = cb0; kb < cb1; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(p.x3 ? &conv_full[s] : &raw_full[s], ph);
+          tc_fence_after();
+          if (lane == 0) {   // always the same thread: tcgen05.commit tracks the MMAs issued by the committing thread
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sb = sa + A_BYTES;
+            const uint32_t sal = sb + B_BYTES, sbl = sal + A_BYTES;     // lo tiles (TF32X3)
+            const bool first_kb = (kb == cb0);
+            if (p.x3) {
+              // small cross terms first, the dominant hi*hi term last
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32(d_tmem, make_smem_desc(sal + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                          make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, (first_kb && kk == 0) ? 0u : 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32(d_tmem, make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                          make_smem_desc(sbl + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32(d_tmem, make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                          make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, 1u);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32(d_tmem, make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                          make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, (first_kb && kk == 0) ? 0u : 1u);
+            }
+            umma_commit(&empty[s]);                          // smem stage free once these MMAs retire
+            if (kb == cb1 - 1) umma_commit(&tmem_full[buf]);  // chunk / tile accumulator complete -> epilogue
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================================== splitter (TF32X3) =====================================
+    if (p.x3) {
+      const int tid = threadIdx.x - 64;   // 0..127
+      uint32_t it = 0;
+      constexpr uint32_t VECS = (A_BYTES + B_BYTES) / 16;   // float4 count of the raw [A|B] block
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile / (p.n_tiles * p.m_tiles);
+        const int split = t % p.splits;
+        const int kb0 = split * p.kblocks_per_split;
+        int kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&raw_full[s], ph);
+          uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
+          uint4* lo = hi + VECS;
+#pragma unroll 4
+          for (uint32_t i = tid; i < VECS; i += 128) {
+            const uint4 v = hi[i];
+            uint4 h, l;
+            h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+            if (p.mask_hi) hi[i] = h;
+            lo[i] = l;
+          }
+          fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
+          mbar_arrive(&conv_full[s]);
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int ew = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row_in_tile = ew * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    uint32_t uit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+      const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+      const int split = t % p.splits;
+      const int batch = t / p.splits;
+      const int64_t b0 = batch / p.batch1, b1 = batch % p.batch1;
+      const int kb0 = split * p.kblocks_per_split;
+      int kb1 = kb0 + p.kblocks_per_split;
+      if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+      const int nchunks = (kb1 - kb0 + p.chunk_kb - 1) / p.chunk_kb;
+      const int64_t gm = (int64_t)m_tile * TC_BM + row_in_tile;
+      const bool row_ok = gm < p.m;
+      float* crow;
+      if (p.partial) crow = p.partial + (((int64_t)split * p.batches + batch) * p.m + gm) * p.n;
+      else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
+      for (int ch = 0; ch < nchunks; ++ch, ++uit) {
+        const uint32_t buf = p.chunked ? 0u : (uit & 1);
+        const uint32_t buf_ph = p.chunked ? (uit & 1) : ((uit >> 1) & 1);
+        mbar_wait(&tmem_full[buf], buf_ph);
+        tc_fence_after();
+        const uint32_t x_addr = tmem_base + lane_base + buf * BN;
+        const uint32_t y_addr = tmem_base + lane_base + BN;          // running total (chunked mode only)
+        const bool last = (ch == nchunks - 1);
+        if (!last) {
+          // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation inside the
+          // tensor core truncates; bounding the chain length keeps the result fp32-faithful for any K)
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t x[32];
+            tmem_ld_32x32b_x32(x_addr + c0, x);
+            if (ch > 0) {
+              uint32_t y[32];
+              tmem_ld_32x32b_x32(y_addr + c0, y);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __float_as_uint(__uint_as_float(x[j]) + __uint_as_float(y[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            tmem_st_32x32b_x32(y_addr + c0, x);
+          }
+          tmem_st_wait();
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(x_addr + c0, r);
+            if (nchunks > 1) {
+              uint32_t y[32];
+              tmem_ld_32x32b_x32(y_addr + c0, y);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(y[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            const int64_t gn0 = (int64_t)n_tile * BN + c0;
+            if (row_ok && gn0 < p.n) {
+              float* dst = crow + gn0;
+              const bool full = (gn0 + 32 <= p.n);
+              if (p.partial) {
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else {
+                  for (int j = 0; j < 32 && gn0 + j < p.n; ++j) dst[j] = __uint_as_float(r[j]);
+                }
+              } else {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
+                if (p.beta != 0.f) {
+                  for (int j = 0; j < 32 && gn0 + j < p.n; ++j) v[j] += p.beta * dst[j];
+                }
+                if (p.bias) {
+                  for (int j = 0; j < 32 && gn0 + j < p.n; ++j) v[j] += __ldg(p.bias + gn0 + j);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tc_act<1>(v[j]);
+                } else if (p.act == 2) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tc_act<2>(v[j]);
+                } else if (p.act == 3) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tc_act<3>(v[j]);
+                }
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                  for (int j = 0; j < 32 && gn0 + j < p.n; ++j) dst[j] = v[j];
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);               // 128 arrivals release the buffer to the MMA warp
+      }
+    }
+  }
+
+  // teardown: every role has left its loop; the MMA warp's last commits were consumed by the epilogue
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// split-K second pass: C = alpha * sum_s partial[s] + beta*C + bias, activation.  One thread per 4 outputs.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, TcParams p) {
+  const int64_t per_batch = p.m * p.n;
+  const int64_t total = per_batch * p.batches;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + (int64_t)sp * total + i);
+    const int64_t batch = i / per_batch, rem = i - batch * per_batch;
+    const int64_t gm = rem / p.n, gn = rem - gm * p.n;
+    const int64_t b0 = batch / p.batch1, b1 = batch % p.batch1;
+    float* dst = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc + gn;
+    float v = p.alpha * s;
+    if (p.beta != 0.f) v += p.beta * *dst;
+    if (p.bias) v += __ldg(p.bias + gn);
+    if (p.act == 1) v = tc_act<1>(v);
+    else if (p.act == 2) v = tc_act<2>(v);
+    else if (p.act == 3) v = tc_act<3>(v);
+    *dst = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved through the runtime: no link-time dependency on libcuda (the library must load on CPU-only hosts)
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct OperandPlan {
+  bool mn_major;
+  int64_t inner, rows, ld;     // global matrix as stored: `rows` rows of `inner` contiguous elements
+  int box_rows;
+};
+
+static int encode_operand(CUtensorMap* map, const float* base, const OperandPlan& o, int64_t batch0, int64_t batch1,
+                          int64_t stride0, int64_t stride1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05): cuTensorMapEncodeTiled is not available");
+  // dims: inner, rows, batch1, batch0.  A size-1 batch axis may carry stride 0: give it a legal dummy stride.
+  cuuint64_t dims[4] = {(cuuint64_t)o.inner, (cuuint64_t)o.rows, (cuuint64_t)batch1, (cuuint64_t)batch0};
+  const int64_t fallback = o.ld * o.rows;
+  int64_t s1 = (batch1 > 1) ? stride1 : fallback, s0 = (batch0 > 1) ? stride0 : fallback;
+  if (s1 <= 0) s1 = fallback;
+  if (s0 <= 0) s0 = fallback;
+  cuuint64_t strides[3] = {(cuuint64_t)o.ld * 4, (cuuint64_t)s1 * 4, (cuuint64_t)s0 * 4};
+  cuuint32_t box[4] = {32u, (cuuint32_t)o.box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   o.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B200AD_OK;
+}
+
+static int pick_bn(int64_t n) {
+  const char* env = getenv("B200AD_TC_BN");
+  if (env) {
+    int v = atoi(env);
+    if (v == 64 || v == 128 || v == 256) return v;
+  }
+  if (n <= 64) return 64;
+  if (n <= 128) return 128;
+  return 256;
+}
+
+struct TcPlan {
+  int bn, stages, splits, kblocks_total, kblocks_per_split, m_tiles, n_tiles, batches;
+  uint32_t smem_bytes;
+  bool x3;
+};
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = B200AD_NUM_SMS;
+  }
+  return n;
+}
+
+static TcPlan make_plan(const GemmArgs& g, int precision) {
+  TcPlan pl;
+  pl.x3 = (precision == B200AD_GEMM_TF32X3);
+  pl.bn = pick_bn(g.n);
+  const uint32_t stage = (TC_BM * TC_BK * 4 + pl.bn * TC_BK * 4) * (pl.x3 ? 2 : 1);
+  int st = (int)((TC_SMEM_LIMIT - 1024 - 256) / stage);
+  if (st > 8) st = 8;
+  const char* env = getenv("B200AD_TC_STAGES");
+  if (env && atoi(env) >= 1 && atoi(env) <= st) st = atoi(env);
+  pl.stages = st;
+  pl.smem_bytes = (uint32_t)st * stage + 1024 + 256;
+  pl.m_tiles = (int)ceil_div(g.m, TC_BM);
+  pl.n_tiles = (int)ceil_div(g.n, pl.bn);
+  pl.batches = (int)(g.batch0 * g.batch1);
+  pl.kblocks_total = (int)ceil_div(g.k, TC_BK);
+  // split-K when the output tiles cannot fill the machine and K is deep
+  const int64_t tiles = (int64_t)pl.m_tiles * pl.n_tiles * pl.batches;
+  int splits = 1;
+  const int sms = num_sms();
+  if (tiles < sms && pl.kblocks_total >= 16) {
+    splits = (int)(sms / tiles);
+    const int max_by_k = pl.kblocks_total / 8;       // keep >= 8 k-blocks per split
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+  }
+  const char* es = getenv("B200AD_TC_SPLITS");
+  if (es && atoi(es) >= 1) splits = atoi(es);
+  pl.kblocks_per_split = (int)ceil_div(pl.kblocks_total, splits);
+  pl.splits = (int)ceil_div(pl.kblocks_total, pl.kblocks_per_split);   // no empty splits
+  return pl;
+}
+
+bool gemm_tc_supported(const GemmArgs& g, int precision, const char** why) {
+  auto no = [&](const char* w) { if (why) *why = w; return false; };
+  if (precision != B200AD_GEMM_TF32X3 && precision != B200AD_GEMM_TF32)
+    return no("only TF32 / TF32X3 are built on the tcgen05 path (bf16 variant pending)");
+  if (g.m < 1 || g.n < 1 || g.k < 1) return no("empty problem");
+  if (g.k < 16 || g.m * g.n * g.k < (int64_t)(1 << 18)) return no("problem too small for the TMA path");
+  if ((reinterpret_cast<uintptr_t>(g.a) & 15) || (reinterpret_cast<uintptr_t>(g.b) & 15)) return no("operand base not 16B aligned");
+  if ((g.lda & 3) || (g.ldb & 3)) return no("leading dimension not a multiple of 4 elements (TMA stride must be 16B)");
+  if ((g.a_stride0 & 3) || (g.a_stride1 & 3) || (g.b_stride0 & 3) || (g.b_stride1 & 3)) return no("batch stride not 16B aligned");
+  if (g.batch0 > 1 && (g.a_stride0 <= 0 || g.b_stride0 <= 0)) return no("broadcast (stride 0) batch operands use the SIMT path");
+  if (g.batch1 > 1 && (g.a_stride1 <= 0 || g.b_stride1 <= 0)) return no("broadcast (stride 0) batch operands use the SIMT path");
+  if (g.m >= (1ll << 31) || g.n >= (1ll << 31) || g.k >= (1ll << 31)) return no("dimension too large");
+  if (g.batch0 * g.batch1 >= (1ll << 24)) return no("too many batches");
+  if (get_encode_fn() == nullptr) return no("cuTensorMapEncodeTiled unavailable (no driver)");
+  return true;
+}
+
+int64_t gemm_tc_workspace_bytes(const GemmArgs& g, int precision) {
+  if (g.m < 1 || g.n < 1 || g.k < 1) return 0;
+  TcPlan pl = make_plan(g, precision);
+  if (pl.splits <= 1) return 0;
+  return (int64_t)pl.splits * pl.batches * g.m * g.n * 4;
+}
+
+int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  TcPlan pl = make_plan(g, precision);
+  const int64_t need = pl.splits > 1 ? (int64_t)pl.splits * pl.batches * g.m * g.n * 4 : 0;
+  if (need > 0 && (!ws || ws_bytes < need)) {
+    // not enough workspace for split-K: run un-split
+    pl.splits = 1;
+    pl.kblocks_per_split = pl.kblocks_total;
+  }
+  OperandPlan oa, ob;
+  oa.mn_major = g.trans_a != 0;                       // stored (K x M): M contiguous
+  oa.inner = oa.mn_major ? g.m : g.k;
+  oa.rows = oa.mn_major ? g.k : g.m;
+  oa.ld = g.lda;
+  oa.box_rows = oa.mn_major ? 32 : TC_BM;
+  ob.mn_major = g.trans_b == 0;                       // stored (K x N): N contiguous
+  ob.inner = ob.mn_major ? g.n : g.k;
+  ob.rows = ob.mn_major ? g.k : g.n;
+  ob.ld = g.ldb;
+  ob.box_rows = ob.mn_major ? 32 : pl.bn;
+  CUtensorMap map_a, map_b;
+  int rc = encode_operand(&map_a, g.a, oa, g.batch0, g.batch1, g.a_stride0, g.a_stride1);
+  if (rc) return rc;
+  rc = encode_operand(&map_b, g.b, ob, g.batch0, g.batch1, g.b_stride0, g.b_stride1);
+  if (rc) return rc;
+
+  TcParams p;
+  p.c = g.c; p.c_in = g.c; p.bias = g.bias;
+  p.partial = pl.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+  p.m = g.m; p.n = g.n; p.k = g.k;
+  p.ldc = g.ldc; p.c_stride0 = g.c_stride0; p.c_stride1 = g.c_stride1;
+  p.batch1 = g.batch1;
+  p.batches = pl.batches; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splits = pl.splits;
+  p.kblocks_total = pl.kblocks_total; p.kblocks_per_split = pl.kblocks_per_split;
+  p.a_mn_major = oa.mn_major; p.b_mn_major = ob.mn_major;
+  p.x3 = pl.x3 ? 1 : 0;
+  const char* mh = getenv("B200AD_TC_MASK_HI");
+  p.mask_hi = mh ? atoi(mh) : 1;
+  p.act = g.act; p.alpha = g.alpha; p.beta = g.beta;
+  // TMEM accumulation chain length: 4 k-blocks = 128 K-elements (see the epilogue's fold).  Measured on B200
+  // (profiles/gemm_tc_probe.py): max err/sqrt(K) 6.5e-6 at K=4096 (fp32 SIMT: 1.6e-5) for a 3 % slowdown; 8
+  // k-blocks give 1.2e-5, no chunking grows linearly with K.  Single-pass TF32 is a 10-bit-mantissa probe
+  // anyway, so it accumulates the whole K range in place.
+  const char* ck = getenv("B200AD_TC_CHUNK_KB");
+  int chunk_kb = ck ? atoi(ck) : 4;
+  if (chunk_kb < 1 || !pl.x3) chunk_kb = 1 << 30;
+  p.chunked = (pl.kblocks_per_split > chunk_kb) ? 1 : 0;
+  p.chunk_kb = p.chunked ? chunk_kb : (1 << 30);
+
+  const int64_t total_tiles = (int64_t)pl.batches * pl.splits * pl.m_tiles * pl.n_tiles;
+  if (total_tiles >= (1ll << 31)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): too many tiles");
+  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  cudaError_t e;
+#define LAUNCH_BN(BNV)                                                                                          \
+  do {                                                                                                          \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      e = cudaFuncSetAttribute(gemm_tc_kernel<BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT); \
+      if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05): smem attribute: %s", cudaGetErrorString(e)); \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    gemm_tc_kernel<BNV><<<grid, TC_THREADS, pl.smem_bytes, s>>>(map_a, map_b, p, pl.stages);                    \
+  } while (0)
+  if (pl.bn == 64) LAUNCH_BN(64);
+  else if (pl.bn == 128) LAUNCH_BN(128);
+  else LAUNCH_BN(256);
+#undef LAUNCH_BN
+  count_launch();
+  rc = check_launch("gemm(tcgen05)");
+  if (rc) return rc;
+  if (pl.splits > 1) {
+    const int64_t total = g.m * g.n * pl.batches;
+    splitk_reduce_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(ws), pl.splits, p);
+    count_launch();
+    rc = check_launch("gemm(tcgen05 split-K reduce)");
+  }
+  return rc;
+}
+
 }  // namespace b200ad

@@ -674,6 +674,29 @@ def get_gemm_precision():
     return _default_precision[0]
 
 
+class GemmTimer:
+    """Optional per-launch CUDA-event timing of the GEMM launches (bench.py's roofline leg): events are
+    recorded on the launching stream right before/after each b200ad_gemm call."""
+
+    def __init__(self):
+        self.records = []   # (key, flops, start_event, end_event)
+
+    def summary(self):
+        """{key: (launches, total_ms, flops_per_launch)} — call after a device synchronize."""
+        out = {}
+        for key, flops, e0, e1 in self.records:
+            n, ms, _ = out.get(key, (0, 0.0, flops))
+            out[key] = (n + 1, ms + e0.elapsed_time(e1), flops)
+        return out
+
+
+_gemm_timer = [None]
+
+
+def set_gemm_timer(timer):
+    _gemm_timer[0] = timer
+
+
 def _mat_layout(t, rows, cols):
     """(trans, ld) for the last two axes of torch view `t`, or None if it must be copied."""
     sr, sc = t.stride(-2), t.stride(-1)
@@ -767,7 +790,15 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
     ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
     wptr = ws.data_ptr() if ws is not None else None
     pa, pb, pc = ta.data_ptr(), tb.data_ptr(), tc.data_ptr()
-    if not outer:
+    timer = _gemm_timer[0]
+    if timer is not None and not outer:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.b200ad_gemm(ctypes.byref(d), pa, pb, pc, bias_ptr, wptr, ws_bytes, s))
+        e1.record()
+        timer.records.append(((M, N, K, d.batch0 * d.batch1, la[0], lb[0], prec),
+                              2.0 * M * N * K * d.batch0 * d.batch1, e0, e1))
+    elif not outer:
         L.check(lib.b200ad_gemm(ctypes.byref(d), pa, pb, pc, bias_ptr, wptr, ws_bytes, s))
     else:  # more than two non-mergeable batch axes: loop the outermost ones on the host
         import itertools

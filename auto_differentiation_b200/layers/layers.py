@@ -515,7 +515,11 @@ class MultiHeadAttention:
         self.cache = (q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk))
         return out
 
-    def backward(self, dout=None):
+    def backward(self, dout=None, notify=None):
+        """`notify(i)` (optional) is called right after the last kernel writing gradient bucket i was
+        enqueued (1 = wo, 2 = wv, 3 = wk, 4 = wq) so a data-parallel reducer can start that all-reduce
+        while the rest of the backward still runs.  With `self.input_grads = False` the three GEMMs
+        producing d(query/key/value) are skipped (the reference tape always computes them)."""
         if dout is None:
             return None   # the reference's backward is a stub (layers.py:1366-1367)
         wq, wk, wv, wo = self.weights
@@ -523,19 +527,30 @@ class MultiHeadAttention:
         beta = 1.0 if self.accumulate else 0.0
         d2 = _dev(dout).reshape(B * S, wo.shape[1]).contiguous()
         D.matmul(O2, d2, trans_a=True, out=self.grads[3], beta=beta)             # dwo
+        if notify:
+            notify(1)
         dO = D.matmul(d2, wo, trans_b=True).reshape(B, S, h, dk)
         dOh = dO.transpose(0, 2, 1, 3)
         dP = D.matmul(dOh, Vh, trans_b=True)                                     # (B,h,S,S)
         dV = D.empty((B, S, h, dk))
         D.matmul(P, dOh, trans_a=True, out=dV.transpose(0, 2, 1, 3))
+        dV2 = dV.reshape(B * S, h * dk)
+        D.matmul(v2, dV2, trans_a=True, out=self.grads[2], beta=beta)            # dwv
+        if notify:
+            notify(2)
         dS = D.softmax_bwd_lastaxis(dP, P, out_scale=1.0 / math.sqrt(dk), out=dP)
         dQ, dK = D.empty((B, S, h, dk)), D.empty((B, S, h, dk))
         D.matmul(dS, Kh, out=dQ.transpose(0, 2, 1, 3))
         D.matmul(dS, Qh, trans_a=True, out=dK.transpose(0, 2, 1, 3))
-        dQ2, dK2, dV2 = (a.reshape(B * S, h * dk) for a in (dQ, dK, dV))
-        D.matmul(q2, dQ2, trans_a=True, out=self.grads[0], beta=beta)
-        D.matmul(k2, dK2, trans_a=True, out=self.grads[1], beta=beta)
-        D.matmul(v2, dV2, trans_a=True, out=self.grads[2], beta=beta)
+        dQ2, dK2 = dQ.reshape(B * S, h * dk), dK.reshape(B * S, h * dk)
+        D.matmul(k2, dK2, trans_a=True, out=self.grads[1], beta=beta)            # dwk
+        if notify:
+            notify(3)
+        D.matmul(q2, dQ2, trans_a=True, out=self.grads[0], beta=beta)            # dwq
+        if notify:
+            notify(4)
+        if not getattr(self, "input_grads", True):
+            return None
         dquery = D.matmul(dQ2, wq, trans_b=True).reshape(B, S, Dm)
         dkey = D.matmul(dK2, wk, trans_b=True).reshape(B, S, Dm)
         dvalue = D.matmul(dV2, wv, trans_b=True).reshape(B, S, Dm)

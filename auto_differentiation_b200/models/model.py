@@ -29,6 +29,54 @@ def _flatten_into(arrays):
     return flat, views
 
 
+class _ChunkFeeder:
+    """Double-buffered host->device streaming of row chunks of a host array (copy stream + events).
+    On a CPU-only test backend it degenerates to synchronous per-chunk uploads."""
+
+    def __init__(self, x, mb):
+        import torch
+        self.torch = torch
+        self.x = x
+        self.mb = mb
+        self.n = len(x)
+        self.async_ok = (D._DEVICE == "cuda" and isinstance(x, np.ndarray) and x.dtype == np.float32
+                         and x.flags.c_contiguous)
+        if self.async_ok:
+            self.src = torch.from_numpy(x)
+            self.stream = torch.cuda.Stream()
+            self.bufs = [torch.empty((mb,) + tuple(x.shape[1:]), dtype=torch.float32, device="cuda") for _ in range(2)]
+            self.ready = [None, None]
+            self.free = [None, None]
+            self._issue(0)
+
+    def _issue(self, c):
+        lo, hi = c * self.mb, min(self.n, (c + 1) * self.mb)
+        if lo >= self.n:
+            return
+        torch, slot = self.torch, c & 1
+        with torch.cuda.stream(self.stream):
+            if self.free[slot] is not None:
+                self.stream.wait_event(self.free[slot])         # the kernels of chunk c-2 are done with it
+            self.bufs[slot][:hi - lo].copy_(self.src[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.ready[slot] = ev
+
+    def get(self, c):
+        lo, hi = c * self.mb, min(self.n, (c + 1) * self.mb)
+        if not self.async_ok:
+            return asarray(np.asarray(self.x[lo:hi]))
+        self._issue(c + 1)
+        self.torch.cuda.current_stream().wait_event(self.ready[c & 1])
+        return DeviceArray(self.bufs[c & 1][:hi - lo])
+
+    def release(self, c):
+        if self.async_ok:
+            ev = self.torch.cuda.Event()
+            ev.record(self.torch.cuda.current_stream())
+            self.free[c & 1] = ev
+
+
 class TapeMLP:
     """Config 1: softmax(tanh(x@W1+b1)@W2+b2, 2) + mean cross-entropy, built op by op on the tape
     (`auto_grad` Matrix / gradient()) every step, like a user of the reference would."""
@@ -178,20 +226,25 @@ class AttentionClassifier:
 
     def forward(self, x, t, q=None):
         """x: (B_local, S, d) DeviceArray or host array; t: (B_local,) labels. Returns the mean loss
-        contribution of this rank (sum over ranks = global mean loss) as a 0-d DeviceArray."""
+        contribution of this rank (sum over ranks = global mean loss) as a 0-d DeviceArray.
+
+        Host input (NumPy fp32; page-locked memory makes the copies asynchronous) is streamed: the
+        host->device copy of micro-batch c+1 runs on a copy stream while micro-batch c computes."""
         B = len(x)
         gb = self.global_batch or B
         mb = min(self.micro_batch, B)
         self.zero_grads()
         t_dev = D.as_index(t)
         nchunks = (B + mb - 1) // mb
+        feeder = None if isinstance(x, DeviceArray) else _ChunkFeeder(x, mb)
         for c in range(nchunks):
             lo, hi = c * mb, min(B, (c + 1) * mb)
-            xc = x[lo:hi]
-            xc = xc if isinstance(xc, DeviceArray) else asarray(xc)
+            xc = x[lo:hi] if feeder is None else feeder.get(c)
             last = (c == nchunks - 1)
             notify = self.reducer.bucket_ready if (last and self.reducer is not None) else None
             self.chunk_step(xc, t_dev[lo:hi], (hi - lo) / gb, notify)
+            if feeder is not None:
+                feeder.release(c)
         return self.loss_buf.reshape(())
 
     def backward(self):

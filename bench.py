@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 autodiff hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # one rank per GPU (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+Headline workload (BASELINE.json configs[4], the config the metric "fwd+bwd+update steps/sec at 1/2/4/8
+B200" is quoted on): config 5 — MultiHeadAttention(d=512, 8 heads) on x (B,512,512) -> mean over the sequence
+-> affine 512->256 + tanh -> affine 256->10 -> softmax-CE, Adam, GLOBAL batch 8192 split evenly over the
+ranks (strong scaling), micro-batches of 256 sequences with on-device gradient accumulation, gradient
+all-reduce over NCCL overlapped with the last micro-batch's backward.  One "step" = forward + backward +
+update over the whole global batch.
+
+`value`  : whole-job steps/s with the rank's inputs already resident in HBM.
+`e2e`    : the same step through the public model API (`model.forward(x_host, t)`; `Trainer.fit` makes this
+           call) with HOST inputs: the host->device copies of every micro-batch (pinned memory, streamed on
+           a copy stream) and the device->host read of the loss are inside the timed region.
+Other workloads (`--workload c1|c2|c3|c4`) print their own line; see profiles/ for the collected tables.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GLOBAL_BATCH = 8192
+SEQ, DMODEL, HEADS, HIDDEN, CLASSES = 512, 512, 8, 256, 10
+C5_FLOP_PER_SEQ = 4831838208 + 3 * (2 * 512 * 256 + 2 * 256 * 10)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: the oracle (a NumPy port of the reference algorithm) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def c5_params_np(seed=1239, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    d = DMODEL
+    ws = [rng.standard_normal((d, d)) / np.sqrt(d) for _ in range(4)]
+    W1 = rng.standard_normal((d, HIDDEN)) / np.sqrt(d)
+    W2 = rng.standard_normal((HIDDEN, CLASSES)) / np.sqrt(HIDDEN)
+    return [w.astype(dtype) for w in ws + [W1, np.zeros(HIDDEN), W2, np.zeros(CLASSES)]]
+
+
+def cpu_reference_steps(steps, warmup, sample_seqs=4):
+    """Times the oracle's config-5 step (tape-twin MHA with the reference's per-path DFS backward + head +
+    Adam, fp64 like the reference's default) on `sample_seqs` sequences; returns (steps/s scaled to the
+    full 8192-sequence step, seconds per sampled step)."""
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(1239)
+    params = c5_params_np()
+    x = rng.standard_normal((sample_seqs, SEQ, DMODEL))
+    t = rng.integers(0, CLASSES, sample_seqs)
+    opt = O.Adam(lr=1e-3)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, grads, _ = O.c5_model_step(x, t, params, heads=HEADS)
+        opt.update(params, [g.reshape(p.shape) for g, p in zip(grads, params)])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = float(np.median(times))
+    return (sample_seqs / sec) / GLOBAL_BATCH, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    value, sec = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 1)), sample)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "fwd+bwd+update steps/sec", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, args.micro_batch),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d of %d sequences per step (S=512, d=512, 8 heads), fp64 NumPy port of the "
+                                   "reference tape + Adam, %.3f s per sample, scaled linearly" % (sample, GLOBAL_BATCH, sec)},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, micro_batch):
+    return {"workload": "c5: MHA(d=512,h=8)+mean-pool+MLP(512-256-10)+softmax-CE, Adam; BASELINE configs[4]",
+            "global_batch": GLOBAL_BATCH, "seq_len": SEQ, "d_model": DMODEL, "heads": HEADS,
+            "micro_batch": micro_batch, "params": 1182474, "parallelism": "dp%d" % n_gpus,
+            "l2": "per-step working set (>= 8.6 GB of inputs per rank at N=1) is far larger than the 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import auto_differentiation_b200 as pkg
+    from auto_differentiation_b200 import _lib as L, device as D
+    from auto_differentiation_b200.data_parallel import GradientReducer, shard_rows
+    from auto_differentiation_b200.models.model import AttentionClassifier
+    from auto_differentiation_b200.utils.optimizer import Adam
+
+    pkg.set_gemm_precision(args.precision)
+    lo, hi = shard_rows(GLOBAL_BATCH, rank, world)
+    b_local = hi - lo
+    model = AttentionClassifier(DMODEL, HEADS, HIDDEN, CLASSES, seed=1239, micro_batch=args.micro_batch)
+    model.global_batch = GLOBAL_BATCH
+    model.reducer = GradientReducer(model.flat_grads.t, model.bucket_slices()) if world > 1 else None
+    opt = Adam(lr=1e-3)
+
+    gen = torch.Generator(device="cuda").manual_seed(1239 + rank)
+    x_dev = D.DeviceArray(torch.randn((b_local, SEQ, DMODEL), generator=gen, device="cuda"))   # synthetic inputs
+    t_host = np.random.default_rng(1239 + rank).integers(0, CLASSES, b_local)
+    t_dev = D.as_index(t_host)
+
+    def step(x, t):
+        loss = model.forward(x, t)
+        model.backward()
+        opt.update(model.weights, model.grads)
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(x, t, steps, warmup, read_loss, timer=None):
+        for _ in range(warmup):
+            loss = step(x, t)
+            if read_loss:
+                float(loss)
+        sync_all()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        D.set_gemm_timer(timer)
+        launches0 = L.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            loss = step(x, t)
+            if read_loss:
+                last = float(loss)               # device -> host read of the step's loss
+        e1.record()
+        torch.cuda.synchronize()
+        D.set_gemm_timer(None)
+        ms = e0.elapsed_time(e1)
+        launches = L.launch_count() - launches0
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        return ms / steps, launches, clocks, (last if last is not None else float(loss))
+
+    # ---- device-resident throughput (`value`) ----
+    timer = D.GemmTimer()
+    ms_step, launches, clocks, loss_val = timed(x_dev, t_dev, args.steps, args.warmup, False, timer)
+    gemm = timer.summary()
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        x_host_t = torch.empty((b_local, SEQ, DMODEL), dtype=torch.float32, pin_memory=True)
+        x_host_t.copy_(x_dev.t)                          # same synthetic inputs, now in pinned host memory
+        x_host = x_host_t.numpy()
+        e2e_steps = max(1, min(args.steps, 3))
+        ms_e2e, _, _, _ = timed(x_host, t_host, e2e_steps, 1, True)
+        e2e = {"value": 1e3 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(b_local * SEQ * DMODEL * 4 + b_local * 8), "d2h_bytes_per_step": 4,
+               "steps": e2e_steps, "api": "AttentionClassifier.forward(x_host, t) / backward() / Adam.update"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    # dominant kernel = the GEMM shape with the largest accumulated device time in the timed region
+    roof = None
+    if gemm:
+        key, (n, ms_tot, flops) = max(gemm.items(), key=lambda kv: kv[1][1])
+        total_gemm_ms = sum(v[1] for v in gemm.values())
+        avg_ms = ms_tot / n
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        peak = pk["bf16_sustained"]
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % pk["src"],
+                "kernel": "b200ad_gemm M=%d N=%d K=%d batches=%d transA=%d transB=%d precision=%d" % key,
+                "launches_timed": n, "avg_launch_ms": avg_ms,
+                "share_of_step": ms_tot / (ms_step * args.steps), "all_gemm_share_of_step": total_gemm_ms / (ms_step * args.steps),
+                "step_tflops": C5_FLOP_PER_SEQ * GLOBAL_BATCH / world / (ms_step * 1e-3) / 1e12}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec = cpu_reference_steps(2, 1, 4)
+        cpu = {"value": v, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "4 of %d sequences per step (S=512, d=512, 8 heads), fp64 NumPy port of the reference tape + "
+                         "Adam, %.3f s per sample, scaled linearly" % (GLOBAL_BATCH, sec)}
+    line = {
+        "metric": "fwd+bwd+update steps/sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": {"auto": "f32", "fp32": "f32", "tf32x3": "f32", "bf16": "bf16", "tf32": "tf32"}[args.precision],
+        "data": "synthetic", "config": workload_config(world, args.micro_batch), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "loss": loss_val,
+        "gemm_precision": args.precision,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "bf16", "tf32"])
+    ap.add_argument("--micro-batch", type=int, default=256)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH,
+                    help="profiling aid only (ncu captures): the headline number is always quoted at 8192")
+    args = ap.parse_args()
+    global GLOBAL_BATCH
+    GLOBAL_BATCH = args.global_batch
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
+    from profiles import workloads
+    return workloads.run(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -541,13 +541,12 @@ def mlp_tape_step(x, labels, W1, b1, W2, b2):
     return loss, y.val, [w1.grad, B1.grad, w2.grad, B2.grad], X.grad
 
 
-def c5_model_step(x, labels, params):
+def c5_model_step(x, labels, params, heads=8):
     """Config 5 model: MHA(q=k=v=x) -> mean over the sequence -> affine 512->256 + tanh ->
     affine 256->10 -> softmax-CE, forward + backward; returns (loss, grads in params order).
     MHA runs on the tape twin (mha_tape); the head reuses the layer formulas."""
     wq, wk, wv, wo, W1, b1, W2, b2 = params
     B, S, Dm = x.shape
-    heads = 8 if wq.shape[1] % 8 == 0 else 1
     out, leaves = mha_tape(x, x, x, wq, wk, wv, wo, heads)
     a = out.val                                   # (B,S,H)
     pooled = a.sum(axis=1) / S                    # mean over the sequence
