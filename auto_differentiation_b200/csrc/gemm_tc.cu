@@ -12,8 +12,8 @@
 // Structure (persistent, warp-specialised, one CTA per SM, static tile scheduler):
 //   warp 0      TMA producer: cp.async.bulk.tensor (4-D maps: inner, rows, batch1, batch0; 128B swizzle)
 //   warp 1      MMA issuer (one elected lane): tcgen05.mma 128 x BN x 8, accumulators in TMEM (double buffered)
-//   warps 2-5   splitter (TF32X3 only): raw tile -> masked hi (in place) + lo tile, fence.proxy.async
-//   warps 6-9   epilogue: tcgen05.ld TMEM -> registers -> alpha/beta/bias/activation -> global
+//   warps 2-9   splitter (TF32X3 only): raw tile -> masked hi (in place) + lo tile, fence.proxy.async
+//   warps 10-13 epilogue: tcgen05.ld TMEM -> registers -> alpha/beta/bias/activation -> global
 // Pipelines: raw_full / conv_full / empty mbarriers over a ring of smem stages, tmem_full / tmem_empty over
 // the two accumulator buffers, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Both operand majors are fed natively: a row-major (rows x K) operand is K-major, a (K x cols) row-major
@@ -27,8 +27,11 @@
 namespace b200ad {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                 // 32 fp32 = 128 B = one swizzle-128B row
-constexpr int TC_THREADS = 320;           // 10 warps
+constexpr int TC_BK = 32;                 // 32 fp32 = 128 B rows (K-major: swizzle-128B).  BK=16 (swizzle-64B, 4-deep
+                                          // ring) was measured slower: smaller TMA boxes, same smem-bandwidth bound
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_SPLIT_THREADS = TC_SPLIT_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_SPLIT_THREADS + 128;   // TMA, MMA, 8 splitter warps, 4 epilogue warps
 constexpr uint32_t TC_SMEM_LIMIT = 232448;  // 227 KB
 
 // ---------------------------------------------------------------------------------------------------------
@@ -126,6 +129,50 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit to the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
 // UMMA shared-memory matrix descriptor (sm100: version 1).  Offsets in bytes.
 // layout: 2 = SWIZZLE_128B (16 B atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32 B atoms, 4-row
 // period) — the ONLY layout tcgen05 accepts for MN-major tf32 operands.
@@ -165,6 +212,7 @@ struct TcParams {
   int64_t batch1;
   int32_t batches, m_tiles, n_tiles, splits, kblocks_total, kblocks_per_split;
   int32_t a_mn_major, b_mn_major, x3, mask_hi, act;
+  int32_t probe;               // diagnostic bits: 1 = skip the TMA loads, 2 = skip the split (3 = pure MMA + epilogue)
   int32_t chunk_kb, chunked;   // TMEM accumulation chunk (k-blocks); chunked: buffer 0 = chunk sum X, buffer 1 = running total Y
   float alpha, beta;
 };
@@ -204,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&conv_full[s], 128);
+      mbar_init(&conv_full[s], TC_SPLIT_THREADS);
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -241,6 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + A_BYTES;
+          if (p.probe & 1) { mbar_arrive(&raw_full[s]); continue; }
           mbar_expect_tx(&raw_full[s], A_BYTES + B_BYTES);
           const int k0 = kb * TC_BK;
           if (!p.a_mn_major) {
@@ -248,14 +297,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BM / 32; ++c)
-              tma_load_4d(&map_a, &raw_full[s], sa + c * 4096, m_tile * TC_BM + c * 32, k0, b1, b0);
+              tma_load_4d(&map_a, &raw_full[s], sa + c * (128 * TC_BK), m_tile * TC_BM + c * 32, k0, b1, b0);
           }
           if (!p.b_mn_major) {
             tma_load_4d(&map_b, &raw_full[s], sb, k0, n_tile * BN, b1, b0);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c)
-              tma_load_4d(&map_b, &raw_full[s], sb + c * 4096, n_tile * BN + c * 32, k0, b1, b0);
+              tma_load_4d(&map_b, &raw_full[s], sb + c * (128 * TC_BK), n_tile * BN + c * 32, k0, b1, b0);
           }
         }
       }
@@ -265,12 +314,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
                            ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO), k-step = +32 B inside the atom.
-    // MN-major (SWIZZLE_128B_BASE32B): 32-element chunks 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO),
-    // k-step (8 rows) = +1024 B.
-    const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
-    const uint32_t a_sbo = p.a_mn_major ? 512u : 1024u, b_sbo = p.b_mn_major ? 512u : 1024u;
-    const uint32_t a_lay = p.a_mn_major ? 1u : 2u, b_lay = p.b_mn_major ? 1u : 2u;
+    // K-major (SWIZZLE_128B for BK=32 / SWIZZLE_64B for BK=16): rows of 4*BK B, 8-row groups 32*BK B apart (SBO),
+    // k-step = +32 B inside the swizzle atom.
+    // MN-major (SWIZZLE_128B_BASE32B): 32-element chunks 128*BK B apart (LBO), 4-k-row groups 512 B apart
+    // (SBO), k-step (8 rows) = +1024 B.
+    constexpr uint32_t MN_LBO = 128u * TC_BK;
+    const uint32_t a_lbo = p.a_mn_major ? MN_LBO : 16u, b_lbo = p.b_mn_major ? MN_LBO : 16u;
+    constexpr uint32_t K_SBO = 32u * TC_BK, K_LAY = (TC_BK == 32) ? 2u : 4u;
+    const uint32_t a_sbo = p.a_mn_major ? 512u : K_SBO, b_sbo = p.b_mn_major ? 512u : K_SBO;
+    const uint32_t a_lay = p.a_mn_major ? 1u : K_LAY, b_lay = p.b_mn_major ? 1u : K_LAY;
     const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
     uint32_t it = 0, uit = 0;   // k-block counter (smem ring) and accumulation-unit counter (TMEM buffers)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -324,10 +376,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + TC_SPLIT_WARPS) {
     // ===================================== splitter (TF32X3) =====================================
     if (p.x3) {
-      const int tid = threadIdx.x - 64;   // 0..127
+      const int tid = threadIdx.x - 64;   // 0..TC_SPLIT_THREADS-1
       uint32_t it = 0;
       constexpr uint32_t VECS = (A_BYTES + B_BYTES) / 16;   // float4 count of the raw [A|B] block
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -342,8 +394,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&raw_full[s], ph);
           uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
           uint4* lo = hi + VECS;
-#pragma unroll 4
-          for (uint32_t i = tid; i < VECS; i += 128) {
+          if (p.probe & 2) { mbar_arrive(&conv_full[s]); continue; }
+#pragma unroll 6
+          for (uint32_t i = tid; i < VECS; i += TC_SPLIT_THREADS) {
             const uint4 v = hi[i];
             uint4 h, l;
             h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
@@ -479,6 +532,318 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =========================================================================================================
+// CTA-pair kernel (TF32X3 only): one 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2,
+// UMMA M=256, N=256).  CTA r of the pair owns rows [128r, 128r+128) of the tile and stages columns
+// [128r, 128r+128) of the B tile, so each SM loads / splits / serves half as much B as the 1-CTA kernel:
+// 64 KB stages -> a 3-deep ring (the 1-CTA kernel only fits 2 stages and exposes TMA latency + split time),
+// half the L2->SM operand traffic, and half the shared-memory operand reads per MMA.
+// Roles per CTA are the same as above; only the leader CTA (rank 0) issues MMAs.  Cross-CTA signalling:
+//   conv_full[s]   (leader)  <- 512 splitter threads of both CTAs (remote mbarrier.arrive via mapa)
+//   empty[s]       (both)    <- tcgen05.commit ... multicast::cluster
+//   tmem_full[b]   (both)    <- tcgen05.commit ... multicast::cluster
+//   tmem_empty[b]  (leader)  <- 256 epilogue threads of both CTAs
+// =========================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const TcParams p, const int stages) {
+  constexpr int BN = 256;
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;            // this CTA's 128 rows of A
+  constexpr uint32_t B_BYTES = (BN / 2) * TC_BK * 4;         // this CTA's half of the B tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // smem: a 4-deep ring of raw (= hi) tiles filled by TMA and a 2-deep ring of lo tiles filled by the splitter:
+  // TMA gets three k-blocks of lead time while the lo tiles only need to stay one k-block ahead of the MMA.
+  constexpr uint32_t raw_bytes = A_BYTES + B_BYTES;           // 32 KB
+  constexpr int R = 4, LS = 2;
+  (void)stages;
+  uint8_t* lo_base = smem + (size_t)R * raw_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_base + (size_t)LS * raw_bytes);
+  uint64_t* raw_full = bars;                 // [R]  TMA -> splitter (local)
+  uint64_t* empty = bars + R;                // [R]  MMA -> TMA (both CTAs, multicast commit)
+  uint64_t* conv_full = bars + 2 * R;        // [LS] splitter -> MMA (leader, 512 arrivals)
+  uint64_t* lo_empty = conv_full + LS;       // [LS] MMA -> splitter (both CTAs, multicast commit)
+  uint64_t* tmem_full = lo_empty + LS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < LS; ++s) {
+      mbar_init(&conv_full[s], 2 * TC_SPLIT_THREADS);
+      mbar_init(&lo_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();                      // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int total_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;   // m_tiles counts 256-row tiles
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+        int t = tile;
+        const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+        const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+        const int split = t % p.splits;
+        const int batch = t / p.splits;
+        const int b0 = (int)(batch / p.batch1), b1 = (int)(batch % p.batch1);
+        const int kb0 = split * p.kblocks_per_split;
+        int kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+        const int m0 = m_tile * 256 + (int)rank * TC_BM;
+        const int n0 = n_tile * BN + (int)rank * (BN / 2);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % R;
+          const uint32_t ph = (it / R) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * raw_bytes;
+          uint8_t* sb = sa + A_BYTES;
+          if (p.probe & 1) { mbar_arrive(&raw_full[s]); continue; }
+          mbar_expect_tx(&raw_full[s], A_BYTES + B_BYTES);
+          const int k0 = kb * TC_BK;
+          if (!p.a_mn_major) {
+            tma_load_4d(&map_a, &raw_full[s], sa, k0, m0, b1, b0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 32; ++c)
+              tma_load_4d(&map_a, &raw_full[s], sa + c * (128 * TC_BK), m0 + c * 32, k0, b1, b0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_4d(&map_b, &raw_full[s], sb, k0, n0, b1, b0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(&map_b, &raw_full[s], sb + c * (128 * TC_BK), n0 + c * 32, k0, b1, b0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =====================================
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t MN_LBO = 128u * TC_BK;
+      const uint32_t a_lbo = p.a_mn_major ? MN_LBO : 16u, b_lbo = p.b_mn_major ? MN_LBO : 16u;
+      constexpr uint32_t K_SBO = 32u * TC_BK, K_LAY = (TC_BK == 32) ? 2u : 4u;
+      const uint32_t a_sbo = p.a_mn_major ? 512u : K_SBO, b_sbo = p.b_mn_major ? 512u : K_SBO;
+      const uint32_t a_lay = p.a_mn_major ? 1u : K_LAY, b_lay = p.b_mn_major ? 1u : K_LAY;
+      const uint32_t a_kstep = p.a_mn_major ? 1024u : 32u, b_kstep = p.b_mn_major ? 1024u : 32u;
+      uint32_t it = 0, uit = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+        int t = tile / (p.n_tiles * p.m_tiles);
+        const int split = t % p.splits;
+        const int kb0 = split * p.kblocks_per_split;
+        int kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+        for (int cb0 = kb0; cb0 < kb1; cb0 += p.chunk_kb, ++uit) {
+          int cb1 = cb0 + p.chunk_kb;
+          if (cb1 > kb1) cb1 = kb1;
+          const uint32_t buf = p.chunked ? 0u : (uit & 1);
+          const uint32_t buf_ph = p.chunked ? (uit & 1) : ((uit >> 1) & 1);
+          mbar_wait(&tmem_empty[buf], buf_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (int kb = cb0; kb < cb1; ++kb, ++it) {
+            const int s = it % R, ls = it % LS;
+            const uint32_t lph = (it / LS) & 1;
+            mbar_wait(&conv_full[ls], lph);        // both CTAs' hi/lo tiles of this k-block are in place
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = smem_u32(smem + (size_t)s * raw_bytes);
+              const uint32_t sb = sa + A_BYTES;
+              const uint32_t sal = smem_u32(lo_base + (size_t)ls * raw_bytes), sbl = sal + A_BYTES;
+              const bool first_kb = (kb == cb0);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma2_tf32(d_tmem, make_smem_desc(sal + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                           make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, (first_kb && kk == 0) ? 0u : 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma2_tf32(d_tmem, make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                           make_smem_desc(sbl + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma2_tf32(d_tmem, make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo, a_lay),
+                           make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc, 1u);
+              umma2_commit_mc(&empty[s]);                          // frees the raw stage in BOTH CTAs
+              umma2_commit_mc(&lo_empty[ls]);                      // ... and the lo stage
+              if (kb == cb1 - 1) umma2_commit_mc(&tmem_full[buf]);  // accumulator ready in BOTH CTAs
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp < 2 + TC_SPLIT_WARPS) {
+    // ===================================== splitter (both CTAs) =====================================
+    const int tid = threadIdx.x - 64;
+    uint32_t it = 0;
+    constexpr uint32_t VECS = (A_BYTES + B_BYTES) / 16;
+    for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+      int t = tile / (p.n_tiles * p.m_tiles);
+      const int split = t % p.splits;
+      const int kb0 = split * p.kblocks_per_split;
+      int kb1 = kb0 + p.kblocks_per_split;
+      if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % R, ls = it % LS;
+        mbar_wait(&raw_full[s], (it / R) & 1);
+        mbar_wait(&lo_empty[ls], ((it / LS) & 1) ^ 1);
+        uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * raw_bytes);
+        uint4* lo = reinterpret_cast<uint4*>(lo_base + (size_t)ls * raw_bytes);
+        if (!(p.probe & 2)) {
+#pragma unroll 4
+          for (uint32_t i = tid; i < VECS; i += TC_SPLIT_THREADS) {
+            const uint4 v = hi[i];
+            uint4 h, l;
+            h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+            if (p.mask_hi) hi[i] = h;
+            lo[i] = l;
+          }
+          fence_proxy_async();
+        }
+        mbar_arrive_cluster(&conv_full[ls], 0);     // the leader's barrier counts both CTAs' splitter threads
+      }
+    }
+  } else {
+    // ===================================== epilogue (both CTAs, own 128 rows) =====================================
+    const int ew = warp & 3;
+    const int row_in_tile = ew * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    uint32_t uit = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+      int t = tile;
+      const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+      const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+      const int split = t % p.splits;
+      const int batch = t / p.splits;
+      const int64_t b0 = batch / p.batch1, b1 = batch % p.batch1;
+      const int kb0 = split * p.kblocks_per_split;
+      int kb1 = kb0 + p.kblocks_per_split;
+      if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+      const int nchunks = (kb1 - kb0 + p.chunk_kb - 1) / p.chunk_kb;
+      const int64_t gm = (int64_t)m_tile * 256 + rank * TC_BM + row_in_tile;
+      const bool row_ok = gm < p.m;
+      float* crow;
+      if (p.partial) crow = p.partial + (((int64_t)split * p.batches + batch) * p.m + gm) * p.n;
+      else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
+      for (int ch = 0; ch < nchunks; ++ch, ++uit) {
+        const uint32_t buf = p.chunked ? 0u : (uit & 1);
+        const uint32_t buf_ph = p.chunked ? (uit & 1) : ((uit >> 1) & 1);
+        mbar_wait(&tmem_full[buf], buf_ph);
+        tc_fence_after();
+        const uint32_t x_addr = tmem_base + lane_base + buf * BN;
+        const uint32_t y_addr = tmem_base + lane_base + BN;
+        const bool last = (ch == nchunks - 1);
+        if (!last) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t x[32];
+            tmem_ld_32x32b_x32(x_addr + c0, x);
+            if (ch > 0) {
+              uint32_t y[32];
+              tmem_ld_32x32b_x32(y_addr + c0, y);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __float_as_uint(__uint_as_float(x[j]) + __uint_as_float(y[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            tmem_st_32x32b_x32(y_addr + c0, x);
+          }
+          tmem_st_wait();
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(x_addr + c0, r);
+            if (nchunks > 1) {
+              uint32_t y[32];
+              tmem_ld_32x32b_x32(y_addr + c0, y);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(y[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            const int64_t gn0 = (int64_t)n_tile * BN + c0;
+            if (row_ok && gn0 < p.n) {
+              float* dst = crow + gn0;
+              const bool full = (gn0 + 32 <= p.n);
+              float v[32];
+              if (p.partial) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
+                if (p.beta != 0.f) {
+                  for (int j = 0; j < 32 && gn0 + j < p.n; ++j) v[j] += p.beta * dst[j];
+                }
+                if (p.bias) {
+                  for (int j = 0; j < 32 && gn0 + j < p.n; ++j) v[j] += __ldg(p.bias + gn0 + j);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tc_act<1>(v[j]);
+                } else if (p.act == 2) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tc_act<2>(v[j]);
+                } else if (p.act == 3) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tc_act<3>(v[j]);
+                }
+              }
+              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                for (int j = 0; j < 32 && gn0 + j < p.n; ++j) dst[j] = v[j];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(&tmem_empty[buf], 0);    // leader's MMA warp waits for both CTAs' epilogues
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // the peer's smem / barriers / TMEM stay valid until both CTAs are done
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
 // split-K second pass: C = alpha * sum_s partial[s] + beta*C + bias, activation.  One thread per 4 outputs.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, TcParams p) {
   const int64_t per_batch = p.m * p.n;
@@ -539,11 +904,13 @@ static int encode_operand(CUtensorMap* map, const float* base, const OperandPlan
   if (s1 <= 0) s1 = fallback;
   if (s0 <= 0) s0 = fallback;
   cuuint64_t strides[3] = {(cuuint64_t)o.ld * 4, (cuuint64_t)s1 * 4, (cuuint64_t)s0 * 4};
-  cuuint32_t box[4] = {32u, (cuuint32_t)o.box_rows, 1u, 1u};
+  cuuint32_t box[4] = {o.mn_major ? 32u : (cuuint32_t)TC_BK, (cuuint32_t)o.box_rows, 1u, 1u};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   o.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   o.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                              : (TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
   return B200AD_OK;
@@ -564,6 +931,7 @@ struct TcPlan {
   int bn, stages, splits, kblocks_total, kblocks_per_split, m_tiles, n_tiles, batches;
   uint32_t smem_bytes;
   bool x3;
+  bool pair;     // CTA-pair kernel (cta_group::2, 256 x 256 tiles)
 };
 
 static int num_sms() {
@@ -580,24 +948,34 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   TcPlan pl;
   pl.x3 = (precision == B200AD_GEMM_TF32X3);
   pl.bn = pick_bn(g.n);
-  const uint32_t stage = (TC_BM * TC_BK * 4 + pl.bn * TC_BK * 4) * (pl.x3 ? 2 : 1);
+  // CTA-pair kernel: opt-in.  Measured on B200 (profiles/r1_gemm_tc_probe.md): +3..7 % on 4096^3 / 8192^3, but
+  // -5 % on the (131072 x 512 x 512) projection shapes of config 5 (the chunk fold waits for two epilogues).
+  const char* ep = getenv("B200AD_TC_PAIR");
+  const int pair_mode = ep ? atoi(ep) : 0;
+  pl.pair = pl.x3 && pl.bn == 256 && g.m > TC_BM && pair_mode != 0;
+  const uint32_t stage = pl.pair ? (TC_BM * TC_BK * 4 + (pl.bn / 2) * TC_BK * 4) * 2
+                                 : (TC_BM * TC_BK * 4 + pl.bn * TC_BK * 4) * (pl.x3 ? 2 : 1);
   int st = (int)((TC_SMEM_LIMIT - 1024 - 256) / stage);
   if (st > 8) st = 8;
   const char* env = getenv("B200AD_TC_STAGES");
   if (env && atoi(env) >= 1 && atoi(env) <= st) st = atoi(env);
   pl.stages = st;
   pl.smem_bytes = (uint32_t)st * stage + 1024 + 256;
-  pl.m_tiles = (int)ceil_div(g.m, TC_BM);
+  if (pl.pair) {   // 4 raw stages + 2 lo stages of 32 KB
+    pl.stages = 4;
+    pl.smem_bytes = 6u * (TC_BM * TC_BK * 4 + (pl.bn / 2) * TC_BK * 4) + 1024 + 256;
+  }
+  pl.m_tiles = (int)ceil_div(g.m, pl.pair ? 2 * TC_BM : TC_BM);
   pl.n_tiles = (int)ceil_div(g.n, pl.bn);
   pl.batches = (int)(g.batch0 * g.batch1);
   pl.kblocks_total = (int)ceil_div(g.k, TC_BK);
   // split-K when the output tiles cannot fill the machine and K is deep
   const int64_t tiles = (int64_t)pl.m_tiles * pl.n_tiles * pl.batches;
   int splits = 1;
-  const int sms = num_sms();
-  if (tiles < sms && pl.kblocks_total >= 16) {
+  const int sms = pl.pair ? num_sms() / 2 : num_sms();   // schedulable units: CTAs or CTA pairs
+  if (tiles < sms && pl.kblocks_total * TC_BK >= 512) {
     splits = (int)(sms / tiles);
-    const int max_by_k = pl.kblocks_total / 8;       // keep >= 8 k-blocks per split
+    const int max_by_k = pl.kblocks_total * TC_BK / 256;   // keep >= 256 K-elements per split
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
@@ -646,12 +1024,12 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   oa.inner = oa.mn_major ? g.m : g.k;
   oa.rows = oa.mn_major ? g.k : g.m;
   oa.ld = g.lda;
-  oa.box_rows = oa.mn_major ? 32 : TC_BM;
+  oa.box_rows = oa.mn_major ? TC_BK : TC_BM;
   ob.mn_major = g.trans_b == 0;                       // stored (K x N): N contiguous
   ob.inner = ob.mn_major ? g.n : g.k;
   ob.rows = ob.mn_major ? g.k : g.n;
   ob.ld = g.ldb;
-  ob.box_rows = ob.mn_major ? 32 : pl.bn;
+  ob.box_rows = ob.mn_major ? TC_BK : (pl.pair ? pl.bn / 2 : pl.bn);
   CUtensorMap map_a, map_b;
   int rc = encode_operand(&map_a, g.a, oa, g.batch0, g.batch1, g.a_stride0, g.a_stride1);
   if (rc) return rc;
@@ -668,15 +1046,20 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   p.kblocks_total = pl.kblocks_total; p.kblocks_per_split = pl.kblocks_per_split;
   p.a_mn_major = oa.mn_major; p.b_mn_major = ob.mn_major;
   p.x3 = pl.x3 ? 1 : 0;
+  // tcgen05 reads fp32 smem operands as tf32 by IGNORING the 13 low mantissa bits (measured: identical error with
+  // and without rewriting the hi tile, profiles/gemm_tc_probe.py "x3 without hi masking"), so the raw tile already
+  // is Ah = trunc(A); only the lo tile is materialised.  B200AD_TC_MASK_HI=1 restores the explicit rewrite.
   const char* mh = getenv("B200AD_TC_MASK_HI");
-  p.mask_hi = mh ? atoi(mh) : 1;
+  p.mask_hi = mh ? atoi(mh) : 0;
   p.act = g.act; p.alpha = g.alpha; p.beta = g.beta;
-  // TMEM accumulation chain length: 4 k-blocks = 128 K-elements (see the epilogue's fold).  Measured on B200
+  const char* pb = getenv("B200AD_TC_PROBE");
+  p.probe = pb ? atoi(pb) : 0;
+  // TMEM accumulation chain length: 128 K-elements (see the epilogue's fold).  Measured on B200
   // (profiles/gemm_tc_probe.py): max err/sqrt(K) 6.5e-6 at K=4096 (fp32 SIMT: 1.6e-5) for a 3 % slowdown; 8
   // k-blocks give 1.2e-5, no chunking grows linearly with K.  Single-pass TF32 is a 10-bit-mantissa probe
   // anyway, so it accumulates the whole K range in place.
   const char* ck = getenv("B200AD_TC_CHUNK_KB");
-  int chunk_kb = ck ? atoi(ck) : 4;
+  int chunk_kb = ck ? atoi(ck) : 128 / TC_BK;
   if (chunk_kb < 1 || !pl.x3) chunk_kb = 1 << 30;
   p.chunked = (pl.kblocks_per_split > chunk_kb) ? 1 : 0;
   p.chunk_kb = p.chunked ? chunk_kb : (1 << 30);
@@ -685,6 +1068,27 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   if (total_tiles >= (1ll << 31)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): too many tiles");
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   cudaError_t e;
+  if (pl.pair) {
+    static bool attr2 = false;
+    if (!attr2) {
+      e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+      if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05 pair): smem attribute: %s", cudaGetErrorString(e));
+      attr2 = true;
+    }
+    const int pairs = num_sms() / 2;
+    const int grid2 = 2 * (int)(total_tiles < pairs ? total_tiles : pairs);
+    gemm_tc2_kernel<<<grid2, TC_THREADS, pl.smem_bytes, s>>>(map_a, map_b, p, pl.stages);   // __cluster_dims__(2,1,1)
+    count_launch();
+    rc = check_launch("gemm(tcgen05 pair)");
+    if (rc) return rc;
+    if (pl.splits > 1) {
+      const int64_t total = g.m * g.n * pl.batches;
+      splitk_reduce_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(ws), pl.splits, p);
+      count_launch();
+      rc = check_launch("gemm(tcgen05 split-K reduce)");
+    }
+    return rc;
+  }
 #define LAUNCH_BN(BNV)                                                                                          \
   do {                                                                                                          \
     static bool attr_set = false;                                                                               \

@@ -299,11 +299,10 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH,
+    ap.add_argument("--global-batch", type=int, default=8192,
                     help="profiling aid only (ncu captures): the headline number is always quoted at 8192")
     args = ap.parse_args()
-    global GLOBAL_BATCH
-    GLOBAL_BATCH = args.global_batch
+    globals()["GLOBAL_BATCH"] = args.global_batch
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c5":

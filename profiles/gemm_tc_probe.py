@@ -10,7 +10,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks"]
+GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling"]
 
 
 def run_group(group):
@@ -105,6 +105,19 @@ def run_group(group):
         case("bias tanh", 256, 256, 128, prec="tf32x3", bias=True, act=1)
         case("bias relu tails", 200, 100, 96, prec="tf32x3", bias=True, act=3)
         case("split-K beta bias", 256, 256, 8192, ta=True, prec="tf32x3", beta=1.0, bias=True)
+    elif group == "ceiling":
+        os.environ["B200AD_TC_CHUNK_KB"] = "100000"
+        print("-- probe bits: 1 = no TMA, 2 = no split, 3 = pure MMA + epilogue (results are garbage, only the rate matters)", flush=True)
+        for pair in ("1", "0"):
+            os.environ["B200AD_TC_PAIR"] = pair
+            for probe in ("0", "1", "2", "3"):
+                os.environ["B200AD_TC_PROBE"] = probe
+                case("pair=%s probe=%s x3" % (pair, probe), 8192, 8192, 8192, tb=True, prec="tf32x3", time_it=True)
+        os.environ["B200AD_TC_PAIR"] = "1"
+        for probe in ("0", "1", "2", "3"):
+            os.environ["B200AD_TC_PROBE"] = probe
+            case("pair=1 probe=%s projection" % probe, 131072, 512, 512, prec="tf32x3", time_it=True)
+        os.environ.pop("B200AD_TC_PROBE"); os.environ.pop("B200AD_TC_CHUNK_KB"); os.environ.pop("B200AD_TC_PAIR")
     elif group == "chunks":
         for ck in ("2", "4", "8", "16"):
             os.environ["B200AD_TC_CHUNK_KB"] = ck

@@ -328,4 +328,4 @@ def test_large_size_properties():
     assert_close(gb.reshape(-1), np.asarray(gb2), rtol=1e-5, atol=1e-6, what="fused colsum == unfused")
     # softmax rows sum to one; linearity of the GEMM in its first operand
     sm = D.softmax_lastaxis(x.reshape(n // 512, 512))
-    assert abs(float(D.sum_axis(sm, None)) - n // 512) < 1e-2
+    assert abs(float(D.sum_axis(sm, None)) - n // 512) < 1e-5 * (n // 512)       # fp32 sum of ~2e5 row sums
