@@ -105,10 +105,24 @@ def c5_params_np(seed=1239, dtype=np.float64):
     return [w.astype(dtype) for w in ws + [W1, np.zeros(HIDDEN), W2, np.zeros(CLASSES)]]
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/r1_summary.md §3), keyed by the GEMM shape bench.py reports as the dominant kernel.
+NCU_TRAFFIC_BYTES = {
+    (512, 64, 512, 2048): 2416e6 + 262e6,        # batched d_k=64 attention products (algorithmic: 2684 MB)
+    (131072, 512, 512, 1): 269.7e6 + 221.6e6,    # projection (algorithmic: 537 MB)
+}
+
+
 def cpu_reference_steps(steps, warmup, sample_seqs=4):
     """Times the oracle's config-5 step (tape-twin MHA with the reference's per-path DFS backward + head +
     Adam, fp64 like the reference's default) on `sample_seqs` sequences; returns (steps/s scaled to the
-    full 8192-sequence step, seconds per sampled step)."""
+    full 8192-sequence step, seconds per sampled step).  BLAS threads = all host cores (torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise throttle the reference arm)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     from oracle import np_oracle as O
     rng = np.random.default_rng(1239)
     params = c5_params_np()
@@ -263,7 +277,7 @@ def run_c5(args):
         achieved = flops / (avg_ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % pk["src"],
+                "traffic": NCU_TRAFFIC_BYTES.get(tuple(int(v) for v in key[:4])), "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % pk["src"],
                 "kernel": "b200ad_gemm M=%d N=%d K=%d batches=%d transA=%d transB=%d precision=%d" % key,
                 "launches_timed": n, "avg_launch_ms": avg_ms,
                 "share_of_step": ms_tot / (ms_step * args.steps), "all_gemm_share_of_step": total_gemm_ms / (ms_step * args.steps),
@@ -299,6 +313,8 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-elems", type=int, default=0, help="c2 sweep: largest size (default 1e9)")
+    ap.add_argument("--c3-batch", type=int, default=16)
     ap.add_argument("--global-batch", type=int, default=8192,
                     help="profiling aid only (ncu captures): the headline number is always quoted at 8192")
     args = ap.parse_args()

@@ -1,0 +1,205 @@
+"""Secondary workloads (BASELINE.json configs 1-4) — `python bench.py --workload c1|c2|c3|c4`.
+Each prints ONE JSON line; the collected tables live in profiles/r1_workloads.md."""
+import json
+import os
+import time
+
+import numpy as np
+
+
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _time(torch, fn, warmup=3, min_ms=200.0, max_reps=200):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    reps, total = 0, 0.0
+    while total < min_ms and reps < max_reps:
+        e0, e1 = _events(torch)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+        reps += 1
+    return total / reps
+
+
+def run_c2(args, torch, pk):
+    """elementwise + activation gradient sweep: forward + backward of each op, fp32, 1e3..1e9 elements,
+    operand A (N/256, 256), broadcast operand b (1,256); algorithmic bytes/element from SURVEY §8(d)."""
+    from auto_differentiation_b200 import _lib as L, device as D
+    sizes = [10 ** e for e in range(3, 10)]
+    if args.max_elems:
+        sizes = [s for s in sizes if s <= args.max_elems]
+    ops = {"add_bcast": 16, "mul_bcast": 20, "add_same": 24, "mul_same": 32, "exp": 20, "tanh": 20, "sigmoid": 20,
+           "relu": 20}
+    table = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+    for n_req in sizes:
+        n = max(256, n_req // 256 * 256)
+        rows = n // 256
+        gen = torch.Generator(device="cuda").manual_seed(1236)
+        a = D.DeviceArray(torch.rand((rows, 256), generator=gen, device="cuda") + 0.5)
+        g = D.DeviceArray(torch.randn((rows, 256), generator=gen, device="cuda"))
+        b_row = D.DeviceArray(torch.rand((1, 256), generator=gen, device="cuda") + 0.5)
+        b_full = D.DeviceArray(torch.rand((rows, 256), generator=gen, device="cuda") + 0.5)
+        x = D.DeviceArray(torch.randn((rows, 256), generator=gen, device="cuda"))
+        for name, bpe in ops.items():
+            if name.endswith("_bcast") or name.endswith("_same"):
+                op = L.B_ADD if name.startswith("add") else L.B_MUL
+                bb = b_row if name.endswith("_bcast") else b_full
+
+                def fn(op=op, bb=bb):
+                    D.binary(op, a, bb)
+                    D.binary_bwd(op, g, a, bb, True, True, True)
+            else:
+                uop = {"exp": L.U_EXP, "tanh": L.U_TANH, "sigmoid": L.U_SIGMOID, "relu": L.U_RELU}[name]
+
+                def fn(uop=uop):
+                    y = D.unary(uop, x)
+                    D.unary_bwd(uop, g, x=x, y=y)
+
+            def fn_flushed(fn=fn):
+                if n * 4 < (200 << 20):
+                    flush.zero_()          # evict L2 between iterations for working sets that would fit
+                fn()
+            ms_with_flush = _time(torch, fn_flushed, min_ms=100.0)
+            ms_flush = _time(torch, lambda: flush.zero_(), min_ms=50.0) if n * 4 < (200 << 20) else 0.0
+            ms = max(ms_with_flush - ms_flush, 1e-4)
+            table.setdefault(name, {})[str(n_req)] = {"ms": ms, "GBps": n * bpe / ms / 1e6,
+                                                      "frac_hbm": n * bpe / ms / 1e6 / pk["hbm"]}
+        del a, g, b_full, x
+        torch.cuda.empty_cache()
+    big = str(sizes[-1])
+    best = {k: v[big]["frac_hbm"] for k, v in table.items()}
+    return {"metric": "elementwise fwd+bwd algorithmic GB/s", "unit": "GB/s", "value": float(np.mean([v[big]["GBps"] for v in table.values()])),
+            "config": {"workload": "c2: elementwise+activation gradient sweep, fp32, 1e3..%s elements" % big,
+                       "l2": "L2 flushed (256 MB write) between iterations when the working set is < 200 MB"},
+            "roofline": {"bound": "hbm", "peak": pk["hbm"], "unit": "GB/s", "frac_at_largest": best, "peak_source": pk["src"]},
+            "table": table}
+
+
+def run_c1(args, torch, pk):
+    from auto_differentiation_b200.models.model import TapeMLP
+    from auto_differentiation_b200.utils.optimizer import Adam
+    from auto_differentiation_b200 import _lib as L
+    rng = np.random.default_rng(1235)
+    x = rng.standard_normal((64, 784)).astype(np.float32)
+    t = rng.integers(0, 10, 64)
+    m, opt = TapeMLP(), Adam(lr=1e-3)
+    from auto_differentiation_b200 import asarray
+    xd = asarray(x)
+
+    def step():
+        m.forward(xd, t)
+        m.backward()
+        opt.update(m.weights, m.grads)
+    n0 = L.launch_count()
+    step()
+    per_step = L.launch_count() - n0
+    ms = _time(torch, step, warmup=5, min_ms=500.0, max_reps=500)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        step()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) / 50 * 1e3
+    from oracle import np_oracle as O
+    W1, b1, W2, b2 = [np.asarray(w, dtype=np.float64) for w in m.weights]
+    ropt = O.Adam(lr=1e-3)
+    ts = []
+    for i in range(30):
+        t0 = time.perf_counter()
+        _, _, grads, _ = O.mlp_tape_step(x.astype(np.float64), t, W1, b1, W2, b2)
+        ropt.update([W1, b1, W2, b2], grads)
+        ts.append(time.perf_counter() - t0)
+    cpu_ms = float(np.median(ts[5:])) * 1e3
+    return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / wall_ms, "ms_per_step": wall_ms,
+            "device_ms_per_step": ms, "gpu_launches_per_step": int(per_step),
+            "config": {"workload": "c1: tape MLP 784-256-10, batch 64, Adam (eager, launch-latency bound: 78 MFLOP/step)"},
+            "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "same step, fp64 NumPy port of the reference tape"}}
+
+
+def run_c3(args, torch, pk):
+    from auto_differentiation_b200.layers import layers as Ls
+    from auto_differentiation_b200 import device as D
+    B, S, d = args.c3_batch, 512, 512
+    rng = np.random.default_rng(1237)
+    ws = [rng.standard_normal((d, d)) / np.sqrt(d) for _ in range(4)]
+    layer = Ls.MultiHeadAttention(d, d, 8, weights=ws)
+    gen = torch.Generator(device="cuda").manual_seed(1237)
+    x = D.DeviceArray(torch.randn((B, S, d), generator=gen, device="cuda"))
+    dout = D.DeviceArray(torch.randn((B, S, d), generator=gen, device="cuda"))
+
+    def step():
+        layer.forward(x, x, x)
+        layer.backward(dout)
+    ms = _time(torch, step, min_ms=500.0)
+    flops = 4831838208.0 * B
+    from oracle import np_oracle as O
+    xs = rng.standard_normal((2, S, d))
+    t0 = time.perf_counter()
+    out, _ = O.mha_tape(xs, xs, xs, *ws, 8)
+    O.backward(out, np.ones_like(out.val))
+    cpu_s = time.perf_counter() - t0
+    return {"metric": "MHA fwd+bwd steps/sec", "unit": "steps/s", "value": 1e3 / ms, "ms_per_step": ms,
+            "config": {"workload": "c3: MultiHeadAttention fwd+bwd, B=%d, S=512, d=512, 8 heads (3xTF32)" % B},
+            "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": flops / ms / 1e9 / pk["bf16_sustained"], "peak_source": pk["src"] + " bf16 sustained"},
+            "cpu_baseline": {"value": 1.0 / (cpu_s / 2 * B), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "2 of %d sequences, fp64 tape twin, scaled linearly" % B}}
+
+
+def run_c4(args, torch, pk):
+    from auto_differentiation_b200.models.model import RnnLM
+    from auto_differentiation_b200.utils.optimizer import Adam
+    from auto_differentiation_b200 import _lib as L
+    out = {}
+    rng = np.random.default_rng(1238)
+    N, T, V = 64, 256, 1000
+    xs = rng.integers(0, V, (N, T))
+    ts = np.roll(xs, -1, axis=1)
+    for cell in ("rnn", "lstm"):
+        m, opt = RnnLM(vocab=V, wordvec=256, hidden=1024, cell=cell), Adam(lr=1e-3)
+
+        def step():
+            m.forward(xs, ts)
+            m.backward()
+            opt.update(m.weights, m.grads)
+        n0 = L.launch_count()
+        step()
+        launches = L.launch_count() - n0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            step()
+        torch.cuda.synchronize()
+        out[cell] = {"ms_per_step": (time.perf_counter() - t0) / reps * 1e3, "gpu_launches_per_step": int(launches)}
+    flops = 229512314880.0
+    return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / out["rnn"]["ms_per_step"],
+            "ms_per_step": out["rnn"]["ms_per_step"],
+            "config": {"workload": "c4: RNN LM V=1000 D=256 H=1024 T=256 N=64 (tanh cell; LSTM variant in `cells`)"},
+            "cells": out,
+            "roofline": {"bound": "tensor", "achieved": flops / out["rnn"]["ms_per_step"] / 1e9, "unit": "TFLOP/s",
+                         "peak": pk["bf16_sustained"], "note": "sequential M=64 recurrent GEMMs are latency bound"}}
+
+
+def run(args):
+    import torch
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import peaks
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    import auto_differentiation_b200 as pkg
+    pkg.set_gemm_precision(args.precision)
+    pk = peaks()
+    fn = {"c1": run_c1, "c2": run_c2, "c3": run_c3, "c4": run_c4}[args.workload]
+    line = fn(args, torch, pk)
+    line.update({"n_gpus": 1, "dtype": "f32", "data": "synthetic", "gemm_precision": args.precision})
+    print(json.dumps(line))
