@@ -245,7 +245,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
+  // TMEM: two accumulator buffers; when the chunk accumulators can ping-pong (BN <= 128) a third region holds the
+  // running total Y, so the fold of chunk c overlaps the MMAs of chunk c+1.  BN = 256 has room for X and Y only.
+  constexpr bool PINGPONG = (BN <= 128);
+  constexpr uint32_t Y_COL = PINGPONG ? 2 * BN : BN;
+  constexpr uint32_t TMEM_COLS = PINGPONG ? (BN == 64 ? 256 : 512) : 2 * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -334,8 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int cb0 = kb0; cb0 < kb1; cb0 += p.chunk_kb, ++uit) {
         int cb1 = cb0 + p.chunk_kb;
         if (cb1 > kb1) cb1 = kb1;
-        const uint32_t buf = p.chunked ? 0u : (uit & 1);
-        const uint32_t buf_ph = p.chunked ? (uit & 1) : ((uit >> 1) & 1);
+        const bool single = p.chunked && !PINGPONG;        // BN = 256 chunked: X is buffer 0 only
+        const uint32_t buf = single ? 0u : (uit & 1);
+        const uint32_t buf_ph = single ? (uit & 1) : ((uit >> 1) & 1);
         mbar_wait(&tmem_empty[buf], buf_ph ^ 1);          // epilogue has drained / folded this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
@@ -435,12 +440,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.partial) crow = p.partial + (((int64_t)split * p.batches + batch) * p.m + gm) * p.n;
       else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
       for (int ch = 0; ch < nchunks; ++ch, ++uit) {
-        const uint32_t buf = p.chunked ? 0u : (uit & 1);
-        const uint32_t buf_ph = p.chunked ? (uit & 1) : ((uit >> 1) & 1);
+        const bool single = p.chunked && !PINGPONG;
+        const uint32_t buf = single ? 0u : (uit & 1);
+        const uint32_t buf_ph = single ? (uit & 1) : ((uit >> 1) & 1);
         mbar_wait(&tmem_full[buf], buf_ph);
         tc_fence_after();
         const uint32_t x_addr = tmem_base + lane_base + buf * BN;
-        const uint32_t y_addr = tmem_base + lane_base + BN;          // running total (chunked mode only)
+        const uint32_t y_addr = tmem_base + lane_base + Y_COL;       // running total (chunked mode only)
         const bool last = (ch == nchunks - 1);
         if (!last) {
           // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation inside the

@@ -565,3 +565,106 @@ class MultiHeadAttention:
         x = _dev(x)
         batch_size, _, sequence_length, _ = x.shape
         return x.transpose(0, 2, 1, 3).reshape(batch_size, sequence_length, -1)
+
+
+# --------------------------------------------------------------------------------------------------
+# Bahdanau-style dot attention over encoder states
+# --------------------------------------------------------------------------------------------------
+class WeightSum:
+    """c[n] = sum_t a[n,t] * hs[n,t,:]  (reference layers.py:964-989) as one batched (1 x T) @ (T x H) product."""
+
+    def __init__(self):
+        self.weights, self.grads = [], []
+        self.cache = None
+
+    def forward(self, hs, a):
+        hs, a = _dev(hs), _dev(a)
+        N, T, H = hs.shape
+        c = D.matmul(a.reshape(N, 1, T), hs).reshape(N, H)
+        self.cache = (hs, a)
+        return c
+
+    def backward(self, dout):
+        hs, a = self.cache
+        N, T, H = hs.shape
+        d = _dev(dout).reshape(N, 1, H)
+        da = D.matmul(d, hs, trans_b=True).reshape(N, T)            # sum(dout*hs, axis=2)         :984
+        dhs = D.matmul(a.reshape(N, T, 1), d)                       # repeat(dout) * ar            :985
+        return dhs, da
+
+
+class AttentionWeight:
+    """weight = softmax_t(hs[n,t,:] . h[n,:])  (reference layers.py:992-1030)."""
+
+    def __init__(self):
+        self.weights, self.grads = [], []
+        self.cache = None
+
+    def forward(self, hs, h):
+        hs, h = _dev(hs), _dev(h)
+        N, T, H = hs.shape
+        c = D.matmul(hs, h.reshape(N, H, 1)).reshape(N, T)
+        weight = D.softmax_lastaxis(c)
+        self.cache = (hs, h, weight)
+        return weight
+
+    def backward(self, dout):
+        hs, h, weight = self.cache
+        N, T, H = hs.shape
+        ds = D.softmax_bwd_lastaxis(_dev(dout).reshape(N, T), weight)   # common_term                  :1018-1019
+        dh = D.matmul(ds.reshape(N, 1, T), hs).reshape(N, H)            # sum(common*hs, axis=1)       :1023
+        dhs = D.matmul(ds.reshape(N, T, 1), h.reshape(N, 1, H))         # common_term_expanded * h     :1026
+        return dhs, dh
+
+
+class Attention:
+    """AttentionWeight + WeightSum for one decoder step (reference layers.py:1033-1052)."""
+
+    def __init__(self):
+        self.weights, self.grads = [], []
+        self.layers = [AttentionWeight(), WeightSum()]
+        self.hs_weight = None
+
+    def forward(self, hs, h):
+        attention_weight, weight_sum = self.layers
+        a = attention_weight.forward(hs, h)
+        c = weight_sum.forward(hs, a)
+        self.hs_weight = a
+        return c
+
+    def backward(self, dout):
+        attention_weight, weight_sum = self.layers
+        hs0, da = weight_sum.backward(dout)
+        hs1, dh = attention_weight.backward(da)
+        return hs0 + hs1, dh
+
+
+class TimeAttention:
+    """All decoder steps at once (reference layers.py:1055-1083 loops over time in Python): scores =
+    hs_dec @ hs_enc^T, softmax over the encoder axis, context = a @ hs_enc — three batched GEMMs forward, four
+    backward (the two encoder-gradient terms accumulate in the GEMM epilogue)."""
+
+    def __init__(self):
+        self.weights, self.grads = [], []
+        self.layers = []
+        self.hs_weight = None
+        self.cache = None
+
+    def forward(self, hs_enc, hs_dec):
+        hs_enc, hs_dec = _dev(hs_enc), _dev(hs_dec)
+        scores = D.matmul(hs_dec, hs_enc, trans_b=True)          # (N, Td, Te)
+        a = D.softmax_lastaxis(scores)
+        out = D.matmul(a, hs_enc)                                # (N, Td, H)
+        self.hs_weight = a
+        self.cache = (hs_enc, hs_dec, a)
+        return out
+
+    def backward(self, dout):
+        hs_enc, hs_dec, a = self.cache
+        dout = _dev(dout)
+        da = D.matmul(dout, hs_enc, trans_b=True)                # (N, Td, Te)
+        dhs_enc = D.matmul(a, dout, trans_a=True)                # a^T @ dout            (WeightSum term)
+        ds = D.softmax_bwd_lastaxis(da, a, out=da)
+        dhs_dec = D.matmul(ds, hs_enc)                           # (N, Td, H)
+        D.matmul(ds, hs_dec, trans_a=True, out=dhs_enc, beta=1.0)   # + ds^T @ hs_dec     (AttentionWeight term)
+        return dhs_enc, dhs_dec

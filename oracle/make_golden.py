@@ -350,6 +350,29 @@ def gen_optim(L, U):
     save("optim", **out)
 
 
+def gen_attention(L):
+    rng = np.random.default_rng(107)
+    N, Te, Td, H = 3, 6, 4, 5
+    hs = rng.standard_normal((N, Te, H)); h = rng.standard_normal((N, H))
+    out = {}
+    ws = L.WeightSum(); a = L.softmax(rng.standard_normal((N, Te)), 1)
+    c = ws.forward(hs, a); dc = rng.standard_normal(c.shape)
+    dhs, da = ws.backward(dc)
+    out.update(ws_hs=hs, ws_a=a, ws_c=c, ws_dc=dc, ws_dhs=dhs, ws_da=da)
+    aw = L.AttentionWeight(); w = aw.forward(hs, h); dw = rng.standard_normal(w.shape)
+    dhs2, dh2 = aw.backward(dw)
+    out.update(aw_h=h, aw_w=w, aw_dw=dw, aw_dhs=dhs2, aw_dh=dh2)
+    at = L.Attention(); c2 = at.forward(hs, h); dc2 = rng.standard_normal(c2.shape)
+    dhs3, dh3 = at.backward(dc2)
+    out.update(at_c=c2, at_dc=dc2, at_dhs=dhs3, at_dh=dh3)
+    hs_dec = rng.standard_normal((N, Td, H))
+    ta = L.TimeAttention(); o = ta.forward(hs, hs_dec); do = rng.standard_normal(o.shape)
+    dhs_enc, dhs_dec = ta.backward(do)
+    out.update(ta_dec=hs_dec, ta_out=o, ta_do=do, ta_dhs_enc=dhs_enc, ta_dhs_dec=dhs_dec,
+               ta_weights=np.stack(ta.hs_weight, axis=1))
+    save("attention", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found at %s" % ref_loader.REFERENCE_ROOT)
@@ -364,6 +387,7 @@ def main():
     gen_mha(ad, L)
     gen_layers(ad, L, U)
     gen_optim(L, U)
+    gen_attention(L)
 
 
 if __name__ == "__main__":

@@ -565,3 +565,66 @@ def c5_model_step(x, labels, params, heads=8):
     g = leaves
     return loss, [g["wq"].grad, g["wk"].grad, g["wv"].grad, g["wo"].grad, dW1, db1, dW2, db2], \
         g["query"].grad + g["key"].grad + g["value"].grad
+
+
+# ======================================================================================================
+# Bahdanau-style dot attention over encoder states — layers/layers.py:964-1083
+# ======================================================================================================
+def weight_sum_forward(hs, a):                                                    # WeightSum.forward :970-981
+    N, T, H = hs.shape
+    return np.sum(np.reshape(a, (N, T, 1)) * hs, axis=1)
+
+
+def weight_sum_backward(hs, a, dout):                                             # WeightSum.backward :983-989
+    N, T, H = hs.shape
+    d = np.reshape(dout, (N, 1, H))
+    da = np.reshape(np.sum(d * hs, axis=2, keepdims=True), (N, T))
+    dhs = np.repeat(d, repeats=T, axis=1) * np.reshape(a, (N, T, 1))
+    return dhs, da
+
+
+def attention_weight_forward(hs, h):                                              # AttentionWeight.forward :998-1007
+    N, T, H = hs.shape
+    c = np.sum(np.repeat(np.reshape(h, (N, 1, H)), T, 1) * hs, axis=2)
+    return _stable_softmax(c, c.ndim - 1)
+
+
+def attention_weight_backward(hs, h, dout):                                       # AttentionWeight.backward :1009-1030
+    N, T, H = hs.shape
+    rep = np.repeat(np.reshape(h, (N, 1, H)), repeats=T, axis=1)
+    sm = _stable_softmax(np.sum(rep * hs, axis=2), 1)
+    common = sm * dout - sm * np.sum(sm * dout, axis=1, keepdims=True)
+    common_e = np.repeat(common[..., np.newaxis], H, axis=2)
+    dh = np.reshape(np.sum(common_e * hs, axis=1, keepdims=True), (N, H))
+    return common_e * rep, dh
+
+
+def attention_forward(hs, h):                                                     # Attention.forward :1040-1045
+    a = attention_weight_forward(hs, h)
+    return weight_sum_forward(hs, a), a
+
+
+def attention_backward(hs, h, a, dout):                                           # Attention.backward :1047-1052
+    hs0, da = weight_sum_backward(hs, a, dout)
+    hs1, dh = attention_weight_backward(hs, h, da)
+    return hs0 + hs1, dh
+
+
+def time_attention_forward(hs_enc, hs_dec):                                       # TimeAttention.forward :1061-1071
+    N, Td, H = hs_dec.shape
+    out = np.empty(hs_dec.shape)
+    weights = []
+    for i in range(Td):
+        out[:, i, :], a = attention_forward(hs_enc, hs_dec[:, i, :])
+        weights.append(a)
+    return out, weights
+
+
+def time_attention_backward(hs_enc, hs_dec, weights, dout):                       # TimeAttention.backward :1073-1083
+    dhs_dec = np.empty(dout.shape)
+    dhs_enc = 0
+    for i in range(dout.shape[1]):
+        dhs, dh = attention_backward(hs_enc, hs_dec[:, i, :], weights[i], dout[:, i, :])
+        dhs_enc = dhs_enc + dhs
+        dhs_dec[:, i, :] = dh
+    return dhs_enc, dhs_dec
