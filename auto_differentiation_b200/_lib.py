@@ -81,7 +81,8 @@ SIGNATURES = {
     "b200ad_rnn_cell_bwd": (c_int, [P, I64, P, I64, P, I64, P, I64, I64, I64, P]),
     "b200ad_bias_act_fwd": (c_int, [P, I64, P, P, I64, I64, I64, c_int, P]),
     "b200ad_act_bwd": (c_int, [P, I64, P, I64, P, I64, I64, I64, c_int, P]),
-    "b200ad_adam_multi": (c_int, [P, c_int, I64, P, P, c_float, c_float, c_float, c_float, c_float, P]),
+    "b200ad_adam_multi": (c_int, [P, c_int, I64, P, P, c_float, c_float, c_float, c_float, c_float, P, P]),
+    "b200ad_adam_step_scalar": (c_int, [P, ctypes.c_double, ctypes.c_double, ctypes.c_double, P, P]),
     "b200ad_sgd_multi": (c_int, [P, c_int, I64, P, P, c_float, c_float, P]),
     "b200ad_sumsq_multi": (c_int, [P, c_int, I64, P, P, P, P, P]),
     "b200ad_clip_scale_multi": (c_int, [P, c_int, I64, P, P, P, c_float, P]),

@@ -129,7 +129,8 @@ class Function:
         if create_graph:
             raise NotImplementedError("create_graph=True is out of scope of the B200 hot path")
         if grad is None:
-            grad = np.array(1.).reshape(self.shape)  # ValueError unless size 1, like the reference :90
+            np.array(1.).reshape(self.shape)         # ValueError unless size 1, like the reference :90
+            grad = D.full(self.shape, 1.0)           # built on the device (no host copy: CUDA-graph capturable)
         Prime(self, grad=grad)
 
     def reshape(self, *shape):

@@ -35,9 +35,20 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p -= lr_t * m / (sqrtf(v) + eps);  // params[i] -= lr_t * m / (sqrt(v) + 1e-7)         :29
 }
 
+// iter += 1; lr_t = lr*sqrt(1-b2^iter)/(1-b1^iter) in fp64 (the host expression of optimizer.py:22-23), so a
+// captured CUDA graph of the update stays correct across replays without any host involvement.
+__global__ void adam_step_scalar_kernel(int64_t* __restrict__ iter, double lr, double b1, double b2,
+                                        float* __restrict__ lr_t) {
+  const int64_t t = *iter + 1;
+  *iter = t;
+  *lr_t = (float)(lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)));
+}
+
 __global__ void __launch_bounds__(256) adam_multi_kernel(const b200ad_tensor_entry* __restrict__ table,
                                                          const int32_t* __restrict__ ct, const int32_t* __restrict__ ci,
-                                                         float lr_t, float b1c, float b2c, float eps, float gs) {
+                                                         float lr_t, float b1c, float b2c, float eps, float gs,
+                                                         const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev) lr_t = *lr_t_dev;
   const ChunkRef r = chunk_ref(table, ct, ci);
   float* p = r.e->param + r.off;
   const float* g = r.e->grad + r.off;
@@ -133,13 +144,20 @@ static int check_table(const char* who, const void* table, int n_tensors, int64_
 
 extern "C" {
 
+int b200ad_adam_step_scalar(int64_t* iter_dev, double lr, double beta1, double beta2, float* lr_t_dev, void* stream) {
+  B200AD_REQUIRE(iter_dev && lr_t_dev, "adam_step_scalar: null pointer");
+  adam_step_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(iter_dev, lr, beta1, beta2, lr_t_dev);
+  count_launch();
+  return check_launch("adam_step_scalar");
+}
+
 int b200ad_adam_multi(const b200ad_tensor_entry* table_dev, int n_tensors, int64_t total_chunks,
                       const int32_t* chunk_tensor_dev, const int32_t* chunk_index_dev, float lr_t, float beta1,
-                      float beta2, float eps, float grad_scale, void* stream) {
+                      float beta2, float eps, float grad_scale, const float* lr_t_dev, void* stream) {
   int rc = check_table("adam_multi", table_dev, n_tensors, total_chunks, chunk_tensor_dev, chunk_index_dev);
   if (rc) return rc < 0 ? rc : B200AD_OK;
   adam_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk_tensor_dev, chunk_index_dev,
-                                                                              lr_t, 1.f - beta1, 1.f - beta2, eps, grad_scale);
+                                                                              lr_t, 1.f - beta1, 1.f - beta2, eps, grad_scale, lr_t_dev);
   count_launch();
   return check_launch("adam_multi");
 }

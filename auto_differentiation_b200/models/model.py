@@ -97,12 +97,15 @@ class TapeMLP:
     def forward(self, x, t, q=None):
         n = len(x)
         X = ad.Matrix(x, requires_grad=False)
-        onehot = np.zeros((n, self.d_out), dtype=np.float32)
-        onehot[np.arange(n), np.asarray(t).astype(np.int64)] = 1.0               # exact one-hot (host, 64x10)
+        if isinstance(t, DeviceArray) and t.ndim == 2:
+            onehot = t                                                           # device-resident one-hot (graph capture)
+        else:
+            onehot = np.zeros((n, self.d_out), dtype=np.float32)
+            onehot[np.arange(n), np.asarray(t).astype(np.int64)] = 1.0           # exact one-hot (host, 64x10)
         T = ad.Matrix(onehot, requires_grad=False)
         self.y = ad.softmax(ad.tanh(X @ self.W1 + self.b1) @ self.W2 + self.b2, 2)
         picked = ad.sum(self.y * T, axis=1, keepdims=True) + 1e-7                # y[i, t_i] + 1e-7
-        self._loss_node = ad.sum(ad.ln(picked), axis=0, keepdims=True) * ad.Matrix(-1.0 / n, requires_grad=False)
+        self._loss_node = ad.sum(ad.ln(picked), axis=0, keepdims=True) * (-1.0 / n)   # host scalar: folded into a kernel
         return self._loss_node.val.reshape(())
 
     def backward(self):

@@ -60,7 +60,7 @@ class AdamCore:
     """Adam exactly as the reference writes it (NOT torch-Adam): host scalar
     lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m += (1-b1)(g-m); v += (1-b2)(g^2-v); p -= lr_t*m/(sqrt(v)+1e-7)."""
 
-    def __init__(self, lr=0.001, beta1=0.9, beta2=0.999):
+    def __init__(self, lr=0.001, beta1=0.9, beta2=0.999, capturable=False):
         self.lr = lr
         self.beta1 = beta1
         self.beta2 = beta2
@@ -69,6 +69,11 @@ class AdamCore:
         self.v = None
         self.grad_scale = 1.0  # multiplies g on the fly (1/world_size after a sum all-reduce)
         self._table = None
+        # capturable: the step counter and lr_t live on the device (b200ad_adam_step_scalar), so `update` can be
+        # captured in a CUDA graph and replayed; `iter` on the host then counts eager calls only.
+        self.capturable = capturable
+        self._iter_dev = None
+        self._lr_dev = None
 
     def update(self, params, grads):
         if self.m is None:
@@ -79,9 +84,20 @@ class AdamCore:
         if self._table is None or self._table.key != TensorTable.make_key(params, grads):
             self._table = TensorTable(params, grads, self.m, self.v)
         self.iter += 1
+        if self.capturable:
+            if self._iter_dev is None:
+                self._iter_dev = D.zeros((1,), torch.int64)
+                self._iter_dev.t.fill_(self.iter - 1)
+                self._lr_dev = D.zeros((1,))
+            lib = L.load()
+            L.check(lib.b200ad_adam_step_scalar(self._iter_dev.ptr, float(self.lr), float(self.beta1), float(self.beta2),
+                                                self._lr_dev.ptr, D.stream_ptr()))
+            L.check(lib.b200ad_adam_multi(*self._table.args(), 0.0, float(self.beta1), float(self.beta2), 1e-7,
+                                          float(self.grad_scale), self._lr_dev.ptr, D.stream_ptr()))
+            return
         lr_t = self.lr * np.sqrt(1.0 - self.beta2 ** self.iter) / (1.0 - self.beta1 ** self.iter)
         L.check(L.load().b200ad_adam_multi(*self._table.args(), float(lr_t), float(self.beta1), float(self.beta2),
-                                           1e-7, float(self.grad_scale), D.stream_ptr()))
+                                           1e-7, float(self.grad_scale), None, D.stream_ptr()))
 
 
 class SGDCore:

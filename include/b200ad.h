@@ -270,7 +270,13 @@ typedef struct b200ad_tensor_entry {
 } b200ad_tensor_entry;
 int b200ad_adam_multi(const b200ad_tensor_entry* table_dev, int n_tensors, int64_t total_chunks,
                       const int32_t* chunk_tensor_dev, const int32_t* chunk_index_dev, float lr_t,
-                      float beta1, float beta2, float eps, float grad_scale, void* stream);
+                      float beta1, float beta2, float eps, float grad_scale,
+                      const float* lr_t_dev /* NULL: use lr_t; else read the step size from the device */,
+                      void* stream);
+/* CUDA-graph friendly step scalar: iter_dev[0] += 1; lr_t_dev[0] = lr*sqrt(1-beta2^iter)/(1-beta1^iter) in fp64
+ * (utils/optimizer.py:21-23 evaluated on the device). */
+int b200ad_adam_step_scalar(int64_t* iter_dev, double lr, double beta1, double beta2, float* lr_t_dev,
+                            void* stream);
 int b200ad_sgd_multi(const b200ad_tensor_entry* table_dev, int n_tensors, int64_t total_chunks,
                      const int32_t* chunk_tensor_dev, const int32_t* chunk_index_dev, float lr,
                      float grad_scale, void* stream);

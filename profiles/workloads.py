@@ -106,6 +106,28 @@ def run_c1(args, torch, pk):
         step()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) / 50 * 1e3
+    # the same step captured once in a CUDA graph (device-resident one-hot labels, capturable Adam)
+    from auto_differentiation_b200.graph import GraphedStep
+    m2, opt2 = TapeMLP(), Adam(lr=1e-3, capturable=True)
+    onehot = np.zeros((64, 10), dtype=np.float32)
+    onehot[np.arange(64), t] = 1.0
+    td = asarray(onehot)
+
+    def gstep():
+        loss = m2.forward(xd, td)
+        m2.backward()
+        opt2.update(m2.weights, m2.grads)
+        return loss
+    g = GraphedStep(gstep)
+    for _ in range(20):
+        g()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(500):
+        g()
+    torch.cuda.synchronize()
+    graph_ms = (time.perf_counter() - t0) / 500 * 1e3
+    graph_loss = float(g.result)
     from oracle import np_oracle as O
     W1, b1, W2, b2 = [np.asarray(w, dtype=np.float64) for w in m.weights]
     ropt = O.Adam(lr=1e-3)
@@ -118,6 +140,7 @@ def run_c1(args, torch, pk):
     cpu_ms = float(np.median(ts[5:])) * 1e3
     return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / wall_ms, "ms_per_step": wall_ms,
             "device_ms_per_step": ms, "gpu_launches_per_step": int(per_step),
+            "cuda_graph": {"steps_per_s": 1e3 / graph_ms, "ms_per_step": graph_ms, "loss_after_523_steps": graph_loss},
             "config": {"workload": "c1: tape MLP 784-256-10, batch 64, Adam (eager, launch-latency bound: 78 MFLOP/step)"},
             "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "same step, fp64 NumPy port of the reference tape"}}
@@ -162,6 +185,9 @@ def run_c4(args, torch, pk):
     N, T, V = 64, 256, 1000
     xs = rng.integers(0, V, (N, T))
     ts = np.roll(xs, -1, axis=1)
+    from auto_differentiation_b200 import device as D
+    from auto_differentiation_b200.graph import GraphedStep
+    xs_d, ts_d = D.as_index(xs), D.as_index(ts)
     for cell in ("rnn", "lstm"):
         m, opt = RnnLM(vocab=V, wordvec=256, hidden=1024, cell=cell), Adam(lr=1e-3)
 
@@ -179,6 +205,22 @@ def run_c4(args, torch, pk):
             step()
         torch.cuda.synchronize()
         out[cell] = {"ms_per_step": (time.perf_counter() - t0) / reps * 1e3, "gpu_launches_per_step": int(launches)}
+        m2, opt2 = RnnLM(vocab=V, wordvec=256, hidden=1024, cell=cell), Adam(lr=1e-3, capturable=True)
+
+        def gstep():
+            loss = m2.forward(xs_d, ts_d)
+            m2.backward()
+            opt2.update(m2.weights, m2.grads)
+            return loss
+        g = GraphedStep(gstep, warmup=2)
+        g(); g()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            g()
+        torch.cuda.synchronize()
+        out[cell]["cuda_graph_ms_per_step"] = (time.perf_counter() - t0) / 10 * 1e3
+        out[cell]["loss_after_graph_steps"] = float(g.result)
     flops = 229512314880.0
     return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / out["rnn"]["ms_per_step"],
             "ms_per_step": out["rnn"]["ms_per_step"],

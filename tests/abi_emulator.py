@@ -426,8 +426,17 @@ class Emulator:
         raw = np.ctypeslib.as_array((ctypes.c_int64 * (5 * n)).from_address(int(table))).reshape(n, 5)
         return [tuple(int(v) for v in row) for row in raw]
 
-    def b200ad_adam_multi(self, table, n, chunks, ct, ci, lr_t, b1, b2, eps, gs, s):
+    def b200ad_adam_step_scalar(self, iter_dev, lr, b1, b2, lr_t_dev, s):
         self.launches += 1
+        it = _i64(iter_dev, 1)
+        it[0] += 1
+        _f32(lr_t_dev, 1)[0] = lr * np.sqrt(1.0 - b2 ** int(it[0])) / (1.0 - b1 ** int(it[0]))
+        return 0
+
+    def b200ad_adam_multi(self, table, n, chunks, ct, ci, lr_t, b1, b2, eps, gs, lr_t_dev, s):
+        self.launches += 1
+        if lr_t_dev:
+            lr_t = float(_f32(lr_t_dev, 1)[0])
         for p, g, m, v, numel in self._entries(table, n):
             P, G, M, V = _f32(p, numel), _f32(g, numel).astype(np.float64) * gs, _f32(m, numel), _f32(v, numel)
             m64 = M + (1 - b1) * (G - M)
