@@ -99,6 +99,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (lane = row, column = k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // tcgen05.commit: the mbarrier is arrived on when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -212,6 +222,7 @@ struct TcParams {
   int64_t batch1;
   int32_t batches, m_tiles, n_tiles, splits, kblocks_total, kblocks_per_split;
   int32_t a_mn_major, b_mn_major, x3, mask_hi, act;
+  int32_t a_tmem;              // BN = 64, TF32X3: the splitter stores the hi/lo A tiles into TMEM (TS-mode MMAs)
   int32_t probe;               // diagnostic bits: 1 = skip the TMA loads, 2 = skip the split (3 = pure MMA + epilogue)
   int32_t chunk_kb, chunked;   // TMEM accumulation chunk (k-blocks); chunked: buffer 0 = chunk sum X, buffer 1 = running total Y
   float alpha, beta;
@@ -249,7 +260,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // running total Y, so the fold of chunk c overlaps the MMAs of chunk c+1.  BN = 256 has room for X and Y only.
   constexpr bool PINGPONG = (BN <= 128);
   constexpr uint32_t Y_COL = PINGPONG ? 2 * BN : BN;
-  constexpr uint32_t TMEM_COLS = PINGPONG ? (BN == 64 ? 256 : 512) : 2 * BN;
+  // BN = 64 additionally keeps a ring of A tiles in TMEM (hi: 32 columns, lo: 32 columns per stage, <= 4 stages):
+  // every tf32 tcgen05.mma pays ~128 cycles for fetching its 4 KB A operand from shared memory regardless of N
+  // (measured), which caps N = 64 tiles at 25 % of the tensor rate; with A in TMEM the MMA takes N/2 cycles.
+  constexpr uint32_t A_TMEM_COL = 3 * BN;                       // after X0, X1, Y
+  constexpr uint32_t TMEM_COLS = PINGPONG ? (BN == 64 ? 512 : 512) : 2 * BN;
+  const bool a_tmem = (BN == 64) && p.a_tmem && p.x3 && stages <= 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -354,7 +370,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t sb = sa + A_BYTES;
             const uint32_t sal = sb + B_BYTES, sbl = sal + A_BYTES;     // lo tiles (TF32X3)
             const bool first_kb = (kb == cb0);
-            if (p.x3) {
+            if (a_tmem) {
+              const uint32_t idesc_ts = idesc & ~(1u << 15);          // A from TMEM is always K-major
+              const uint32_t ah = tmem_base + A_TMEM_COL + (uint32_t)s * 64u, al = ah + 32u;
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32_ts(d_tmem, al + kk * 8, make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc_ts,
+                             (first_kb && kk == 0) ? 0u : 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32_ts(d_tmem, ah + kk * 8, make_smem_desc(sbl + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc_ts, 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma_tf32_ts(d_tmem, ah + kk * 8, make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lay), idesc_ts, 1u);
+            } else if (p.x3) {
               // small cross terms first, the dominant hi*hi term last
 #pragma unroll
               for (int kk = 0; kk < TC_BK / 8; ++kk)
@@ -400,6 +429,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
           uint4* lo = hi + VECS;
           if (p.probe & 2) { mbar_arrive(&conv_full[s]); continue; }
+          if (a_tmem) {
+            // A: each thread owns one row (TMEM lane) and stores its 32 k-values as hi (warps 2-5) or lo (6-9)
+            const int q = warp & 3, half = (warp - 2) >> 2;
+            const int r = q * 32 + lane;
+            const uint8_t* sa = smem + (size_t)s * stage_bytes;
+            uint32_t v[32];
+            if (!p.a_mn_major) {          // K-major, SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
+              const uint4* row = reinterpret_cast<const uint4*>(sa + r * 128);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 t4 = row[c ^ (r & 7)];
+                v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+              }
+            } else {                      // MN-major, SWIZZLE_128B_BASE32B: 32 B granule g of k-row kk sits at g ^ (kk & 3)
+              const uint8_t* chunk = sa + (r >> 5) * (128 * TC_BK);
+              const int ml = r & 31;
+#pragma unroll
+              for (int kk = 0; kk < 32; ++kk)
+                v[kk] = *reinterpret_cast<const uint32_t*>(chunk + kk * 128 + ((((ml >> 3) ^ (kk & 3)) << 5) | ((ml & 7) << 2)));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t h = v[j] & 0xffffe000u;
+              v[j] = half ? (__float_as_uint(__uint_as_float(v[j]) - __uint_as_float(h)) & 0xffffe000u) : h;
+            }
+            tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + A_TMEM_COL + (uint32_t)s * 64u + (half ? 32u : 0u), v);
+            // B: lo tile in shared memory, as before
+            constexpr uint32_t A_VECS = A_BYTES / 16;
+            for (uint32_t i = A_VECS + tid; i < VECS; i += TC_SPLIT_THREADS) {
+              const uint4 bv = hi[i];
+              uint4 l;
+              l.x = __float_as_uint(__uint_as_float(bv.x) - __uint_as_float(bv.x & 0xffffe000u)) & 0xffffe000u;
+              l.y = __float_as_uint(__uint_as_float(bv.y) - __uint_as_float(bv.y & 0xffffe000u)) & 0xffffe000u;
+              l.z = __float_as_uint(__uint_as_float(bv.z) - __uint_as_float(bv.z & 0xffffe000u)) & 0xffffe000u;
+              l.w = __float_as_uint(__uint_as_float(bv.w) - __uint_as_float(bv.w & 0xffffe000u)) & 0xffffe000u;
+              lo[i] = l;
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(&conv_full[s]);
+            continue;
+          }
 #pragma unroll 6
           for (uint32_t i = tid; i < VECS; i += TC_SPLIT_THREADS) {
             const uint4 v = hi[i];
@@ -1058,6 +1130,8 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   const char* mh = getenv("B200AD_TC_MASK_HI");
   p.mask_hi = mh ? atoi(mh) : 0;
   p.act = g.act; p.alpha = g.alpha; p.beta = g.beta;
+  const char* at = getenv("B200AD_TC_ATMEM");
+  p.a_tmem = at ? atoi(at) : 1;
   const char* pb = getenv("B200AD_TC_PROBE");
   p.probe = pb ? atoi(pb) : 0;
   // TMEM accumulation chain length: 128 K-elements (see the epilogue's fold).  Measured on B200

@@ -10,7 +10,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling"]
+GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling", "atmem"]
 
 
 def run_group(group):
@@ -105,6 +105,20 @@ def run_group(group):
         case("bias tanh", 256, 256, 128, prec="tf32x3", bias=True, act=1)
         case("bias relu tails", 200, 100, 96, prec="tf32x3", bias=True, act=3)
         case("split-K beta bias", 256, 256, 8192, ta=True, prec="tf32x3", beta=1.0, bias=True)
+    elif group == "atmem":
+        os.environ["B200AD_TC_BN"] = "64"
+        for at in ("1", "0"):
+            os.environ["B200AD_TC_ATMEM"] = at
+            print("-- BN=64 forced, A-from-TMEM = %s" % at, flush=True)
+            for ta in (False, True):
+                for tb in (False, True):
+                    case("layout", 256, 192, 256, ta=ta, tb=tb, prec="tf32x3")
+            case("tails", 200, 60, 1000, prec="tf32x3")
+            case("tails TN", 200, 60, 1000, ta=True, prec="tf32x3")
+            case("C5 PV", 512, 64, 512, batch=(256, 8), prec="tf32x3", time_it=True)
+            case("C5 dV (TN)", 512, 64, 512, ta=True, batch=(256, 8), prec="tf32x3", time_it=True)
+            case("square 4096 BN64", 4096, 4096, 4096, tb=True, prec="tf32x3", time_it=True)
+        os.environ.pop("B200AD_TC_BN"); os.environ.pop("B200AD_TC_ATMEM")
     elif group == "ceiling":
         os.environ["B200AD_TC_CHUNK_KB"] = "100000"
         print("-- probe bits: 1 = no TMA, 2 = no split, 3 = pure MMA + epilogue (results are garbage, only the rate matters)", flush=True)
