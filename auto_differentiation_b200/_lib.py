@@ -37,6 +37,16 @@ class GemmDesc(Structure):
                 ("alpha", c_float), ("beta", c_float)]
 
 
+class AttnStrides(Structure):
+    _fields_ = [("batch", c_int64), ("head", c_int64), ("row", c_int64)]
+
+
+class AttnDesc(Structure):
+    _fields_ = [("batch", c_int64), ("heads", c_int64), ("seq_q", c_int64), ("seq_kv", c_int64),
+                ("head_dim", c_int64), ("scale", c_float), ("reserved", c_int32),
+                ("q", AttnStrides), ("k", AttnStrides), ("v", AttnStrides), ("o", AttnStrides)]
+
+
 class TensorEntry(Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("m", c_void_p), ("v", c_void_p),
                 ("numel", c_int64)]
@@ -75,6 +85,10 @@ SIGNATURES = {
     "b200ad_gemm": (c_int, [POINTER(GemmDesc), P, P, P, P, P, I64, P]),
     "b200ad_gemm_supported": (c_int, [POINTER(GemmDesc), P, P, P]),
     "b200ad_gemm_workspace_bytes": (c_int64, [POINTER(GemmDesc)]),
+    "b200ad_attn_supported": (c_int, [POINTER(AttnDesc)]),
+    "b200ad_attn_fwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P]),
+    "b200ad_attn_bwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),
+    "b200ad_attn_bwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P, P, P, P, P, P]),
     "b200ad_lstm_cell_fwd": (c_int, [P, I64, P, I64, P, I64, P, I64, P, I64, I64, I64, P]),
     "b200ad_lstm_cell_bwd": (c_int, [P, I64, P, I64, P, P, I64, P, I64, P, I64, P, I64, P, I64, P,
                                      I64, I64, P]),

@@ -1,0 +1,675 @@
+// Fused multi-head attention core on tcgen05 / TMEM / TMA (sm_100a): the S x S score / probability matrices
+// never leave the SM.
+//
+// Replaces, for MultiHeadAttention (reference layers.py:1351-1357 forward, and the tape backward of
+// Test/MultiHeadAttentionTest.py:70-85): np.matmul(Q, K^T) / sqrt(d_k), exp/sum softmax, np.matmul(P, V), and in
+// the backward the five products dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dO o O)) / sqrt(d_k),
+// dQ = dS K, dK = dS^T Q.
+//
+// One generic "attention pass" kernel, four modes.  A CTA owns a 128-row tile (TMEM lanes = rows) of one
+// (batch, head) and walks the other sequence dimension in blocks of 64 columns:
+//     X = A1 . B1^T   (128 x 64, K = d_k)         [Y = A2 . B2^T   in the two-score modes]
+//     Z = elementwise(X [,Y])                     (row owner threads, registers)
+//     OUT_blk = Z . B3 (128 x d_k, K = 64)        folded into a register-resident running total (RN adds)
+//   mode   lanes   A1  A2   B1  B2   B3       elementwise                                   output
+//   FWD    q rows  Q   -    K   -    V        online softmax (running max / sum, rescale)   O, LSE (log2 domain)
+//   DV     kv rows K   -    Q   -    dO       P^T = exp2(X c2 - lse[col])                   dV
+//   DQ     q rows  Q   dO   K   V    K        Z = P (Y - D[row]) c                          dQ
+//   DK     kv rows K   V    Q   dO   Q        Z = P^T (Y - D[col]) c                        dK
+// All contractions are fp32-faithful 3xTF32 (A = Ah + Al, B = Bh + Bl; Al.Bh + Ah.Bl + Ah.Bh), every MMA is
+// TS-mode: the A operand (the 128-row tile, and Z) lives in TMEM as hi/lo column groups written by threads, so
+// a 128 x 64 x 8 tf32 MMA costs 32 cycles (an A operand in shared memory would cost 128, measured in gemm_tc.cu).
+// The B operands stream through a 7-slot ring of 32 KB shared-memory slots (raw tile from TMA + lo tile from
+// the converter warps), in exactly the order the MMA warp consumes them.
+//
+// Warp roles (384 threads = 3 warpgroups, one CTA per SM, persistent over work items; setmaxnreg moves registers
+// from the first two warpgroups to the row owners):
+//   warp 0      TMA producer            warp 1      MMA issuer (one lane)         warps 2-3 idle
+//   warps 4-7   converter: A tiles smem -> TMEM (hi/lo), B tiles raw -> lo (in smem)
+//   warps 8-11  row owners: TMEM -> registers -> softmax / dS -> TMEM (Z hi/lo), fold of OUT_blk, epilogue
+// TMEM (512 columns):  A1 hi/lo [0,128)  |  one-score modes: X0/Zhi0 L0 X1/Zhi1 L1 [128,384) OUT [384,448)
+//                      A2 hi/lo [128,256) | two-score modes: X0/Zlo0 X1/Zlo1 [256,384) Y/Zhi [384,448) OUT [448,512)
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace b200ad {
+
+constexpr int AT_DK = 64;                    // head dimension this kernel is built for
+constexpr int AT_BM = 128;                   // rows (TMEM lanes) per work item
+constexpr int AT_BC = 64;                    // columns per block
+constexpr int AT_NSLOT = 7;
+constexpr uint32_t AT_SLOT = 32768;          // [raw 16 KB | lo 16 KB] for a B block, or one raw A tile
+constexpr int AT_THREADS = 384;              // 3 warpgroups: {TMA, MMA, 2 idle}, converter, row owners
+constexpr uint32_t AT_SMEM = AT_NSLOT * AT_SLOT + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*column stats*/;
+
+enum { AT_FWD = 0, AT_DV = 1, AT_DQ = 2, AT_DKM = 3 };
+
+struct AttnParams {
+  float* out;                // FWD: O; DV: dV; DQ: dQ; DK: dK    element (b, h, row, d) at out + b*bs + h*hs + row*ld + d
+  int64_t out_bs, out_hs, out_ld;
+  float* lse_w;              // FWD: (B, H, R) log2-domain log-sum-exp, written
+  const float* lse;          // other modes: the same array, read ((B, H, Sq))
+  const float* dvec;         // DQ / DK: D[b, h, s] = sum_d dO * O
+  int32_t H, R, C;           // heads; extent of the lane dimension; extent of the column dimension
+  int32_t row_tiles, nb, total_items;
+  float c2, c;               // scale * log2(e), scale
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t tf32_hi(uint32_t v) { return v & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t v, uint32_t h) {
+  return __float_as_uint(__uint_as_float(v) - __uint_as_float(h)) & 0xffffe000u;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+               const __grid_constant__ CUtensorMap map_b3, const AttnParams p) {
+  constexpr bool HAS2 = (MODE == AT_DQ || MODE == AT_DKM);
+  constexpr bool ROWSTAT = (MODE == AT_FWD || MODE == AT_DQ);   // lanes are query rows
+  constexpr uint32_t A1_COL = 0, A2_COL = 128;
+  constexpr uint32_t X_COL0 = HAS2 ? 256u : 128u;
+  constexpr uint32_t X_STRIDE = HAS2 ? 64u : 128u;
+  constexpr uint32_t Y_COL = 384;
+  constexpr uint32_t OUT_COL = HAS2 ? 448u : 384u;
+  constexpr uint32_t TMEM_COLS = 512;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)AT_NSLOT * AT_SLOT);
+  uint64_t* full = bars;                       // [NSLOT] TMA -> converter
+  uint64_t* conv = bars + AT_NSLOT;            // [NSLOT] converter -> MMA (128 arrivals): lo tile in smem / A tile in TMEM
+  uint64_t* empty = bars + 2 * AT_NSLOT;       // [NSLOT] MMA commit (B slots) / converter (A slots) -> TMA
+  uint64_t* a_empty = bars + 3 * AT_NSLOT;     // [2] MMA commit -> converter: last score MMA of the item retired
+  uint64_t* x_full = a_empty + 2;              // [2] MMA commit -> row owners
+  uint64_t* z_full = x_full + 2;               // [2] row owners -> MMA (128 arrivals)
+  uint64_t* y_full = z_full + 2;               // [1]
+  uint64_t* out_full = y_full + 1;             // [1] MMA commit -> row owners
+  uint64_t* out_empty = out_full + 1;          // [1] row owners -> MMA (128 arrivals)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(out_empty + 1);
+  float* colstat = reinterpret_cast<float*>(smem + (size_t)AT_NSLOT * AT_SLOT + 512);   // [2 buffers][2 vectors][64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b1);
+    tma_prefetch_desc(&map_b3);
+    if (HAS2) {
+      tma_prefetch_desc(&map_a2);
+      tma_prefetch_desc(&map_b2);
+    }
+    for (int s = 0; s < AT_NSLOT; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&x_full[i], 1);
+      mbar_init(&z_full[i], 128);
+    }
+    mbar_init(y_full, 1);
+    mbar_init(out_full, 1);
+    mbar_init(out_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const int nb = p.nb;
+
+  // register budgets are set INSIDE each warpgroup's branch so that ptxas allocates per role
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t op = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int rt = item % p.row_tiles, bh = item / p.row_tiles;
+        const int h = bh % p.H, b = bh / p.H;
+        const int row0 = rt * AT_BM;
+        auto acquire = [&](uint32_t bytes, uint64_t*& bar) -> uint8_t* {
+          const uint32_t s = op % AT_NSLOT;
+          mbar_wait(&empty[s], ((op / AT_NSLOT) & 1) ^ 1);
+          mbar_expect_tx(&full[s], bytes);
+          bar = &full[s];
+          ++op;
+          return smem + (size_t)s * AT_SLOT;
+        };
+        auto load_a = [&](const CUtensorMap* m) {          // 128 rows x 64: two 32-float halves, SWIZZLE_128B
+          uint64_t* bar;
+          uint8_t* dst = acquire(32768u, bar);
+          tma_load_4d(m, bar, dst, 0, row0, h, b);
+          tma_load_4d(m, bar, dst + 16384, 32, row0, h, b);
+        };
+        auto load_k = [&](const CUtensorMap* m, int col0) {   // K-major B block: 64 rows x 64
+          uint64_t* bar;
+          uint8_t* dst = acquire(16384u, bar);
+          tma_load_4d(m, bar, dst, 0, col0, h, b);
+          tma_load_4d(m, bar, dst + 8192, 32, col0, h, b);
+        };
+        auto load_mn = [&](const CUtensorMap* m, int col0) {  // MN-major B block: 64 k-rows x 64 (32 x 32 boxes)
+          uint64_t* bar;
+          uint8_t* dst = acquire(16384u, bar);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_4d(m, bar, dst + kb * 8192 + c * 4096, c * 32, col0 + kb * 32, h, b);
+        };
+        load_a(&map_a1);
+        if (HAS2) load_a(&map_a2);
+        load_k(&map_b1, 0);
+        if (HAS2) load_k(&map_b2, 0);
+        for (int j = 1; j <= nb; ++j) {
+          if (j < nb) load_k(&map_b1, j * AT_BC);
+          load_mn(&map_b3, (j - 1) * AT_BC);
+          if (HAS2 && j < nb) load_k(&map_b2, j * AT_BC);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    // instruction descriptor: D = f32, A = B = tf32, A K-major (TMEM), N = 64, M = 128; bit 16 = B MN-major
+    constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) |
+                                 ((uint32_t)(AT_BM >> 4) << 24);
+    constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
+    uint32_t op = 0, it = 0, gb = 0;
+    // score MMA: D[128 x 64] = A(TMEM, hi at a_col, lo at a_col + 64) . B^T (K-major slot: two 8 KB halves)
+    auto score = [&](uint32_t a_col, uint32_t d_col, uint64_t* done, uint64_t* a_done) {
+      const uint32_t s = op % AT_NSLOT;
+      mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
+      ++op;
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sb = smem_u32(smem + (size_t)s * AT_SLOT);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t a = tmem_base + a_col + (t == 0 ? 64u : 0u);
+          const uint32_t bo = sb + (t == 1 ? 16384u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_tf32_ts(tmem_base + d_col, a + kk * 8,
+                         make_smem_desc(bo + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), IDESC_K,
+                         (t | kk) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        umma_commit(done);
+        if (a_done) umma_commit(a_done);
+      }
+      __syncwarp();
+    };
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      // the A tiles' ring slots: the converter signals "hi/lo in TMEM" on the slot's conv barrier
+      const uint32_t s_a1 = op % AT_NSLOT, ph_a1 = (op / AT_NSLOT) & 1;
+      ++op;
+      const uint32_t s_a2 = op % AT_NSLOT, ph_a2 = (op / AT_NSLOT) & 1;
+      if (HAS2) ++op;
+      mbar_wait(&conv[s_a1], ph_a1);
+      tc_fence_after();
+      score(A1_COL, X_COL0 + (gb & 1) * X_STRIDE, &x_full[gb & 1], nb == 1 ? &a_empty[0] : nullptr);
+      if (HAS2) {
+        mbar_wait(&conv[s_a2], ph_a2);
+        tc_fence_after();
+        score(A2_COL, Y_COL, y_full, nb == 1 ? &a_empty[1] : nullptr);
+      }
+      for (int j = 1; j <= nb; ++j) {
+        if (j < nb) {
+          const uint32_t g = gb + j;
+          score(A1_COL, X_COL0 + (g & 1) * X_STRIDE, &x_full[g & 1], j == nb - 1 ? &a_empty[0] : nullptr);
+        }
+        {
+          // OUT_blk = Z(g) . B3(g): Z hi/lo from TMEM, B3 MN-major from the slot
+          const uint32_t g = gb + j - 1;
+          const uint32_t xb = X_COL0 + (g & 1) * X_STRIDE;
+          const uint32_t zhi = HAS2 ? Y_COL : xb, zlo = HAS2 ? xb : xb + 64u;
+          mbar_wait(&z_full[g & 1], (g >> 1) & 1);
+          mbar_wait(out_empty, (g & 1) ^ 1);
+          const uint32_t s = op % AT_NSLOT;
+          mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
+          ++op;
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sb = smem_u32(smem + (size_t)s * AT_SLOT);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const uint32_t a = tmem_base + (t == 0 ? zlo : zhi);
+              const uint32_t bo = sb + (t == 1 ? 16384u : 0u);
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_tf32_ts(tmem_base + OUT_COL, a + kk * 8,
+                             make_smem_desc(bo + (kk >> 2) * 8192 + (kk & 3) * 1024, 4096, 512, 1), IDESC_MN,
+                             (t | kk) ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
+            umma_commit(out_full);
+          }
+          __syncwarp();
+        }
+        if (HAS2 && j < nb) score(A2_COL, Y_COL, y_full, j == nb - 1 ? &a_empty[1] : nullptr);
+      }
+      gb += nb;
+    }
+  }
+  } else if (warp < 8) {
+    // ===================================== converter =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    const int tid = threadIdx.x - 128;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t op = 0, it = 0;
+    auto conv_a = [&](int which) {
+      const uint32_t s = op % AT_NSLOT;
+      mbar_wait(&full[s], (op / AT_NSLOT) & 1);
+      ++op;
+      mbar_wait(&a_empty[which], (it & 1) ^ 1);
+      tc_fence_after();
+      const uint8_t* slot = smem + (size_t)s * AT_SLOT;
+      const uint32_t col = which ? A2_COL : A1_COL;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint4* row = reinterpret_cast<const uint4*>(slot + hh * 16384 + r * 128);
+        uint32_t v[32], l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {     // SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
+          const uint4 t4 = row[c ^ (r & 7)];
+          v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t hi = tf32_hi(v[j]);
+          l[j] = tf32_lo(v[j], hi);
+          v[j] = hi;
+        }
+        tmem_st_32x32b_x32(lane_base + col + hh * 32, v);
+        tmem_st_32x32b_x32(lane_base + col + 64 + hh * 32, l);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&conv[s]);              // A tile (hi/lo) is in TMEM; keeps the slot's conv phase in step with its uses
+      named_bar_sync(1, 128);             // every converter thread has read its row: the slot can be refilled
+      if (tid == 0) mbar_arrive(&empty[s]);
+    };
+    auto conv_b = [&]() {
+      const uint32_t s = op % AT_NSLOT;
+      mbar_wait(&full[s], (op / AT_NSLOT) & 1);
+      ++op;
+      uint4* raw = reinterpret_cast<uint4*>(smem + (size_t)s * AT_SLOT);
+      uint4* lo = raw + 1024;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 v = raw[tid + i * 128];
+        uint4 l;
+        l.x = tf32_lo(v.x, tf32_hi(v.x));
+        l.y = tf32_lo(v.y, tf32_hi(v.y));
+        l.z = tf32_lo(v.z, tf32_hi(v.z));
+        l.w = tf32_lo(v.w, tf32_hi(v.w));
+        lo[tid + i * 128] = l;
+      }
+      fence_proxy_async();                // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&conv[s]);
+    };
+    const int n_b = (HAS2 ? 3 : 2) * nb;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      conv_a(0);
+      if (HAS2) conv_a(1);
+      for (int i = 0; i < n_b; ++i) conv_b();
+    }
+  } else {
+    // ===================================== row owners =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int tid = threadIdx.x - 256;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t gb = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int rt = item % p.row_tiles, bh = item / p.row_tiles;
+      const int h = bh % p.H, b = bh / p.H;
+      const int grow = rt * AT_BM + r;
+      const bool row_ok = grow < p.R;
+      float run[AT_DK];
+#pragma unroll
+      for (int d = 0; d < AT_DK; ++d) run[d] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;     // FWD
+      float ls_r = 0.f, d_r = 0.f;                             // DQ: per-row statistics
+      if (MODE == AT_DQ && row_ok) {
+        ls_r = __ldg(p.lse + (int64_t)bh * p.R + grow);
+        d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow);
+      }
+      // fold OUT_blk(g) into the running total: run = run * a + OUT
+      auto fold = [&](uint32_t g, float a) {
+        mbar_wait(out_full, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(lane_base + OUT_COL + hh * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 32; ++d) {
+            if (MODE == AT_FWD) run[hh * 32 + d] = fmaf(run[hh * 32 + d], a, __uint_as_float(o[d]));
+            else run[hh * 32 + d] += __uint_as_float(o[d]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(out_empty);
+      };
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t g = gb + j;
+        const uint32_t bsel = g & 1;
+        const uint32_t xaddr = lane_base + X_COL0 + bsel * X_STRIDE;
+        const int col0 = j * AT_BC;
+        float* cs = colstat + bsel * 128;
+        if (!ROWSTAT) {
+          // per-column statistics of this block (lse, and D in the DK mode) -> shared memory
+          if (tid < 64) {
+            const int col = col0 + tid;
+            cs[tid] = (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) : INFINITY;
+          } else if (MODE == AT_DKM) {
+            const int col = col0 + tid - 64;
+            cs[tid] = (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) : 0.f;
+          }
+          named_bar_sync(2, 128);
+        }
+        mbar_wait(&x_full[bsel], (g >> 1) & 1);
+        tc_fence_after();
+        if (MODE == AT_FWD) {
+          uint32_t x[64];
+          tmem_ld_32x32b_x32(xaddr, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
+          tmem_ld_32x32b_x32(xaddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
+          tmem_ld_wait();
+          if (col0 + AT_BC > p.C) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (col0 + c >= p.C) x[c] = __float_as_uint(-INFINITY);
+          }
+          float mb = __uint_as_float(x[0]);
+#pragma unroll
+          for (int c = 1; c < 64; ++c) mb = fmaxf(mb, __uint_as_float(x[c]));
+          const float m_new = fmaxf(m_run, mb);
+          const float alpha = exp2f((m_run - m_new) * p.c2);
+          const float mc = m_new * p.c2;
+          float sum = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t lo[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float pv = exp2f(fmaf(__uint_as_float(x[hh * 32 + c]), p.c2, -mc));
+              sum += pv;
+              const uint32_t hi = tf32_hi(__float_as_uint(pv));
+              lo[c] = tf32_lo(__float_as_uint(pv), hi);
+              x[hh * 32 + c] = hi;
+            }
+            tmem_st_32x32b_x32(xaddr + hh * 32, *reinterpret_cast<uint32_t(*)[32]>(&x[hh * 32]));
+            tmem_st_32x32b_x32(xaddr + 64 + hh * 32, lo);
+          }
+          l_run = fmaf(l_run, alpha, sum);
+          m_run = m_new;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&z_full[bsel]);
+          if (j >= 1) fold(g - 1, a_prev);
+          a_prev = alpha;
+        } else if (MODE == AT_DV) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t x[32], lo[32];
+            tmem_ld_32x32b_x32(xaddr + hh * 32, x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float pv = exp2f(fmaf(__uint_as_float(x[c]), p.c2, -cs[hh * 32 + c]));
+              const uint32_t hi = tf32_hi(__float_as_uint(pv));
+              lo[c] = tf32_lo(__float_as_uint(pv), hi);
+              x[c] = hi;
+            }
+            tmem_st_32x32b_x32(xaddr + hh * 32, x);
+            tmem_st_32x32b_x32(xaddr + 64 + hh * 32, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&z_full[bsel]);
+          if (j >= 1) fold(g - 1, 1.f);
+        } else {
+          // DQ / DK: Z = P (Y - D) c;   Z hi -> Y columns, Z lo -> X columns
+          mbar_wait(y_full, g & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t x[32], y[32];
+            tmem_ld_32x32b_x32(xaddr + hh * 32, x);
+            tmem_ld_32x32b_x32(lane_base + Y_COL + hh * 32, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float ls, dd;
+              if (MODE == AT_DQ) {
+                ls = (col0 + hh * 32 + c < p.C) ? ls_r : INFINITY;
+                dd = d_r;
+              } else {
+                ls = cs[hh * 32 + c];
+                dd = cs[64 + hh * 32 + c];
+              }
+              const float pv = exp2f(fmaf(__uint_as_float(x[c]), p.c2, -ls));
+              const float z = pv * (__uint_as_float(y[c]) - dd) * p.c;
+              const uint32_t hi = tf32_hi(__float_as_uint(z));
+              x[c] = tf32_lo(__float_as_uint(z), hi);
+              y[c] = hi;
+            }
+            tmem_st_32x32b_x32(lane_base + Y_COL + hh * 32, y);
+            tmem_st_32x32b_x32(xaddr + hh * 32, x);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&z_full[bsel]);
+          if (j >= 1) fold(g - 1, 1.f);
+        }
+      }
+      fold(gb + nb - 1, a_prev);
+      gb += nb;
+      // epilogue: this thread's row of the output tile
+      if (row_ok) {
+        float* dst = p.out + (int64_t)b * p.out_bs + (int64_t)h * p.out_hs + (int64_t)grow * p.out_ld;
+        float sc = 1.f;
+        if (MODE == AT_FWD) {
+          sc = 1.f / l_run;
+          p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, p.c2, log2f(l_run));
+        }
+#pragma unroll
+        for (int d = 0; d < AT_DK; d += 4)
+          *reinterpret_cast<float4*>(dst + d) = make_float4(run[d] * sc, run[d + 1] * sc, run[d + 2] * sc, run[d + 3] * sc);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// D[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d]: 16 lanes (one float4 each) per (b, h, s) row of 64
+__global__ void __launch_bounds__(256) attn_dvec_kernel(const float* __restrict__ o, const float* __restrict__ dout,
+                                                        float* __restrict__ dvec, int64_t rows_total, int H, int S,
+                                                        int64_t bs, int64_t hs, int64_t ld) {
+  const int sub = threadIdx.x & 15;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 4);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); row < rows_total; row += stride) {
+    // row enumerates (b, h, s) with s fastest: matches the (B, H, S) layout of dvec / lse
+    const int64_t s = row % S, bh = row / S;
+    const int64_t h = bh % H, b = bh / H;
+    const int64_t off = b * bs + h * hs + s * ld + sub * 4;
+    const float4 a = *reinterpret_cast<const float4*>(o + off);
+    const float4 g = *reinterpret_cast<const float4*>(dout + off);
+    float v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+#pragma unroll
+    for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
+    if (sub == 0) dvec[row] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct AttnTensor {
+  const float* ptr;
+  int64_t bs, hs, ld;   // element strides: batch, head, row
+  int64_t rows;         // sequence length of this tensor
+};
+
+static int encode_attn(CUtensorMap* map, const AttnTensor& t, int64_t B, int64_t H, uint32_t box_rows, bool mn_major) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[4] = {(cuuint64_t)AT_DK, (cuuint64_t)t.rows, (cuuint64_t)H, (cuuint64_t)B};
+  // a size-1 axis may carry any stride: give it a legal dummy (multiple of 16 B)
+  const int64_t fallback = t.ld * t.rows;
+  const int64_t hs = (H > 1) ? t.hs : fallback;
+  const int64_t bs = (B > 1) ? t.bs : fallback;
+  if (hs <= 0 || bs <= 0) return set_error(B200AD_ERR_UNSUPPORTED, "attention(tcgen05): broadcast (stride 0) batch / head axes");
+  cuuint64_t strides[3] = {(cuuint64_t)t.ld * 4, (cuuint64_t)hs * 4, (cuuint64_t)bs * 4};
+  cuuint32_t box[4] = {32u, box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B200AD_OK;
+}
+
+static bool tensor_ok(const float* ptr, const b200ad_attn_strides& s) {
+  return ptr && aligned16(ptr) && s.row > 0 && (s.row & 3) == 0 && (s.head & 3) == 0 && (s.batch & 3) == 0 &&
+         s.head >= 0 && s.batch >= 0;
+}
+
+template <int MODE>
+static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTensor& b1, const AttnTensor& b2,
+                       const AttnTensor& b3, AttnParams p, int64_t B, int64_t H, cudaStream_t s) {
+  constexpr bool HAS2 = (MODE == AT_DQ || MODE == AT_DKM);
+  CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3;
+  int rc;
+  if ((rc = encode_attn(&m_a1, a1, B, H, AT_BM, false))) return rc;
+  if ((rc = encode_attn(&m_b1, b1, B, H, AT_BC, false))) return rc;
+  if ((rc = encode_attn(&m_b3, b3, B, H, 32, true))) return rc;
+  if (HAS2) {
+    if ((rc = encode_attn(&m_a2, a2, B, H, AT_BM, false))) return rc;
+    if ((rc = encode_attn(&m_b2, b2, B, H, AT_BC, false))) return rc;
+  } else {
+    m_a2 = m_a1;
+    m_b2 = m_b1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  p.row_tiles = (int32_t)ceil_div(p.R, AT_BM);
+  p.nb = (int32_t)ceil_div(p.C, AT_BC);
+  const int64_t items = B * H * p.row_tiles;
+  p.total_items = (int32_t)items;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_tc_kernel<MODE><<<grid, AT_THREADS, AT_SMEM, s>>>(m_a1, m_a2, m_b1, m_b2, m_b3, p);
+  count_launch();
+  if (getenv("B200AD_ATTN_SYNC")) {     // debugging aid: attribute an asynchronous failure to its pass
+    cudaError_t e = cudaStreamSynchronize(s);
+    fprintf(stderr, "[b200ad] attention pass mode %d (R=%d C=%d nb=%d items=%d): %s\n", MODE, p.R, p.C, p.nb,
+            p.total_items, cudaGetErrorString(e));
+  }
+  return check_launch("attention(tcgen05)");
+}
+
+static int attn_check(const b200ad_attn_desc* d, const char** why) {
+  auto no = [&](const char* w) { if (why) *why = w; return 0; };
+  if (!d) return no("null descriptor");
+  if (d->head_dim != AT_DK) return no("head_dim must be 64");
+  if (d->batch < 1 || d->heads < 1 || d->seq_q < 1 || d->seq_kv < 1) return no("empty problem");
+  if (d->batch * d->heads * ceil_div(d->seq_q > d->seq_kv ? d->seq_q : d->seq_kv, AT_BM) >= (1ll << 31)) return no("too many tiles");
+  if (d->seq_q >= (1ll << 31) || d->seq_kv >= (1ll << 31)) return no("sequence too long");
+  if (get_encode_fn() == nullptr) return no("cuTensorMapEncodeTiled unavailable (no driver)");
+  return 1;
+}
+
+}  // namespace b200ad
+
+using namespace b200ad;
+
+extern "C" {
+
+int b200ad_attn_supported(const b200ad_attn_desc* d) {
+  const char* why = nullptr;
+  if (!attn_check(d, &why)) return 0;
+  const b200ad_attn_strides* ss[4] = {&d->q, &d->k, &d->v, &d->o};
+  for (int i = 0; i < 4; ++i)
+    if (ss[i]->row <= 0 || (ss[i]->row & 3) || (ss[i]->head & 3) || (ss[i]->batch & 3) || ss[i]->head < 0 || ss[i]->batch < 0) return 0;
+  return 1;
+}
+
+int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse,
+                    void* stream) {
+  const char* why = "unsupported";
+  if (!attn_check(d, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "attn_fwd: %s", why);
+  B200AD_REQUIRE(tensor_ok(q, d->q) && tensor_ok(k, d->k) && tensor_ok(v, d->v) && tensor_ok(o, d->o) && lse,
+                 "attn_fwd: null / misaligned tensor or stride not a multiple of 4 elements");
+  AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv};
+  AttnParams p{};
+  p.out = o; p.out_bs = d->o.batch; p.out_hs = d->o.head; p.out_ld = d->o.row;
+  p.lse_w = lse; p.lse = nullptr; p.dvec = nullptr;
+  p.H = (int32_t)d->heads; p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
+  p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
+  return launch_pass<AT_FWD>(tq, tq, tk, tk, tv, p, d->batch, d->heads, (cudaStream_t)stream);
+}
+
+int64_t b200ad_attn_bwd_ws_floats(const b200ad_attn_desc* d) {
+  if (!d) return 0;
+  return d->batch * d->heads * d->seq_q;
+}
+
+int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
+                    const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, void* stream) {
+  const char* why = "unsupported";
+  if (!attn_check(d, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "attn_bwd: %s", why);
+  B200AD_REQUIRE(tensor_ok(q, d->q) && tensor_ok(k, d->k) && tensor_ok(v, d->v) && tensor_ok(o, d->o) &&
+                     tensor_ok(dout, d->o) && tensor_ok(dq, d->q) && tensor_ok(dk, d->k) && tensor_ok(dv, d->v) && lse && ws,
+                 "attn_bwd: null / misaligned tensor or stride not a multiple of 4 elements");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t B = d->batch, H = d->heads;
+  AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q};
+  // D = rowsum(dO o O)
+  const int64_t rows = B * H * d->seq_q;
+  attn_dvec_kernel<<<stream_grid(rows, 16), 256, 0, s>>>(o, dout, ws, rows, (int)H, (int)d->seq_q, d->o.batch, d->o.head,
+                                                         d->o.row);
+  count_launch();
+  int rc = check_launch("attention dvec");
+  if (rc) return rc;
+  AttnParams p{};
+  p.lse_w = nullptr; p.lse = lse; p.dvec = ws;
+  p.H = (int32_t)H;
+  p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
+  // dV: lanes = kv rows, columns = q rows
+  p.out = dv; p.out_bs = d->v.batch; p.out_hs = d->v.head; p.out_ld = d->v.row;
+  p.R = (int32_t)d->seq_kv; p.C = (int32_t)d->seq_q;
+  if ((rc = launch_pass<AT_DV>(tk, tk, tq, tq, tdo, p, B, H, s))) return rc;
+  // dK
+  p.out = dk; p.out_bs = d->k.batch; p.out_hs = d->k.head; p.out_ld = d->k.row;
+  if ((rc = launch_pass<AT_DKM>(tk, tv, tq, tdo, tq, p, B, H, s))) return rc;
+  // dQ: lanes = q rows, columns = kv rows
+  p.out = dq; p.out_bs = d->q.batch; p.out_hs = d->q.head; p.out_ld = d->q.row;
+  p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
+  return launch_pass<AT_DQ>(tq, tdo, tk, tv, tk, p, B, H, s);
+}
+}

@@ -811,6 +811,107 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
 
 
 # --------------------------------------------------------------------------------------------------
+# fused attention core on head-split views (B, h, S, d_k)
+# --------------------------------------------------------------------------------------------------
+_fused_attention = [True]
+
+
+def set_fused_attention(flag):
+    """False routes MultiHeadAttention through the unfused GEMM + softmax kernels (materialised S x S)."""
+    _fused_attention[0] = bool(flag)
+
+
+def _attn_strides(s, t):
+    s.batch, s.head, s.row = (int(t.stride(0)), int(t.stride(1)), int(t.stride(2)))
+
+
+def _attn_desc(q, k, v, o, scale):
+    """q/k/v/o: DeviceArray views (B, h, S, d) with a contiguous last axis, or None if that does not hold."""
+    ts = [x.t for x in (q, k, v, o)]
+    if any(t.dim() != 4 or t.dtype != _F32 or (t.shape[3] > 1 and t.stride(3) != 1) for t in ts):
+        return None
+    B, H, Sq, dk = ts[0].shape
+    Skv = ts[1].shape[2]
+    if tuple(ts[1].shape) != (B, H, Skv, dk) or tuple(ts[2].shape) != (B, H, Skv, dk) or tuple(ts[3].shape) != (B, H, Sq, dk):
+        return None
+    d = L.AttnDesc()
+    d.batch, d.heads, d.seq_q, d.seq_kv, d.head_dim = B, H, Sq, Skv, dk
+    d.scale = float(scale)
+    for s, t in zip((d.q, d.k, d.v, d.o), ts):
+        _attn_strides(s, t)
+    return d
+
+
+def _same_strides(a, b):
+    return all(n == 1 or sa == sb for n, sa, sb in zip(a.shape, a.t.stride(), b.t.stride()))
+
+
+def attn_supported(q, k, v):
+    """True when the fused tcgen05 attention pass can take these head-split views."""
+    if not _fused_attention[0]:
+        return False
+    d = _attn_desc(q, k, v, q, 1.0)
+    return d is not None and bool(_lib().b200ad_attn_supported(ctypes.byref(d)))
+
+
+def _timed(key, flops, call):
+    timer = _gemm_timer[0]
+    if timer is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    timer.records.append((key, flops, e0, e1))
+
+
+def attn_fwd(q, k, v, scale):
+    """O = softmax(scale * q k^T) v per (batch, head).  Returns (O as a (B, h, S, d) view of a (B, S, h, d)
+    buffer — i.e. already in merged-head layout —, lse (B, h, S) in the log2 domain)."""
+    B, H, Sq, dk = q.shape
+    o = empty((B, Sq, H, dk)).transpose(0, 2, 1, 3)
+    lse = empty((B, H, Sq))
+    d = _attn_desc(q, k, v, o, scale)
+    s = stream_ptr()
+    _timed(("attn_fwd", B, H, Sq, k.shape[2], dk), 4.0 * B * H * Sq * k.shape[2] * dk,
+           lambda: L.check(_lib().b200ad_attn_fwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, lse.ptr, s)))
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, dout, lse, scale):
+    """Gradients (dq, dk, dv) of attn_fwd, each a (B, h, S, d) view of a fresh (B, S, h, d) buffer.
+    `dout` must share `o`'s strides."""
+    B, H, Sq, dk = q.shape
+    Skv = k.shape[2]
+    if not _same_strides(dout, o):
+        tmp = empty((B, Sq, H, dk)).transpose(0, 2, 1, 3)
+        strided_copy_(dout, tmp)
+        dout = tmp
+    d = _attn_desc(q, k, v, o, scale)
+
+    def like(x):
+        # same strides as x (the ABI writes dq/dk/dv with q/k/v's strides): allocate in x's memory order
+        order = sorted(range(4), key=lambda i: -x.t.stride(i))
+        buf = torch.empty([x.t.shape[i] for i in order], dtype=_F32, device=x.t.device)
+        inv = [order.index(i) for i in range(4)]
+        out = buf.permute(*inv)
+        return DeviceArray(out)
+
+    dq, dk_, dv = like(q), like(k), like(v)
+    if not (_same_strides(dq, q) and _same_strides(dk_, k) and _same_strides(dv, v)):
+        # q/k/v are slices of wider buffers; the ABI writes dq/dk/dv with q/k/v's strides -> compact the operands once
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        d = _attn_desc(q, k, v, o, scale)
+        dq, dk_, dv = empty(q.shape), empty(k.shape), empty(v.shape)
+    ws = empty((int(_lib().b200ad_attn_bwd_ws_floats(ctypes.byref(d))),))
+    s = stream_ptr()
+    _timed(("attn_bwd", B, H, Sq, Skv, dk), 10.0 * B * H * Sq * Skv * dk,
+           lambda: L.check(_lib().b200ad_attn_bwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr,
+                                                  dq.ptr, dk_.ptr, dv.ptr, ws.ptr, s)))
+    return dq, dk_, dv
+
+
+# --------------------------------------------------------------------------------------------------
 # strided row-wise helpers used by the layers
 # --------------------------------------------------------------------------------------------------
 def _rows_ld(a):

@@ -506,13 +506,22 @@ class MultiHeadAttention:
         q2, k2, v2 = (a.reshape(B * S, Dm) for a in (query, key, value))
         Q, K, V = D.matmul(q2, wq), D.matmul(k2, wk), D.matmul(v2, wv)          # :1347-1349
         Qh, Kh, Vh = (a.reshape(B, S, h, dk).transpose(0, 2, 1, 3) for a in (Q, K, V))
-        scores = D.matmul(Qh, Kh, trans_b=True)                                  # :1355 (scale folded into softmax)
-        P = D.softmax_lastaxis(scores, in_scale=1.0 / math.sqrt(dk))             # :1356
-        O = D.empty((B, S, h, dk))
-        D.matmul(P, Vh, out=O.transpose(0, 2, 1, 3))                             # :1357 written in merged layout
-        O2 = O.reshape(B * S, h * dk)
+        scale = 1.0 / math.sqrt(dk)
+        if D.attn_supported(Qh, Kh, Vh):
+            # fused tcgen05 attention pass (:1355-1357): the S x S scores stay on the SM; only the row log-sum-exp
+            # is kept for the backward
+            Oh, lse = D.attn_fwd(Qh, Kh, Vh, scale)
+            O2 = Oh.transpose(0, 2, 1, 3).reshape(B * S, h * dk)
+            P = None
+        else:
+            scores = D.matmul(Qh, Kh, trans_b=True)                              # :1355 (scale folded into softmax)
+            P = D.softmax_lastaxis(scores, in_scale=scale)                       # :1356
+            O = D.empty((B, S, h, dk))
+            D.matmul(P, Vh, out=O.transpose(0, 2, 1, 3))                         # :1357 written in merged layout
+            O2 = O.reshape(B * S, h * dk)
+            lse = None
         out = D.matmul(O2, wo).reshape(B, S, wo.shape[1])                        # :1360
-        self.cache = (q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk))
+        self.cache = (q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk), lse)
         return out
 
     def backward(self, dout=None, notify=None):
@@ -523,7 +532,7 @@ class MultiHeadAttention:
         if dout is None:
             return None   # the reference's backward is a stub (layers.py:1366-1367)
         wq, wk, wv, wo = self.weights
-        q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk) = self.cache
+        q2, k2, v2, Qh, Kh, Vh, P, O2, (B, S, Dm, h, dk), lse = self.cache
         beta = 1.0 if self.accumulate else 0.0
         d2 = _dev(dout).reshape(B * S, wo.shape[1]).contiguous()
         D.matmul(O2, d2, trans_a=True, out=self.grads[3], beta=beta)             # dwo
@@ -531,17 +540,26 @@ class MultiHeadAttention:
             notify(1)
         dO = D.matmul(d2, wo, trans_b=True).reshape(B, S, h, dk)
         dOh = dO.transpose(0, 2, 1, 3)
-        dP = D.matmul(dOh, Vh, trans_b=True)                                     # (B,h,S,S)
-        dV = D.empty((B, S, h, dk))
-        D.matmul(P, dOh, trans_a=True, out=dV.transpose(0, 2, 1, 3))
-        dV2 = dV.reshape(B * S, h * dk)
-        D.matmul(v2, dV2, trans_a=True, out=self.grads[2], beta=beta)            # dwv
-        if notify:
-            notify(2)
-        dS = D.softmax_bwd_lastaxis(dP, P, out_scale=1.0 / math.sqrt(dk), out=dP)
-        dQ, dK = D.empty((B, S, h, dk)), D.empty((B, S, h, dk))
-        D.matmul(dS, Kh, out=dQ.transpose(0, 2, 1, 3))
-        D.matmul(dS, Qh, trans_a=True, out=dK.transpose(0, 2, 1, 3))
+        if P is None:
+            Oh = O2.reshape(B, S, h, dk).transpose(0, 2, 1, 3)
+            dQh, dKh, dVh = D.attn_bwd(Qh, Kh, Vh, Oh, dOh, lse, 1.0 / math.sqrt(dk))
+            dQ, dK, dV = (g.transpose(0, 2, 1, 3) for g in (dQh, dKh, dVh))      # (B,S,h,dk), contiguous
+            dV2 = dV.reshape(B * S, h * dk)
+            D.matmul(v2, dV2, trans_a=True, out=self.grads[2], beta=beta)        # dwv
+            if notify:
+                notify(2)
+        else:
+            dP = D.matmul(dOh, Vh, trans_b=True)                                 # (B,h,S,S)
+            dV = D.empty((B, S, h, dk))
+            D.matmul(P, dOh, trans_a=True, out=dV.transpose(0, 2, 1, 3))
+            dV2 = dV.reshape(B * S, h * dk)
+            D.matmul(v2, dV2, trans_a=True, out=self.grads[2], beta=beta)        # dwv
+            if notify:
+                notify(2)
+            dS = D.softmax_bwd_lastaxis(dP, P, out_scale=1.0 / math.sqrt(dk), out=dP)
+            dQ, dK = D.empty((B, S, h, dk)), D.empty((B, S, h, dk))
+            D.matmul(dS, Kh, out=dQ.transpose(0, 2, 1, 3))
+            D.matmul(dS, Qh, trans_a=True, out=dK.transpose(0, 2, 1, 3))
         dQ2, dK2 = dQ.reshape(B * S, h * dk), dK.reshape(B * S, h * dk)
         D.matmul(k2, dK2, trans_a=True, out=self.grads[1], beta=beta)            # dwk
         if notify:

@@ -224,6 +224,37 @@ int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float
 int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused multi-head attention core (tcgen05, fp32-faithful 3xTF32; scores never leave the SM).
+ *   fwd:  O = softmax(scale * Q K^T) V  per (batch, head);  lse[b,h,s] = log2-domain log-sum-exp
+ *         of the scaled scores of query row s (kept for the backward instead of the S x S matrix).
+ *         replaces MultiHeadAttention.forward layers.py:1351-1357 (split heads are strided views:
+ *         element (b, h, s, d) of a tensor sits at ptr + b*batch + h*head + s*row + d).
+ *   bwd:  dQ, dK, dV of the same expression given dO (the tape gradients of
+ *         Test/MultiHeadAttentionTest.py:70-85: Matmul :530-533, Divide :1004-1005 without the 1e-8
+ *         that only guards a zero denominator, exp :1058-1060, sum :699-704).
+ *         dO shares `o`'s strides, dQ/dK/dV share q/k/v's.  ws: b200ad_attn_bwd_ws_floats floats.
+ *   Built for head_dim == 64, any seq_q / seq_kv, strides multiples of 4 elements, 16 B aligned
+ *   bases; b200ad_attn_supported says whether the fused path applies (otherwise the caller
+ *   composes the same math from b200ad_gemm + b200ad_softmax_*).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200ad_attn_strides {
+  int64_t batch, head, row; /* element strides */
+} b200ad_attn_strides;
+typedef struct b200ad_attn_desc {
+  int64_t batch, heads, seq_q, seq_kv, head_dim;
+  float scale;
+  int32_t reserved;
+  b200ad_attn_strides q, k, v, o;
+} b200ad_attn_desc;
+int b200ad_attn_supported(const b200ad_attn_desc* d);
+int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
+                    float* o, float* lse, void* stream);
+int64_t b200ad_attn_bwd_ws_floats(const b200ad_attn_desc* d);
+int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
+                    const float* o, const float* dout, const float* lse, float* dq, float* dk,
+                    float* dv, float* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Recurrent cells (elementwise halves; the gate GEMMs go through b200ad_gemm).
  *   lstm fwd: A (N,4H) pre-activations with column blocks [f,g,i,o] = [sigmoid,tanh,sigmoid,sigmoid]
  *             c' = f*c + g*i ; h' = o*tanh(c')     LSTM.forward layers.py:624-646.

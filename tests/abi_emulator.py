@@ -352,6 +352,61 @@ class Emulator:
                 C[...] = r
         return 0
 
+    # ---- fused attention ---------------------------------------------------------------------------
+    @staticmethod
+    def _attn_view(ptr, st, B, H, S, dk):
+        n = (B - 1) * st.batch + (H - 1) * st.head + (S - 1) * st.row + dk
+        flat = _f32(ptr, n)
+        return np.lib.stride_tricks.as_strided(flat, (B, H, S, dk), (st.batch * 4, st.head * 4, st.row * 4, 4))
+
+    def b200ad_attn_supported(self, dref):
+        d = dref._obj if hasattr(dref, "_obj") else dref
+        return 1 if d.head_dim == 64 else 0
+
+    def b200ad_attn_bwd_ws_floats(self, dref):
+        d = dref._obj if hasattr(dref, "_obj") else dref
+        return d.batch * d.heads * d.seq_q
+
+    def _attn_probs(self, d, q, k):
+        Q = self._attn_view(_ival(q), d.q, d.batch, d.heads, d.seq_q, d.head_dim).astype(np.float64)
+        K = self._attn_view(_ival(k), d.k, d.batch, d.heads, d.seq_kv, d.head_dim).astype(np.float64)
+        S = d.scale * (Q @ K.transpose(0, 1, 3, 2))
+        m = S.max(axis=-1, keepdims=True)
+        e = np.exp(S - m)
+        l = e.sum(axis=-1, keepdims=True)
+        return Q, K, e / l, (m + np.log(l))[..., 0]
+
+    def b200ad_attn_fwd(self, dref, q, k, v, o, lse, s):
+        self.launches += 1
+        d = dref._obj if hasattr(dref, "_obj") else dref
+        if d.head_dim != 64:
+            return self._fail("attn_fwd: head_dim must be 64", -3)
+        _, _, P, ln_lse = self._attn_probs(d, q, k)
+        V = self._attn_view(_ival(v), d.v, d.batch, d.heads, d.seq_kv, d.head_dim).astype(np.float64)
+        self._attn_view(_ival(o), d.o, d.batch, d.heads, d.seq_q, d.head_dim)[...] = P @ V
+        _f32(_ival(lse), d.batch * d.heads * d.seq_q)[:] = (ln_lse / np.log(2.0)).reshape(-1)
+        return 0
+
+    def b200ad_attn_bwd(self, dref, q, k, v, o, dout, lse, dq, dk, dv, ws, s):
+        self.launches += 4
+        d = dref._obj if hasattr(dref, "_obj") else dref
+        B, H, Sq, Skv, dkk = d.batch, d.heads, d.seq_q, d.seq_kv, d.head_dim
+        Q = self._attn_view(_ival(q), d.q, B, H, Sq, dkk).astype(np.float64)
+        K = self._attn_view(_ival(k), d.k, B, H, Skv, dkk).astype(np.float64)
+        V = self._attn_view(_ival(v), d.v, B, H, Skv, dkk).astype(np.float64)
+        O = self._attn_view(_ival(o), d.o, B, H, Sq, dkk).astype(np.float64)
+        dO = self._attn_view(_ival(dout), d.o, B, H, Sq, dkk).astype(np.float64)
+        lse2 = _f32(_ival(lse), B * H * Sq).astype(np.float64).reshape(B, H, Sq, 1)
+        P = np.exp2(d.scale * np.log2(np.e) * (Q @ K.transpose(0, 1, 3, 2)) - lse2)      # recomputed from the LSE
+        Dv = (dO * O).sum(axis=-1, keepdims=True)
+        _f32(_ival(ws), B * H * Sq)[:] = Dv.reshape(-1)
+        dP = dO @ V.transpose(0, 1, 3, 2)
+        dS = P * (dP - Dv) * d.scale
+        self._attn_view(_ival(dv), d.v, B, H, Skv, dkk)[...] = P.transpose(0, 1, 3, 2) @ dO
+        self._attn_view(_ival(dk), d.k, B, H, Skv, dkk)[...] = dS.transpose(0, 1, 3, 2) @ Q
+        self._attn_view(_ival(dq), d.q, B, H, Sq, dkk)[...] = dS @ K
+        return 0
+
     # ---- cells -----------------------------------------------------------------------------------
     def b200ad_lstm_cell_fwd(self, a, lda, c_prev, ldcp, gates, ldg, c_next, ldcn, h_next, ldh, n, h, s):
         self.launches += 1

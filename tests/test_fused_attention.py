@@ -1,0 +1,156 @@
+"""Fused attention core (b200ad_attn_fwd / b200ad_attn_bwd) through the C ABI wrappers vs an fp64 NumPy
+statement of the reference math (MultiHeadAttention.forward layers.py:1351-1357 and the tape gradients of
+Test/MultiHeadAttentionTest.py:70-85), and the MultiHeadAttention layer fused vs unfused.
+
+Sizes cover: one 128-row tile / several tiles, one 64-column block / several, ragged tails in both the lane
+and the column dimension (TMA zero fill + column masking), seq_q != seq_kv, more work items than SMs
+(persistent loop, barrier phases across items), strided head-split views of merged (B*S, h*dk) matrices."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import assert_close
+
+
+def _D():
+    from auto_differentiation_b200 import device
+    return device
+
+
+def _ref(q, k, v, do, scale):
+    q, k, v, do = (a.astype(np.float64) for a in (q, k, v, do))
+    s = scale * (q @ k.transpose(0, 1, 3, 2))
+    e = np.exp(s - s.max(-1, keepdims=True))
+    p = e / e.sum(-1, keepdims=True)
+    o = p @ v
+    dv = p.transpose(0, 1, 3, 2) @ do
+    dp = do @ v.transpose(0, 1, 3, 2)
+    ds = p * (dp - (dp * p).sum(-1, keepdims=True)) * scale
+    return o, ds @ k, ds.transpose(0, 1, 3, 2) @ q, dv
+
+
+def _heads(D, a):
+    """(B,h,S,dk) host array -> head-split device VIEW of a merged (B,S,h*dk) buffer (the layer's layout)."""
+    B, h, S, dk = a.shape
+    merged = D.asarray(np.ascontiguousarray(a.transpose(0, 2, 1, 3)).reshape(B, S, h * dk))
+    return merged.reshape(B, S, h, dk).transpose(0, 2, 1, 3)
+
+
+CASES = [
+    # B, h, Sq, Skv
+    (1, 1, 128, 64),
+    (1, 2, 128, 128),
+    (2, 3, 256, 192),
+    (1, 2, 100, 100),      # ragged rows and columns
+    (2, 2, 70, 200),       # Sq < one tile, ragged columns
+    (1, 1, 333, 77),
+    (3, 8, 512, 512),      # config 3/5 shape per sequence
+    (40, 8, 128, 128),     # 320 work items > 148 SMs: persistent loop, odd/even block counts across items
+    (25, 8, 192, 64),      # nb = 1: A tile released by the first score MMA
+]
+
+
+@pytest.mark.parametrize("B,h,Sq,Skv", CASES)
+def test_attn_fwd_bwd_vs_fp64(backend, B, h, Sq, Skv):
+    D = _D()
+    if backend == "emu" and B * h * Sq * Skv > 2_000_000:
+        pytest.skip("CPU emulation: small cases only")
+    dk = 64
+    rng = np.random.default_rng(B * 1000 + Sq + Skv)
+    q = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    k = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+    v = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+    do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    scale = 1.0 / math.sqrt(dk)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    assert D.attn_supported(Q, K, V)
+    O, lse = D.attn_fwd(Q, K, V, scale)
+    o_ref, dq_ref, dk_ref, dv_ref = _ref(q, k, v, do, scale)
+    assert_close(np.asarray(O), o_ref, rtol=2e-5, atol=2e-6, what="O")
+    # lse is the log2-domain log-sum-exp of the scaled scores
+    s = scale * (q.astype(np.float64) @ k.astype(np.float64).transpose(0, 1, 3, 2))
+    m = s.max(-1)
+    lse_ref = (m + np.log(np.exp(s - m[..., None]).sum(-1))) / math.log(2.0)
+    assert_close(np.asarray(lse), lse_ref, rtol=1e-5, atol=1e-6, what="lse")
+    dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    assert_close(np.asarray(dV), dv_ref, rtol=2e-5, atol=2e-6, what="dV")
+    assert_close(np.asarray(dQ), dq_ref, rtol=2e-5, atol=2e-6, what="dQ")
+    assert_close(np.asarray(dK), dk_ref, rtol=2e-5, atol=2e-6, what="dK")
+
+
+def test_attn_large_scores_stable(backend):
+    """Scores of magnitude ~60 (the regime where the reference's naive exp/sum is still finite in fp64):
+    the online softmax must agree with the stable fp64 evaluation."""
+    D = _D()
+    rng = np.random.default_rng(7)
+    B, h, S, dk = 1, 2, 192, 64
+    q = (rng.standard_normal((B, h, S, dk)) * 3).astype(np.float32)
+    k = (rng.standard_normal((B, h, S, dk)) * 3).astype(np.float32)
+    v = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    do = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    scale = 1.0 / math.sqrt(dk)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    O, lse = D.attn_fwd(Q, K, V, scale)
+    o_ref, dq_ref, dk_ref, dv_ref = _ref(q, k, v, do, scale)
+    assert_close(np.asarray(O), o_ref, rtol=5e-5, atol=5e-6, what="O")
+    dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    assert_close(np.asarray(dV), dv_ref, rtol=5e-5, atol=5e-6, what="dV")
+    assert_close(np.asarray(dQ), dq_ref, rtol=5e-5, atol=5e-6, what="dQ")
+    assert_close(np.asarray(dK), dk_ref, rtol=5e-5, atol=5e-6, what="dK")
+
+
+def test_mha_layer_fused_equals_unfused(backend):
+    """The layer's fused path and its GEMM + softmax composition give the same output and gradients."""
+    D = _D()
+    from auto_differentiation_b200.layers import layers as Ls
+    rng = np.random.default_rng(11)
+    B, S, d, h = 2, 160, 512, 8
+    x = rng.standard_normal((B, S, d)).astype(np.float32)
+    ws = [(rng.standard_normal((d, d)) / math.sqrt(d)).astype(np.float32) for _ in range(4)]
+    dout = rng.standard_normal((B, S, d)).astype(np.float32)
+    res = []
+    for fused in (True, False):
+        D.set_fused_attention(fused)
+        try:
+            m = Ls.MultiHeadAttention(d, d, h, weights=[w.copy() for w in ws])
+            out = m.forward(x, x, x)
+            assert (m.cache[6] is None) == fused
+            dx = m.backward(dout)
+            res.append([np.asarray(out)] + [np.asarray(g) for g in m.grads] + [np.asarray(g) for g in dx])
+        finally:
+            D.set_fused_attention(True)
+    names = ["out", "dwq", "dwk", "dwv", "dwo", "dq", "dk", "dv"]
+    for n, a, b in zip(names, res[0], res[1]):
+        assert_close(a, b, rtol=3e-5, atol=3e-6, what=n)
+
+
+@pytest.mark.gpu
+def test_attn_config5_shape_properties():
+    """Config-5 micro-batch shape (256 x 8 heads x 512 x 512 x 64) through size-independent properties:
+    rows of V equal -> O equals that row exactly (softmax sums to one); dV column sums equal dO column sums
+    (P^T 1 = column mass, sum over kv rows of dV = sum over q rows of dO); run-to-run bit reproducibility."""
+    import torch
+    assert torch.cuda.is_available()
+    D = _D()
+    rng = np.random.default_rng(5)
+    B, h, S, dk = 64, 8, 512, 64
+    q = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    k = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    vrow = rng.standard_normal((B, h, 1, dk)).astype(np.float32)
+    v = np.broadcast_to(vrow, (B, h, S, dk)).copy()
+    do = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    scale = 1.0 / math.sqrt(dk)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    O, lse = D.attn_fwd(Q, K, V, scale)
+    o = np.asarray(O)
+    assert np.allclose(o, np.broadcast_to(vrow, o.shape), rtol=2e-5, atol=2e-6)
+    dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    dv = np.asarray(dV).astype(np.float64)
+    assert np.allclose(dv.sum(axis=2), do.astype(np.float64).sum(axis=2), rtol=1e-4, atol=1e-3)
+    # identical V rows -> dP rows are constant -> dS = 0 -> dQ = dK = 0 (up to rounding of dP - D)
+    assert np.abs(np.asarray(dQ)).max() < 1e-3 and np.abs(np.asarray(dK)).max() < 1e-3
+    O2, lse2 = D.attn_fwd(Q, K, V, scale)
+    assert np.array_equal(np.asarray(O2), o) and np.array_equal(np.asarray(lse2), np.asarray(lse))
+    dQ2, dK2, dV2 = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    assert np.array_equal(np.asarray(dV2), np.asarray(dV)) and np.array_equal(np.asarray(dK2), np.asarray(dK))
