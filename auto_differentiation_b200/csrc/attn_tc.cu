@@ -132,7 +132,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t op = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int rt = item % p.row_tiles, bh = item / p.row_tiles;
@@ -190,7 +190,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
       ++op;
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sb = smem_u32(smem + (size_t)s * AT_SLOT);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -238,7 +238,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
           ++op;
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sb = smem_u32(smem + (size_t)s * AT_SLOT);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {

@@ -118,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int t = tile;
@@ -192,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t ph = (it / stages) & 1;
           mbar_wait(p.x3 ? &conv_full[s] : &raw_full[s], ph);
           tc_fence_after();
-          if (lane == 0) {   // always the same thread: tcgen05.commit tracks the MMAs issued by the committing thread
+          if (elect_one()) {   // always the same thread: tcgen05.commit tracks the MMAs issued by the committing thread
             const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t sb = sa + A_BYTES;
             const uint32_t sal = sb + B_BYTES, sbl = sal + A_BYTES;     // lo tiles (TF32X3)
@@ -506,7 +506,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
         int t = tile;
@@ -577,7 +577,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t lph = (it / LS) & 1;
             mbar_wait(&conv_full[ls], lph);        // both CTAs' hi/lo tiles of this k-block are in place
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t sa = smem_u32(smem + (size_t)s * raw_bytes);
               const uint32_t sb = sa + A_BYTES;
               const uint32_t sal = smem_u32(lo_base + (size_t)ls * raw_bytes), sbl = sal + A_BYTES;

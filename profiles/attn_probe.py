@@ -17,6 +17,7 @@ def main():
     import torch
     from auto_differentiation_b200 import device as D
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    timing_only = len(sys.argv) > 1 and sys.argv[1] == "timing"
 
     def heads(a):
         B, h, S, dk = a.shape
@@ -36,7 +37,7 @@ def main():
 
     dk = 64
     scale = 1.0 / math.sqrt(dk)
-    for (B, h, Sq, Skv) in [(1, 1, 128, 64), (1, 1, 128, 128), (1, 2, 256, 256), (2, 3, 100, 200), (4, 8, 512, 512),
+    for (B, h, Sq, Skv) in [] if timing_only else [(1, 1, 128, 64), (1, 1, 128, 128), (1, 2, 256, 256), (2, 3, 100, 200), (4, 8, 512, 512),
                             (40, 8, 128, 192)]:
         rng = np.random.default_rng(Sq + Skv)
         q = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)

@@ -10,7 +10,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling", "atmem"]
+GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling", "atmem", "mmarate"]
 
 
 def run_group(group):
@@ -119,6 +119,19 @@ def run_group(group):
             case("C5 dV (TN)", 512, 64, 512, ta=True, batch=(256, 8), prec="tf32x3", time_it=True)
             case("square 4096 BN64", 4096, 4096, 4096, tb=True, prec="tf32x3", time_it=True)
         os.environ.pop("B200AD_TC_BN"); os.environ.pop("B200AD_TC_ATMEM")
+    elif group == "mmarate":
+        # pure MMA + epilogue (probe 3: no TMA, no split; results are garbage): how does the tcgen05.mma rate depend on N?
+        # per-CTA MMA count for 8192^3 x3: tiles(64 x 8192/BN) / 148 CTAs x 256 k-blocks x 12 MMAs
+        os.environ["B200AD_TC_CHUNK_KB"] = "100000"
+        os.environ["B200AD_TC_PROBE"] = "3"
+        for bn in ("64", "128", "256"):
+            os.environ["B200AD_TC_BN"] = bn
+            for at in ("0", "1"):
+                os.environ["B200AD_TC_ATMEM"] = at
+                case("BN=%s atmem=%s x3" % (bn, at), 8192, 8192, 8192, tb=True, prec="tf32x3", time_it=True)
+            case("BN=%s tf32 1-pass" % bn, 8192, 8192, 8192, tb=True, prec="tf32", time_it=True)
+        for k in ("B200AD_TC_CHUNK_KB", "B200AD_TC_PROBE", "B200AD_TC_BN", "B200AD_TC_ATMEM"):
+            os.environ.pop(k)
     elif group == "ceiling":
         os.environ["B200AD_TC_CHUNK_KB"] = "100000"
         print("-- probe bits: 1 = no TMA, 2 = no split, 3 = pure MMA + epilogue (results are garbage, only the rate matters)", flush=True)

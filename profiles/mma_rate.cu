@@ -1,0 +1,123 @@
+// Microbenchmark: cycles per tcgen05.mma (cta_group::1, M = 128) as a function of N, operand source (A from shared
+// memory = SS, A from TMEM = TS) and kind (tf32: K = 8 per instruction, f16/bf16: K = 16), issued back to back by
+// one thread on fixed operands, one commit at the end.  One CTA per SM on every SM (so the numbers include any
+// chip-level power/clock effects), clock64 around the issue loop + completion wait.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu && ./mma_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../auto_differentiation_b200/csrc/tcgen05.cuh"
+
+using namespace b200ad;
+
+namespace b200ad {
+int set_error(int code, const char* fmt, ...) { return code; }
+void count_launch(int) {}
+}  // namespace b200ad
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+
+// mode: 0 = tf32 SS, 1 = tf32 TS, 2 = bf16 SS, 3 = bf16 TS
+template <int mode>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // zero the operands (64 KB): A tile 128 x 32 fp32 (16 KB) at 0, B tile 256 x 32 fp32 (32 KB) at 16 KB
+  for (int i = threadIdx.x; i < 49152 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    const bool bf16 = mode >= 2, ts = mode & 1;
+    // idesc: D = f32 (1<<4); A/B format: tf32 = 2, bf16 = 1 at bits 7 / 10; K-major both; N>>3 at 17; M>>4 at 24
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      uint64_t bd[4], ad[4];
+      uint32_t at[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bd[k] = make_smem_desc(sb + k * 32, 16, 1024, 2);
+        ad[k] = make_smem_desc(sa + k * 32, 16, 1024, 2);
+        at[k] = tmem_base + 256 + k * 8;
+      }
+      const uint32_t d0 = tmem_base, d1 = tmem_base + (nacc > 1 ? (uint32_t)n : 0u);
+      t0 = clock64();
+      for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t d = (u & 1) ? d1 : d0;
+          if (mode == 0) umma_tf32(d, ad[u & 3], bd[u & 3], idesc, 1u);
+          else if (mode == 1) umma_tf32_ts(d, at[u & 3], bd[u & 3], idesc, 1u);
+          else if (mode == 2) umma_f16_ss(d, ad[u & 3], bd[u & 3], idesc, 1u);
+          else umma_f16_ts(d, at[u & 3], bd[u & 3], idesc, 1u);
+        }
+      }
+      t1 = clock64();
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (lane == 0 && blockIdx.x == 0) {
+      out[0] = t1 - t0;   // issue time
+      out[1] = t2 - t0;   // until all MMAs retired
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, 16);
+  cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  const char* names[4] = {"tf32 SS", "tf32 TS", "bf16 SS", "bf16 TS"};
+  const int iters = 4096;
+  printf("cycles per tcgen05.mma (M=128, cta_group::1), %d back-to-back MMAs, 148 CTAs\n", iters);
+  printf("%-8s %5s %5s %12s %12s\n", "mode", "N", "nacc", "issue cyc", "total cyc");
+  for (int mode = 0; mode < 4; ++mode)
+    for (int n : {16, 32, 64, 128, 256})
+      for (int nacc : {1, 2}) {
+        if (nacc * n > 256) continue;
+        if (mode == 0) rate_kernel<0><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else if (mode == 1) rate_kernel<1><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else if (mode == 2) rate_kernel<2><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else rate_kernel<3><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+          printf("%s N=%d: %s\n", names[mode], n, cudaGetErrorString(e));
+          return 1;
+        }
+        long long h[2];
+        cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
+        printf("%-8s %5d %5d %12.1f %12.1f\n", names[mode], n, nacc, (double)h[0] / iters, (double)h[1] / iters);
+      }
+  return 0;
+}
