@@ -39,10 +39,10 @@ namespace b200ad {
 constexpr int AT_DK = 64;                    // head dimension this kernel is built for
 constexpr int AT_BM = 128;                   // rows (TMEM lanes) per work item
 constexpr int AT_BC = 64;                    // columns per block
-constexpr int AT_NSLOT = 7;
+constexpr int AT_NSLOT = 6;                  // ring slots; a 7th 32 KB region stages the output tile for the TMA store
 constexpr uint32_t AT_SLOT = 32768;          // [raw 16 KB | lo 16 KB] for a B block, or one raw A tile
 constexpr int AT_THREADS = 384;              // 3 warpgroups: {TMA, MMA, 2 idle}, converter, row owners
-constexpr uint32_t AT_SMEM = AT_NSLOT * AT_SLOT + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*column stats*/;
+constexpr uint32_t AT_SMEM = (AT_NSLOT + 1) * AT_SLOT + 1024 /*align*/;   // + ~1.3 KB static (barriers, column stats)
 
 enum { AT_FWD = 0, AT_DV = 1, AT_DQ = 2, AT_DKM = 3 };
 
@@ -55,21 +55,52 @@ struct AttnParams {
   int32_t H, R, C;           // heads; extent of the lane dimension; extent of the column dimension
   int32_t row_tiles, nb, total_items;
   float c2, c;               // scale * log2(e), scale
+  long long* prof;           // -DAT_PROFILE: per-role cycle counters of block 0 (debug builds only)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+#ifdef AT_PROFILE
+#define AT_T(var) const long long var = clock64()
+#define AT_ACC(slot, a, b) prof_acc[slot] += (b) - (a)
+#else
+#define AT_T(var)
+#define AT_ACC(slot, a, b)
+#endif
 __device__ __forceinline__ uint32_t tf32_hi(uint32_t v) { return v & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(uint32_t v, uint32_t h) {
   return __float_as_uint(__uint_as_float(v) - __uint_as_float(h)) & 0xffffe000u;
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {      // one MUFU; results below 2^-126 flush to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
-               const __grid_constant__ CUtensorMap map_b3, const AttnParams p) {
+               const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_out,
+               const AttnParams p) {
   constexpr bool HAS2 = (MODE == AT_DQ || MODE == AT_DKM);
   constexpr bool ROWSTAT = (MODE == AT_FWD || MODE == AT_DQ);   // lanes are query rows
   constexpr uint32_t A1_COL = 0, A2_COL = 128;
@@ -81,7 +112,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)AT_NSLOT * AT_SLOT);
+  uint8_t* out_stage = smem + (size_t)AT_NSLOT * AT_SLOT;   // 32 KB: the output tile, two SWIZZLE_128B halves
+  __shared__ uint64_t bars[3 * AT_NSLOT + 12];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float colstat[2][128];           // [buffer][lse (64) | D (64)] of the current column block
   uint64_t* full = bars;                       // [NSLOT] TMA -> converter
   uint64_t* conv = bars + AT_NSLOT;            // [NSLOT] converter -> MMA (128 arrivals): lo tile in smem / A tile in TMEM
   uint64_t* empty = bars + 2 * AT_NSLOT;       // [NSLOT] MMA commit (B slots) / converter (A slots) -> TMA
@@ -91,8 +125,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   uint64_t* y_full = z_full + 2;               // [1]
   uint64_t* out_full = y_full + 1;             // [1] MMA commit -> row owners
   uint64_t* out_empty = out_full + 1;          // [1] row owners -> MMA (128 arrivals)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(out_empty + 1);
-  float* colstat = reinterpret_cast<float*>(smem + (size_t)AT_NSLOT * AT_SLOT + 512);   // [2 buffers][2 vectors][64]
+  uint32_t* tmem_base_slot = &tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +134,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b1);
     tma_prefetch_desc(&map_b3);
+    tma_prefetch_desc(&map_out);
     if (HAS2) {
       tma_prefetch_desc(&map_a2);
       tma_prefetch_desc(&map_b2);
@@ -184,22 +218,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
                                  ((uint32_t)(AT_BM >> 4) << 24);
     constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
     uint32_t op = 0, it = 0, gb = 0;
+#ifdef AT_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = clock64();
+#endif
     // score MMA: D[128 x 64] = A(TMEM, hi at a_col, lo at a_col + 64) . B^T (K-major slot: two 8 KB halves)
     auto score = [&](uint32_t a_col, uint32_t d_col, uint64_t* done, uint64_t* a_done) {
       const uint32_t s = op % AT_NSLOT;
+      AT_T(w0);
       mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
+      AT_T(w1);
+      AT_ACC(0, w0, w1);
       ++op;
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sb = smem_u32(smem + (size_t)s * AT_SLOT);
+        // descriptor of the slot base; each MMA adds a compile-time byte offset (>> 4) to the address field
+        const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 16, 1024, 2);
+        const uint32_t dst = tmem_base + d_col, a_hi = tmem_base + a_col, a_lo = a_hi + 64u;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t a = tmem_base + a_col + (t == 0 ? 64u : 0u);
-          const uint32_t bo = sb + (t == 1 ? 16384u : 0u);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_tf32_ts(tmem_base + d_col, a + kk * 8,
-                         make_smem_desc(bo + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), IDESC_K,
+            umma_tf32_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
+                         d0 + (uint64_t)(((t == 1 ? 16384 : 0) + (kk >> 2) * 8192 + (kk & 3) * 32) >> 4), IDESC_K,
                          (t | kk) ? 1u : 0u);
         }
         umma_commit(&empty[s]);
@@ -232,22 +273,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           const uint32_t g = gb + j - 1;
           const uint32_t xb = X_COL0 + (g & 1) * X_STRIDE;
           const uint32_t zhi = HAS2 ? Y_COL : xb, zlo = HAS2 ? xb : xb + 64u;
+          AT_T(w0);
           mbar_wait(&z_full[g & 1], (g >> 1) & 1);
+          AT_T(w1);
           mbar_wait(out_empty, (g & 1) ^ 1);
+          AT_T(w2);
           const uint32_t s = op % AT_NSLOT;
           mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
+          AT_T(w3);
+          AT_ACC(1, w0, w1);
+          AT_ACC(2, w1, w2);
+          AT_ACC(0, w2, w3);
           ++op;
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sb = smem_u32(smem + (size_t)s * AT_SLOT);
+            const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 4096, 512, 1);
+            const uint32_t dst = tmem_base + OUT_COL, a_hi = tmem_base + zhi, a_lo = tmem_base + zlo;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-              const uint32_t a = tmem_base + (t == 0 ? zlo : zhi);
-              const uint32_t bo = sb + (t == 1 ? 16384u : 0u);
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
-                umma_tf32_ts(tmem_base + OUT_COL, a + kk * 8,
-                             make_smem_desc(bo + (kk >> 2) * 8192 + (kk & 3) * 1024, 4096, 512, 1), IDESC_MN,
+                umma_tf32_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
+                             d0 + (uint64_t)(((t == 1 ? 16384 : 0) + (kk >> 2) * 8192 + (kk & 3) * 1024) >> 4), IDESC_MN,
                              (t | kk) ? 1u : 0u);
             }
             umma_commit(&empty[s]);
@@ -259,6 +306,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       }
       gb += nb;
     }
+#ifdef AT_PROFILE
+    if (p.prof && blockIdx.x == 0 && lane == 0) {
+      p.prof[0] = clock64() - prof_t0;   // MMA warp total
+      p.prof[1] = prof_acc[0];           // waiting for converted operand slots
+      p.prof[2] = prof_acc[1];           // waiting for Z (row owners)
+      p.prof[3] = prof_acc[2];           // waiting for the OUT buffer to be drained
+    }
+#endif
   }
   } else if (warp < 8) {
     // ===================================== converter =====================================
@@ -274,15 +329,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       ++op;
       mbar_wait(&a_empty[which], (it & 1) ^ 1);
       tc_fence_after();
-      const uint8_t* slot = smem + (size_t)s * AT_SLOT;
+      const uint32_t slot = smem_u32(smem + (size_t)s * AT_SLOT);
       const uint32_t col = which ? A2_COL : A1_COL;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        const uint4* row = reinterpret_cast<const uint4*>(slot + hh * 16384 + r * 128);
+        const uint32_t row = slot + hh * 16384 + r * 128;
         uint32_t v[32], l[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {     // SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
-          const uint4 t4 = row[c ^ (r & 7)];
+          const uint4 t4 = lds128(row + ((c ^ (r & 7)) << 4));
           v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
         }
 #pragma unroll
@@ -304,17 +359,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       const uint32_t s = op % AT_NSLOT;
       mbar_wait(&full[s], (op / AT_NSLOT) & 1);
       ++op;
-      uint4* raw = reinterpret_cast<uint4*>(smem + (size_t)s * AT_SLOT);
-      uint4* lo = raw + 1024;
+      const uint32_t raw = smem_u32(smem + (size_t)s * AT_SLOT) + tid * 16;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint4 v = raw[tid + i * 128];
+        const uint4 v = lds128(raw + i * 2048);
         uint4 l;
         l.x = tf32_lo(v.x, tf32_hi(v.x));
         l.y = tf32_lo(v.y, tf32_hi(v.y));
         l.z = tf32_lo(v.z, tf32_hi(v.z));
         l.w = tf32_lo(v.w, tf32_hi(v.w));
-        lo[tid + i * 128] = l;
+        sts128(raw + 16384 + i * 2048, l);
       }
       fence_proxy_async();                // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&conv[s]);
@@ -333,6 +387,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t gb = 0;
+#ifdef AT_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = clock64();
+#endif
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int rt = item % p.row_tiles, bh = item / p.row_tiles;
       const int h = bh % p.H, b = bh / p.H;
@@ -349,7 +407,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       }
       // fold OUT_blk(g) into the running total: run = run * a + OUT
       auto fold = [&](uint32_t g, float a) {
+        AT_T(f0);
         mbar_wait(out_full, g & 1);
+        AT_T(f1);
+        AT_ACC(1, f0, f1);
         tc_fence_after();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -364,13 +425,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         }
         tc_fence_before();
         mbar_arrive(out_empty);
+        AT_T(f2);
+        AT_ACC(2, f1, f2);
       };
       for (int j = 0; j < nb; ++j) {
         const uint32_t g = gb + j;
         const uint32_t bsel = g & 1;
         const uint32_t xaddr = lane_base + X_COL0 + bsel * X_STRIDE;
         const int col0 = j * AT_BC;
-        float* cs = colstat + bsel * 128;
+        float* cs = colstat[bsel];
         if (!ROWSTAT) {
           // per-column statistics of this block (lse, and D in the DK mode) -> shared memory
           if (tid < 64) {
@@ -382,13 +445,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           }
           named_bar_sync(2, 128);
         }
+        AT_T(x0);
         mbar_wait(&x_full[bsel], (g >> 1) & 1);
+        AT_T(x1);
+        AT_ACC(0, x0, x1);
         tc_fence_after();
         if (MODE == AT_FWD) {
           uint32_t x[64];
           tmem_ld_32x32b_x32(xaddr, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
           tmem_ld_32x32b_x32(xaddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
           tmem_ld_wait();
+          AT_T(x2);
+          AT_ACC(3, x1, x2);
           if (col0 + AT_BC > p.C) {
 #pragma unroll
             for (int c = 0; c < 64; ++c)
@@ -398,7 +466,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
 #pragma unroll
           for (int c = 1; c < 64; ++c) mb = fmaxf(mb, __uint_as_float(x[c]));
           const float m_new = fmaxf(m_run, mb);
-          const float alpha = exp2f((m_run - m_new) * p.c2);
+          const float alpha = fast_exp2((m_run - m_new) * p.c2);
           const float mc = m_new * p.c2;
           float sum = 0.f;
 #pragma unroll
@@ -406,7 +474,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
             uint32_t lo[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const float pv = exp2f(fmaf(__uint_as_float(x[hh * 32 + c]), p.c2, -mc));
+              const float pv = fast_exp2(fmaf(__uint_as_float(x[hh * 32 + c]), p.c2, -mc));
               sum += pv;
               const uint32_t hi = tf32_hi(__float_as_uint(pv));
               lo[c] = tf32_lo(__float_as_uint(pv), hi);
@@ -417,9 +485,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           }
           l_run = fmaf(l_run, alpha, sum);
           m_run = m_new;
+          AT_T(x3);
+          AT_ACC(4, x2, x3);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&z_full[bsel]);
+          AT_T(x4);
+          AT_ACC(5, x3, x4);
           if (j >= 1) fold(g - 1, a_prev);
           a_prev = alpha;
         } else if (MODE == AT_DV) {
@@ -430,7 +502,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const float pv = exp2f(fmaf(__uint_as_float(x[c]), p.c2, -cs[hh * 32 + c]));
+              const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -cs[hh * 32 + c]));
               const uint32_t hi = tf32_hi(__float_as_uint(pv));
               lo[c] = tf32_lo(__float_as_uint(pv), hi);
               x[c] = hi;
@@ -462,7 +534,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
                 ls = cs[hh * 32 + c];
                 dd = cs[64 + hh * 32 + c];
               }
-              const float pv = exp2f(fmaf(__uint_as_float(x[c]), p.c2, -ls));
+              const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls));
               const float z = pv * (__uint_as_float(y[c]) - dd) * p.c;
               const uint32_t hi = tf32_hi(__float_as_uint(z));
               x[c] = tf32_lo(__float_as_uint(z), hi);
@@ -479,19 +551,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       }
       fold(gb + nb - 1, a_prev);
       gb += nb;
-      // epilogue: this thread's row of the output tile
-      if (row_ok) {
-        float* dst = p.out + (int64_t)b * p.out_bs + (int64_t)h * p.out_hs + (int64_t)grow * p.out_ld;
+      AT_T(e0);
+      // epilogue: stage the tile in shared memory (two SWIZZLE_128B halves, conflict-free row writes), one thread
+      // issues the TMA stores (coalesced, asynchronous, rows beyond R are clipped by the tensor map)
+      if (tid == 0) bulk_wait_read0();          // the previous item's store has finished reading the staging tile
+      named_bar_sync(3, 128);
+      {
         float sc = 1.f;
         if (MODE == AT_FWD) {
           sc = 1.f / l_run;
-          p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, p.c2, log2f(l_run));
+          if (row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, p.c2, log2f(l_run));
         }
+        const uint32_t srow = smem_u32(out_stage) + r * 128;
 #pragma unroll
-        for (int d = 0; d < AT_DK; d += 4)
-          *reinterpret_cast<float4*>(dst + d) = make_float4(run[d] * sc, run[d + 1] * sc, run[d + 2] * sc, run[d + 3] * sc);
+        for (int c = 0; c < 16; ++c) {
+          uint4 v;
+          v.x = __float_as_uint(run[4 * c] * sc); v.y = __float_as_uint(run[4 * c + 1] * sc);
+          v.z = __float_as_uint(run[4 * c + 2] * sc); v.w = __float_as_uint(run[4 * c + 3] * sc);
+          sts128(srow + (c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4), v);
+        }
       }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (tid == 0) {
+        tma_store_4d(&map_out, out_stage, 0, rt * AT_BM, h, b);
+        tma_store_4d(&map_out, out_stage + 16384, 32, rt * AT_BM, h, b);
+        bulk_commit();
+      }
+      AT_T(e1);
+      AT_ACC(6, e0, e1);
     }
+    if (tid == 0) bulk_wait0();                 // all output tiles have been written
+#ifdef AT_PROFILE
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 256) {
+      p.prof[8] = clock64() - prof_t0;   // row owner total
+      p.prof[9] = prof_acc[0];           // waiting for X (score MMA)
+      p.prof[10] = prof_acc[1];          // waiting for OUT (second MMA)
+      p.prof[11] = prof_acc[2];          // fold (TMEM load + FMAs)
+      p.prof[12] = prof_acc[3];          // FWD: TMEM load of X
+      p.prof[13] = prof_acc[4];          // FWD: softmax arithmetic + TMEM store issue
+      p.prof[14] = prof_acc[5];          // FWD: wait::st + arrive
+      p.prof[15] = prof_acc[6];          // epilogue stores
+    }
+#endif
   }
 
   tc_fence_before();
@@ -558,8 +660,10 @@ template <int MODE>
 static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTensor& b1, const AttnTensor& b2,
                        const AttnTensor& b3, AttnParams p, int64_t B, int64_t H, cudaStream_t s) {
   constexpr bool HAS2 = (MODE == AT_DQ || MODE == AT_DKM);
-  CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3;
+  CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_out;
   int rc;
+  AttnTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
+  if ((rc = encode_attn(&m_out, to, B, H, AT_BM, false))) return rc;
   if ((rc = encode_attn(&m_a1, a1, B, H, AT_BM, false))) return rc;
   if ((rc = encode_attn(&m_b1, b1, B, H, AT_BC, false))) return rc;
   if ((rc = encode_attn(&m_b3, b3, B, H, 32, true))) return rc;
@@ -581,8 +685,26 @@ static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTen
   const int64_t items = B * H * p.row_tiles;
   p.total_items = (int32_t)items;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_tc_kernel<MODE><<<grid, AT_THREADS, AT_SMEM, s>>>(m_a1, m_a2, m_b1, m_b2, m_b3, p);
+#ifdef AT_PROFILE
+  static long long* prof_dev = nullptr;
+  if (!prof_dev) cudaMalloc(&prof_dev, 16 * sizeof(long long));
+  cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), s);
+  p.prof = prof_dev;
+#endif
+  attn_tc_kernel<MODE><<<grid, AT_THREADS, AT_SMEM, s>>>(m_a1, m_a2, m_b1, m_b2, m_b3, m_out, p);
   count_launch();
+#ifdef AT_PROFILE
+  {
+    long long h[16];
+    cudaMemcpyAsync(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    const double blocks = (double)ceil_div(p.total_items - 0, grid) * p.nb;
+    fprintf(stderr, "[at_profile] mode %d items/CTA~%.1f nb=%d | per block: MMA warp total %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f | "
+            "owner total %.0f wait_X %.0f wait_OUT %.0f fold %.0f ldX %.0f math %.0f st+arrive %.0f epilogue %.0f\n", MODE,
+            (double)p.total_items / grid, p.nb, h[0] / blocks, h[1] / blocks, h[2] / blocks, h[3] / blocks, h[8] / blocks, h[9] / blocks,
+            h[10] / blocks, h[11] / blocks, h[12] / blocks, h[13] / blocks, h[14] / blocks, h[15] / blocks);
+  }
+#endif
   if (getenv("B200AD_ATTN_SYNC")) {     // debugging aid: attribute an asynchronous failure to its pass
     cudaError_t e = cudaStreamSynchronize(s);
     fprintf(stderr, "[b200ad] attention pass mode %d (R=%d C=%d nb=%d items=%d): %s\n", MODE, p.R, p.C, p.nb,
