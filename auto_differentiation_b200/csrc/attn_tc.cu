@@ -103,6 +103,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
                const AttnParams p) {
   constexpr bool HAS2 = (MODE == AT_DQ || MODE == AT_DKM);
   constexpr bool ROWSTAT = (MODE == AT_FWD || MODE == AT_DQ);   // lanes are query rows
+  constexpr bool PAIR = (MODE != AT_FWD);                       // two column blocks per OUT accumulator chain
   constexpr uint32_t A1_COL = 0, A2_COL = 128;
   constexpr uint32_t X_COL0 = HAS2 ? 256u : 128u;
   constexpr uint32_t X_STRIDE = HAS2 ? 64u : 128u;
@@ -217,7 +218,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) |
                                  ((uint32_t)(AT_BM >> 4) << 24);
     constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
-    uint32_t op = 0, it = 0, gb = 0;
+    uint32_t op = 0, it = 0, gb = 0, fo = 0;    // ring op, item, global block and fold (OUT accumulator use) counters
 #ifdef AT_PROFILE
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
@@ -269,14 +270,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           score(A1_COL, X_COL0 + (g & 1) * X_STRIDE, &x_full[g & 1], j == nb - 1 ? &a_empty[0] : nullptr);
         }
         {
-          // OUT_blk = Z(g) . B3(g): Z hi/lo from TMEM, B3 MN-major from the slot
+          // OUT_blk (+)= Z(g) . B3(g): Z hi/lo from TMEM, B3 MN-major from the slot.  The backward modes chain two
+          // blocks (128 K-elements) per accumulator before the row owners fold it; the lo term (which reads the Y
+          // columns in the two-score modes) goes first so that Y(j) can overwrite them while the hi terms run.
           const uint32_t g = gb + j - 1;
           const uint32_t xb = X_COL0 + (g & 1) * X_STRIDE;
-          const uint32_t zhi = HAS2 ? Y_COL : xb, zlo = HAS2 ? xb : xb + 64u;
+          const uint32_t zhi = xb, zlo = HAS2 ? Y_COL : xb + 64u;
+          const bool first = !PAIR || ((j - 1) & 1) == 0;
+          const bool last = !PAIR || ((j - 1) & 1) == 1 || j == nb;
           AT_T(w0);
           mbar_wait(&z_full[g & 1], (g >> 1) & 1);
           AT_T(w1);
-          mbar_wait(out_empty, (g & 1) ^ 1);
+          if (first) mbar_wait(out_empty, (fo & 1) ^ 1);
           AT_T(w2);
           const uint32_t s = op % AT_NSLOT;
           mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
@@ -286,23 +291,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           AT_ACC(0, w2, w3);
           ++op;
           tc_fence_after();
+          const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 4096, 512, 1);
+          const uint32_t dst = tmem_base + OUT_COL, a_hi = tmem_base + zhi, a_lo = tmem_base + zlo;
           if (elect_one()) {
-            const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 4096, 512, 1);
-            const uint32_t dst = tmem_base + OUT_COL, a_hi = tmem_base + zhi, a_lo = tmem_base + zlo;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk)
-                umma_tf32_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
-                             d0 + (uint64_t)(((t == 1 ? 16384 : 0) + (kk >> 2) * 8192 + (kk & 3) * 1024) >> 4), IDESC_MN,
-                             (t | kk) ? 1u : 0u);
-            }
-            umma_commit(&empty[s]);
-            umma_commit(out_full);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_tf32_ts(dst, a_lo + kk * 8, d0 + (uint64_t)(((kk >> 2) * 8192 + (kk & 3) * 1024) >> 4), IDESC_MN,
+                           (kk || !first) ? 1u : 0u);
           }
           __syncwarp();
+          if (HAS2 && j < nb) score(A2_COL, Y_COL, y_full, j == nb - 1 ? &a_empty[1] : nullptr);
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 1; t < 3; ++t) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_tf32_ts(dst, a_hi + kk * 8,
+                             d0 + (uint64_t)(((t == 1 ? 16384 : 0) + (kk >> 2) * 8192 + (kk & 3) * 1024) >> 4), IDESC_MN, 1u);
+            }
+            umma_commit(&empty[s]);
+            if (last) umma_commit(out_full);
+          }
+          __syncwarp();
+          if (last) ++fo;
         }
-        if (HAS2 && j < nb) score(A2_COL, Y_COL, y_full, j == nb - 1 ? &a_empty[1] : nullptr);
       }
       gb += nb;
     }
@@ -386,7 +398,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t gb = 0;
+    uint32_t gb = 0, fo = 0;
 #ifdef AT_PROFILE
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
@@ -406,9 +418,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow);
       }
       // fold OUT_blk(g) into the running total: run = run * a + OUT
-      auto fold = [&](uint32_t g, float a) {
+      auto fold = [&](float a) {
         AT_T(f0);
-        mbar_wait(out_full, g & 1);
+        mbar_wait(out_full, fo & 1);
+        ++fo;
         AT_T(f1);
         AT_ACC(1, f0, f1);
         tc_fence_after();
@@ -428,6 +441,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         AT_T(f2);
         AT_ACC(2, f1, f2);
       };
+      auto load_colstat = [&](int c0) -> float {
+        if (tid < 64) {
+          const int col = c0 + tid;
+          return (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) : INFINITY;
+        }
+        if (MODE == AT_DKM) {
+          const int col = c0 + tid - 64;
+          return (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) : 0.f;
+        }
+        return 0.f;
+      };
+      float cs_next = ROWSTAT ? 0.f : load_colstat(0);
       for (int j = 0; j < nb; ++j) {
         const uint32_t g = gb + j;
         const uint32_t bsel = g & 1;
@@ -435,15 +460,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         const int col0 = j * AT_BC;
         float* cs = colstat[bsel];
         if (!ROWSTAT) {
-          // per-column statistics of this block (lse, and D in the DK mode) -> shared memory
-          if (tid < 64) {
-            const int col = col0 + tid;
-            cs[tid] = (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) : INFINITY;
-          } else if (MODE == AT_DKM) {
-            const int col = col0 + tid - 64;
-            cs[tid] = (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) : 0.f;
-          }
+          // per-column statistics of this block (lse, and D in the DK mode) -> shared memory; the next block's
+          // values are fetched now so that the global-load latency hides behind this block's work
+          cs[tid] = cs_next;
           named_bar_sync(2, 128);
+          if (j + 1 < nb) cs_next = load_colstat(col0 + AT_BC);
         }
         AT_T(x0);
         mbar_wait(&x_full[bsel], (g >> 1) & 1);
@@ -462,20 +483,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
             for (int c = 0; c < 64; ++c)
               if (col0 + c >= p.C) x[c] = __float_as_uint(-INFINITY);
           }
-          float mb = __uint_as_float(x[0]);
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c = 1; c < 64; ++c) mb = fmaxf(mb, __uint_as_float(x[c]));
+          for (int c = 0; c < 64; ++c) mx[c & 3] = fmaxf(mx[c & 3], __uint_as_float(x[c]));
+          const float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           const float m_new = fmaxf(m_run, mb);
           const float alpha = fast_exp2((m_run - m_new) * p.c2);
           const float mc = m_new * p.c2;
-          float sum = 0.f;
+          float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t lo[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float pv = fast_exp2(fmaf(__uint_as_float(x[hh * 32 + c]), p.c2, -mc));
-              sum += pv;
+              sm[c & 3] += pv;
               const uint32_t hi = tf32_hi(__float_as_uint(pv));
               lo[c] = tf32_lo(__float_as_uint(pv), hi);
               x[hh * 32 + c] = hi;
@@ -483,7 +505,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
             tmem_st_32x32b_x32(xaddr + hh * 32, *reinterpret_cast<uint32_t(*)[32]>(&x[hh * 32]));
             tmem_st_32x32b_x32(xaddr + 64 + hh * 32, lo);
           }
-          l_run = fmaf(l_run, alpha, sum);
+          l_run = fmaf(l_run, alpha, (sm[0] + sm[1]) + (sm[2] + sm[3]));
           m_run = m_new;
           AT_T(x3);
           AT_ACC(4, x2, x3);
@@ -492,7 +514,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           mbar_arrive(&z_full[bsel]);
           AT_T(x4);
           AT_ACC(5, x3, x4);
-          if (j >= 1) fold(g - 1, a_prev);
+          if (j >= 1) fold(a_prev);
           a_prev = alpha;
         } else if (MODE == AT_DV) {
 #pragma unroll
@@ -513,9 +535,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&z_full[bsel]);
-          if (j >= 1) fold(g - 1, 1.f);
+          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         } else {
-          // DQ / DK: Z = P (Y - D) c;   Z hi -> Y columns, Z lo -> X columns
+          // DQ / DK: Z = P (Y - D) c;   Z hi -> X columns, Z lo -> Y columns
           mbar_wait(y_full, g & 1);
           tc_fence_after();
 #pragma unroll
@@ -537,19 +559,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
               const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls));
               const float z = pv * (__uint_as_float(y[c]) - dd) * p.c;
               const uint32_t hi = tf32_hi(__float_as_uint(z));
-              x[c] = tf32_lo(__float_as_uint(z), hi);
-              y[c] = hi;
+              y[c] = tf32_lo(__float_as_uint(z), hi);
+              x[c] = hi;
             }
-            tmem_st_32x32b_x32(lane_base + Y_COL + hh * 32, y);
             tmem_st_32x32b_x32(xaddr + hh * 32, x);
+            tmem_st_32x32b_x32(lane_base + Y_COL + hh * 32, y);
           }
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&z_full[bsel]);
-          if (j >= 1) fold(g - 1, 1.f);
+          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         }
       }
-      fold(gb + nb - 1, a_prev);
+      fold(a_prev);
       gb += nb;
       AT_T(e0);
       // epilogue: stage the tile in shared memory (two SWIZZLE_128B halves, conflict-free row writes), one thread
