@@ -749,6 +749,323 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
+// =========================================================================================================
+// CTA-pair kernel, generation 3 (TF32X3): 256 x 256 tiles on cta_group::2 with
+//   * the A operand in TENSOR MEMORY (TS-mode MMAs): the splitter writes hi/lo A rows straight into a 4-stage
+//     TMEM ring, so A costs no shared-memory write and no MMA-side shared-memory read;
+//   * the running total of the chunked accumulation in REGISTERS (8 epilogue warps x 128 columns per thread),
+//     which frees the TMEM columns the A ring needs (X 256 + A ring 4 x 64 = 512).
+// Shared-memory traffic per k-block and CTA drops from ~192 KB (gemm_tc2_kernel: at the 128 B/clk limit) to
+// ~128 KB (TMA 32 + splitter 48 + MMA B-half reads 48), which moves the kernel from shared-memory-bound to
+// MMA-bound.  One ring of 4 stages; a stage = {raw A 16 KB, raw B half 16 KB, lo B half 16 KB, A hi/lo 64 TMEM
+// columns}, filled by TMA, converted by the splitter, released by one multicast tcgen05.commit.
+// Warps (512 threads = 4 warpgroups; setmaxnreg moves registers to the epilogue):
+//   0 TMA   1 MMA (leader CTA)   2-3 idle   4-7 splitter (A rows -> TMEM, then the B lo tile)
+//   8-15 epilogue (lane quarter = warp & 3, column half = (warp - 8) >> 2)
+// =========================================================================================================
+constexpr int TC3_THREADS = 512;
+constexpr int TC3_STAGES = 4;
+constexpr uint32_t TC3_STAGE_BYTES = 3 * 16384;
+
+__device__ __forceinline__ void umma2_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint4 tc_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t tc_lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tc_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  constexpr int BN = 256;
+  constexpr int R = TC3_STAGES;
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;            // 16 KB: this CTA's 128 rows of A (raw)
+  constexpr uint32_t B_BYTES = (BN / 2) * TC_BK * 4;         // 16 KB: this CTA's half of the B tile
+  constexpr uint32_t A_RING_COL = 256;                       // TMEM: X [0,256), A ring stage s: hi 256+64s, lo +32
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bars[3 * R + 2];
+  __shared__ uint32_t tmem_base_smem;
+  uint64_t* raw_full = bars;             // [R] TMA -> splitter (local)
+  uint64_t* conv_full = bars + R;        // [R] splitters of BOTH CTAs -> leader's MMA warp (512 arrivals)
+  uint64_t* empty = bars + 2 * R;        // [R] MMA commit (multicast) -> TMA + splitter of both CTAs
+  uint64_t* tmem_full = bars + 3 * R;    // MMA commit (multicast) -> epilogue of both CTAs
+  uint64_t* tmem_empty = tmem_full + 1;  // epilogues of both CTAs (512 arrivals) -> leader's MMA warp
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&conv_full[s], 2 * 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 2 * 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int total_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;   // m_tiles counts 256-row tiles
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================================== TMA producer (both CTAs) =====================================
+      if (elect_one()) {
+        uint32_t it = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+          int t = tile;
+          const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+          const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+          const int split = t % p.splits;
+          const int batch = t / p.splits;
+          const int b0 = (int)(batch / p.batch1), b1 = (int)(batch % p.batch1);
+          const int kb0 = split * p.kblocks_per_split;
+          int kb1 = kb0 + p.kblocks_per_split;
+          if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+          const int m0 = m_tile * 256 + (int)rank * TC_BM;
+          const int n0 = n_tile * BN + (int)rank * (BN / 2);
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % R;
+            mbar_wait(&empty[s], ((it / R) & 1) ^ 1);
+            uint8_t* sa = smem + (size_t)s * TC3_STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            mbar_expect_tx(&raw_full[s], A_BYTES + B_BYTES);
+            const int k0 = kb * TC_BK;
+            if (!p.a_mn_major) {
+              tma_load_4d(&map_a, &raw_full[s], sa, k0, m0, b1, b0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < TC_BM / 32; ++c)
+                tma_load_4d(&map_a, &raw_full[s], sa + c * (128 * TC_BK), m0 + c * 32, k0, b1, b0);
+            }
+            if (!p.b_mn_major) {
+              tma_load_4d(&map_b, &raw_full[s], sb, k0, n0, b1, b0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_4d(&map_b, &raw_full[s], sb + c * (128 * TC_BK), n0 + c * 32, k0, b1, b0);
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ===================================== MMA issuer (leader CTA) =====================================
+      // A from TMEM is always K-major; idesc: D=f32, A=B=tf32, N=256, M=256
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.b_mn_major << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t b_lbo = p.b_mn_major ? 128u * TC_BK : 16u, b_sbo = p.b_mn_major ? 512u : 32u * TC_BK;
+      const uint32_t b_lay = p.b_mn_major ? 1u : 2u, b_kstep = p.b_mn_major ? 1024u : 32u;
+      uint32_t it = 0, uit = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+        int t = tile / (p.n_tiles * p.m_tiles);
+        const int split = t % p.splits;
+        const int kb0 = split * p.kblocks_per_split;
+        int kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+        for (int cb0 = kb0; cb0 < kb1; cb0 += p.chunk_kb, ++uit) {
+          int cb1 = cb0 + p.chunk_kb;
+          if (cb1 > kb1) cb1 = kb1;
+          mbar_wait(tmem_empty, (uit & 1) ^ 1);            // both epilogues have read the previous chunk sum
+          tc_fence_after();
+          for (int kb = cb0; kb < cb1; ++kb, ++it) {
+            const int s = it % R;
+            mbar_wait(&conv_full[s], (it / R) & 1);         // both CTAs: A hi/lo in TMEM, B lo tile in smem
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sb = smem_u32(smem + (size_t)s * TC3_STAGE_BYTES) + A_BYTES;
+              const uint64_t bh = make_smem_desc(sb, b_lbo, b_sbo, b_lay);
+              const uint64_t bl = make_smem_desc(sb + B_BYTES, b_lbo, b_sbo, b_lay);
+              const uint32_t ah = tmem_base + A_RING_COL + (uint32_t)s * 64u, al = ah + 32u;
+              const bool first_kb = (kb == cb0);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma2_tf32_ts(tmem_base, al + kk * 8, bh + (uint64_t)((kk * b_kstep) >> 4), idesc, (first_kb && kk == 0) ? 0u : 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma2_tf32_ts(tmem_base, ah + kk * 8, bl + (uint64_t)((kk * b_kstep) >> 4), idesc, 1u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk)
+                umma2_tf32_ts(tmem_base, ah + kk * 8, bh + (uint64_t)((kk * b_kstep) >> 4), idesc, 1u);
+              umma2_commit_mc(&empty[s]);                    // frees the stage (smem + A ring columns) in BOTH CTAs
+              if (kb == cb1 - 1) umma2_commit_mc(tmem_full);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================================== splitter (both CTAs) =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                            // A part: the row (TMEM lane) this thread owns
+    const int btid = threadIdx.x - 128;                     // B part: 0..127
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+      int t = tile / (p.n_tiles * p.m_tiles);
+      const int split = t % p.splits;
+      const int kb0 = split * p.kblocks_per_split;
+      int kb1 = kb0 + p.kblocks_per_split;
+      if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % R;
+        mbar_wait(&raw_full[s], (it / R) & 1);
+        const uint32_t sa = smem_u32(smem + (size_t)s * TC3_STAGE_BYTES);
+        {
+          uint32_t v[32], l[32];
+          if (!p.a_mn_major) {          // K-major, SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
+            const uint32_t row = sa + r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 t4 = tc_lds128(row + ((c ^ (r & 7)) << 4));
+              v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+            }
+          } else {                      // MN-major, SWIZZLE_128B_BASE32B: 32 B granule g of k-row kk sits at g ^ (kk & 3)
+            const uint32_t chunk = sa + (r >> 5) * (128 * TC_BK);
+            const int ml = r & 31;
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk)
+              v[kk] = tc_lds32(chunk + kk * 128 + ((((ml >> 3) ^ (kk & 3)) << 5) | ((ml & 7) << 2)));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t h = v[j] & 0xffffe000u;
+            l[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(h)) & 0xffffe000u;
+            v[j] = h;
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + A_RING_COL + (uint32_t)s * 64u;
+          tmem_st_32x32b_x32(ta, v);
+          tmem_st_32x32b_x32(ta + 32, l);
+        }
+        {
+          const uint32_t sb = sa + A_BYTES + btid * 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 bv = tc_lds128(sb + i * 2048);
+            uint4 lo;
+            lo.x = __float_as_uint(__uint_as_float(bv.x) - __uint_as_float(bv.x & 0xffffe000u)) & 0xffffe000u;
+            lo.y = __float_as_uint(__uint_as_float(bv.y) - __uint_as_float(bv.y & 0xffffe000u)) & 0xffffe000u;
+            lo.z = __float_as_uint(__uint_as_float(bv.z) - __uint_as_float(bv.z & 0xffffe000u)) & 0xffffe000u;
+            lo.w = __float_as_uint(__uint_as_float(bv.w) - __uint_as_float(bv.w & 0xffffe000u)) & 0xffffe000u;
+            tc_sts128(sb + B_BYTES + i * 2048, lo);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive_cluster(&conv_full[s], 0);     // the leader's barrier counts both CTAs' splitter threads
+      }
+    }
+  } else {
+    // ===================================== epilogue (both CTAs, own 128 rows) =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    const int q = warp & 3;
+    const int hf = (warp - 8) >> 2;                         // column half of the 256-wide tile
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t x_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hf * 128u;
+    uint32_t uit = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+      int t = tile;
+      const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+      const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+      const int split = t % p.splits;
+      const int batch = t / p.splits;
+      const int64_t b0 = batch / p.batch1, b1 = batch % p.batch1;
+      const int kb0 = split * p.kblocks_per_split;
+      int kb1 = kb0 + p.kblocks_per_split;
+      if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+      const int nchunks = (kb1 - kb0 + p.chunk_kb - 1) / p.chunk_kb;
+      const int64_t gm = (int64_t)m_tile * 256 + rank * TC_BM + row_in_tile;
+      const bool row_ok = gm < p.m;
+      float* crow;
+      if (p.partial) crow = p.partial + (((int64_t)split * p.batches + batch) * p.m + gm) * p.n;
+      else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
+      float y[128];                                          // running total of this thread's 128 columns
+      for (int ch = 0; ch < nchunks; ++ch, ++uit) {
+        mbar_wait(tmem_full, uit & 1);
+        tc_fence_after();
+        // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation truncates)
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t x[16];
+          tmem_ld_32x32b_x16(x_addr + c0, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[c0 + j] = (ch == 0) ? __uint_as_float(x[j]) : y[c0 + j] + __uint_as_float(x[j]);
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(tmem_empty, 0);                  // X may be overwritten by the next chunk's MMAs
+      }
+      // tile epilogue from registers (every index into y[] is a compile-time constant: the array stays in registers)
+      const int64_t gn_base = (int64_t)n_tile * BN + hf * 128;
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow + gn_base) & 15) == 0);
+      if (row_ok) {
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 4) {
+          const int64_t gn0 = gn_base + c0;
+          if (gn0 < p.n) {
+            float* dst = crow + gn0;
+            float v[4] = {y[c0], y[c0 + 1], y[c0 + 2], y[c0 + 3]};
+            const bool full = (gn0 + 4 <= p.n);
+            if (!p.partial) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[j] *= p.alpha;
+                if (gn0 + j < p.n) {
+                  if (p.beta != 0.f) v[j] += p.beta * dst[j];
+                  if (p.bias) v[j] += __ldg(p.bias + gn0 + j);
+                }
+                if (p.act == 1) v[j] = tc_act<1>(v[j]);
+                else if (p.act == 2) v[j] = tc_act<2>(v[j]);
+                else if (p.act == 3) v[j] = tc_act<3>(v[j]);
+              }
+            }
+            if (full && vec_ok) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (gn0 + j < p.n) dst[j] = v[j];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // the peer's smem / barriers / TMEM stay valid until both CTAs are done
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
 // split-K second pass: C = alpha * sum_s partial[s] + beta*C + bias, activation.  One thread per 4 outputs.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, TcParams p) {
   const int64_t per_batch = p.m * p.n;
@@ -833,6 +1150,7 @@ struct TcPlan {
   uint32_t smem_bytes;
   bool x3;
   bool pair;     // CTA-pair kernel (cta_group::2, 256 x 256 tiles)
+  bool gen3;     // ... generation 3: A operand in TMEM, running totals in registers (gemm_tc3_kernel)
 };
 
 int num_sms() {
@@ -852,8 +1170,17 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   // CTA-pair kernel: opt-in.  Measured on B200 (profiles/r1_gemm_tc_probe.md): +3..7 % on 4096^3 / 8192^3, but
   // -5 % on the (131072 x 512 x 512) projection shapes of config 5 (the chunk fold waits for two epilogues).
   const char* ep = getenv("B200AD_TC_PAIR");
-  const int pair_mode = ep ? atoi(ep) : 0;
-  pl.pair = pl.x3 && pl.bn == 256 && g.m > TC_BM && pair_mode != 0;
+  const int pair_mode = ep ? atoi(ep) : 2;       // 2 = automatic
+  // Measured on B200 (profiles/r1_summary.md): the generation-3 pair kernel (A in TMEM, running totals in
+  // registers) wins on deep accumulations (split-K weight gradients 179 -> 225 TFLOP/s, 8192^3 192 -> 215) but its
+  // single-buffered accumulator exposes the fold at every chunk, so short-K tiles (K = 512 projections) stay on the
+  // 1-CTA kernel with double-buffered accumulators.  B200AD_TC_PAIR: 0 = never, 1 = gemm_tc2_kernel, 3 = always gen3.
+  const int64_t m_tiles256 = ceil_div(g.m, 2 * TC_BM), n_tiles256 = ceil_div(g.n, 256);
+  const int64_t tiles256 = m_tiles256 * n_tiles256 * g.batch0 * g.batch1;
+  const int64_t kblocks = ceil_div(g.k, TC_BK);
+  const bool deep_k = (tiles256 >= num_sms() / 2) ? (kblocks >= 128) : (kblocks * tiles256 >= 64 * (num_sms() / 2));
+  pl.pair = pl.x3 && pl.bn == 256 && g.m > TC_BM && (pair_mode == 1 || pair_mode == 3 || (pair_mode == 2 && deep_k));
+  pl.gen3 = pl.pair && pair_mode != 1;
   const uint32_t stage = pl.pair ? (TC_BM * TC_BK * 4 + (pl.bn / 2) * TC_BK * 4) * 2
                                  : (TC_BM * TC_BK * 4 + pl.bn * TC_BK * 4) * (pl.x3 ? 2 : 1);
   int st = (int)((TC_SMEM_LIMIT - 1024 - 256) / stage);
@@ -866,6 +1193,7 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
     pl.stages = 4;
     pl.smem_bytes = 6u * (TC_BM * TC_BK * 4 + (pl.bn / 2) * TC_BK * 4) + 1024 + 256;
   }
+  if (pl.gen3) pl.smem_bytes = TC3_STAGES * TC3_STAGE_BYTES + 1024;
   pl.m_tiles = (int)ceil_div(g.m, pl.pair ? 2 * TC_BM : TC_BM);
   pl.n_tiles = (int)ceil_div(g.n, pl.bn);
   pl.batches = (int)(g.batch0 * g.batch1);
@@ -971,6 +1299,27 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   if (total_tiles >= (1ll << 31)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): too many tiles");
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   cudaError_t e;
+  if (pl.gen3) {
+    static bool attr3 = false;
+    if (!attr3) {
+      e = cudaFuncSetAttribute(gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT - 1024);
+      if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05 pair/TS): smem attribute: %s", cudaGetErrorString(e));
+      attr3 = true;
+    }
+    const int pairs = num_sms() / 2;
+    const int grid3 = 2 * (int)(total_tiles < pairs ? total_tiles : pairs);
+    gemm_tc3_kernel<<<grid3, TC3_THREADS, pl.smem_bytes, s>>>(map_a, map_b, p);   // __cluster_dims__(2,1,1)
+    count_launch();
+    rc = check_launch("gemm(tcgen05 pair/TS)");
+    if (rc) return rc;
+    if (pl.splits > 1) {
+      const int64_t total = g.m * g.n * pl.batches;
+      splitk_reduce_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(ws), pl.splits, p);
+      count_launch();
+      rc = check_launch("gemm(tcgen05 split-K reduce)");
+    }
+    return rc;
+  }
   if (pl.pair) {
     static bool attr2 = false;
     if (!attr2) {

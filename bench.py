@@ -283,12 +283,12 @@ def run_c5(args):
             kname = "b200ad_gemm M=%d N=%d K=%d batches=%d transA=%d transB=%d precision=%d" % key
             traffic = NCU_TRAFFIC_BYTES.get(tuple(int(v) for v in key[:4]))
         # every timed tensor-core kernel family with its share of the step (the dominant one is `kernel`)
-        fam = sorted(((("%s" % (k[0],)) if isinstance(k[0], str) else "gemm %dx%dx%d b%d" % k[:4], v[1]) for k, v in gemm.items()),
-                     key=lambda kv: -kv[1])
+        fam = sorted(((("%s" % (k[0],)) if isinstance(k[0], str) else "gemm %dx%dx%d b%d %s%s" % (k[:4] + ("NT"[k[4]], "NT"[k[5]])), v[1])
+                      for k, v in gemm.items()), key=lambda kv: -kv[1])
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % pk["src"],
                 "kernel": kname,
-                "shares": {k: round(v / (ms_step * args.steps), 4) for k, v in fam[:6]},
+                "shares": {k: round(v / (ms_step * args.steps), 4) for k, v in fam[:8]},
                 "launches_timed": n, "avg_launch_ms": avg_ms,
                 "share_of_step": ms_tot / (ms_step * args.steps), "all_gemm_share_of_step": total_gemm_ms / (ms_step * args.steps),
                 "step_tflops": C5_FLOP_PER_SEQ * GLOBAL_BATCH / world / (ms_step * 1e-3) / 1e12}
