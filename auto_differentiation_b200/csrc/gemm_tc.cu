@@ -800,13 +800,13 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   constexpr uint32_t TMEM_COLS = 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bars[3 * R + 2];
+  __shared__ uint64_t bars[3 * R + 4];
   __shared__ uint32_t tmem_base_smem;
   uint64_t* raw_full = bars;             // [R] TMA -> splitter (local)
   uint64_t* conv_full = bars + R;        // [R] splitters of BOTH CTAs -> leader's MMA warp (512 arrivals)
   uint64_t* empty = bars + 2 * R;        // [R] MMA commit (multicast) -> TMA + splitter of both CTAs
-  uint64_t* tmem_full = bars + 3 * R;    // MMA commit (multicast) -> epilogue of both CTAs
-  uint64_t* tmem_empty = tmem_full + 1;  // epilogues of both CTAs (512 arrivals) -> leader's MMA warp
+  uint64_t* tmem_full = bars + 3 * R;    // [2: column half] MMA commit (multicast) -> epilogue of both CTAs
+  uint64_t* tmem_empty = tmem_full + 2;  // [2] that half's epilogue warps of both CTAs (256 arrivals) -> leader's MMA warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -820,8 +820,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_init(&conv_full[s], 2 * 128);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 2 * 256);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&tmem_full[h], 1);
+      mbar_init(&tmem_empty[h], 2 * 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(&tmem_base_smem, TMEM_COLS);
@@ -850,7 +852,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           int kb1 = kb0 + p.kblocks_per_split;
           if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
           const int m0 = m_tile * 256 + (int)rank * TC_BM;
-          const int n0 = n_tile * BN + (int)rank * (BN / 2);
+          // column half h of the tile = columns [128h, 128h + 128); CTA r stages columns 128h + 64r .. + 64 of each half
+          const int n0 = n_tile * BN + (int)rank * 64;
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % R;
             mbar_wait(&empty[s], ((it / R) & 1) ^ 1);
@@ -866,20 +869,24 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tma_load_4d(&map_a, &raw_full[s], sa + c * (128 * TC_BK), m0 + c * 32, k0, b1, b0);
             }
             if (!p.b_mn_major) {
-              tma_load_4d(&map_b, &raw_full[s], sb, k0, n0, b1, b0);
+              tma_load_4d(&map_b, &raw_full[s], sb, k0, n0, b1, b0);                 // 64-row boxes
+              tma_load_4d(&map_b, &raw_full[s], sb + 8192, k0, n0 + 128, b1, b0);
             } else {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c)
-                tma_load_4d(&map_b, &raw_full[s], sb + c * (128 * TC_BK), n0 + c * 32, k0, b1, b0);
+              for (int c = 0; c < 4; ++c)
+                tma_load_4d(&map_b, &raw_full[s], sb + c * (128 * TC_BK), n0 + (c >> 1) * 128 + (c & 1) * 32, k0, b1, b0);
             }
           }
         }
       }
     } else if (warp == 1 && rank == 0) {
       // ===================================== MMA issuer (leader CTA) =====================================
-      // A from TMEM is always K-major; idesc: D=f32, A=B=tf32, N=256, M=256
+      // A from TMEM is always K-major; idesc: D=f32, A=B=tf32, N=128 (one column half per MMA), M=256.
+      // The two column halves are separate accumulation chains advanced in sub-steps of two k-blocks
+      // (a a b b | a a b b per 128-K chunk), so the epilogue folds half a while the MMAs of half b run:
+      // the fold latency is hidden without a second accumulator buffer.
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.b_mn_major << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                             ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t b_lbo = p.b_mn_major ? 128u * TC_BK : 16u, b_sbo = p.b_mn_major ? 512u : 32u * TC_BK;
       const uint32_t b_lay = p.b_mn_major ? 1u : 2u, b_kstep = p.b_mn_major ? 1024u : 32u;
       uint32_t it = 0, uit = 0;
@@ -892,31 +899,44 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int cb0 = kb0; cb0 < kb1; cb0 += p.chunk_kb, ++uit) {
           int cb1 = cb0 + p.chunk_kb;
           if (cb1 > kb1) cb1 = kb1;
-          mbar_wait(tmem_empty, (uit & 1) ^ 1);            // both epilogues have read the previous chunk sum
-          tc_fence_after();
-          for (int kb = cb0; kb < cb1; ++kb, ++it) {
-            const int s = it % R;
-            mbar_wait(&conv_full[s], (it / R) & 1);         // both CTAs: A hi/lo in TMEM, B lo tile in smem
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t sb = smem_u32(smem + (size_t)s * TC3_STAGE_BYTES) + A_BYTES;
-              const uint64_t bh = make_smem_desc(sb, b_lbo, b_sbo, b_lay);
-              const uint64_t bl = make_smem_desc(sb + B_BYTES, b_lbo, b_sbo, b_lay);
-              const uint32_t ah = tmem_base + A_RING_COL + (uint32_t)s * 64u, al = ah + 32u;
-              const bool first_kb = (kb == cb0);
+          for (int s0 = cb0; s0 < cb1; s0 += 2) {
+            const int s1 = (s0 + 2 < cb1) ? s0 + 2 : cb1;
 #pragma unroll
-              for (int kk = 0; kk < TC_BK / 8; ++kk)
-                umma2_tf32_ts(tmem_base, al + kk * 8, bh + (uint64_t)((kk * b_kstep) >> 4), idesc, (first_kb && kk == 0) ? 0u : 1u);
+            for (int h = 0; h < 2; ++h) {
+              if (s0 == cb0) {
+                mbar_wait(&tmem_empty[h], (uit & 1) ^ 1);     // that half's epilogues have read the previous chunk sum
+                tc_fence_after();
+              }
+              for (int kb = s0; kb < s1; ++kb) {
+                const uint32_t its = it + (uint32_t)(kb - s0);
+                const int s = its % R;
+                if (h == 0) {
+                  mbar_wait(&conv_full[s], (its / R) & 1);    // both CTAs: A hi/lo in TMEM, B lo tile in smem
+                  tc_fence_after();
+                }
+                if (elect_one()) {
+                  const uint32_t sb = smem_u32(smem + (size_t)s * TC3_STAGE_BYTES) + A_BYTES + (uint32_t)h * 8192u;
+                  const uint64_t bh = make_smem_desc(sb, b_lbo, b_sbo, b_lay);
+                  const uint64_t bl = make_smem_desc(sb + B_BYTES, b_lbo, b_sbo, b_lay);
+                  const uint32_t ah = tmem_base + A_RING_COL + (uint32_t)s * 64u, al = ah + 32u;
+                  const uint32_t d = tmem_base + (uint32_t)h * 128u;
+                  const bool first_kb = (kb == cb0);
 #pragma unroll
-              for (int kk = 0; kk < TC_BK / 8; ++kk)
-                umma2_tf32_ts(tmem_base, ah + kk * 8, bl + (uint64_t)((kk * b_kstep) >> 4), idesc, 1u);
+                  for (int kk = 0; kk < TC_BK / 8; ++kk)
+                    umma2_tf32_ts(d, al + kk * 8, bh + (uint64_t)((kk * b_kstep) >> 4), idesc, (first_kb && kk == 0) ? 0u : 1u);
 #pragma unroll
-              for (int kk = 0; kk < TC_BK / 8; ++kk)
-                umma2_tf32_ts(tmem_base, ah + kk * 8, bh + (uint64_t)((kk * b_kstep) >> 4), idesc, 1u);
-              umma2_commit_mc(&empty[s]);                    // frees the stage (smem + A ring columns) in BOTH CTAs
-              if (kb == cb1 - 1) umma2_commit_mc(tmem_full);
+                  for (int kk = 0; kk < TC_BK / 8; ++kk)
+                    umma2_tf32_ts(d, ah + kk * 8, bl + (uint64_t)((kk * b_kstep) >> 4), idesc, 1u);
+#pragma unroll
+                  for (int kk = 0; kk < TC_BK / 8; ++kk)
+                    umma2_tf32_ts(d, ah + kk * 8, bh + (uint64_t)((kk * b_kstep) >> 4), idesc, 1u);
+                  if (h == 1) umma2_commit_mc(&empty[s]);      // frees the stage (smem + A ring columns) in BOTH CTAs
+                  if (kb == cb1 - 1) umma2_commit_mc(&tmem_full[h]);
+                }
+                __syncwarp();
+              }
             }
-            __syncwarp();
+            it += (uint32_t)(s1 - s0);
           }
         }
       }
@@ -1009,7 +1029,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
       float y[128];                                          // running total of this thread's 128 columns
       for (int ch = 0; ch < nchunks; ++ch, ++uit) {
-        mbar_wait(tmem_full, uit & 1);
+        mbar_wait(&tmem_full[hf], uit & 1);
         tc_fence_after();
         // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation truncates)
 #pragma unroll
@@ -1021,7 +1041,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int j = 0; j < 16; ++j) y[c0 + j] = (ch == 0) ? __uint_as_float(x[j]) : y[c0 + j] + __uint_as_float(x[j]);
         }
         tc_fence_before();
-        mbar_arrive_cluster(tmem_empty, 0);                  // X may be overwritten by the next chunk's MMAs
+        mbar_arrive_cluster(&tmem_empty[hf], 0);             // this half of X may be overwritten by the next chunk's MMAs
       }
       // tile epilogue from registers (every index into y[] is a compile-time constant: the array stays in registers)
       const int64_t gn_base = (int64_t)n_tile * BN + hf * 128;
@@ -1258,7 +1278,7 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   ob.inner = ob.mn_major ? g.n : g.k;
   ob.rows = ob.mn_major ? g.k : g.n;
   ob.ld = g.ldb;
-  ob.box_rows = ob.mn_major ? TC_BK : (pl.pair ? pl.bn / 2 : pl.bn);
+  ob.box_rows = ob.mn_major ? TC_BK : (pl.gen3 ? 64 : (pl.pair ? pl.bn / 2 : pl.bn));
   CUtensorMap map_a, map_b;
   int rc = encode_operand(&map_a, g.a, oa, g.batch0, g.batch1, g.a_stride0, g.a_stride1);
   if (rc) return rc;
