@@ -50,7 +50,8 @@ struct TcParams {
   int32_t batches, m_tiles, n_tiles, splits, kblocks_total, kblocks_per_split;
   int32_t a_mn_major, b_mn_major, x3, mask_hi, act;
   int32_t a_tmem;              // BN = 64, TF32X3: the splitter stores the hi/lo A tiles into TMEM (TS-mode MMAs)
-  int32_t probe;               // diagnostic bits: 1 = skip the TMA loads, 2 = skip the split (3 = pure MMA + epilogue)
+  int32_t probe;               // diagnostic bits: 1 = skip the TMA loads, 2 = skip the split (3 = pure MMA + epilogue), 4 = skip the stores
+  int32_t tma_store;           // gemm_tc3_kernel: the output tile leaves through shared memory + cp.async.bulk.tensor stores
   int32_t chunk_kb, chunked;   // TMEM accumulation chunk (k-blocks); chunked: buffer 0 = chunk sum X, buffer 1 = running total Y
   float alpha, beta;
 };
@@ -381,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tmem_ld_wait();
             }
             const int64_t gn0 = (int64_t)n_tile * BN + c0;
-            if (row_ok && gn0 < p.n) {
+            if (row_ok && gn0 < p.n && !(p.probe & 4)) {
               float* dst = crow + gn0;
               const bool full = (gn0 + 32 <= p.n);
               if (p.partial) {
@@ -791,7 +792,8 @@ __device__ __forceinline__ void tc_sts128(uint32_t addr, const uint4& v) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
-gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   constexpr int BN = 256;
   constexpr int R = TC3_STAGES;
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;            // 16 KB: this CTA's 128 rows of A (raw)
@@ -890,6 +892,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t b_lbo = p.b_mn_major ? 128u * TC_BK : 16u, b_sbo = p.b_mn_major ? 512u : 32u * TC_BK;
       const uint32_t b_lay = p.b_mn_major ? 1u : 2u, b_kstep = p.b_mn_major ? 1024u : 32u;
       uint32_t it = 0, uit = 0;
+#ifdef TC3_PROFILE
+      long long w_conv = 0, w_empty = 0; const long long t_start = clock64();
+#endif
       for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
         int t = tile / (p.n_tiles * p.m_tiles);
         const int split = t % p.splits;
@@ -904,14 +909,26 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               if (s0 == cb0) {
+#ifdef TC3_PROFILE
+                const long long q0 = clock64();
+#endif
                 mbar_wait(&tmem_empty[h], (uit & 1) ^ 1);     // that half's epilogues have read the previous chunk sum
+#ifdef TC3_PROFILE
+                w_empty += clock64() - q0;
+#endif
                 tc_fence_after();
               }
               for (int kb = s0; kb < s1; ++kb) {
                 const uint32_t its = it + (uint32_t)(kb - s0);
                 const int s = its % R;
                 if (h == 0) {
+#ifdef TC3_PROFILE
+                  const long long q0 = clock64();
+#endif
                   mbar_wait(&conv_full[s], (its / R) & 1);    // both CTAs: A hi/lo in TMEM, B lo tile in smem
+#ifdef TC3_PROFILE
+                  w_conv += clock64() - q0;
+#endif
                   tc_fence_after();
                 }
                 if (elect_one()) {
@@ -940,6 +957,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
+#ifdef TC3_PROFILE
+      if (blockIdx.x == 0 && lane == 0)
+        printf("[tc3] MMA warp: total %lld cycles, k-blocks %u, wait conv %lld, wait tmem_empty %lld\n", clock64() - t_start, it, w_conv, w_empty);
+#endif
     }
   } else if (warp < 8) {
     // ===================================== splitter (both CTAs) =====================================
@@ -948,6 +969,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int r = q * 32 + lane;                            // A part: the row (TMEM lane) this thread owns
     const int btid = threadIdx.x - 128;                     // B part: 0..127
     uint32_t it = 0;
+#ifdef TC3_PROFILE
+    long long w_raw = 0; const long long t_start = clock64();
+#endif
     for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
       int t = tile / (p.n_tiles * p.m_tiles);
       const int split = t % p.splits;
@@ -956,7 +980,14 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % R;
+#ifdef TC3_PROFILE
+        const long long q0 = clock64();
+#endif
         mbar_wait(&raw_full[s], (it / R) & 1);
+#ifdef TC3_PROFILE
+        w_raw += clock64() - q0;
+#endif
+
         const uint32_t sa = smem_u32(smem + (size_t)s * TC3_STAGE_BYTES);
         {
           uint32_t v[32], l[32];
@@ -1003,6 +1034,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_arrive_cluster(&conv_full[s], 0);     // the leader's barrier counts both CTAs' splitter threads
       }
     }
+#ifdef TC3_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 128)
+      printf("[tc3] splitter: total %lld cycles, wait raw_full (TMA) %lld\n", clock64() - t_start, w_raw);
+#endif
   } else {
     // ===================================== epilogue (both CTAs, own 128 rows) =====================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
@@ -1011,6 +1046,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int row_in_tile = q * 32 + lane;
     const uint32_t x_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hf * 128u;
     uint32_t uit = 0;
+#ifdef TC3_PROFILE
+    long long w_full = 0, t_fold = 0, t_store = 0; const long long t_start = clock64();
+#endif
     for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
       int t = tile;
       const int n_tile = t % p.n_tiles; t /= p.n_tiles;
@@ -1029,7 +1067,13 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
       float y[128];                                          // running total of this thread's 128 columns
       for (int ch = 0; ch < nchunks; ++ch, ++uit) {
+#ifdef TC3_PROFILE
+        const long long q0 = clock64();
+#endif
         mbar_wait(&tmem_full[hf], uit & 1);
+#ifdef TC3_PROFILE
+        const long long q1 = clock64(); w_full += q1 - q0;
+#endif
         tc_fence_after();
         // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation truncates)
 #pragma unroll
@@ -1042,11 +1086,59 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         tc_fence_before();
         mbar_arrive_cluster(&tmem_empty[hf], 0);             // this half of X may be overwritten by the next chunk's MMAs
+#ifdef TC3_PROFILE
+        t_fold += clock64() - q1;
+#endif
       }
+#ifdef TC3_PROFILE
+      const long long q2 = clock64();
+#endif
       // tile epilogue from registers (every index into y[] is a compile-time constant: the array stays in registers)
       const int64_t gn_base = (int64_t)n_tile * BN + hf * 128;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow + gn_base) & 15) == 0);
-      if (row_ok) {
+      if (p.tma_store && !(p.probe & 4)) {
+        // Output through a per-warp 4 KB staging tile (32 rows x 32 columns, SWIZZLE_128B) and asynchronous TMA
+        // stores: measured on B200, 8 warps per SM storing a 128 KB tile from registers reach only ~4 B/clk per SM
+        // (each warp waits on its own outstanding writes) and stall the accumulator hand-off for ~66 k cycles per
+        // tile; the bulk store engine keeps the writes in flight while the warps return to the next fold.  Rows and
+        // columns beyond M / N are clipped by the tensor map.
+        const uint32_t stg = smem_u32(smem + (size_t)R * TC3_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
+        const int m_row0 = m_tile * 256 + (int)rank * TC_BM + q * 32;
+        const int c2 = p.partial ? batch : (int)b1, c3 = p.partial ? split : (int)b0;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          const int n_col0 = n_tile * BN + hf * 128 + c0;
+          if (n_col0 < p.n && m_row0 < p.m) {                 // warp-uniform
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float v[4] = {y[c0 + 4 * c], y[c0 + 4 * c + 1], y[c0 + 4 * c + 2], y[c0 + 4 * c + 3]};
+              if (!p.partial) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[j] *= p.alpha;
+                  if (p.bias && n_col0 + 4 * c + j < p.n) v[j] += __ldg(p.bias + n_col0 + 4 * c + j);
+                  if (p.act == 1) v[j] = tc_act<1>(v[j]);
+                  else if (p.act == 2) v[j] = tc_act<2>(v[j]);
+                  else if (p.act == 3) v[j] = tc_act<3>(v[j]);
+                }
+              }
+              uint4 v4;
+              v4.x = __float_as_uint(v[0]); v4.y = __float_as_uint(v[1]); v4.z = __float_as_uint(v[2]); v4.w = __float_as_uint(v[3]);
+              tc_sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), v4);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_c),
+                           "r"(stg), "r"(n_col0), "r"(m_row0), "r"(c2), "r"(c3)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+      } else if (row_ok && !(p.probe & 4)) {   // probe bit 4 (diagnostic): skip the global stores
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 4) {
           const int64_t gn0 = gn_base + c0;
@@ -1077,7 +1169,15 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
+#ifdef TC3_PROFILE
+      t_store += clock64() - q2;
+#endif
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every output tile has been written
+#ifdef TC3_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 256)
+      printf("[tc3] epilogue: total %lld cycles, chunks %u, wait tmem_full %lld, fold %lld, store %lld\n", clock64() - t_start, uit, w_full, t_fold, t_store);
+#endif
   }
 
   tc_fence_before();
@@ -1213,7 +1313,7 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
     pl.stages = 4;
     pl.smem_bytes = 6u * (TC_BM * TC_BK * 4 + (pl.bn / 2) * TC_BK * 4) + 1024 + 256;
   }
-  if (pl.gen3) pl.smem_bytes = TC3_STAGES * TC3_STAGE_BYTES + 1024;
+  if (pl.gen3) pl.smem_bytes = TC3_STAGES * TC3_STAGE_BYTES + 8 * 4096 + 1024;   // ring + per-warp store staging
   pl.m_tiles = (int)ceil_div(g.m, pl.pair ? 2 * TC_BM : TC_BM);
   pl.n_tiles = (int)ceil_div(g.n, pl.bn);
   pl.batches = (int)(g.batch0 * g.batch1);
@@ -1303,6 +1403,7 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   p.act = g.act; p.alpha = g.alpha; p.beta = g.beta;
   const char* at = getenv("B200AD_TC_ATMEM");
   p.a_tmem = at ? atoi(at) : 1;
+  p.tma_store = 0;
   const char* pb = getenv("B200AD_TC_PROBE");
   p.probe = pb ? atoi(pb) : 0;
   // TMEM accumulation chain length: 128 K-elements (see the epilogue's fold).  Measured on B200
@@ -1328,7 +1429,30 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
     }
     const int pairs = num_sms() / 2;
     const int grid3 = 2 * (int)(total_tiles < pairs ? total_tiles : pairs);
-    gemm_tc3_kernel<<<grid3, TC3_THREADS, pl.smem_bytes, s>>>(map_a, map_b, p);   // __cluster_dims__(2,1,1)
+    // output tensor map (TMA stores): C itself, or the split-K partial buffer [split][batch][M][N]
+    CUtensorMap map_c = map_a;
+    p.tma_store = 0;
+    {
+      const float* cbase = p.partial ? p.partial : g.c;
+      const int64_t ld = p.partial ? g.n : g.ldc;
+      const int64_t s1 = p.partial ? g.m * g.n : g.c_stride1, s0 = p.partial ? (int64_t)pl.batches * g.m * g.n : g.c_stride0;
+      const int64_t d2 = p.partial ? pl.batches : g.batch1, d3 = p.partial ? pl.splits : g.batch0;
+      const bool ok = (p.partial || g.beta == 0.f) && aligned16(cbase) && (ld & 3) == 0 && (d2 <= 1 || (s1 > 0 && (s1 & 3) == 0)) &&
+                      (d3 <= 1 || (s0 > 0 && (s0 & 3) == 0)) && !getenv("B200AD_TC_NO_TMA_STORE");
+      if (ok) {
+        EncodeTiledFn enc = get_encode_fn();
+        const int64_t fb = ld * g.m;
+        cuuint64_t dims[4] = {(cuuint64_t)g.n, (cuuint64_t)g.m, (cuuint64_t)d2, (cuuint64_t)d3};
+        cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)(d2 > 1 ? s1 : fb) * 4, (cuuint64_t)(d3 > 1 ? s0 : fb) * 4};
+        cuuint32_t box[4] = {32u, 32u, 1u, 1u};
+        cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        CUresult r = enc(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(cbase), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) p.tma_store = 1;
+      }
+    }
+    gemm_tc3_kernel<<<grid3, TC3_THREADS, pl.smem_bytes, s>>>(map_a, map_b, map_c, p);   // __cluster_dims__(2,1,1)
     count_launch();
     rc = check_launch("gemm(tcgen05 pair/TS)");
     if (rc) return rc;
