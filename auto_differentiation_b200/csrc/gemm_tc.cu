@@ -1093,41 +1093,74 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #ifdef TC3_PROFILE
       const long long q2 = clock64();
 #endif
-      // tile epilogue from registers (every index into y[] is a compile-time constant: the array stays in registers)
-      const int64_t gn_base = (int64_t)n_tile * BN + hf * 128;
-      const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow + gn_base) & 15) == 0);
-      if (p.tma_store && !(p.probe & 4)) {
-        // Output through a per-warp 4 KB staging tile (32 rows x 32 columns, SWIZZLE_128B) and asynchronous TMA
-        // stores: measured on B200, 8 warps per SM storing a 128 KB tile from registers reach only ~4 B/clk per SM
-        // (each warp waits on its own outstanding writes) and stall the accumulator hand-off for ~66 k cycles per
-        // tile; the bulk store engine keeps the writes in flight while the warps return to the next fold.  Rows and
-        // columns beyond M / N are clipped by the tensor map.
-        const uint32_t stg = smem_u32(smem + (size_t)R * TC3_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
-        const int m_row0 = m_tile * 256 + (int)rank * TC_BM + q * 32;
-        const int c2 = p.partial ? batch : (int)b1, c3 = p.partial ? split : (int)b0;
+      // Tile epilogue.  Code size matters here: a fully unrolled alpha/beta/bias/activation epilogue over 128 register
+      // columns made this kernel 24 k instructions (390 KB) and the store phase instruction-fetch bound (~66 k cycles
+      // per tile, measured).  So the unrolled part only moves the registers into a per-warp 4 KB staging tile
+      // (32 rows x 32 columns, SWIZZLE_128B; every index into y[] is a compile-time constant), a ROLLED loop applies
+      // the epilogue math on row-contiguous segments, and the tile leaves either through cp.async.bulk.tensor stores
+      // (asynchronous; rows / columns beyond M / N are clipped by the tensor map) or through coalesced stores.
+      const uint32_t stg = smem_u32(smem + (size_t)R * TC3_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
+      const int m_row0 = m_tile * 256 + (int)rank * TC_BM + q * 32;       // first row of this warp
+      const int c2 = p.partial ? batch : (int)b1, c3 = p.partial ? split : (int)b0;
+      const bool identity = p.partial || (p.alpha == 1.f && p.beta == 0.f && !p.bias && p.act == 0);
+      float* cwarp;
+      if (p.partial) cwarp = p.partial + (((int64_t)split * p.batches + batch) * p.m + m_row0) * p.n;
+      else cwarp = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + (int64_t)m_row0 * p.ldc;
+      const int64_t row_pitch = p.partial ? p.n : p.ldc;
+      const int sub_row = lane >> 3, chunk = lane & 7;
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          const int n_col0 = n_tile * BN + hf * 128 + c0;
-          if (n_col0 < p.n && m_row0 < p.m) {                 // warp-uniform
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
-            __syncwarp();
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int n_col0 = n_tile * BN + hf * 128 + c0;
+        if (n_col0 < p.n && m_row0 < p.m && !(p.probe & 4)) {            // warp-uniform; probe bit 4 skips the stores
+          if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free
+          __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float v[4] = {y[c0 + 4 * c], y[c0 + 4 * c + 1], y[c0 + 4 * c + 2], y[c0 + 4 * c + 3]};
+          for (int c = 0; c < 8; ++c) {
+            uint4 v4;
+            v4.x = __float_as_uint(y[c0 + 4 * c]); v4.y = __float_as_uint(y[c0 + 4 * c + 1]);
+            v4.z = __float_as_uint(y[c0 + 4 * c + 2]); v4.w = __float_as_uint(y[c0 + 4 * c + 3]);
+            tc_sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), v4);
+          }
+          __syncwarp();
+          if (!identity || !p.tma_store) {
+            const int gn0 = n_col0 + chunk * 4;
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int rl = 4 * i + sub_row;
+              const uint32_t sa = stg + rl * 128 + ((chunk ^ (rl & 7)) << 4);
+              const uint4 v4 = tc_lds128(sa);
+              float v[4] = {__uint_as_float(v4.x), __uint_as_float(v4.y), __uint_as_float(v4.z), __uint_as_float(v4.w)};
+              float* dst = cwarp + (int64_t)rl * row_pitch + gn0;
+              const bool in_range = (m_row0 + rl < p.m) && (gn0 < p.n);
               if (!p.partial) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   v[j] *= p.alpha;
-                  if (p.bias && n_col0 + 4 * c + j < p.n) v[j] += __ldg(p.bias + n_col0 + 4 * c + j);
+                  if (in_range && gn0 + j < p.n) {
+                    if (p.beta != 0.f) v[j] += p.beta * dst[j];
+                    if (p.bias) v[j] += __ldg(p.bias + gn0 + j);
+                  }
                   if (p.act == 1) v[j] = tc_act<1>(v[j]);
                   else if (p.act == 2) v[j] = tc_act<2>(v[j]);
                   else if (p.act == 3) v[j] = tc_act<3>(v[j]);
                 }
               }
-              uint4 v4;
-              v4.x = __float_as_uint(v[0]); v4.y = __float_as_uint(v[1]); v4.z = __float_as_uint(v[2]); v4.w = __float_as_uint(v[3]);
-              tc_sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), v4);
+              if (p.tma_store) {
+                uint4 o4;
+                o4.x = __float_as_uint(v[0]); o4.y = __float_as_uint(v[1]); o4.z = __float_as_uint(v[2]); o4.w = __float_as_uint(v[3]);
+                tc_sts128(sa, o4);
+              } else if (in_range) {
+                if (gn0 + 4 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (gn0 + j < p.n) dst[j] = v[j];
+                }
+              }
             }
+          }
+          if (p.tma_store) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -1135,36 +1168,6 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                            "r"(stg), "r"(n_col0), "r"(m_row0), "r"(c2), "r"(c3)
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-        }
-      } else if (row_ok && !(p.probe & 4)) {   // probe bit 4 (diagnostic): skip the global stores
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 4) {
-          const int64_t gn0 = gn_base + c0;
-          if (gn0 < p.n) {
-            float* dst = crow + gn0;
-            float v[4] = {y[c0], y[c0 + 1], y[c0 + 2], y[c0 + 3]};
-            const bool full = (gn0 + 4 <= p.n);
-            if (!p.partial) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v[j] *= p.alpha;
-                if (gn0 + j < p.n) {
-                  if (p.beta != 0.f) v[j] += p.beta * dst[j];
-                  if (p.bias) v[j] += __ldg(p.bias + gn0 + j);
-                }
-                if (p.act == 1) v[j] = tc_act<1>(v[j]);
-                else if (p.act == 2) v[j] = tc_act<2>(v[j]);
-                else if (p.act == 3) v[j] = tc_act<3>(v[j]);
-              }
-            }
-            if (full && vec_ok) {
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (gn0 + j < p.n) dst[j] = v[j];
             }
           }
         }
@@ -1290,11 +1293,11 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   // CTA-pair kernel: opt-in.  Measured on B200 (profiles/r1_gemm_tc_probe.md): +3..7 % on 4096^3 / 8192^3, but
   // -5 % on the (131072 x 512 x 512) projection shapes of config 5 (the chunk fold waits for two epilogues).
   const char* ep = getenv("B200AD_TC_PAIR");
-  const int pair_mode = ep ? atoi(ep) : 2;       // 2 = automatic
-  // Measured on B200 (profiles/r1_summary.md): the generation-3 pair kernel (A in TMEM, running totals in
-  // registers) wins on deep accumulations (split-K weight gradients 179 -> 225 TFLOP/s, 8192^3 192 -> 215) but its
-  // single-buffered accumulator exposes the fold at every chunk, so short-K tiles (K = 512 projections) stay on the
-  // 1-CTA kernel with double-buffered accumulators.  B200AD_TC_PAIR: 0 = never, 1 = gemm_tc2_kernel, 3 = always gen3.
+  const int pair_mode = ep ? atoi(ep) : 3;
+  // Measured on B200 (profiles/r1_summary.md §4): the generation-3 pair kernel (A in TMEM, running totals in registers,
+  // interleaved half-tile chains, compact TMA-store epilogue) beats the 1-CTA kernel on every 256-wide shape:
+  // 131072 x 512 x 512 projections 150 -> 236, 8192^3 192 -> 260, split-K dW 179 -> 234, K = 256 gates 139 -> 225 TFLOP/s.
+  // B200AD_TC_PAIR: 0 = never, 1 = gemm_tc2_kernel, 2 = gen3 for deep-K problems only, 3 = gen3 whenever eligible.
   const int64_t m_tiles256 = ceil_div(g.m, 2 * TC_BM), n_tiles256 = ceil_div(g.n, 256);
   const int64_t tiles256 = m_tiles256 * n_tiles256 * g.batch0 * g.batch1;
   const int64_t kblocks = ceil_div(g.k, TC_BK);
