@@ -37,6 +37,7 @@ int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float
   if (fill_args(d, a, b, const_cast<float*>(c), nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32 || d->precision == B200AD_GEMM_AUTO) return 1;
   const char* why = nullptr;
+  if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_supported(g, &why) ? 1 : 0;
   return gemm_tc_supported(g, d->precision, &why) ? 1 : 0;
 }
 
@@ -44,6 +45,7 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d) {
   GemmArgs g;
   if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32) return 0;
+  if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_workspace_bytes(g);
   const int prec = d->precision == B200AD_GEMM_AUTO ? B200AD_GEMM_TF32X3 : d->precision;
   return gemm_tc_workspace_bytes(g, prec);
 }
@@ -63,6 +65,10 @@ int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float
   }
   if (prec == B200AD_GEMM_FP32 || g.k == 0) return gemm_simt_launch(g, s);
   const char* why = "unsupported";
+  if (prec == B200AD_GEMM_BF16) {
+    if (!gemm_bf16_supported(g, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(bf16): %s", why);
+    return gemm_bf16_launch(g, workspace, workspace_bytes, s);
+  }
   if (!gemm_tc_supported(g, prec, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): %s", why);
   return gemm_tc_launch(g, prec, workspace, workspace_bytes, s);
 }

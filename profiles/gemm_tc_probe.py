@@ -10,7 +10,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling", "atmem", "mmarate"]
+GROUPS = ["basic", "layouts", "x3", "batched", "epilogue", "perf", "chunks", "ceiling", "atmem", "mmarate", "bf16"]
 
 
 def run_group(group):
@@ -119,6 +119,28 @@ def run_group(group):
             case("C5 dV (TN)", 512, 64, 512, ta=True, batch=(256, 8), prec="tf32x3", time_it=True)
             case("square 4096 BN64", 4096, 4096, 4096, tb=True, prec="tf32x3", time_it=True)
         os.environ.pop("B200AD_TC_BN"); os.environ.pop("B200AD_TC_ATMEM")
+    elif group == "bf16":
+        # bf16 variant: error vs fp64 is dominated by the bf16 rounding of the inputs (~2^-9 relative per operand)
+        for ta in (False, True):
+            for tb in (False, True):
+                case("bf16 layout", 256, 512, 256, ta=ta, tb=tb, prec="bf16")
+        case("bf16 tails", 200, 300, 1000, prec="bf16")
+        case("bf16 K=784 (C1)", 64, 256, 784, prec="bf16")
+        case("bf16 batched", 512, 512, 64, tb=True, batch=(4, 8), prec="bf16")
+        case("bf16 split-K dW", 512, 512, 32768, ta=True, prec="bf16")
+        case("bf16 bias tanh", 256, 256, 128, prec="bf16", bias=True, act=1)
+        case("bf16 beta", 256, 256, 512, prec="bf16", beta=1.0)
+        for shape in ((4096, 4096, 4096), (8192, 8192, 8192)):
+            case("bf16 square (incl. conversion)", *shape, tb=True, prec="bf16", time_it=True)
+        case("bf16 C5 projection (incl. conversion)", 131072, 512, 512, prec="bf16", time_it=True)
+        case("bf16 C5 dW (incl. conversion)", 512, 512, 131072, ta=True, prec="bf16", time_it=True)
+        os.environ["B200AD_BF16_SKIP_CVT"] = "1"
+        print("-- tensor-core kernel alone (conversion skipped: operands are whatever the workspace holds)", flush=True)
+        for shape in ((4096, 4096, 4096), (8192, 8192, 8192)):
+            case("bf16 square kernel-only", *shape, tb=True, prec="bf16", time_it=True)
+        case("bf16 C5 projection kernel-only", 131072, 512, 512, prec="bf16", time_it=True)
+        case("bf16 C5 dW kernel-only", 512, 512, 131072, ta=True, prec="bf16", time_it=True)
+        os.environ.pop("B200AD_BF16_SKIP_CVT")
     elif group == "mmarate":
         # pure MMA + epilogue (probe 3: no TMA, no split; results are garbage): how does the tcgen05.mma rate depend on N?
         # per-CTA MMA count for 8192^3 x3: tiles(64 x 8192/BN) / 148 CTAs x 256 k-blocks x 12 MMAs

@@ -222,6 +222,33 @@ def test_gemm_fp32_all_layouts(backend, M, N, K):
     assert_close(c, 0.5 * ref + 2.0 * c0.astype(np.float32), what="alpha/beta", **tol)
 
 
+@pytest.mark.parametrize("M,N,K,ta,tb", [(256, 512, 256, False, False), (200, 300, 1000, False, True), (64, 256, 784, True, False),
+                                         (512, 512, 8192, True, True), (300, 72, 96, False, False)])
+def test_gemm_bf16_variant_stated_tolerance(backend, M, N, K, ta, tb):
+    """bf16 tensor-core variant (B200AD_GEMM_BF16): operands rounded to bf16, fp32 accumulation.  Stated tolerance:
+    |err| <= 2^-7 * (|A| @ |B|) elementwise (each operand carries a 2^-9 relative rounding error), and the result must
+    match the same product evaluated in fp64 on bf16-ROUNDED inputs to fp32-accumulation accuracy."""
+    D = _D()
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    got = np.asarray(D.matmul(D.asarray(A), D.asarray(B), trans_a=ta, trans_b=tb, precision="bf16", bias=D.asarray(bias)),
+                     dtype=np.float64)
+    Aop = (A.T if ta else A).astype(np.float64)
+    Bop = (B.T if tb else B).astype(np.float64)
+    exact = Aop @ Bop + bias
+    bound = 2.0 ** -7 * (np.abs(Aop) @ np.abs(Bop)) + 1e-6
+    assert np.all(np.abs(got - exact) <= bound), float(np.max(np.abs(got - exact) / bound))
+    if backend == "cuda":
+        def bf16_round(x):                       # round-to-nearest-even to 8 significant bits
+            u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+            u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+            return u.astype(np.uint32).view(np.float32).astype(np.float64)
+        ref = bf16_round(A.T if ta else A) @ bf16_round(B.T if tb else B) + bias
+        assert_close(got, ref, rtol=2e-5, atol=2e-5 * np.sqrt(K), what="bf16 GEMM vs fp64 on bf16-rounded inputs")
+
+
 def test_gemm_batched_strided_views(backend):
     D = _D()
     rng = np.random.default_rng(16)
