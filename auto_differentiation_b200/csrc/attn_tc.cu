@@ -22,11 +22,11 @@
 // The B operands stream through a 7-slot ring of 32 KB shared-memory slots (raw tile from TMA + lo tile from
 // the converter warps), in exactly the order the MMA warp consumes them.
 //
-// Warp roles (384 threads = 3 warpgroups, one CTA per SM, persistent over work items; setmaxnreg moves registers
-// from the first two warpgroups to the row owners):
-//   warp 0      TMA producer            warp 1      MMA issuer (one lane)         warps 2-3 idle
+// Warp roles (512 threads = 4 warpgroups, one CTA per SM, persistent over work items; setmaxnreg 80 / 112 / 152 / 152):
+//   warp 0      TMA producer            warp 1      MMA issuer (one elected lane)  warps 2-3 idle
 //   warps 4-7   converter: A tiles smem -> TMEM (hi/lo), B tiles raw -> lo (in smem)
-//   warps 8-11  row owners: TMEM -> registers -> softmax / dS -> TMEM (Z hi/lo), fold of OUT_blk, epilogue
+//   warps 8-15  row owners (two groups): a thread owns one row and half of the columns: TMEM -> registers ->
+//               softmax / dS -> TMEM (Z hi/lo), fold of its half of OUT_blk, epilogue
 // TMEM (512 columns):  A1 hi/lo [0,128)  |  one-score modes: X0/Zhi0 L0 X1/Zhi1 L1 [128,384) OUT [384,448)
 //                      A2 hi/lo [128,256) | two-score modes: X0/Zlo0 X1/Zlo1 [256,384) Y/Zhi [384,448) OUT [448,512)
 #include "common.cuh"
@@ -41,8 +41,8 @@ constexpr int AT_BM = 128;                   // rows (TMEM lanes) per work item
 constexpr int AT_BC = 64;                    // columns per block
 constexpr int AT_NSLOT = 6;                  // ring slots; a 7th 32 KB region stages the output tile for the TMA store
 constexpr uint32_t AT_SLOT = 32768;          // [raw 16 KB | lo 16 KB] for a B block, or one raw A tile
-constexpr int AT_THREADS = 384;              // 3 warpgroups: {TMA, MMA, 2 idle}, converter, row owners
-constexpr uint32_t AT_SMEM = (AT_NSLOT + 1) * AT_SLOT + 1024 /*align*/;   // + ~1.3 KB static (barriers, column stats)
+constexpr int AT_THREADS = 512;              // 4 warpgroups: {TMA, MMA, 2 idle}, converter, 2 x row owners
+constexpr uint32_t AT_SMEM = (AT_NSLOT + 1) * AT_SLOT + 1024 /*align*/;   // + ~1.3 KB static (barriers, column / row statistics)
 
 enum { AT_FWD = 0, AT_DV = 1, AT_DQ = 2, AT_DKM = 3 };
 
@@ -116,7 +116,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   uint8_t* out_stage = smem + (size_t)AT_NSLOT * AT_SLOT;   // 32 KB: the output tile, two SWIZZLE_128B halves
   __shared__ uint64_t bars[3 * AT_NSLOT + 12];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float colstat[2][128];           // [buffer][lse (64) | D (64)] of the current column block
+  // DV / DK: [buffer][lse (64) | D (64)] of the current column block;  FWD: [owner group][row] row-maximum / row-sum
+  // exchange between the two owners of a row (the modes never need both, so they share the 1 KB)
+  __shared__ __align__(16) float colstat[2][128];
+  float (*rowx)[128] = colstat;
   uint64_t* full = bars;                       // [NSLOT] TMA -> converter
   uint64_t* conv = bars + AT_NSLOT;            // [NSLOT] converter -> MMA (128 arrivals): lo tile in smem / A tile in TMEM
   uint64_t* empty = bars + 2 * AT_NSLOT;       // [NSLOT] MMA commit (B slots) / converter (A slots) -> TMA
@@ -148,11 +151,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_empty[i], 1);
       mbar_init(&x_full[i], 1);
-      mbar_init(&z_full[i], 128);
+      mbar_init(&z_full[i], 256);
     }
     mbar_init(y_full, 1);
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 128);
+    mbar_init(out_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
@@ -164,7 +167,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
 
   // register budgets are set INSIDE each warpgroup's branch so that ptxas allocates per role
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
@@ -329,7 +332,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   }
   } else if (warp < 8) {
     // ===================================== converter =====================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     const int tid = threadIdx.x - 128;
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -393,11 +396,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     }
   } else {
     // ===================================== row owners =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int tid = threadIdx.x - 256;
+    // Two warpgroups; a thread owns one row (TMEM lane) and HALF of the columns: group gi handles columns
+    // [32 gi, 32 gi + 32) of every 64-column score block and of the d_k = 64 output.  Halving the per-thread work
+    // halves the elementwise latency on the MMA <-> owner critical path; only the forward's row maximum (and the
+    // final row sum) need an exchange between the two owners of a row, through shared memory.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int tid = threadIdx.x - 256;                   // 0..255
+    const int gi = (warp - 8) >> 2;                      // column half
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t cofs = (uint32_t)gi * 32u;            // this group's column offset inside a 64-column region
     uint32_t gb = 0, fo = 0;
 #ifdef AT_PROFILE
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -408,16 +417,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       const int h = bh % p.H, b = bh / p.H;
       const int grow = rt * AT_BM + r;
       const bool row_ok = grow < p.R;
-      float run[AT_DK];
+      float run[32];
 #pragma unroll
-      for (int d = 0; d < AT_DK; ++d) run[d] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;     // FWD
+      for (int d = 0; d < 32; ++d) run[d] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;     // FWD (l_run: this group's share of the row sum)
       float ls_r = 0.f, d_r = 0.f;                             // DQ: per-row statistics
       if (MODE == AT_DQ && row_ok) {
         ls_r = __ldg(p.lse + (int64_t)bh * p.R + grow);
         d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow);
       }
-      // fold OUT_blk(g) into the running total: run = run * a + OUT
+      // fold this group's half of OUT_blk into the running total: run = run * a + OUT
       auto fold = [&](float a) {
         AT_T(f0);
         mbar_wait(out_full, fo & 1);
@@ -425,16 +434,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         AT_T(f1);
         AT_ACC(1, f0, f1);
         tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(lane_base + OUT_COL + cofs, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(lane_base + OUT_COL + hh * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int d = 0; d < 32; ++d) {
-            if (MODE == AT_FWD) run[hh * 32 + d] = fmaf(run[hh * 32 + d], a, __uint_as_float(o[d]));
-            else run[hh * 32 + d] += __uint_as_float(o[d]);
-          }
+        for (int d = 0; d < 32; ++d) {
+          if (MODE == AT_FWD) run[d] = fmaf(run[d], a, __uint_as_float(o[d]));
+          else run[d] += __uint_as_float(o[d]);
         }
         tc_fence_before();
         mbar_arrive(out_empty);
@@ -446,7 +452,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           const int col = c0 + tid;
           return (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) : INFINITY;
         }
-        if (MODE == AT_DKM) {
+        if (MODE == AT_DKM && tid < 128) {
           const int col = c0 + tid - 64;
           return (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) : 0.f;
         }
@@ -456,15 +462,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       for (int j = 0; j < nb; ++j) {
         const uint32_t g = gb + j;
         const uint32_t bsel = g & 1;
-        const uint32_t xaddr = lane_base + X_COL0 + bsel * X_STRIDE;
-        const int col0 = j * AT_BC;
+        const uint32_t xaddr = lane_base + X_COL0 + bsel * X_STRIDE + cofs;
+        const int col0 = j * AT_BC + (int)cofs;          // first global column of this group's half
         float* cs = colstat[bsel];
         if (!ROWSTAT) {
           // per-column statistics of this block (lse, and D in the DK mode) -> shared memory; the next block's
           // values are fetched now so that the global-load latency hides behind this block's work
-          cs[tid] = cs_next;
-          named_bar_sync(2, 128);
-          if (j + 1 < nb) cs_next = load_colstat(col0 + AT_BC);
+          if (tid < 128) cs[tid] = cs_next;
+          named_bar_sync(2, 256);
+          if (j + 1 < nb) cs_next = load_colstat((j + 1) * AT_BC);
         }
         AT_T(x0);
         mbar_wait(&x_full[bsel], (g >> 1) & 1);
@@ -472,39 +478,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         AT_ACC(0, x0, x1);
         tc_fence_after();
         if (MODE == AT_FWD) {
-          uint32_t x[64];
-          tmem_ld_32x32b_x32(xaddr, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
-          tmem_ld_32x32b_x32(xaddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
+          uint32_t x[32], lo[32];
+          tmem_ld_32x32b_x32(xaddr, x);
           tmem_ld_wait();
           AT_T(x2);
           AT_ACC(3, x1, x2);
-          if (col0 + AT_BC > p.C) {
+          if (col0 + 32 > p.C) {
 #pragma unroll
-            for (int c = 0; c < 64; ++c)
+            for (int c = 0; c < 32; ++c)
               if (col0 + c >= p.C) x[c] = __float_as_uint(-INFINITY);
           }
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c = 0; c < 64; ++c) mx[c & 3] = fmaxf(mx[c & 3], __uint_as_float(x[c]));
-          const float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          for (int c = 0; c < 32; ++c) mx[c & 3] = fmaxf(mx[c & 3], __uint_as_float(x[c]));
+          float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          // the row maximum over all 64 columns: exchange with the other owner of this row
+          named_bar_sync(5, 256);                    // the previous block's exchange has been read by both groups
+          rowx[gi][r] = mb;
+          named_bar_sync(4, 256);
+          mb = fmaxf(mb, rowx[gi ^ 1][r]);
           const float m_new = fmaxf(m_run, mb);
           const float alpha = fast_exp2((m_run - m_new) * p.c2);
           const float mc = m_new * p.c2;
           float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t lo[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float pv = fast_exp2(fmaf(__uint_as_float(x[hh * 32 + c]), p.c2, -mc));
-              sm[c & 3] += pv;
-              const uint32_t hi = tf32_hi(__float_as_uint(pv));
-              lo[c] = tf32_lo(__float_as_uint(pv), hi);
-              x[hh * 32 + c] = hi;
-            }
-            tmem_st_32x32b_x32(xaddr + hh * 32, *reinterpret_cast<uint32_t(*)[32]>(&x[hh * 32]));
-            tmem_st_32x32b_x32(xaddr + 64 + hh * 32, lo);
+          for (int c = 0; c < 32; ++c) {
+            const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -mc));
+            sm[c & 3] += pv;
+            const uint32_t hi = tf32_hi(__float_as_uint(pv));
+            lo[c] = tf32_lo(__float_as_uint(pv), hi);
+            x[c] = hi;
           }
+          tmem_st_32x32b_x32(xaddr, x);
+          tmem_st_32x32b_x32(xaddr + 64, lo);
           l_run = fmaf(l_run, alpha, (sm[0] + sm[1]) + (sm[2] + sm[3]));
           m_run = m_new;
           AT_T(x3);
@@ -517,21 +523,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           if (j >= 1) fold(a_prev);
           a_prev = alpha;
         } else if (MODE == AT_DV) {
+          uint32_t x[32], lo[32];
+          tmem_ld_32x32b_x32(xaddr, x);
+          tmem_ld_wait();
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t x[32], lo[32];
-            tmem_ld_32x32b_x32(xaddr + hh * 32, x);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -cs[hh * 32 + c]));
-              const uint32_t hi = tf32_hi(__float_as_uint(pv));
-              lo[c] = tf32_lo(__float_as_uint(pv), hi);
-              x[c] = hi;
-            }
-            tmem_st_32x32b_x32(xaddr + hh * 32, x);
-            tmem_st_32x32b_x32(xaddr + 64 + hh * 32, lo);
+          for (int c = 0; c < 32; ++c) {
+            const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -cs[cofs + c]));
+            const uint32_t hi = tf32_hi(__float_as_uint(pv));
+            lo[c] = tf32_lo(__float_as_uint(pv), hi);
+            x[c] = hi;
           }
+          tmem_st_32x32b_x32(xaddr, x);
+          tmem_st_32x32b_x32(xaddr + 64, lo);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&z_full[bsel]);
@@ -540,31 +543,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           // DQ / DK: Z = P (Y - D) c;   Z hi -> X columns, Z lo -> Y columns
           mbar_wait(y_full, g & 1);
           tc_fence_after();
+          uint32_t x[32], y[32];
+          tmem_ld_32x32b_x32(xaddr, x);
+          tmem_ld_32x32b_x32(lane_base + Y_COL + cofs, y);
+          tmem_ld_wait();
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t x[32], y[32];
-            tmem_ld_32x32b_x32(xaddr + hh * 32, x);
-            tmem_ld_32x32b_x32(lane_base + Y_COL + hh * 32, y);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float ls, dd;
-              if (MODE == AT_DQ) {
-                ls = (col0 + hh * 32 + c < p.C) ? ls_r : INFINITY;
-                dd = d_r;
-              } else {
-                ls = cs[hh * 32 + c];
-                dd = cs[64 + hh * 32 + c];
-              }
-              const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls));
-              const float z = pv * (__uint_as_float(y[c]) - dd) * p.c;
-              const uint32_t hi = tf32_hi(__float_as_uint(z));
-              y[c] = tf32_lo(__float_as_uint(z), hi);
-              x[c] = hi;
+          for (int c = 0; c < 32; ++c) {
+            float ls, dd;
+            if (MODE == AT_DQ) {
+              ls = (col0 + c < p.C) ? ls_r : INFINITY;
+              dd = d_r;
+            } else {
+              ls = cs[cofs + c];
+              dd = cs[64 + cofs + c];
             }
-            tmem_st_32x32b_x32(xaddr + hh * 32, x);
-            tmem_st_32x32b_x32(lane_base + Y_COL + hh * 32, y);
+            const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls));
+            const float z = pv * (__uint_as_float(y[c]) - dd) * p.c;
+            const uint32_t hi = tf32_hi(__float_as_uint(z));
+            y[c] = tf32_lo(__float_as_uint(z), hi);
+            x[c] = hi;
           }
+          tmem_st_32x32b_x32(xaddr, x);
+          tmem_st_32x32b_x32(lane_base + Y_COL + cofs, y);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&z_full[bsel]);
@@ -574,27 +574,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       fold(a_prev);
       gb += nb;
       AT_T(e0);
-      // epilogue: stage the tile in shared memory (two SWIZZLE_128B halves, conflict-free row writes), one thread
-      // issues the TMA stores (coalesced, asynchronous, rows beyond R are clipped by the tensor map)
+      // epilogue: stage the tile in shared memory (two SWIZZLE_128B halves = the two groups' column halves,
+      // conflict-free row writes), one thread issues the TMA stores (coalesced, asynchronous, rows beyond R are
+      // clipped by the tensor map)
       if (tid == 0) bulk_wait_read0();          // the previous item's store has finished reading the staging tile
-      named_bar_sync(3, 128);
+      float sc = 1.f;
+      if (MODE == AT_FWD) {
+        named_bar_sync(5, 256);                 // the last block's exchange has been read by both groups
+        rowx[gi][r] = l_run;                    // row sum = both groups' shares
+      }
+      named_bar_sync(3, 256);
+      if (MODE == AT_FWD) {
+        const float l_tot = l_run + rowx[gi ^ 1][r];
+        sc = 1.f / l_tot;
+        if (gi == 0 && row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, p.c2, log2f(l_tot));
+      }
       {
-        float sc = 1.f;
-        if (MODE == AT_FWD) {
-          sc = 1.f / l_run;
-          if (row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, p.c2, log2f(l_run));
-        }
-        const uint32_t srow = smem_u32(out_stage) + r * 128;
+        const uint32_t srow = smem_u32(out_stage) + (uint32_t)gi * 16384u + r * 128;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 8; ++c) {
           uint4 v;
           v.x = __float_as_uint(run[4 * c] * sc); v.y = __float_as_uint(run[4 * c + 1] * sc);
           v.z = __float_as_uint(run[4 * c + 2] * sc); v.w = __float_as_uint(run[4 * c + 3] * sc);
-          sts128(srow + (c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4), v);
+          sts128(srow + ((c ^ (r & 7)) << 4), v);
         }
       }
       fence_proxy_async();
-      named_bar_sync(3, 128);
+      named_bar_sync(3, 256);
       if (tid == 0) {
         tma_store_4d(&map_out, out_stage, 0, rt * AT_BM, h, b);
         tma_store_4d(&map_out, out_stage + 16384, 32, rt * AT_BM, h, b);
