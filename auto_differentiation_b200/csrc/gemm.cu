@@ -46,6 +46,9 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d) {
   if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32) return 0;
   if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_workspace_bytes(g);
+  if (d->precision == B200AD_GEMM_AUTO && d->m <= 64 && d->m >= 1 && d->batch0 * d->batch1 == 1 && !d->trans_a &&
+      d->k >= 256 && !(d->k & 31) && d->n >= 256 && d->n <= 2048 && !(d->n & 7) && !(d->lda & 3) && !(d->ldb & 3))
+    return 0;   // skinny recurrent-step kernel (pointer alignment is checked at launch; a fallback then runs un-split)
   const int prec = d->precision == B200AD_GEMM_AUTO ? B200AD_GEMM_TF32X3 : d->precision;
   return gemm_tc_workspace_bytes(g, prec);
 }
@@ -59,6 +62,7 @@ int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float
   B200AD_REQUIRE(c && (g.k == 0 || (a && b)), "gemm: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   int prec = d->precision;
+  if (prec == B200AD_GEMM_AUTO && g.k > 0 && gemm_skinny_supported(g)) return gemm_skinny_launch(g, s);
   if (prec == B200AD_GEMM_AUTO) {
     const char* why = nullptr;
     prec = gemm_tc_supported(g, B200AD_GEMM_TF32X3, &why) ? B200AD_GEMM_TF32X3 : B200AD_GEMM_FP32;

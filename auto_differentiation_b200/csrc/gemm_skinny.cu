@@ -1,0 +1,128 @@
+// Skinny GEMM for the recurrent time steps: C (M x N) = act(alpha * A (M x K) @ op(B) + beta * C + bias), M <= 64.
+// Replaces np.dot(h_prev, Wh) in RNN.forward layers.py:171 / LSTM.forward :632 and np.dot(dA, Wh.T) in their
+// backward (:180, :667) — 2 x T strictly sequential products of a 64-row state with a resident weight matrix.
+// These are latency-bound: a 134 MFLOP product cannot fill 128-row tensor-core tiles, and the tcgen05 path spent
+// ~48 us per step (split-K + reduce, two launches).  Here one launch spreads the N columns over the whole chip
+// (one CTA per 8 columns: 128 CTAs for H = 1024, 512 for the LSTM's 4H), the 8 warps of a CTA split K, every lane
+// owns 2 rows x 8 columns in registers, and the epilogue (beta * C, bias, tanh / sigmoid / relu) is fused, so a tanh
+// RNN step is ONE launch.  Exact fp32 FMA accumulation, deterministic reduction order.
+#include "common.cuh"
+#include "gemm_internal.cuh"
+#include <stdlib.h>
+
+namespace b200ad {
+
+constexpr int SK_BN = 8;
+constexpr int SK_WARPS = 8;
+constexpr int SK_THREADS = SK_WARPS * 32;
+
+template <int ACT>
+__device__ __forceinline__ float sk_act(float x) {
+  if constexpr (ACT == 1) return tanhf(x);
+  else if constexpr (ACT == 2) return 1.f / (1.f + expf(-x));
+  else if constexpr (ACT == 3) return (x > 0.f || x != x) ? x : 0.f;
+  else return x;
+}
+
+template <bool TRANS_B>
+__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float bsm[SK_WARPS][32][SK_BN];     // per warp: a 32 (k) x 8 (n) chunk of op(B)
+  __shared__ __align__(16) float red[SK_WARPS][64][SK_BN];     // per warp partial sums
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n0 = (int64_t)blockIdx.x * SK_BN;
+  const int M = (int)g.m;
+  const int64_t K = g.k;
+  const int chunks = (int)(K / 32);
+  const int per_warp = (chunks + SK_WARPS - 1) / SK_WARPS;
+  const int c_begin = warp * per_warp, c_end = min(chunks, c_begin + per_warp);
+  const int r0 = 2 * lane, r1 = r0 + 1;
+  const float* a0p = g.a + (int64_t)(r0 < M ? r0 : 0) * g.lda;
+  const float* a1p = g.a + (int64_t)(r1 < M ? r1 : 0) * g.lda;
+  float acc0[SK_BN], acc1[SK_BN];
+#pragma unroll
+  for (int j = 0; j < SK_BN; ++j) acc0[j] = acc1[j] = 0.f;
+
+  for (int c = c_begin; c < c_end; ++c) {
+    const int64_t k0 = (int64_t)c * 32;
+    // stage the B chunk: bsm[warp][k][n] = op(B)[k0 + k][n0 + n]
+    if (!TRANS_B) {            // B stored (K x N), n contiguous: lane = k row, two float4
+      const float4* src = reinterpret_cast<const float4*>(g.b + (k0 + lane) * g.ldb + n0);
+      const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+      *reinterpret_cast<float4*>(&bsm[warp][lane][0]) = v0;
+      *reinterpret_cast<float4*>(&bsm[warp][lane][4]) = v1;
+    } else {                   // B stored (N x K), k contiguous: lane -> (n = lane >> 2, 8 consecutive k)
+      const int n = lane >> 2, kq = (lane & 3) * 8;
+      const float4* src = reinterpret_cast<const float4*>(g.b + (n0 + n) * g.ldb + k0 + kq);
+      const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+      bsm[warp][kq + 0][n] = v0.x; bsm[warp][kq + 1][n] = v0.y; bsm[warp][kq + 2][n] = v0.z; bsm[warp][kq + 3][n] = v0.w;
+      bsm[warp][kq + 4][n] = v1.x; bsm[warp][kq + 5][n] = v1.y; bsm[warp][kq + 6][n] = v1.z; bsm[warp][kq + 7][n] = v1.w;
+    }
+    // this lane's two A rows, 32 k values each
+    float a0[32], a1[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(a0p + k0) + q);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(a1p + k0) + q);
+      a0[4 * q] = u.x; a0[4 * q + 1] = u.y; a0[4 * q + 2] = u.z; a0[4 * q + 3] = u.w;
+      a1[4 * q] = w.x; a1[4 * q + 1] = w.y; a1[4 * q + 2] = w.z; a1[4 * q + 3] = w.w;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&bsm[warp][k][0]);     // broadcast reads
+      const float4 b1 = *reinterpret_cast<const float4*>(&bsm[warp][k][4]);
+      const float bb[SK_BN] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < SK_BN; ++j) {
+        acc0[j] = fmaf(a0[k], bb[j], acc0[j]);
+        acc1[j] = fmaf(a1[k], bb[j], acc1[j]);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < SK_BN; ++j) {
+    red[warp][r0][j] = acc0[j];
+    red[warp][r1][j] = acc1[j];
+  }
+  __syncthreads();
+  // 512 outputs, 2 per thread, warps summed in a fixed order
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int idx = threadIdx.x + o * SK_THREADS;
+    const int row = idx >> 3, col = idx & 7;
+    if (row < M) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < SK_WARPS; ++w) s += red[w][row][col];
+      float* dst = g.c + (int64_t)row * g.ldc + n0 + col;
+      float v = g.alpha * s;
+      if (g.beta != 0.f) v += g.beta * *dst;
+      if (g.bias) v += __ldg(g.bias + n0 + col);
+      if (g.act == 1) v = sk_act<1>(v);
+      else if (g.act == 2) v = sk_act<2>(v);
+      else if (g.act == 3) v = sk_act<3>(v);
+      *dst = v;
+    }
+  }
+}
+
+bool gemm_skinny_supported(const GemmArgs& g) {
+  if (getenv("B200AD_NO_SKINNY")) return false;
+  if (g.m < 1 || g.m > 64 || g.batch0 * g.batch1 != 1 || g.trans_a) return false;
+  // N <= 2048: every CTA re-reads the whole A panel (M x K) from L2, which stops paying beyond ~256 CTAs (the LSTM's
+  // 4H = 4096 columns run faster on the tensor-core path: measured 14.7 vs 30.7 ms per graph-captured step)
+  if (g.k < 256 || (g.k & 31) || g.n < 256 || g.n > 2048 || (g.n & 7)) return false;
+  if ((g.lda & 3) || (g.ldb & 3) || !aligned16(g.a) || !aligned16(g.b)) return false;
+  return true;
+}
+
+int gemm_skinny_launch(const GemmArgs& g, cudaStream_t s) {
+  const int grid = (int)(g.n / SK_BN);
+  if (g.trans_b) gemm_skinny_kernel<true><<<grid, SK_THREADS, 0, s>>>(g);
+  else gemm_skinny_kernel<false><<<grid, SK_THREADS, 0, s>>>(g);
+  count_launch();
+  return check_launch("gemm(skinny)");
+}
+
+}  // namespace b200ad

@@ -282,12 +282,14 @@ class TimeRNN(_TimeRecurrent):
         H = wh.shape[0]
         if not self.stateful or self.h is None:
             self.h = D.zeros((N, H))
-        xs_tm, pre = self._project_inputs(xs)
         hs_ext = D.empty((T + 1, N, H))       # hs_ext[t] = h_{t-1}; hs_ext[0] = initial state
         D.copy_into_(self.h, hs_ext[0])
+        # x@Wx + b for all steps in ONE GEMM, written straight into hs_ext[1:]; each step then completes its slice in
+        # place: hs_ext[t+1] = tanh(hs_ext[t+1] + h_{t-1} @ Wh) — one launch per step (fused beta / tanh epilogue)
+        xs_tm = xs.transpose(1, 0, 2).contiguous()
+        D.matmul(xs_tm.reshape(T * N, Dm), wx, bias=b.reshape(-1), out=hs_ext[1:].reshape(T * N, H))
         for t in range(T):
-            D.matmul(hs_ext[t], wh, out=pre[t], beta=1.0)        # pre_t += h_{t-1} @ Wh
-            D.bias_act(pre[t], None, L.ACT_TANH, out=hs_ext[t + 1])
+            D.matmul(hs_ext[t], wh, out=hs_ext[t + 1], beta=1.0, act=L.ACT_TANH)
         self.h = hs_ext[T]
         self._cache = (xs_tm, hs_ext)
         return hs_ext[1:].transpose(1, 0, 2)

@@ -249,6 +249,27 @@ def test_gemm_bf16_variant_stated_tolerance(backend, M, N, K, ta, tb):
         assert_close(got, ref, rtol=2e-5, atol=2e-5 * np.sqrt(K), what="bf16 GEMM vs fp64 on bf16-rounded inputs")
 
 
+@pytest.mark.parametrize("M,N,K,tb,act,beta", [(64, 1024, 1024, False, 1, 1.0), (64, 1024, 1024, True, 0, 0.0), (17, 2048, 1024, False, 0, 1.0),
+                                               (1, 256, 256, True, 2, 0.0), (64, 512, 2048, False, 3, 0.5)])
+def test_gemm_skinny_recurrent_step(backend, M, N, K, tb, act, beta):
+    """The M <= 64 recurrent-step kernel (fused beta * C + bias + activation epilogue), both B layouts, strided
+    output rows (a time slice of an (N, T, H) tensor), vs fp64."""
+    D, L = _D(), _Lc()
+    rng = np.random.default_rng(M * 7 + N + K)
+    A = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    C0 = rng.standard_normal((M, 3, N)).astype(np.float32)
+    out_full = D.asarray(C0.copy())                           # (the CPU emulation would alias the host array)
+    out = out_full[:, 1, :]                                   # row stride 3N
+    D.matmul(D.asarray(A), D.asarray(B), trans_b=tb, out=out, beta=beta, bias=D.asarray(bias), act=act)
+    ref = A.astype(np.float64) @ (B.T if tb else B).astype(np.float64) + beta * C0[:, 1, :].astype(np.float64) + bias
+    ref = {0: lambda v: v, 1: np.tanh, 2: lambda v: 1 / (1 + np.exp(-v)), 3: lambda v: np.maximum(v, 0)}[act](ref)
+    got = np.asarray(out_full)
+    assert_close(got[:, 1, :], ref, rtol=2e-5, atol=2e-6, what="skinny GEMM")
+    assert np.array_equal(got[:, 0, :], C0[:, 0, :]) and np.array_equal(got[:, 2, :], C0[:, 2, :])
+
+
 def test_gemm_batched_strided_views(backend):
     D = _D()
     rng = np.random.default_rng(16)
