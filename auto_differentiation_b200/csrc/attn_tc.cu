@@ -95,7 +95,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int MODE>
+// CP = CTA pair (cluster of two CTAs, cta_group::2 MMAs with M = 256): CTA r owns row tile 2 * unit + r and stages HALF of
+// every B block (32 of the 64 score columns / 32 of the 64 output columns), so the MMA-side shared-memory reads, the TMA
+// fill and the converter work per CTA are halved: the 1-CTA passes are bound by exactly that traffic (~125 B/clk at full
+// MMA rate).  All cross-role barriers that the MMA warp waits on live in the leader CTA (remote arrives), everything the
+// MMA warp signals is a multicast commit.
+template <int MODE, bool CP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
@@ -133,6 +138,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CP ? cluster_ctarank() : 0u;
+  const int unit_id = CP ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, units = CP ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // signalling helpers: barriers the MMA warp waits on live in the leader CTA; its own signals reach both CTAs
+  // one arrival per WARP in pair mode (cluster-scope release arrives are expensive: ~500 cycles each when all 32 lanes
+  // issue them); every lane has completed its own tcgen05.wait::st / fence before the __syncwarp
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (CP) {
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0); }
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+  auto mma_commit = [&](uint64_t* bar) { if (CP) umma2_commit_mc(bar); else umma_commit(bar); };
+  auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t desc, uint32_t idesc, uint32_t acc) {
+    if (CP) umma2_tf32_ts(d, a, desc, idesc, acc); else umma_tf32_ts(d, a, desc, idesc, acc);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a1);
@@ -145,22 +167,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     }
     for (int s = 0; s < AT_NSLOT; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], 128);
+      mbar_init(&conv[s], CP ? 8 : 128);          // pair mode: one arrival per converter warp of both CTAs
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_empty[i], 1);
       mbar_init(&x_full[i], 1);
-      mbar_init(&z_full[i], 256);
+      mbar_init(&z_full[i], CP ? 16 : 256);       // pair mode: one arrival per owner warp of both CTAs
     }
     mbar_init(y_full, 1);
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 256);
+    mbar_init(out_empty, CP ? 16 : 256);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  if (warp == 1) { if (CP) tmem_alloc2(tmem_base_slot, TMEM_COLS); else tmem_alloc(tmem_base_slot, TMEM_COLS); }
   tc_fence_before();
-  __syncthreads();
+  if (CP) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   const int nb = p.nb;
@@ -172,8 +194,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       uint32_t op = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const int rt = item % p.row_tiles, bh = item / p.row_tiles;
+      for (int item = unit_id; item < p.total_items; item += units) {
+        const int rt = (item % p.row_tiles) * (CP ? 2 : 1) + (int)rank, bh = item / p.row_tiles;
         const int h = bh % p.H, b = bh / p.H;
         const int row0 = rt * AT_BM;
         auto acquire = [&](uint32_t bytes, uint64_t*& bar) -> uint8_t* {
@@ -190,19 +212,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           tma_load_4d(m, bar, dst, 0, row0, h, b);
           tma_load_4d(m, bar, dst + 16384, 32, row0, h, b);
         };
-        auto load_k = [&](const CUtensorMap* m, int col0) {   // K-major B block: 64 rows x 64
+        auto load_k = [&](const CUtensorMap* m, int col0) {   // K-major B block: 64 rows x 64 (pair: this CTA's 32 rows)
           uint64_t* bar;
-          uint8_t* dst = acquire(16384u, bar);
-          tma_load_4d(m, bar, dst, 0, col0, h, b);
-          tma_load_4d(m, bar, dst + 8192, 32, col0, h, b);
+          if (CP) {
+            uint8_t* dst = acquire(8192u, bar);
+            tma_load_4d(m, bar, dst, 0, col0 + 32 * (int)rank, h, b);
+            tma_load_4d(m, bar, dst + 4096, 32, col0 + 32 * (int)rank, h, b);
+          } else {
+            uint8_t* dst = acquire(16384u, bar);
+            tma_load_4d(m, bar, dst, 0, col0, h, b);
+            tma_load_4d(m, bar, dst + 8192, 32, col0, h, b);
+          }
         };
         auto load_mn = [&](const CUtensorMap* m, int col0) {  // MN-major B block: 64 k-rows x 64 (32 x 32 boxes)
           uint64_t* bar;
-          uint8_t* dst = acquire(16384u, bar);
+          if (CP) {                                           // pair: this CTA's 32 output columns (d), all 64 k-rows
+            uint8_t* dst = acquire(8192u, bar);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
+            for (int kb = 0; kb < 2; ++kb) tma_load_4d(m, bar, dst + kb * 4096, 32 * (int)rank, col0 + kb * 32, h, b);
+          } else {
+            uint8_t* dst = acquire(16384u, bar);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) tma_load_4d(m, bar, dst + kb * 8192 + c * 4096, c * 32, col0 + kb * 32, h, b);
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) tma_load_4d(m, bar, dst + kb * 8192 + c * 4096, c * 32, col0 + kb * 32, h, b);
+          }
         };
         load_a(&map_a1);
         if (HAS2) load_a(&map_a2);
@@ -215,12 +249,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 && rank == 0) {
+    // ===================================== MMA issuer (leader CTA of a pair) =====================================
     // instruction descriptor: D = f32, A = B = tf32, A K-major (TMEM), N = 64, M = 128; bit 16 = B MN-major
     constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) |
-                                 ((uint32_t)(AT_BM >> 4) << 24);
+                                 ((uint32_t)((CP ? 256 : AT_BM) >> 4) << 24);
     constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
+    constexpr uint32_t LO_OFF = CP ? 8192u : 16384u, KHALF = CP ? 4096u : 8192u;   // slot layout: [raw | lo], two k halves each
     uint32_t op = 0, it = 0, gb = 0, fo = 0;    // ring op, item, global block and fold (OUT accumulator use) counters
 #ifdef AT_PROFILE
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -243,17 +278,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         for (int t = 0; t < 3; ++t) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_tf32_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
-                         d0 + (uint64_t)(((t == 1 ? 16384 : 0) + (kk >> 2) * 8192 + (kk & 3) * 32) >> 4), IDESC_K,
-                         (t | kk) ? 1u : 0u);
+            mma_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
+                   d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 32u) >> 4), IDESC_K, (t | kk) ? 1u : 0u);
         }
-        umma_commit(&empty[s]);
-        umma_commit(done);
-        if (a_done) umma_commit(a_done);
+        mma_commit(&empty[s]);
+        mma_commit(done);
+        if (a_done) mma_commit(a_done);
       }
       __syncwarp();
     };
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    for (int item = unit_id; item < p.total_items; item += units, ++it) {
       // the A tiles' ring slots: the converter signals "hi/lo in TMEM" on the slot's conv barrier
       const uint32_t s_a1 = op % AT_NSLOT, ph_a1 = (op / AT_NSLOT) & 1;
       ++op;
@@ -299,8 +333,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
-              umma_tf32_ts(dst, a_lo + kk * 8, d0 + (uint64_t)(((kk >> 2) * 8192 + (kk & 3) * 1024) >> 4), IDESC_MN,
-                           (kk || !first) ? 1u : 0u);
+              mma_ts(dst, a_lo + kk * 8, d0 + (uint64_t)(((kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN,
+                     (kk || !first) ? 1u : 0u);
           }
           __syncwarp();
           if (HAS2 && j < nb) score(A2_COL, Y_COL, y_full, j == nb - 1 ? &a_empty[1] : nullptr);
@@ -309,11 +343,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
             for (int t = 1; t < 3; ++t) {
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
-                umma_tf32_ts(dst, a_hi + kk * 8,
-                             d0 + (uint64_t)(((t == 1 ? 16384 : 0) + (kk >> 2) * 8192 + (kk & 3) * 1024) >> 4), IDESC_MN, 1u);
+                mma_ts(dst, a_hi + kk * 8,
+                       d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN, 1u);
             }
-            umma_commit(&empty[s]);
-            if (last) umma_commit(out_full);
+            mma_commit(&empty[s]);
+            if (last) mma_commit(out_full);
           }
           __syncwarp();
           if (last) ++fo;
@@ -366,7 +400,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&conv[s]);              // A tile (hi/lo) is in TMEM; keeps the slot's conv phase in step with its uses
+      arrive_leader(&conv[s]);            // A tile (hi/lo) is in TMEM; keeps the slot's conv phase in step with its uses
       named_bar_sync(1, 128);             // every converter thread has read its row: the slot can be refilled
       if (tid == 0) mbar_arrive(&empty[s]);
     };
@@ -376,20 +410,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       ++op;
       const uint32_t raw = smem_u32(smem + (size_t)s * AT_SLOT) + tid * 16;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < (CP ? 4 : 8); ++i) {                // pair: 8 KB raw -> 8 KB lo per CTA
         const uint4 v = lds128(raw + i * 2048);
         uint4 l;
         l.x = tf32_lo(v.x, tf32_hi(v.x));
         l.y = tf32_lo(v.y, tf32_hi(v.y));
         l.z = tf32_lo(v.z, tf32_hi(v.z));
         l.w = tf32_lo(v.w, tf32_hi(v.w));
-        sts128(raw + 16384 + i * 2048, l);
+        sts128(raw + (CP ? 8192 : 16384) + i * 2048, l);
       }
       fence_proxy_async();                // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&conv[s]);
+      arrive_leader(&conv[s]);
     };
     const int n_b = (HAS2 ? 3 : 2) * nb;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    for (int item = unit_id; item < p.total_items; item += units, ++it) {
       conv_a(0);
       if (HAS2) conv_a(1);
       for (int i = 0; i < n_b; ++i) conv_b();
@@ -412,8 +446,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
 #endif
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const int rt = item % p.row_tiles, bh = item / p.row_tiles;
+    for (int item = unit_id; item < p.total_items; item += units) {
+      const int rt = (item % p.row_tiles) * (CP ? 2 : 1) + (int)rank, bh = item / p.row_tiles;
       const int h = bh % p.H, b = bh / p.H;
       const int grow = rt * AT_BM + r;
       const bool row_ok = grow < p.R;
@@ -443,7 +477,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           else run[d] += __uint_as_float(o[d]);
         }
         tc_fence_before();
-        mbar_arrive(out_empty);
+        arrive_leader(out_empty);
         AT_T(f2);
         AT_ACC(2, f1, f2);
       };
@@ -517,7 +551,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           AT_ACC(4, x2, x3);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&z_full[bsel]);
+          arrive_leader(&z_full[bsel]);
           AT_T(x4);
           AT_ACC(5, x3, x4);
           if (j >= 1) fold(a_prev);
@@ -537,7 +571,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           tmem_st_32x32b_x32(xaddr + 64, lo);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&z_full[bsel]);
+          arrive_leader(&z_full[bsel]);
           if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         } else {
           // DQ / DK: Z = P (Y - D) c;   Z hi -> X columns, Z lo -> Y columns
@@ -567,7 +601,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           tmem_st_32x32b_x32(lane_base + Y_COL + cofs, y);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&z_full[bsel]);
+          arrive_leader(&z_full[bsel]);
           if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         }
       }
@@ -625,9 +659,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CP) cluster_sync_all(); else __syncthreads();     // the peer's smem / barriers / TMEM stay valid until both CTAs are done
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) { if (CP) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // D[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d]: 16 lanes (one float4 each) per (b, h, s) row of 64
@@ -684,42 +718,60 @@ static bool tensor_ok(const float* ptr, const b200ad_attn_strides& s) {
          s.head >= 0 && s.batch >= 0;
 }
 
-template <int MODE>
-static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTensor& b1, const AttnTensor& b2,
-                       const AttnTensor& b3, AttnParams p, int64_t B, int64_t H, cudaStream_t s) {
+template <int MODE, bool CP>
+static int launch_pass_impl(const AttnTensor& a1, const AttnTensor& a2, const AttnTensor& b1, const AttnTensor& b2,
+                            const AttnTensor& b3, AttnParams p, int64_t B, int64_t H, cudaStream_t s) {
   constexpr bool HAS2 = (MODE == AT_DQ || MODE == AT_DKM);
+  constexpr uint32_t BROWS = CP ? 32u : (uint32_t)AT_BC;      // rows of a K-major B block staged per CTA
   CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_out;
   int rc;
   AttnTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
   if ((rc = encode_attn(&m_out, to, B, H, AT_BM, false))) return rc;
   if ((rc = encode_attn(&m_a1, a1, B, H, AT_BM, false))) return rc;
-  if ((rc = encode_attn(&m_b1, b1, B, H, AT_BC, false))) return rc;
+  if ((rc = encode_attn(&m_b1, b1, B, H, BROWS, false))) return rc;
   if ((rc = encode_attn(&m_b3, b3, B, H, 32, true))) return rc;
   if (HAS2) {
     if ((rc = encode_attn(&m_a2, a2, B, H, AT_BM, false))) return rc;
-    if ((rc = encode_attn(&m_b2, b2, B, H, AT_BC, false))) return rc;
+    if ((rc = encode_attn(&m_b2, b2, B, H, BROWS, false))) return rc;
   } else {
     m_a2 = m_a1;
     m_b2 = m_b1;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<MODE, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess && CP) e = cudaFuncSetAttribute(attn_tc_kernel<MODE, CP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  p.row_tiles = (int32_t)ceil_div(p.R, AT_BM);
+  p.row_tiles = (int32_t)ceil_div(ceil_div(p.R, AT_BM), CP ? 2 : 1);      // work units per (batch, head): tiles or tile pairs
   p.nb = (int32_t)ceil_div(p.C, AT_BC);
   const int64_t items = B * H * p.row_tiles;
   p.total_items = (int32_t)items;
-  const int grid = (int)(items < num_sms() ? items : num_sms());
+  const int max_units = CP ? num_sms() / 2 : num_sms();
+  const int grid = (CP ? 2 : 1) * (int)(items < max_units ? items : max_units);
 #ifdef AT_PROFILE
   static long long* prof_dev = nullptr;
   if (!prof_dev) cudaMalloc(&prof_dev, 16 * sizeof(long long));
   cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), s);
   p.prof = prof_dev;
 #endif
-  attn_tc_kernel<MODE><<<grid, AT_THREADS, AT_SMEM, s>>>(m_a1, m_a2, m_b1, m_b2, m_b3, m_out, p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(AT_THREADS);
+    cfg.dynamicSmemBytes = AT_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CP ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<MODE, CP>, m_a1, m_a2, m_b1, m_b2, m_b3, m_out, p);
+    if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): launch: %s", cudaGetErrorString(e));
+  }
   count_launch();
 #ifdef AT_PROFILE
   {
@@ -739,6 +791,18 @@ static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTen
             p.total_items, cudaGetErrorString(e));
   }
   return check_launch("attention(tcgen05)");
+}
+
+// Default: the 1-CTA passes.  B200AD_ATTN_PAIR=1 selects the CTA-pair variant (cta_group::2, each CTA stages half of every
+// B block).  Measured on B200 at the config-5 micro-batch: pair forward 1.01 ms vs 0.66 ms, backward 3.36 vs 2.62 ms —
+// parity-green but slower: the N = 64 MMAs of a pair and the cluster-scope hand-offs between the MMA warp and the row
+// owners cost more than the halved shared-memory traffic saves.
+template <int MODE>
+static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTensor& b1, const AttnTensor& b2,
+                       const AttnTensor& b3, AttnParams p, int64_t B, int64_t H, cudaStream_t s) {
+  const char* e = getenv("B200AD_ATTN_PAIR");
+  if (e && atoi(e) == 1) return launch_pass_impl<MODE, true>(a1, a2, b1, b2, b3, p, B, H, s);
+  return launch_pass_impl<MODE, false>(a1, a2, b1, b2, b3, p, B, H, s);
 }
 
 static int attn_check(const b200ad_attn_desc* d, const char** why) {
