@@ -56,6 +56,8 @@ struct AttnParams {
   int32_t row_tiles, nb, total_items;
   float c2, c;               // scale * log2(e), scale
   long long* prof;           // -DAT_PROFILE: per-role cycle counters of block 0 (debug builds only)
+  int32_t probe;             // diagnostic bits (results are garbage, only the rate matters): 1 = converter skips the B lo
+                             // tiles, 2 = row owners skip the elementwise math and the Z stores, 4 = no TMA loads
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -201,7 +203,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         auto acquire = [&](uint32_t bytes, uint64_t*& bar) -> uint8_t* {
           const uint32_t s = op % AT_NSLOT;
           mbar_wait(&empty[s], ((op / AT_NSLOT) & 1) ^ 1);
-          mbar_expect_tx(&full[s], bytes);
+          if (p.probe & 4) mbar_arrive(&full[s]); else mbar_expect_tx(&full[s], bytes);
           bar = &full[s];
           ++op;
           return smem + (size_t)s * AT_SLOT;
@@ -209,11 +211,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         auto load_a = [&](const CUtensorMap* m) {          // 128 rows x 64: two 32-float halves, SWIZZLE_128B
           uint64_t* bar;
           uint8_t* dst = acquire(32768u, bar);
+          if (p.probe & 4) return;
           tma_load_4d(m, bar, dst, 0, row0, h, b);
           tma_load_4d(m, bar, dst + 16384, 32, row0, h, b);
         };
         auto load_k = [&](const CUtensorMap* m, int col0) {   // K-major B block: 64 rows x 64 (pair: this CTA's 32 rows)
           uint64_t* bar;
+          if (p.probe & 4) { acquire(0u, bar); return; }
           if (CP) {
             uint8_t* dst = acquire(8192u, bar);
             tma_load_4d(m, bar, dst, 0, col0 + 32 * (int)rank, h, b);
@@ -226,6 +230,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         };
         auto load_mn = [&](const CUtensorMap* m, int col0) {  // MN-major B block: 64 k-rows x 64 (32 x 32 boxes)
           uint64_t* bar;
+          if (p.probe & 4) { acquire(0u, bar); return; }
           if (CP) {                                           // pair: this CTA's 32 output columns (d), all 64 k-rows
             uint8_t* dst = acquire(8192u, bar);
 #pragma unroll
@@ -409,8 +414,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       mbar_wait(&full[s], (op / AT_NSLOT) & 1);
       ++op;
       const uint32_t raw = smem_u32(smem + (size_t)s * AT_SLOT) + tid * 16;
+      const int n_vec = (p.probe & 1) ? 0 : (CP ? 4 : 8);
 #pragma unroll
-      for (int i = 0; i < (CP ? 4 : 8); ++i) {                // pair: 8 KB raw -> 8 KB lo per CTA
+      for (int i = 0; i < 8; ++i) {                           // pair: 8 KB raw -> 8 KB lo per CTA
+        if (i >= n_vec) break;
         const uint4 v = lds128(raw + i * 2048);
         uint4 l;
         l.x = tf32_lo(v.x, tf32_hi(v.x));
@@ -511,7 +518,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         AT_T(x1);
         AT_ACC(0, x0, x1);
         tc_fence_after();
-        if (MODE == AT_FWD) {
+        if (p.probe & 2) {
+          if (HAS2) mbar_wait(y_full, g & 1);
+          tc_fence_before();
+          arrive_leader(&z_full[bsel]);
+          if (MODE == AT_FWD ? (j >= 1) : (j >= 1 && ((j - 1) & 1))) fold(1.f);
+        } else if (MODE == AT_FWD) {
           uint32_t x[32], lo[32];
           tmem_ld_32x32b_x32(xaddr, x);
           tmem_ld_wait();
@@ -744,6 +756,7 @@ static int launch_pass_impl(const AttnTensor& a1, const AttnTensor& a2, const At
     if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  { const char* pb = getenv("B200AD_ATTN_PROBE"); p.probe = pb ? atoi(pb) : 0; }
   p.row_tiles = (int32_t)ceil_div(ceil_div(p.R, AT_BM), CP ? 2 : 1);      // work units per (batch, head): tiles or tile pairs
   p.nb = (int32_t)ceil_div(p.C, AT_BC);
   const int64_t items = B * H * p.row_tiles;

@@ -27,7 +27,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, 
 }
 
 // mode: 0 = tf32 SS, 1 = tf32 TS, 2 = bf16 SS, 3 = bf16 TS
-template <int mode>
+template <int mode, bool BMN>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc
     const bool bf16 = mode >= 2, ts = mode & 1;
     // idesc: D = f32 (1<<4); A/B format: tf32 = 2, bf16 = 1 at bits 7 / 10; K-major both; N>>3 at 17; M>>4 at 24
     const uint32_t fmt = bf16 ? 1u : 2u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((BMN ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t sa = smem_u32(smem), sb = sa + 16384;
     long long t0 = 0, t1 = 0;
     if (elect_one()) {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc
       uint32_t at[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        bd[k] = make_smem_desc(sb + k * 32, 16, 1024, 2);
+        bd[k] = BMN ? make_smem_desc(sb + k * 1024, 4096, 512, 1) : make_smem_desc(sb + k * 32, 16, 1024, 2);
         ad[k] = make_smem_desc(sa + k * 32, 16, 1024, 2);
         at[k] = tmem_base + 256 + k * 8;
       }
@@ -94,22 +94,26 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 16);
-  cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
-  cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
-  cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
-  cudaFuncSetAttribute(rate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
-  const char* names[4] = {"tf32 SS", "tf32 TS", "bf16 SS", "bf16 TS"};
+  cudaFuncSetAttribute(rate_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  cudaFuncSetAttribute(rate_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  const char* names[6] = {"tf32 SS", "tf32 TS", "bf16 SS", "bf16 TS", "tf32 SS Bmn", "tf32 TS Bmn"};
   const int iters = 4096;
   printf("cycles per tcgen05.mma (M=128, cta_group::1), %d back-to-back MMAs, 148 CTAs\n", iters);
-  printf("%-8s %5s %5s %12s %12s\n", "mode", "N", "nacc", "issue cyc", "total cyc");
-  for (int mode = 0; mode < 4; ++mode)
+  printf("%-12s %5s %5s %12s %12s\n", "mode", "N", "nacc", "issue cyc", "total cyc");
+  for (int mode = 0; mode < 6; ++mode)
     for (int n : {16, 32, 64, 128, 256})
       for (int nacc : {1, 2}) {
         if (nacc * n > 256) continue;
-        if (mode == 0) rate_kernel<0><<<148, 128, 66560>>>(n, iters, nacc, d_out);
-        else if (mode == 1) rate_kernel<1><<<148, 128, 66560>>>(n, iters, nacc, d_out);
-        else if (mode == 2) rate_kernel<2><<<148, 128, 66560>>>(n, iters, nacc, d_out);
-        else rate_kernel<3><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        if (mode == 0) rate_kernel<0, false><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else if (mode == 1) rate_kernel<1, false><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else if (mode == 2) rate_kernel<2, false><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else if (mode == 3) rate_kernel<3, false><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else if (mode == 4) rate_kernel<0, true><<<148, 128, 66560>>>(n, iters, nacc, d_out);
+        else rate_kernel<1, true><<<148, 128, 66560>>>(n, iters, nacc, d_out);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
           printf("%s N=%d: %s\n", names[mode], n, cudaGetErrorString(e));
@@ -117,7 +121,7 @@ int main() {
         }
         long long h[2];
         cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
-        printf("%-8s %5d %5d %12.1f %12.1f\n", names[mode], n, nacc, (double)h[0] / iters, (double)h[1] / iters);
+        printf("%-12s %5d %5d %12.1f %12.1f\n", names[mode], n, nacc, (double)h[0] / iters, (double)h[1] / iters);
       }
   return 0;
 }

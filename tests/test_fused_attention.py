@@ -79,6 +79,31 @@ def test_attn_fwd_bwd_vs_fp64(backend, B, h, Sq, Skv):
     assert_close(np.asarray(dK), dk_ref, rtol=2e-5, atol=2e-6, what="dK")
 
 
+def test_attn_ragged_fuzz(backend):
+    """Seeded random (batch, heads, seq_q, seq_kv) incl. lengths that are not multiples of the 128-row tile or the
+    64-column block, odd tile counts, one-block and many-block rows."""
+    D = _D()
+    rng = np.random.default_rng(77)
+    dk = 64
+    scale = 1.0 / math.sqrt(dk)
+    for _ in range(6):
+        B, h = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+        Sq, Skv = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        q = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+        k = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+        v = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+        do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+        Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+        O, lse = D.attn_fwd(Q, K, V, scale)
+        o_ref, dq_ref, dk_ref, dv_ref = _ref(q, k, v, do, scale)
+        tag = "B=%d h=%d Sq=%d Skv=%d " % (B, h, Sq, Skv)
+        assert_close(np.asarray(O), o_ref, rtol=2e-5, atol=2e-6, what=tag + "O")
+        dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+        assert_close(np.asarray(dV), dv_ref, rtol=2e-5, atol=2e-6, what=tag + "dV")
+        assert_close(np.asarray(dQ), dq_ref, rtol=2e-5, atol=2e-6, what=tag + "dQ")
+        assert_close(np.asarray(dK), dk_ref, rtol=2e-5, atol=2e-6, what=tag + "dK")
+
+
 def test_attn_large_scores_stable(backend):
     """Scores of magnitude ~60 (the regime where the reference's naive exp/sum is still finite in fp64):
     the online softmax must agree with the stable fp64 evaluation."""

@@ -222,6 +222,49 @@ def test_gemm_fp32_all_layouts(backend, M, N, K):
     assert_close(c, 0.5 * ref + 2.0 * c0.astype(np.float32), what="alpha/beta", **tol)
 
 
+def test_gemm_default_path_fuzz(backend):
+    """The DEFAULT precision (fp32-faithful tensor-core path where the shape allows: generation-3 pair kernel for
+    N, M > 128, 1-CTA kernel otherwise, skinny / SIMT kernels for what TMA cannot take) over seeded random shapes,
+    layouts, batch axes and epilogues, vs fp64.  Covers 256-row / 256-column tile tails, split-K, K tails (K % 32),
+    TMA-store clipping, strided head-split batch views."""
+    D, L = _D(), _Lc()
+    rng = np.random.default_rng(20250)
+    cases = [(257, 259, 96), (384, 640, 512), (130, 1000, 72), (1024, 136, 200), (512, 512, 4160), (300, 300, 33 * 32 + 8),
+             (129, 257, 16), (2048, 264, 64)]
+    for _ in range(10):
+        cases.append((int(rng.integers(1, 700)), int(rng.integers(1, 700)), int(rng.integers(1, 1500))))
+    for idx, (M, N, K) in enumerate(cases):
+        ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+        B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+        ref = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+        kind = idx % 4
+        kw, c0 = {}, None
+        if kind == 1:
+            bias = rng.standard_normal(N).astype(np.float32)
+            kw = dict(bias=D.asarray(bias), act=L.ACT_TANH)
+            ref = np.tanh(ref + bias)
+        elif kind == 2:
+            c0 = rng.standard_normal((M, N)).astype(np.float32)
+            kw = dict(out=D.asarray(c0.copy()), alpha=0.5, beta=1.0)
+            ref = 0.5 * ref + c0
+        elif kind == 3:
+            kw = dict(alpha=-2.0)
+            ref = -2.0 * ref
+        got = D.matmul(D.asarray(A), D.asarray(B), trans_a=ta, trans_b=tb, **kw)
+        assert_close(got, ref, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="case %d M=%d N=%d K=%d ta=%d tb=%d kind=%d" % (idx, M, N, K, ta, tb, kind))
+    # batched head-split views (the MultiHeadAttention projections / unfused score products)
+    Bt, h, S, dk = 3, 4, 160, 72
+    x = rng.standard_normal((Bt, S, h * dk)).astype(np.float32)
+    y = rng.standard_normal((Bt, S, h * dk)).astype(np.float32)
+    xh = D.asarray(x).reshape(Bt, S, h, dk).transpose(0, 2, 1, 3)
+    yh = D.asarray(y).reshape(Bt, S, h, dk).transpose(0, 2, 1, 3)
+    got = D.matmul(xh, yh, trans_b=True)
+    xr = x.reshape(Bt, S, h, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    yr = y.reshape(Bt, S, h, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    assert_close(got, xr @ yr.transpose(0, 1, 3, 2), rtol=2e-5, atol=2e-6 * np.sqrt(dk), what="batched head views")
+
+
 @pytest.mark.parametrize("M,N,K,ta,tb", [(256, 512, 256, False, False), (200, 300, 1000, False, True), (64, 256, 784, True, False),
                                          (512, 512, 8192, True, True), (300, 72, 96, False, False)])
 def test_gemm_bf16_variant_stated_tolerance(backend, M, N, K, ta, tb):
