@@ -28,6 +28,7 @@
 //   warps 8-15  row owners (two groups): a thread owns one row and half of the columns: TMEM -> registers ->
 //               softmax / dS -> TMEM (Z hi/lo), fold of its half of OUT_blk, epilogue
 // TMEM (512 columns):  A1 hi/lo [0,128)  |  one-score modes: X0/Zhi0 L0 X1/Zhi1 L1 [128,384) OUT [384,448)
+//                      (one-score modes: a second OUT accumulator at [448,512))
 //                      A2 hi/lo [128,256) | two-score modes: X0/Zlo0 X1/Zlo1 [256,384) Y/Zhi [384,448) OUT [448,512)
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -121,7 +122,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + (size_t)AT_NSLOT * AT_SLOT;   // 32 KB: the output tile, two SWIZZLE_128B halves
-  __shared__ uint64_t bars[3 * AT_NSLOT + 12];
+  __shared__ uint64_t bars[3 * AT_NSLOT + 14];
   __shared__ uint32_t tmem_base_smem;
   // DV / DK: [buffer][lse (64) | D (64)] of the current column block;  FWD: [owner group][row] row-maximum / row-sum
   // exchange between the two owners of a row (the modes never need both, so they share the 1 KB)
@@ -134,9 +135,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
   uint64_t* x_full = a_empty + 2;              // [2] MMA commit -> row owners
   uint64_t* z_full = x_full + 2;               // [2] row owners -> MMA (128 arrivals)
   uint64_t* y_full = z_full + 2;               // [1]
-  uint64_t* out_full = y_full + 1;             // [1] MMA commit -> row owners
-  uint64_t* out_empty = out_full + 1;          // [1] row owners -> MMA (128 arrivals)
+  uint64_t* out_full = y_full + 1;             // [2] MMA commit -> row owners (one-score modes double-buffer the OUT accumulator)
+  uint64_t* out_empty = out_full + 2;          // [2] row owners -> MMA
   uint32_t* tmem_base_slot = &tmem_base_smem;
+  // One-score modes have 64 spare TMEM columns: a second OUT accumulator, so OUT(j) never waits for the fold of
+  // OUT(j-1) (that wait put two mbarrier wake-ups and a TMEM read on the MMA warp's critical path every block).
+  constexpr uint32_t OUT_BUFS = HAS2 ? 1u : 2u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,8 +182,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       mbar_init(&z_full[i], CP ? 16 : 256);       // pair mode: one arrival per owner warp of both CTAs
     }
     mbar_init(y_full, 1);
-    mbar_init(out_full, 1);
-    mbar_init(out_empty, CP ? 16 : 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&out_full[i], 1);
+      mbar_init(&out_empty[i], CP ? 16 : 256);
+    }
     fence_barrier_init();
   }
   if (warp == 1) { if (CP) tmem_alloc2(tmem_base_slot, TMEM_COLS); else tmem_alloc(tmem_base_slot, TMEM_COLS); }
@@ -323,7 +329,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           AT_T(w0);
           mbar_wait(&z_full[g & 1], (g >> 1) & 1);
           AT_T(w1);
-          if (first) mbar_wait(out_empty, (fo & 1) ^ 1);
+          const uint32_t ob = fo % OUT_BUFS, oph = (fo / OUT_BUFS) & 1;   // OUT accumulator buffer and its phase
+          if (first) mbar_wait(&out_empty[ob], oph ^ 1);
           AT_T(w2);
           const uint32_t s = op % AT_NSLOT;
           mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
@@ -334,7 +341,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           ++op;
           tc_fence_after();
           const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 4096, 512, 1);
-          const uint32_t dst = tmem_base + OUT_COL, a_hi = tmem_base + zhi, a_lo = tmem_base + zlo;
+          const uint32_t dst = tmem_base + OUT_COL + ob * 64u, a_hi = tmem_base + zhi, a_lo = tmem_base + zlo;
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
@@ -352,7 +359,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
                        d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN, 1u);
             }
             mma_commit(&empty[s]);
-            if (last) mma_commit(out_full);
+            if (last) mma_commit(&out_full[ob]);
           }
           __syncwarp();
           if (last) ++fo;
@@ -470,13 +477,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       // fold this group's half of OUT_blk into the running total: run = run * a + OUT
       auto fold = [&](float a) {
         AT_T(f0);
-        mbar_wait(out_full, fo & 1);
+        const uint32_t ob = fo % OUT_BUFS, oph = (fo / OUT_BUFS) & 1;
+        mbar_wait(&out_full[ob], oph);
         ++fo;
         AT_T(f1);
         AT_ACC(1, f0, f1);
         tc_fence_after();
         uint32_t o[32];
-        tmem_ld_32x32b_x32(lane_base + OUT_COL + cofs, o);
+        tmem_ld_32x32b_x32(lane_base + OUT_COL + ob * 64u + cofs, o);
         tmem_ld_wait();
 #pragma unroll
         for (int d = 0; d < 32; ++d) {
@@ -484,7 +492,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           else run[d] += __uint_as_float(o[d]);
         }
         tc_fence_before();
-        arrive_leader(out_empty);
+        arrive_leader(&out_empty[ob]);
         AT_T(f2);
         AT_ACC(2, f1, f2);
       };

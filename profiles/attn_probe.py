@@ -17,7 +17,8 @@ def main():
     import torch
     from auto_differentiation_b200 import device as D
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-    timing_only = len(sys.argv) > 1 and sys.argv[1] == "timing"
+    timing_only = len(sys.argv) > 1 and sys.argv[1] in ("timing", "fwdonly")
+    fwd_only = len(sys.argv) > 1 and sys.argv[1] == "fwdonly"
 
     def heads(a):
         B, h, S, dk = a.shape
@@ -64,11 +65,14 @@ def main():
     Q, K, V, dO = (D.DeviceArray(b).reshape(B, S, h, dk).transpose(0, 2, 1, 3) for b in bufs)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     O, lse = D.attn_fwd(Q, K, V, scale)
-    D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    if not fwd_only:
+        D.attn_bwd(Q, K, V, O, dO, lse, scale)
     torch.cuda.synchronize()
     iters = 5
     for name, fn, flops in (("fwd", lambda: D.attn_fwd(Q, K, V, scale), 4.0 * B * h * S * S * dk),
                             ("bwd", lambda: D.attn_bwd(Q, K, V, O, dO, lse, scale), 10.0 * B * h * S * S * dk)):
+        if fwd_only and name == "bwd":
+            continue
         ms = []
         for _ in range(iters):
             flush.zero_()

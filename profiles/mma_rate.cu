@@ -91,6 +91,71 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// Attention-like MMA stream (TS, N = 64): groups of 24 MMAs (3 terms x 8 k-steps) alternating between a "score" group
+// (A = columns 0..127, D = X_b, K-major B) and an "output" group (A = the X_b / L_b columns, D = OUT, MN-major B), with the
+// commits the attention kernel issues (2 per group).  variant: 0 = as described, 1 = no commits inside the loop,
+// 2 = all groups use the same A columns / D (no operand switching), 3 = B operand rotates over 6 smem slots of 32 KB
+__global__ void __launch_bounds__(128, 1) attn_stream_kernel(int variant, int groups, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int g = 0; g < groups; ++g) {
+        const bool outg = (variant != 2) && (g & 1);
+        const uint32_t slot = smem_u32(smem) + (variant == 3 ? (uint32_t)(g % 6) * 32768u : 0u);
+        const uint32_t xb = 128u + (uint32_t)((g >> 1) & 1) * 128u;
+        const uint32_t d = tmem_base + (outg ? 384u : xb);
+        const uint32_t a_hi = tmem_base + (outg ? xb : 0u), a_lo = a_hi + 64u;
+        const uint64_t d0 = outg ? make_smem_desc(slot, 4096, 512, 1) : make_smem_desc(slot, 16, 1024, 2);
+        const uint32_t kstep = outg ? 1024u : 32u;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_tf32_ts(d, (t == 0 ? a_lo : a_hi) + kk * 8,
+                         d0 + (uint64_t)(((t == 1 ? 16384u : 0u) + (kk >> 2) * 8192u + (kk & 3) * kstep) >> 4),
+                         outg ? IDESC_MN : IDESC_K, (t | kk) ? 1u : 0u);
+        }
+        if (variant != 1) {
+          umma_commit(&bars[1 + (g & 1)]);
+          umma_commit(&bars[3]);
+        }
+      }
+      t1 = clock64();
+      umma_commit(&bars[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], 0);
+    const long long t2 = clock64();
+    if (lane == 0 && blockIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 16);
@@ -123,5 +188,18 @@ int main() {
         cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
         printf("%-12s %5d %5d %12.1f %12.1f\n", names[mode], n, nacc, (double)h[0] / iters, (double)h[1] / iters);
       }
+  {
+    cudaFuncSetAttribute(attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 197632);
+    const int groups = 512;
+    const char* vn[4] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots"};
+    for (int v = 0; v < 4; ++v) {
+      attn_stream_kernel<<<148, 128, 197632>>>(v, groups, d_out);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("attn stream: %s\n", cudaGetErrorString(e)); return 1; }
+      long long h[2];
+      cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
+      printf("%-44s issue %.1f  total %.1f cycles per MMA (24 MMAs per group)\n", vn[v], (double)h[0] / (groups * 24), (double)h[1] / (groups * 24));
+    }
+  }
   return 0;
 }
