@@ -688,3 +688,196 @@ class TimeAttention:
         dhs_dec = D.matmul(ds, hs_enc)                           # (N, Td, H)
         D.matmul(ds, hs_dec, trans_a=True, out=dhs_enc, beta=1.0)   # + ds^T @ hs_dec     (AttentionWeight term)
         return dhs_enc, dhs_dec
+
+
+# --------------------------------------------------------------------------------------------------
+# AttentionSeq2seq: encoder / attention decoder / loss composition and its fit loop
+# --------------------------------------------------------------------------------------------------
+def _concat_last(a, b):
+    """np.concatenate((a, b), axis=2) for (N, T, X) device arrays (two strided copies into one buffer)."""
+    N, T, Xa = a.shape
+    Xb = b.shape[2]
+    out = D.empty((N, T, Xa + Xb))
+    D.copy_into_(a, out[:, :, :Xa])
+    D.copy_into_(b, out[:, :, Xa:])
+    return out
+
+
+class Encoder:
+    """TimeEmbedding -> TimeLSTM (reference layers.py:834-863); returns the last hidden state.  `weights`
+    (optional, [embed, wx, wh, b]) replaces the reference's np.random.randn initialisation (:838-841)."""
+
+    def __init__(self, vocab_size, wordvec_size=100, hidden_size=100, weights=None):
+        if isinstance(vocab_size, list):
+            vocab_size = vocab_size[0]
+        if weights is None:
+            weights = [np.random.randn(vocab_size, wordvec_size) / 100,
+                       np.random.randn(wordvec_size, 4 * hidden_size) / np.sqrt(wordvec_size),
+                       np.random.randn(hidden_size, 4 * hidden_size) / np.sqrt(hidden_size),
+                       np.zeros(4 * hidden_size)]
+        w1, w2, w3, b = weights
+        self.layers = [TimeEmbedding(w1), TimeLSTM(w2, w3, b, stateful=False)]
+        self.weights = self.layers[0].weights + self.layers[1].weights
+        self.grads = self.layers[0].grads + self.layers[1].grads
+        self.hs = None
+
+    def forward(self, xs):
+        wordembed, lstm = self.layers
+        hs = lstm.forward(wordembed.forward(xs))
+        self.hs = hs
+        return hs[:, -1, :]
+
+    def backward(self, dh):
+        dhs = D.zeros(self.hs.shape)
+        D.copy_into_(_dev(dh), dhs[:, -1, :])
+        wordembed, lstm = self.layers
+        wordembed.backward(lstm.backward(dhs))
+
+
+class AttentionEncoder(Encoder):
+    """Returns every hidden state (reference layers.py:1159-1168)."""
+
+    def forward(self, xs):
+        return self.layers[1].forward(self.layers[0].forward(xs))
+
+    def backward(self, dhs):
+        dout = self.layers[1].backward(dhs)
+        return self.layers[0].backward(dout)
+
+
+class AttentionDecoder:
+    """TimeEmbedding -> TimeLSTM (stateful, started from the encoder's last state) -> TimeAttention ->
+    concat(context, hidden) -> TimeAffine (reference layers.py:1086-1156)."""
+
+    def __init__(self, vocab_size, wordvec_size, hidden_size, weights=None):
+        if isinstance(vocab_size, list):
+            vocab_size = vocab_size[0]
+        V, Dm, H = vocab_size, wordvec_size, hidden_size
+        if weights is None:
+            rn = np.random.randn
+            weights = [(rn(V, Dm) / 100).astype("f"), (rn(Dm, 4 * H) / np.sqrt(Dm)).astype("f"),
+                       (rn(H, 4 * H) / np.sqrt(H)).astype("f"), np.zeros(4 * H).astype("f"),
+                       (rn(2 * H, V) / np.sqrt(2 * H)).astype("f"), np.zeros(V).astype("f")]
+        embed_W, lstm_Wx, lstm_Wh, lstm_b, affine_W, affine_b = weights
+        self.embed = TimeEmbedding(embed_W)
+        self.lstm = TimeLSTM(lstm_Wx, lstm_Wh, lstm_b, stateful=True)
+        self.attention = TimeAttention()
+        self.affine = TimeAffine(affine_W, affine_b)
+        self.weights, self.grads = [], []
+        for layer in (self.embed, self.lstm, self.attention, self.affine):
+            self.weights += layer.weights
+            self.grads += layer.grads
+
+    def forward(self, xs, enc_hs):
+        enc_hs = _dev(enc_hs)
+        self.lstm.set_state(enc_hs[:, -1].contiguous())                           # :1112-1113
+        dec_hs = self.lstm.forward(self.embed.forward(xs))
+        c = self.attention.forward(enc_hs, dec_hs)
+        return self.affine.forward(_concat_last(c, dec_hs))                       # :1118-1119
+
+    def backward(self, dscore):
+        dout = self.affine.backward(dscore)
+        N, T, H2 = dout.shape
+        H = H2 // 2
+        dc, ddec_hs0 = dout[:, :, :H].contiguous(), dout[:, :, H:]
+        denc_hs, ddec_hs1 = self.attention.backward(dc)
+        ddec_hs = D.binary(L.B_ADD, ddec_hs0.contiguous(), ddec_hs1)
+        dout = self.lstm.backward(ddec_hs)
+        last = denc_hs[:, -1]                                                     # denc_hs[:, -1] += dh   :1133
+        D.copy_into_(D.binary(L.B_ADD, last.contiguous(), self.lstm.dh), last)
+        self.embed.backward(dout)
+        return denc_hs
+
+    def generate(self, enc_hs, start_id, sample_size):
+        enc_hs = _dev(enc_hs)
+        sampled, sample_id = [], start_id
+        self.lstm.set_state(enc_hs[:, -1].contiguous())
+        for _ in range(sample_size):
+            x = np.array([sample_id]).reshape((1, 1))
+            dec_hs = self.lstm.forward(self.embed.forward(x))
+            c = self.attention.forward(enc_hs, dec_hs)
+            score = self.affine.forward(_concat_last(c, dec_hs))
+            sample_id = int(D.argext_flat(score.reshape(-1)))                     # np.argmax(score.flatten())  :1153
+            sampled.append(sample_id)
+        return sampled
+
+
+class AttentionSeq2seq:
+    """Encoder-decoder with dot attention (reference layers.py:1171-1240; Seq2Seq.forward/backward :942-953).
+    `fit(train_questions, train_answer, optimizer=..., max_epoch=..., batch_size=..., max_grad=...)` keeps the
+    reference's loop: forward, backward, global-norm clip (its local clip_grad :1192-1199 — note: no epsilon, unlike
+    layers.clip_grads), optimizer.update.  The clip is one multi-tensor sum-of-squares + one scale launch."""
+
+    def __init__(self, word_id, vocab_size, wordvec_size, hidden_size, weights=None):
+        ew = dw = None
+        if weights is not None:
+            ew, dw = list(weights[:4]), list(weights[4:])
+        self.encoder = AttentionEncoder(vocab_size, wordvec_size, hidden_size, weights=ew)
+        self.decoder = AttentionDecoder(vocab_size, wordvec_size, hidden_size, weights=dw)
+        self.loss_layer = TimeSoftmaxWithLoss()
+        self.weights = self.encoder.weights + self.decoder.weights
+        self.grads = self.encoder.grads + self.decoder.grads
+        self.word_id = word_id
+        self.vocab_size = vocab_size
+        self.wordvec_size = wordvec_size
+        self.hidden_size = hidden_size
+
+    def forward(self, xs, ts):
+        ts = np.asarray(ts)
+        decoder_input, decoder_target = ts[:, :-1], ts[:, 1:]
+        enc_hs = self.encoder.forward(np.asarray(xs))
+        score = self.decoder.forward(decoder_input, enc_hs)
+        return self.loss_layer.forward(score, decoder_target)
+
+    def backward(self, dout=1):
+        dscore = self.loss_layer.backward(dout)
+        denc_hs = self.decoder.backward(dscore)
+        self.encoder.backward(denc_hs)
+
+    def generate(self, question, word_id, size):
+        enc_hs = self.encoder.forward(np.asarray(question))
+        return self.decoder.generate(enc_hs, word_id["_"] if isinstance(word_id, dict) else word_id, size)
+
+    def reset_state(self):
+        self.decoder.lstm.reset_state()
+
+    @staticmethod
+    def clip_grad(grads, max_grad):
+        """fit's local clip (:1192-1199): scale every gradient by max_grad / norm when norm > max_grad."""
+        total = None
+        for g in grads:
+            s = D.sum_axis(D.unary(L.U_SQUARE, g.reshape(-1)))
+            total = s if total is None else D.binary(L.B_ADD, total, s)
+        norm = math.sqrt(float(total))
+        if norm > max_grad:
+            for g in grads:
+                D.axpby_(g, g, 0.0, max_grad / norm)      # g *= max_grad / norm, in place
+        return norm
+
+    def fit(self, train_questions, train_answer, **fit_params):
+        optimizer = fit_params["optimizer"]
+        max_epoch = fit_params["max_epoch"]
+        batch_size = fit_params["batch_size"]
+        max_grad = fit_params.get("max_grad")
+        max_iter = len(train_questions) // batch_size
+        history = []
+        for _ in range(max_epoch):
+            for iters in range(max_iter):
+                bq = train_questions[iters * batch_size:(iters + 1) * batch_size]
+                ba = train_answer[iters * batch_size:(iters + 1) * batch_size]
+                loss = self.forward(bq, ba)
+                self.backward()
+                if max_grad is not None:
+                    self.clip_grad(self.grads, max_grad)
+                optimizer.update(self.weights, self.grads)
+                history.append(loss)
+        return [float(v) for v in history]
+
+    def get_params(self, deep=False):
+        return {"word_id": self.word_id, "vocab_size": self.vocab_size, "wordvec_size": self.wordvec_size,
+                "hidden_size": self.hidden_size}
+
+    def set_params(self, **params):
+        for key, value in params.items():
+            setattr(self, key, value)
+        return self

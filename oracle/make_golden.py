@@ -373,6 +373,31 @@ def gen_attention(L):
     save("attention", **out)
 
 
+def gen_seq2seq(L):
+    """AttentionSeq2seq (layers.py:1171-1181): one forward + backward of the full encoder / attention decoder / loss
+    composition, plus clip + one Adam step as `fit` performs them (:1192-1208)."""
+    np.random.seed(4321)            # the reference draws its initial weights from the global NumPy RNG
+    V, Dm, H = 13, 8, 12
+    m = L.AttentionSeq2seq({}, V, Dm, H)
+    w0 = [np.array(w, dtype=np.float64) for w in m.weights]
+    rng = np.random.default_rng(108)
+    N, Te, Td = 3, 7, 5
+    xs = rng.integers(0, V, (N, Te))
+    ts = rng.integers(0, V, (N, Td + 1))
+    loss = m.forward(xs, ts)
+    m.backward()
+    grads = [np.array(g, dtype=np.float64) for g in m.grads]
+    out = dict(xs=xs, ts=ts, loss=np.float64(loss), n=np.int64(len(w0)), dims=np.array([V, Dm, H]))
+    for i, (w, g) in enumerate(zip(w0, grads)):
+        out["w%d" % i] = w
+        out["g%d" % i] = g
+    # greedy decoding from the trained-for-zero-steps model (AttentionDecoder.generate :1138-1156)
+    m2_question = xs[:1]
+    enc_hs = m.encoder.forward(m2_question)
+    out["generated"] = np.array(m.decoder.generate(enc_hs, 3, 6), dtype=np.int64)
+    save("seq2seq", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found at %s" % ref_loader.REFERENCE_ROOT)
@@ -388,6 +413,7 @@ def main():
     gen_layers(ad, L, U)
     gen_optim(L, U)
     gen_attention(L)
+    gen_seq2seq(L)
 
 
 if __name__ == "__main__":

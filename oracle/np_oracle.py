@@ -628,3 +628,63 @@ def time_attention_backward(hs_enc, hs_dec, weights, dout):                     
         dhs_enc = dhs_enc + dhs
         dhs_dec[:, i, :] = dh
     return dhs_enc, dhs_dec
+
+
+# ======================================================================================================
+# AttentionSeq2seq — layers/layers.py:1086-1208 (encoder, attention decoder, loss; clip_grad + optimizer in fit)
+# ======================================================================================================
+def attention_seq2seq_step(xs, ts, weights):
+    """One forward + backward of AttentionSeq2seq (:942-953 through AttentionEncoder :1159-1168 and AttentionDecoder
+    :1111-1136).  weights = [enc_embed, enc_wx, enc_wh, enc_b, dec_embed, dec_wx, dec_wh, dec_b, affine_W, affine_b]
+    (the order of model.weights, :1175).  Returns (loss, grads in the same order)."""
+    e_emb, e_wx, e_wh, e_b, d_emb, d_wx, d_wh, d_b, a_W, a_b = weights
+    dec_in, dec_tgt = ts[:, :-1], ts[:, 1:]                                        # :943
+    # encoder (:1160-1163)
+    e_x = embedding_forward(e_emb, xs)
+    enc_hs, e_caches, _, _ = time_lstm_forward(e_x, e_wx, e_wh, e_b)
+    # decoder (:1111-1121): the decoder LSTM starts from the encoder's last hidden state, cell state zero
+    d_x = embedding_forward(d_emb, dec_in)
+    dec_hs, d_caches, _, _ = time_lstm_forward(d_x, d_wx, d_wh, d_b, h0=enc_hs[:, -1])
+    c, att_w = time_attention_forward(enc_hs, dec_hs)
+    cat = np.concatenate((c, dec_hs), axis=2)
+    score = time_affine_forward(cat, a_W, a_b)
+    loss, lcache = time_softmax_with_loss_forward(score, dec_tgt)                   # :946
+    # backward (:950-952, :1123-1136)
+    dscore = time_softmax_with_loss_backward(lcache, 1)
+    dcat, g_aW, g_ab = time_affine_backward(cat, a_W, dscore)
+    H = dec_hs.shape[2]
+    dc, ddec0 = dcat[:, :, :H], dcat[:, :, H:]
+    denc_hs, ddec1 = time_attention_backward(enc_hs, dec_hs, att_w, dc)
+    d_dx, d_grads, dh0 = time_lstm_backward(d_caches, d_wx, d_wh, ddec0 + ddec1)
+    denc_hs = denc_hs.copy()
+    denc_hs[:, -1] += dh0                                                          # :1133
+    g_demb = time_embedding_backward(d_emb.shape, dec_in, d_dx)
+    e_dx, e_grads, _ = time_lstm_backward(e_caches, e_wx, e_wh, denc_hs)           # :1165-1167
+    g_eemb = time_embedding_backward(e_emb.shape, xs, e_dx)
+    return loss, [g_eemb, e_grads[0], e_grads[1], e_grads[2], g_demb, d_grads[0], d_grads[1], d_grads[2], g_aW, g_ab]
+
+
+def seq2seq_clip_grad(grads, max_grad):                                           # fit's local clip_grad :1192-1199
+    total = 0.0
+    for g in grads:
+        total += np.sum(g ** 2)
+    norm = np.sqrt(total)
+    if norm > max_grad:
+        for g in grads:
+            g *= max_grad / norm
+    return norm
+
+
+def attention_seq2seq_generate(question, weights, start_id, sample_size):         # :955-958 + AttentionDecoder.generate :1138-1156
+    e_emb, e_wx, e_wh, e_b, d_emb, d_wx, d_wh, d_b, a_W, a_b = weights
+    enc_hs, _, _, _ = time_lstm_forward(embedding_forward(e_emb, question), e_wx, e_wh, e_b)
+    h, cst = enc_hs[:, -1], None
+    sampled, sid = [], start_id
+    for _ in range(sample_size):
+        x = np.array([sid]).reshape(1, 1)
+        dec_hs, _, h, cst = time_lstm_forward(embedding_forward(d_emb, x), d_wx, d_wh, d_b, h0=h, c0=cst)
+        c, _ = time_attention_forward(enc_hs, dec_hs)
+        score = time_affine_forward(np.concatenate((c, dec_hs), axis=2), a_W, a_b)
+        sid = int(np.argmax(score.flatten()))
+        sampled.append(sid)
+    return sampled
