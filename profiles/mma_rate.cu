@@ -94,8 +94,11 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int nacc
 // Attention-like MMA stream (TS, N = 64): groups of 24 MMAs (3 terms x 8 k-steps) alternating between a "score" group
 // (A = columns 0..127, D = X_b, K-major B) and an "output" group (A = the X_b / L_b columns, D = OUT, MN-major B), with the
 // commits the attention kernel issues (2 per group).  variant: 0 = as described, 1 = no commits inside the loop,
-// 2 = all groups use the same A columns / D (no operand switching), 3 = B operand rotates over 6 smem slots of 32 KB
-__global__ void __launch_bounds__(128, 1) attn_stream_kernel(int variant, int groups, long long* out) {
+// 2 = all groups use the same A columns / D (no operand switching), 3 = B operand rotates over 6 smem slots of 32 KB,
+// 4 / 5 / 6 = variant 0 while four other warps stream tcgen05.ld / tcgen05.st / both on TMEM columns the MMAs do not touch
+__global__ void __launch_bounds__(160, 1) attn_stream_kernel(int variant, int groups, long long* out) {
+  __shared__ volatile int done_flag;
+  if (threadIdx.x == 0) done_flag = 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bars[4];
@@ -145,10 +148,22 @@ __global__ void __launch_bounds__(128, 1) attn_stream_kernel(int variant, int gr
     __syncwarp();
     mbar_wait(&bars[0], 0);
     const long long t2 = clock64();
+    done_flag = 1;
     if (lane == 0 && blockIdx.x == 0) {
       out[0] = t1 - t0;
       out[1] = t2 - t0;
     }
+  } else if (variant >= 4) {
+    // thread-side TMEM traffic on columns [448, 512) (not used by the MMA stream)
+    const uint32_t addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 448u;
+    uint32_t x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = i;
+    while (!done_flag) {
+      if (variant == 4 || variant == 6) { tmem_ld_32x32b_x32(addr, x); tmem_ld_wait(); }
+      if (variant == 5 || variant == 6) { tmem_st_32x32b_x32(addr + 32, x); tmem_st_wait(); }
+    }
+    if (x[3] == 0x12345678u) out[2] = 1;
   }
   tc_fence_before();
   __syncthreads();
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(128, 1) attn_stream_kernel(int variant, int gr
 
 int main() {
   long long* d_out;
-  cudaMalloc(&d_out, 16);
+  cudaMalloc(&d_out, 64);
   cudaFuncSetAttribute(rate_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
   cudaFuncSetAttribute(rate_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
   cudaFuncSetAttribute(rate_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
@@ -191,9 +206,10 @@ int main() {
   {
     cudaFuncSetAttribute(attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 197632);
     const int groups = 512;
-    const char* vn[4] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots"};
-    for (int v = 0; v < 4; ++v) {
-      attn_stream_kernel<<<148, 128, 197632>>>(v, groups, d_out);
+    const char* vn[7] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots",
+                         "... + 4 warps streaming tcgen05.ld", "... + 4 warps streaming tcgen05.st", "... + 4 warps streaming ld + st"};
+    for (int v = 0; v < 7; ++v) {
+      attn_stream_kernel<<<148, 160, 197632>>>(v, groups, d_out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("attn stream: %s\n", cudaGetErrorString(e)); return 1; }
       long long h[2];
