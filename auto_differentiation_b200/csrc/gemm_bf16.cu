@@ -216,7 +216,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         const int n_col0 = n_tile * BN + hf * 128 + g * 32;
         if (n_col0 < p.n && m_row0 < p.m) {                  // warp-uniform
-          if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -266,7 +266,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (p.tma_store) {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {          // the same (lowest) lane every time: bulk groups are per thread
               asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_c),
                            "r"(stg), "r"(n_col0), "r"(m_row0), "r"(c2), "r"(c3)
                            : "memory");
@@ -276,7 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();

@@ -1103,7 +1103,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int c0 = 0; c0 < 128; c0 += 32) {
         const int n_col0 = n_tile * BN + hf * 128 + c0;
         if (n_col0 < p.n && m_row0 < p.m && !(p.probe & 4)) {            // warp-uniform; probe bit 4 skips the stores
-          if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free
+          if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -1154,7 +1154,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (p.tma_store) {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {          // the same (lowest) lane every time: bulk groups are per thread
               asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_c),
                            "r"(stg), "r"(n_col0), "r"(m_row0), "r"(c2), "r"(c3)
                            : "memory");
@@ -1167,7 +1167,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       t_store += clock64() - q2;
 #endif
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every output tile has been written
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every output tile has been written
 #ifdef TC3_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 256)
       printf("[tc3] epilogue: total %lld cycles, chunks %u, wait tmem_full %lld, fold %lld, store %lld\n", clock64() - t_start, uit, w_full, t_fold, t_store);
