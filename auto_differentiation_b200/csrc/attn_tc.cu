@@ -272,98 +272,103 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
 #endif
-    // score MMA: D[128 x 64] = A(TMEM, hi at a_col, lo at a_col + 64) . B^T (K-major slot: two 8 KB halves)
-    auto score = [&](uint32_t a_col, uint32_t d_col, uint64_t* done, uint64_t* a_done) {
+    // Measured (profiles/mma_rate.cu): every mbarrier wait / tcgen05.fence of the issuing thread travels through the same
+    // in-order queue as the MMAs; with 32-cycle N = 64 MMAs the queue drains during each such round trip (~250-340
+    // cycles).  So the role has ONE synchronisation point per block: all waits of the block's MMA groups first
+    // (Z, the OUT accumulator, and the operand slots of OUT(j-1), Y(j) and X(j+1)), one fence, then every MMA of the
+    // block back to back inside one elected region.  The ring order (= consumption order) is unchanged.
+    auto wait_slot = [&]() -> uint32_t {                       // next ring slot: converted operand (or A tile) is in place
       const uint32_t s = op % AT_NSLOT;
       AT_T(w0);
       mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
       AT_T(w1);
       AT_ACC(0, w0, w1);
       ++op;
-      tc_fence_after();
-      if (elect_one()) {
-        // descriptor of the slot base; each MMA adds a compile-time byte offset (>> 4) to the address field
-        const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 16, 1024, 2);
-        const uint32_t dst = tmem_base + d_col, a_hi = tmem_base + a_col, a_lo = a_hi + 64u;
+      return s;
+    };
+    // score MMAs: D[128 x 64] = A(TMEM, hi at a_col, lo at a_col + 64) . B^T (K-major slot: two k halves); ELECTED thread
+    auto issue_score = [&](uint32_t s, uint32_t a_col, uint32_t d_col, uint64_t* done, uint64_t* a_done) {
+      const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 16, 1024, 2);
+      const uint32_t dst = tmem_base + d_col, a_hi = tmem_base + a_col, a_lo = a_hi + 64u;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
+      for (int t = 0; t < 3; ++t) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            mma_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
-                   d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 32u) >> 4), IDESC_K, (t | kk) ? 1u : 0u);
-        }
-        mma_commit(&empty[s]);
-        mma_commit(done);
-        if (a_done) mma_commit(a_done);
+        for (int kk = 0; kk < 8; ++kk)
+          mma_ts(dst, (t == 0 ? a_lo : a_hi) + kk * 8,
+                 d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 32u) >> 4), IDESC_K, (t | kk) ? 1u : 0u);
       }
-      __syncwarp();
+      mma_commit(&empty[s]);
+      mma_commit(done);
+      if (a_done) mma_commit(a_done);
     };
     for (int item = unit_id; item < p.total_items; item += units, ++it) {
-      // the A tiles' ring slots: the converter signals "hi/lo in TMEM" on the slot's conv barrier
-      const uint32_t s_a1 = op % AT_NSLOT, ph_a1 = (op / AT_NSLOT) & 1;
-      ++op;
-      const uint32_t s_a2 = op % AT_NSLOT, ph_a2 = (op / AT_NSLOT) & 1;
-      if (HAS2) ++op;
-      mbar_wait(&conv[s_a1], ph_a1);
-      tc_fence_after();
-      score(A1_COL, X_COL0 + (gb & 1) * X_STRIDE, &x_full[gb & 1], nb == 1 ? &a_empty[0] : nullptr);
-      if (HAS2) {
-        mbar_wait(&conv[s_a2], ph_a2);
+      // prologue of the item: X(0) [, Y(0)] and X(1); the A tiles' ring slots are consumed by the converter, which
+      // signals "hi/lo in TMEM" on the slot's conv barrier
+      {
+        const uint32_t s_a1 = wait_slot();
+        (void)s_a1;
+        uint32_t s_a2 = 0;
+        if (HAS2) s_a2 = wait_slot();
+        (void)s_a2;
+        const uint32_t s_x0 = wait_slot();
+        uint32_t s_y0 = 0, s_x1 = 0;
+        if (HAS2) s_y0 = wait_slot();
+        if (nb > 1) s_x1 = wait_slot();
         tc_fence_after();
-        score(A2_COL, Y_COL, y_full, nb == 1 ? &a_empty[1] : nullptr);
+        if (elect_one()) {
+          issue_score(s_x0, A1_COL, X_COL0 + (gb & 1) * X_STRIDE, &x_full[gb & 1], nb == 1 ? &a_empty[0] : nullptr);
+          if (HAS2) issue_score(s_y0, A2_COL, Y_COL, y_full, nb == 1 ? &a_empty[1] : nullptr);
+          if (nb > 1) issue_score(s_x1, A1_COL, X_COL0 + ((gb + 1) & 1) * X_STRIDE, &x_full[(gb + 1) & 1], nb == 2 ? &a_empty[0] : nullptr);
+        }
+        __syncwarp();
       }
       for (int j = 1; j <= nb; ++j) {
-        if (j < nb) {
-          const uint32_t g = gb + j;
-          score(A1_COL, X_COL0 + (g & 1) * X_STRIDE, &x_full[g & 1], j == nb - 1 ? &a_empty[0] : nullptr);
-        }
-        {
-          // OUT_blk (+)= Z(g) . B3(g): Z hi/lo from TMEM, B3 MN-major from the slot.  The backward modes chain two
-          // blocks (128 K-elements) per accumulator before the row owners fold it; the lo term (which reads the Y
-          // columns in the two-score modes) goes first so that Y(j) can overwrite them while the hi terms run.
-          const uint32_t g = gb + j - 1;
-          const uint32_t xb = X_COL0 + (g & 1) * X_STRIDE;
-          const uint32_t zhi = xb, zlo = HAS2 ? Y_COL : xb + 64u;
-          const bool first = !PAIR || ((j - 1) & 1) == 0;
-          const bool last = !PAIR || ((j - 1) & 1) == 1 || j == nb;
-          AT_T(w0);
-          mbar_wait(&z_full[g & 1], (g >> 1) & 1);
-          AT_T(w1);
-          const uint32_t ob = fo % OUT_BUFS, oph = (fo / OUT_BUFS) & 1;   // OUT accumulator buffer and its phase
-          if (first) mbar_wait(&out_empty[ob], oph ^ 1);
-          AT_T(w2);
-          const uint32_t s = op % AT_NSLOT;
-          mbar_wait(&conv[s], (op / AT_NSLOT) & 1);
-          AT_T(w3);
-          AT_ACC(1, w0, w1);
-          AT_ACC(2, w1, w2);
-          AT_ACC(0, w2, w3);
-          ++op;
-          tc_fence_after();
-          const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s * AT_SLOT), 4096, 512, 1);
+        // block j-1 closes: OUT_blk (+)= Z(g) . B3(g) with Z hi/lo from TMEM and B3 MN-major from its slot; the backward
+        // modes chain two blocks (128 K-elements) per accumulator before the row owners fold it; in the two-score
+        // modes the lo term (which reads the Y columns) goes first so that Y(j) can overwrite them while the hi terms
+        // run.  X(j+1) follows in the same issue burst.
+        const uint32_t g = gb + j - 1;
+        const uint32_t xb = X_COL0 + (g & 1) * X_STRIDE;
+        const uint32_t zhi = xb, zlo = HAS2 ? Y_COL : xb + 64u;
+        const bool first = !PAIR || ((j - 1) & 1) == 0;
+        const bool last = !PAIR || ((j - 1) & 1) == 1 || j == nb;
+        const uint32_t ob = fo % OUT_BUFS, oph = (fo / OUT_BUFS) & 1;   // OUT accumulator buffer and its phase
+        AT_T(w0);
+        mbar_wait(&z_full[g & 1], (g >> 1) & 1);
+        AT_T(w1);
+        if (first) mbar_wait(&out_empty[ob], oph ^ 1);
+        AT_T(w2);
+        AT_ACC(1, w0, w1);
+        AT_ACC(2, w1, w2);
+        const uint32_t s_o = wait_slot();                                // B3(j-1)
+        uint32_t s_y = 0, s_x = 0;
+        if (HAS2 && j < nb) s_y = wait_slot();                           // B2(j)
+        if (j + 1 < nb) s_x = wait_slot();                               // B1(j+1)
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t d0 = make_smem_desc(smem_u32(smem + (size_t)s_o * AT_SLOT), 4096, 512, 1);
           const uint32_t dst = tmem_base + OUT_COL + ob * 64u, a_hi = tmem_base + zhi, a_lo = tmem_base + zlo;
-          if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts(dst, a_lo + kk * 8, d0 + (uint64_t)(((kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN,
+                   (kk || !first) ? 1u : 0u);
+          if (HAS2 && j < nb) issue_score(s_y, A2_COL, Y_COL, y_full, j == nb - 1 ? &a_empty[1] : nullptr);
+#pragma unroll
+          for (int t = 1; t < 3; ++t) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
-              mma_ts(dst, a_lo + kk * 8, d0 + (uint64_t)(((kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN,
-                     (kk || !first) ? 1u : 0u);
+              mma_ts(dst, a_hi + kk * 8,
+                     d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN, 1u);
           }
-          __syncwarp();
-          if (HAS2 && j < nb) score(A2_COL, Y_COL, y_full, j == nb - 1 ? &a_empty[1] : nullptr);
-          if (elect_one()) {
-#pragma unroll
-            for (int t = 1; t < 3; ++t) {
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk)
-                mma_ts(dst, a_hi + kk * 8,
-                       d0 + (uint64_t)(((t == 1 ? LO_OFF : 0u) + (kk >> 2) * KHALF + (kk & 3) * 1024u) >> 4), IDESC_MN, 1u);
-            }
-            mma_commit(&empty[s]);
-            if (last) mma_commit(&out_full[ob]);
+          mma_commit(&empty[s_o]);
+          if (last) mma_commit(&out_full[ob]);
+          if (j + 1 < nb) {
+            const uint32_t gx = gb + j + 1;
+            issue_score(s_x, A1_COL, X_COL0 + (gx & 1) * X_STRIDE, &x_full[gx & 1], j + 1 == nb - 1 ? &a_empty[0] : nullptr);
           }
-          __syncwarp();
-          if (last) ++fo;
         }
+        __syncwarp();
+        if (last) ++fo;
       }
       gb += nb;
     }

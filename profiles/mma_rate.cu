@@ -102,11 +102,13 @@ __global__ void __launch_bounds__(160, 1) attn_stream_kernel(int variant, int gr
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bars[4];
+  __shared__ uint64_t dummy[3];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&dummy[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -119,6 +121,155 @@ __global__ void __launch_bounds__(160, 1) attn_stream_kernel(int variant, int gr
     constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
     long long t0 = 0, t1 = 0;
+    if (variant == 7) {
+      // the kernel's MMA-role structure: the whole warp loops; per group three waits on (already completed) barriers,
+      // a fence, an elected issue block and a warp sync
+      if (lane == 0) { mbar_arrive(&bars[1]); mbar_arrive(&bars[2]); mbar_arrive(&bars[3]); }   // complete phase 0
+      __syncwarp();
+      t0 = clock64();
+      for (int g = 0; g < groups; ++g) {
+        const bool outg = (g & 1);
+        mbar_wait(&bars[1], 0);
+        mbar_wait(&bars[2], 0);
+        mbar_wait(&bars[3], 0);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t slot = smem_u32(smem) + (uint32_t)(g % 6) * 32768u;
+          const uint32_t xb = 128u + (uint32_t)((g >> 1) & 1) * 128u;
+          const uint32_t d = tmem_base + (outg ? 384u : xb);
+          const uint32_t a_hi = tmem_base + (outg ? xb : 0u), a_lo = a_hi + 64u;
+          const uint64_t d0 = outg ? make_smem_desc(slot, 4096, 512, 1) : make_smem_desc(slot, 16, 1024, 2);
+          const uint32_t kstep = outg ? 1024u : 32u;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_tf32_ts(d, (t == 0 ? a_lo : a_hi) + kk * 8,
+                           d0 + (uint64_t)(((t == 1 ? 16384u : 0u) + (kk >> 2) * 8192u + (kk & 3) * kstep) >> 4),
+                           outg ? IDESC_MN : IDESC_K, (t | kk) ? 1u : 0u);
+          }
+          // commits to barriers nobody waits on (separate from the ones polled above)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[g & 1])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[2])) : "memory");
+        }
+        __syncwarp();
+      }
+      t1 = clock64();
+      if (elect_one()) umma_commit(&bars[0]);
+    } else if (variant == 8 || variant == 9) {
+      // one elected thread runs the whole role, waits included (9: only one wait per group)
+      if (lane == 0) { mbar_arrive(&bars[1]); mbar_arrive(&bars[2]); mbar_arrive(&bars[3]); }
+      __syncwarp();
+      if (elect_one()) {
+        t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+          const bool outg = (g & 1);
+          mbar_wait(&bars[1], 0);
+          if (variant == 8) { mbar_wait(&bars[2], 0); mbar_wait(&bars[3], 0); }
+          tc_fence_after();
+          const uint32_t slot = smem_u32(smem) + (uint32_t)(g % 6) * 32768u;
+          const uint32_t xb = 128u + (uint32_t)((g >> 1) & 1) * 128u;
+          const uint32_t d = tmem_base + (outg ? 384u : xb);
+          const uint32_t a_hi = tmem_base + (outg ? xb : 0u), a_lo = a_hi + 64u;
+          const uint64_t d0 = outg ? make_smem_desc(slot, 4096, 512, 1) : make_smem_desc(slot, 16, 1024, 2);
+          const uint32_t kstep = outg ? 1024u : 32u;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_tf32_ts(d, (t == 0 ? a_lo : a_hi) + kk * 8,
+                           d0 + (uint64_t)(((t == 1 ? 16384u : 0u) + (kk >> 2) * 8192u + (kk & 3) * kstep) >> 4),
+                           outg ? IDESC_MN : IDESC_K, (t | kk) ? 1u : 0u);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[g & 1])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[2])) : "memory");
+        }
+        t1 = clock64();
+        umma_commit(&bars[0]);
+      }
+    } else if (variant >= 13 && variant <= 16) {
+      // one elected thread; 13: 3 x test_wait + fence, 14: 3 x try_wait, no fence, 15: fence only, 16: 3 x test_wait, no fence
+      if (lane == 0) { mbar_arrive(&bars[1]); mbar_arrive(&bars[2]); mbar_arrive(&bars[3]); }
+      __syncwarp();
+      if (elect_one()) {
+        t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+          const bool outg = (g & 1);
+          if (variant == 13 || variant == 16) {
+#pragma unroll
+            for (int b = 1; b <= 3; ++b) {
+              uint32_t ok;
+              do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bars[b])), "r"(0) : "memory");
+              } while (!ok);
+            }
+          }
+          if (variant == 14) { mbar_wait(&bars[1], 0); mbar_wait(&bars[2], 0); mbar_wait(&bars[3], 0); }
+          if (variant == 13 || variant == 15) tc_fence_after();
+          const uint32_t slot = smem_u32(smem) + (uint32_t)(g % 6) * 32768u;
+          const uint32_t xb = 128u + (uint32_t)((g >> 1) & 1) * 128u;
+          const uint32_t d = tmem_base + (outg ? 384u : xb);
+          const uint32_t a_hi = tmem_base + (outg ? xb : 0u), a_lo = a_hi + 64u;
+          const uint64_t d0 = outg ? make_smem_desc(slot, 4096, 512, 1) : make_smem_desc(slot, 16, 1024, 2);
+          const uint32_t kstep = outg ? 1024u : 32u;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_tf32_ts(d, (t == 0 ? a_lo : a_hi) + kk * 8,
+                           d0 + (uint64_t)(((t == 1 ? 16384u : 0u) + (kk >> 2) * 8192u + (kk & 3) * kstep) >> 4),
+                           outg ? IDESC_MN : IDESC_K, (t | kk) ? 1u : 0u);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[g & 1])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[2])) : "memory");
+        }
+        t1 = clock64();
+        umma_commit(&bars[0]);
+      }
+    } else if (variant >= 10 && variant <= 12) {
+      // warp-wide loop; 10: waits only (no tcgen05.fence), 11: fence only (no waits),
+      // 12: the next group's waits + fence are done BEFORE the last 8 MMAs of the current group are issued
+      if (lane == 0) { mbar_arrive(&bars[1]); mbar_arrive(&bars[2]); mbar_arrive(&bars[3]); }
+      __syncwarp();
+      t0 = clock64();
+      for (int g = 0; g < groups; ++g) {
+        const bool outg = (g & 1);
+        if (variant == 10 || (variant == 12 && g == 0)) { mbar_wait(&bars[1], 0); mbar_wait(&bars[2], 0); mbar_wait(&bars[3], 0); }
+        if (variant == 11 || (variant == 12 && g == 0)) tc_fence_after();
+        const uint32_t slot = smem_u32(smem) + (uint32_t)(g % 6) * 32768u;
+        const uint32_t xb = 128u + (uint32_t)((g >> 1) & 1) * 128u;
+        const uint32_t d = tmem_base + (outg ? 384u : xb);
+        const uint32_t a_hi = tmem_base + (outg ? xb : 0u), a_lo = a_hi + 64u;
+        const uint64_t d0 = outg ? make_smem_desc(slot, 4096, 512, 1) : make_smem_desc(slot, 16, 1024, 2);
+        const uint32_t kstep = outg ? 1024u : 32u;
+        if (elect_one()) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_tf32_ts(d, (t == 0 ? a_lo : a_hi) + kk * 8,
+                           d0 + (uint64_t)(((t == 1 ? 16384u : 0u) + (kk >> 2) * 8192u + (kk & 3) * kstep) >> 4),
+                           outg ? IDESC_MN : IDESC_K, (t | kk) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (variant == 12) {      // prefetch the next group's synchronisation while 16 MMAs are queued
+          mbar_wait(&bars[1], 0); mbar_wait(&bars[2], 0); mbar_wait(&bars[3], 0);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_tf32_ts(d, a_hi + kk * 8, d0 + (uint64_t)(((kk >> 2) * 8192u + (kk & 3) * kstep) >> 4), outg ? IDESC_MN : IDESC_K, 1u);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[g & 1])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[2])) : "memory");
+        }
+        __syncwarp();
+      }
+      t1 = clock64();
+      if (elect_one()) umma_commit(&bars[0]);
+    } else
     if (elect_one()) {
       t0 = clock64();
       for (int g = 0; g < groups; ++g) {
@@ -206,9 +357,12 @@ int main() {
   {
     cudaFuncSetAttribute(attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 197632);
     const int groups = 512;
-    const char* vn[7] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots",
-                         "... + 4 warps streaming tcgen05.ld", "... + 4 warps streaming tcgen05.st", "... + 4 warps streaming ld + st"};
-    for (int v = 0; v < 7; ++v) {
+    const char* vn[17] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots",
+                         "... + 4 warps streaming tcgen05.ld", "... + 4 warps streaming tcgen05.st", "... + 4 warps streaming ld + st", "kernel-like role: warp loop, 3 waits + elect + syncwarp per group",
+                         "one elected thread runs the role (3 waits per group)", "one elected thread, 1 wait per group",
+                         "warp loop: 3 waits, no tcgen05.fence", "warp loop: fence only", "warp loop: next group's waits + fence before the last 8 MMAs",
+                         "one thread: 3 x test_wait + fence", "one thread: 3 x try_wait, no fence", "one thread: fence only", "one thread: 3 x test_wait, no fence"};
+    for (int v = 0; v < 17; ++v) {
       attn_stream_kernel<<<148, 160, 197632>>>(v, groups, d_out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("attn stream: %s\n", cudaGetErrorString(e)); return 1; }
