@@ -313,6 +313,34 @@ def test_gemm_skinny_recurrent_step(backend, M, N, K, tb, act, beta):
     assert np.array_equal(got[:, 0, :], C0[:, 0, :]) and np.array_equal(got[:, 2, :], C0[:, 2, :])
 
 
+@pytest.mark.parametrize("M,N,K,prec", [(300, 260, 96, None), (300, 260, 96, "bf16"), (130, 520, 40, None), (100, 100, 64, None),
+                                        (33, 512, 256, None), (513, 300, 4128, None)])
+@pytest.mark.parametrize("col_off", [4, 3])
+def test_gemm_output_guards(backend, M, N, K, prec, col_off):
+    """C is a window of a larger buffer filled with a sentinel: rows above / below and columns left / right of the window
+    must stay untouched (TMA-store clipping for 16 B-aligned windows, guarded direct stores otherwise), for the pair,
+    1-CTA, skinny and bf16 kernels and for split-K."""
+    D = _D()
+    rng = np.random.default_rng(M + N + K + col_off)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    pad = 8
+    big = np.full((M + 2, N + 2 * pad), 7.25, dtype=np.float32)
+    buf = D.asarray(big.copy())
+    out = buf[1:1 + M, col_off:col_off + N]
+    kw = {} if prec is None else dict(precision=prec)
+    D.matmul(D.asarray(A), D.asarray(B), out=out, **kw)
+    got = np.asarray(buf)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    if prec == "bf16":
+        assert np.all(np.abs(got[1:1 + M, col_off:col_off + N] - ref) <= 2.0 ** -7 * (np.abs(A).astype(np.float64) @ np.abs(B)) + 1e-6)
+    else:
+        assert_close(got[1:1 + M, col_off:col_off + N], ref, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="window")
+    mask = np.ones_like(big, dtype=bool)
+    mask[1:1 + M, col_off:col_off + N] = False
+    assert np.all(got[mask] == 7.25), "GEMM wrote outside its output window"
+
+
 def test_gemm_batched_strided_views(backend):
     D = _D()
     rng = np.random.default_rng(16)
