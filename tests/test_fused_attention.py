@@ -104,6 +104,56 @@ def test_attn_ragged_fuzz(backend):
         assert_close(np.asarray(dK), dk_ref, rtol=2e-5, atol=2e-6, what=tag + "dK")
 
 
+@pytest.mark.parametrize("Sq,Skv", [(100, 77), (128, 64), (300, 200)])
+def test_attn_output_guards(backend, Sq, Skv):
+    """Outputs are windows (rows 1..S) of sentinel-filled buffers: the rows before / after every (batch) window, the lse
+    neighbours and the bwd workspace neighbours must stay untouched (TMA-store clipping of ragged tiles)."""
+    import ctypes
+    D = _D()
+    from auto_differentiation_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(Sq * 3 + Skv)
+    B, h, dk = 2, 3, 64
+    scale = 1.0 / math.sqrt(dk)
+    SENT = 3.5
+
+    def window(S, data=None):
+        """(B, S+2, h, dk) buffer; returns (buffer, head-split view of rows 1..S)."""
+        host = np.full((B, S + 2, h, dk), SENT, dtype=np.float32)
+        if data is not None:
+            host[:, 1:S + 1] = data.transpose(0, 2, 1, 3)
+        buf = D.asarray(host)
+        return buf, buf[:, 1:S + 1].transpose(0, 2, 1, 3)
+
+    q = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    k = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+    v = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+    do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    (_, Q), (_, K), (_, V), (_, dO) = window(Sq, q), window(Skv, k), window(Skv, v), window(Sq, do)
+    obuf, O = window(Sq)
+    n_lse = B * h * Sq
+    lse = D.asarray(np.full(n_lse + 16, SENT, dtype=np.float32))
+    d = D._attn_desc(Q, K, V, O, scale)
+    s = D.stream_ptr()
+    L.check(lib.b200ad_attn_fwd(ctypes.byref(d), Q.ptr, K.ptr, V.ptr, O.ptr, lse.ptr + 32, s))
+    o_ref, dq_ref, dk_ref, dv_ref = _ref(q, k, v, do, scale)
+    og = np.asarray(obuf)
+    assert_close(og[:, 1:Sq + 1].transpose(0, 2, 1, 3), o_ref, rtol=2e-5, atol=2e-6, what="O window")
+    assert np.all(og[:, 0] == SENT) and np.all(og[:, Sq + 1] == SENT), "attention forward wrote outside its rows"
+    lg = np.asarray(lse)
+    assert np.all(lg[:8] == SENT) and np.all(lg[8 + n_lse:] == SENT), "lse written out of range"
+    (qb, dQ), (kb, dK), (vb, dV) = window(Sq), window(Skv), window(Skv)
+    ws = D.asarray(np.full(n_lse + 16, SENT, dtype=np.float32))
+    L.check(lib.b200ad_attn_bwd(ctypes.byref(d), Q.ptr, K.ptr, V.ptr, O.ptr, dO.ptr, lse.ptr + 32, dQ.ptr, dK.ptr, dV.ptr,
+                                ws.ptr + 32, s))
+    for name, buf, S, ref in (("dQ", qb, Sq, dq_ref), ("dK", kb, Skv, dk_ref), ("dV", vb, Skv, dv_ref)):
+        g = np.asarray(buf)
+        assert_close(g[:, 1:S + 1].transpose(0, 2, 1, 3), ref, rtol=2e-5, atol=2e-6, what=name + " window")
+        assert np.all(g[:, 0] == SENT) and np.all(g[:, S + 1] == SENT), name + " written outside its rows"
+    wg = np.asarray(ws)
+    assert np.all(wg[:8] == SENT) and np.all(wg[8 + n_lse:] == SENT), "backward workspace written out of range"
+
+
 def test_attn_large_scores_stable(backend):
     """Scores of magnitude ~60 (the regime where the reference's naive exp/sum is still finite in fp64):
     the online softmax must agree with the stable fp64 evaluation."""
