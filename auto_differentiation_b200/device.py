@@ -28,12 +28,24 @@ def _prod(xs):
 _DEVICE = "cuda"  # where buffers live; the package itself only ever computes on a CUDA device
 
 
+_cuda_ok = [False]
+
+
 def require_cuda():
+    if _cuda_ok[0]:
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("auto_differentiation_b200: no CUDA device — the B200 path has no CPU fallback")
+    _cuda_ok[0] = True        # availability cannot change within a process: skip the (slow) query on every allocation
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (the launch stream of every kernel)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -171,7 +171,7 @@ class AttentionClassifier:
     buckets, overlapped with the tail of the last micro-batch).  Gradients are those of the mean loss
     over `global_batch` rows, so a sum all-reduce over ranks gives the single-process gradient."""
 
-    def __init__(self, d_model=512, heads=8, hidden=256, classes=10, seed=1239, micro_batch=256, reducer=None,
+    def __init__(self, d_model=512, heads=8, hidden=256, classes=10, seed=1239, micro_batch=512, reducer=None,
                  input_grads=True):
         rng = np.random.default_rng(seed)
         d = d_model

@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "bf16", "tf32"])
-    ap.add_argument("--micro-batch", type=int, default=256)
+    ap.add_argument("--micro-batch", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-elems", type=int, default=0, help="c2 sweep: largest size (default 1e9)")
