@@ -7,7 +7,7 @@
 Headline workload (BASELINE.json configs[4], the config the metric "fwd+bwd+update steps/sec at 1/2/4/8
 B200" is quoted on): config 5 — MultiHeadAttention(d=512, 8 heads) on x (B,512,512) -> mean over the sequence
 -> affine 512->256 + tanh -> affine 256->10 -> softmax-CE, Adam, GLOBAL batch 8192 split evenly over the
-ranks (strong scaling), micro-batches of 256 sequences with on-device gradient accumulation, gradient
+ranks (strong scaling), micro-batches of 512 / 256 sequences with on-device gradient accumulation, gradient
 all-reduce over NCCL overlapped with the last micro-batch's backward.  One "step" = forward + backward +
 update over the whole global batch.
 
@@ -323,7 +323,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "bf16", "tf32"])
-    ap.add_argument("--micro-batch", type=int, default=512)
+    ap.add_argument("--micro-batch", type=int, default=0,
+                    help="sequences per micro-batch; 0 = automatic: 512 when a rank holds >= 4096 sequences, else 256 (at least\n"
+                         "four host->device chunks per step so the input stream overlaps the compute)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-elems", type=int, default=0, help="c2 sweep: largest size (default 1e9)")
@@ -332,6 +334,8 @@ def main():
                     help="profiling aid only (ncu captures): the headline number is always quoted at 8192")
     args = ap.parse_args()
     globals()["GLOBAL_BATCH"] = args.global_batch
+    if args.micro_batch <= 0:
+        args.micro_batch = 512 if args.global_batch // max(1, args.gpus) >= 4096 else 256
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c5":
