@@ -46,9 +46,11 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d) {
   if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32) return 0;
   if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_workspace_bytes(g);
-  if (d->precision == B200AD_GEMM_AUTO && d->m <= 64 && d->m >= 1 && d->batch0 * d->batch1 == 1 && !d->trans_a &&
-      d->k >= 256 && d->k <= 2048 && !(d->k & 31) && d->n >= 256 && d->n <= 2048 && !(d->n & 7) && !(d->lda & 3) && !(d->ldb & 3))
-    return 0;   // skinny recurrent-step kernel (pointer alignment is checked at launch; a fallback then runs un-split)
+  if (d->precision == B200AD_GEMM_AUTO && gemm_skinny_supported(g)) {
+    // skinny recurrent-step kernels need no workspace.  (Pointer alignment is part of the check; with the null pointers
+    // of this query it passes, and a misaligned operand at launch time falls back to an un-split tensor-core launch.)
+    return 0;
+  }
   const int prec = d->precision == B200AD_GEMM_AUTO ? B200AD_GEMM_TF32X3 : d->precision;
   return gemm_tc_workspace_bytes(g, prec);
 }

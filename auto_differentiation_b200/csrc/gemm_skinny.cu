@@ -8,6 +8,7 @@
 // RNN step is ONE launch.  Exact fp32 FMA accumulation, deterministic reduction order.
 #include "common.cuh"
 #include "gemm_internal.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 namespace b200ad {
@@ -107,7 +108,116 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const GemmArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cluster variant: a 2-D decomposition (64 output columns x one eighth of K per CTA) with the eight K-partials of a
+// column group reduced through DISTRIBUTED SHARED MEMORY inside a thread-block cluster of 8.  Every operand element
+// is read from L2 exactly once per column group (A: N/64 x, B: once), where the kernel above re-reads the whole A
+// panel in every CTA; the reduction order over the cluster ranks is fixed (deterministic).
+//   grid = 8 * (N / 64) CTAs, cluster (8,1,1): rank = K-slice, blockIdx.x / 8 = column group.  256 threads: 4 x 4 outputs each.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SC_BN = 64, SC_KC = 32, SC_CL = 8;
+
+template <bool TRANS_B>
+__global__ void __cluster_dims__(SC_CL, 1, 1) __launch_bounds__(256) gemm_skinny_cluster_kernel(const GemmArgs g) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ __align__(16) float As[SC_KC][64];          // [k][row]
+  __shared__ __align__(16) float Bs[SC_KC][SC_BN];       // [k][col]
+  __shared__ __align__(16) float part[64][SC_BN];        // this CTA's K-partial of the 64 x 64 output block
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int64_t n0 = (int64_t)(blockIdx.x / SC_CL) * SC_BN;
+  const int M = (int)g.m;
+  const int64_t kslice = g.k / SC_CL, kbeg = (int64_t)rank * kslice;
+  const int ty = tid >> 4, tx = tid & 15;                 // 16 x 16 threads, 4 rows x 4 columns each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = kbeg; k0 < kbeg + kslice; k0 += SC_KC) {
+    // A chunk: 64 rows x 32 k (row-major source, k contiguous): 512 float4, 2 per thread -> As[k][row]
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int v = tid + i * 256;
+      const int row = v >> 3, kq = (v & 7) * 4;
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < M) a4 = __ldg(reinterpret_cast<const float4*>(g.a + (int64_t)row * g.lda + k0 + kq));
+      As[kq][row] = a4.x; As[kq + 1][row] = a4.y; As[kq + 2][row] = a4.z; As[kq + 3][row] = a4.w;
+    }
+    // B chunk: 32 k x 64 columns -> Bs[k][col]
+    if (!TRANS_B) {            // stored (K x N), columns contiguous: 512 float4, 2 per thread
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int v = tid + i * 256;
+        const int kk = v >> 4, cq = (v & 15) * 4;
+        *reinterpret_cast<float4*>(&Bs[kk][cq]) = __ldg(reinterpret_cast<const float4*>(g.b + (k0 + kk) * g.ldb + n0 + cq));
+      }
+    } else {                   // stored (N x K), k contiguous
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int v = tid + i * 256;
+        const int col = v >> 3, kq = (v & 7) * 4;
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.b + (n0 + col) * g.ldb + k0 + kq));
+        Bs[kq][col] = b4.x; Bs[kq + 1][col] = b4.y; Bs[kq + 2][col] = b4.z; Bs[kq + 3][col] = b4.w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SC_KC; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(&part[ty * 4 + i][tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  cluster.sync();                                          // every CTA's partial is visible cluster-wide
+  // CTA `rank` reduces rows [8 rank, 8 rank + 8) x 64 columns over the 8 partials (fixed order) and applies the epilogue
+  {
+    const int row = rank * 8 + (tid >> 5), col = (tid & 31) * 2;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < SC_CL; ++r) {
+      const float* peer = cluster.map_shared_rank(&part[0][0], r);
+      const float2 v = *reinterpret_cast<const float2*>(peer + row * SC_BN + col);
+      s0 += v.x;
+      s1 += v.y;
+    }
+    if (row < M) {
+      float* dst = g.c + (int64_t)row * g.ldc + n0 + col;
+      float v[2] = {g.alpha * s0, g.alpha * s1};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (g.beta != 0.f) v[j] += g.beta * dst[j];
+        if (g.bias) v[j] += __ldg(g.bias + n0 + col + j);
+        if (g.act == 1) v[j] = sk_act<1>(v[j]);
+        else if (g.act == 2) v[j] = sk_act<2>(v[j]);
+        else if (g.act == 3) v[j] = sk_act<3>(v[j]);
+        dst[j] = v[j];
+      }
+    }
+  }
+  cluster.sync();                                          // peers may still be reading this CTA's partial
+}
+
+static bool skinny_cluster_ok(const GemmArgs& g) {
+  if (getenv("B200AD_NO_SKINNY_CLUSTER")) return false;
+  // measured crossover against the tensor-core path (profiles/skinny_probe.py): wins for the H = 1024 tanh-RNN step
+  // (one wave of 128 CTAs), loses beyond ~2 waves or K > 2048 (the LSTM's 4H-wide / 4H-deep products)
+  return g.m >= 1 && g.m <= 64 && g.batch0 * g.batch1 == 1 && !g.trans_a && g.k >= 256 && g.k <= 2048 &&
+         (g.k % (SC_CL * SC_KC)) == 0 && g.n >= 64 && g.n <= 2048 && (g.n % SC_BN) == 0 && (g.lda & 3) == 0 && (g.ldb & 3) == 0 && aligned16(g.a) && aligned16(g.b);
+}
+
 bool gemm_skinny_supported(const GemmArgs& g) {
+  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g)) return true;
   if (getenv("B200AD_NO_SKINNY")) return false;
   if (g.m < 1 || g.m > 64 || g.batch0 * g.batch1 != 1 || g.trans_a) return false;
   // N <= 2048: every CTA re-reads the whole A panel (M x K) from L2, which stops paying beyond ~256 CTAs (the LSTM's
@@ -120,6 +230,13 @@ bool gemm_skinny_supported(const GemmArgs& g) {
 }
 
 int gemm_skinny_launch(const GemmArgs& g, cudaStream_t s) {
+  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g)) {
+    const int grid_c = (int)(g.n / SC_BN) * SC_CL;
+    if (g.trans_b) gemm_skinny_cluster_kernel<true><<<grid_c, 256, 0, s>>>(g);
+    else gemm_skinny_cluster_kernel<false><<<grid_c, 256, 0, s>>>(g);
+    count_launch();
+    return check_launch("gemm(skinny, cluster)");
+  }
   const int grid = (int)(g.n / SK_BN);
   if (g.trans_b) gemm_skinny_kernel<true><<<grid, SK_THREADS, 0, s>>>(g);
   else gemm_skinny_kernel<false><<<grid, SK_THREADS, 0, s>>>(g);

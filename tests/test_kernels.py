@@ -293,7 +293,8 @@ def test_gemm_bf16_variant_stated_tolerance(backend, M, N, K, ta, tb):
 
 
 @pytest.mark.parametrize("M,N,K,tb,act,beta", [(64, 1024, 1024, False, 1, 1.0), (64, 1024, 1024, True, 0, 0.0), (17, 2048, 1024, False, 0, 1.0),
-                                               (1, 256, 256, True, 2, 0.0), (64, 512, 2048, False, 3, 0.5), (64, 1024, 4096, True, 0, 0.0)])
+                                               (1, 256, 256, True, 2, 0.0), (64, 512, 2048, False, 3, 0.5), (64, 1024, 4096, True, 0, 0.0),
+                                               (64, 264, 1024, False, 1, 1.0), (40, 328, 992, True, 0, 0.0)])
 def test_gemm_skinny_recurrent_step(backend, M, N, K, tb, act, beta):
     """The M <= 64 recurrent-step kernel (fused beta * C + bias + activation epilogue), both B layouts, strided
     output rows (a time slice of an (N, T, H) tensor), vs fp64."""
