@@ -282,6 +282,8 @@ def run_c5(args):
         if isinstance(key[0], str):     # fused attention pass: ("attn_fwd" | "attn_bwd", B, H, Sq, Skv, dk)
             kname = "b200ad_%s batch=%d heads=%d seq_q=%d seq_kv=%d head_dim=%d (3xTF32)" % key
             traffic = NCU_TRAFFIC_BYTES.get(key[0])
+            if traffic is not None:
+                traffic = traffic * key[1] / 256.0      # the ncu capture was taken at 256 sequences per launch; traffic is linear in it
         else:
             kname = "b200ad_gemm M=%d N=%d K=%d batches=%d transA=%d transB=%d precision=%d" % key
             traffic = NCU_TRAFFIC_BYTES.get(tuple(int(v) for v in key[:4]))
