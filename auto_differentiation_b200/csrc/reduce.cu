@@ -120,6 +120,39 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x,
   }
 }
 
+// TimeDropout forward (reference layers.py:685-692): mask = (u > ratio) * scale, y = x * mask; the uniform draws u are
+// the caller's (device RNG, or the reference's host stream for parity runs).
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                                                          float* __restrict__ mask, float* __restrict__ y, int64_t n,
+                                                          float ratio, float scale, int vec_ok) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 xv = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+      const float4 uv = ldg_stream(reinterpret_cast<const float4*>(u) + i);
+      float4 mv;
+      mv.x = uv.x > ratio ? scale : 0.f; mv.y = uv.y > ratio ? scale : 0.f;
+      mv.z = uv.z > ratio ? scale : 0.f; mv.w = uv.w > ratio ? scale : 0.f;
+      reinterpret_cast<float4*>(mask)[i] = mv;
+      reinterpret_cast<float4*>(y)[i] = make_float4(xv.x * mv.x, xv.y * mv.y, xv.z * mv.z, xv.w * mv.w);
+    }
+    const int64_t t = (n4 << 2) + tid;
+    if (t < n) {
+      const float m = u[t] > ratio ? scale : 0.f;
+      mask[t] = m;
+      y[t] = x[t] * m;
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += stride) {
+      const float m = __ldg(u + i) > ratio ? scale : 0.f;
+      mask[i] = m;
+      y[i] = __ldg(x + i) * m;
+    }
+  }
+}
+
 struct StridedDesc {
   int rank;
   int out_strided;
@@ -341,6 +374,18 @@ int b200ad_axpby(const float* x, float* y, int64_t n, float a, float b, void* st
   axpby_kernel<<<stream_grid(vec_ok ? (n + 3) / 4 : n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, a, b, vec_ok);
   count_launch();
   return check_launch("axpby");
+}
+
+int b200ad_dropout_fwd(const float* x, const float* u, float* mask, float* y, int64_t n, float ratio,
+                       float scale, void* stream) {
+  B200AD_REQUIRE(n >= 0, "dropout_fwd: negative n");
+  if (n == 0) return B200AD_OK;
+  B200AD_REQUIRE(x && u && mask && y, "dropout_fwd: null pointer");
+  const int vec_ok = aligned16(x) && aligned16(u) && aligned16(mask) && aligned16(y);
+  dropout_fwd_kernel<<<stream_grid(vec_ok ? (n + 3) / 4 : n, 256), 256, 0, (cudaStream_t)stream>>>(x, u, mask, y, n, ratio,
+                                                                                                  scale, vec_ok);
+  count_launch();
+  return check_launch("dropout_fwd");
 }
 
 int b200ad_strided_copy(const float* in, float* out, int rank, const int64_t* shape,

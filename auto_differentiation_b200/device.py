@@ -370,6 +370,24 @@ def axpby_(x, y, a, b):
     return y
 
 
+def dropout_fwd(x, u, ratio, scale):
+    """(y, mask): mask = (u > ratio) * scale, y = x * mask in one pass (reference TimeDropout.forward
+    layers.py:685-692); `u` holds the uniform draws, same size as x."""
+    x = x.contiguous()
+    u = u.contiguous()
+    if u.size != x.size:
+        raise ValueError("dropout: %d uniform draws for %d elements" % (u.size, x.size))
+    y, mask = empty(x.shape), empty(x.shape)
+    L.check(_lib().b200ad_dropout_fwd(x.ptr, u.ptr, mask.ptr, y.ptr, x.size, float(ratio), float(scale), stream_ptr()))
+    return y, mask
+
+
+def uniform(shape):
+    """U[0,1) draws on the device (torch's CUDA generator: plumbing, like the allocator)."""
+    require_cuda()
+    return DeviceArray(torch.rand(tuple(int(s) for s in shape), dtype=_F32, device=_DEVICE))
+
+
 def broadcast_to(a, shape):
     shape = tuple(int(s) for s in shape)
     if a.shape == shape:

@@ -450,6 +450,158 @@ class TimeEmbedding:
         return None
 
 
+class TimeDropout:
+    """Inverted dropout over a whole (N,T,H) block (reference layers.py:678-697): train mode draws
+    `u`, keeps where u > ratio and scales by 1/(1-ratio); eval mode is the identity.  The draws come
+    from the device generator; `reference_rng=True` takes them from the host `np.random.rand` stream
+    in the reference's order, so that a run seeded like the reference reproduces its masks exactly."""
+
+    def __init__(self, dropout_ratio=0.5, reference_rng=False):
+        self.weights, self.grads = [], []
+        self.dropout_ratio = dropout_ratio
+        self.mask = None
+        self.train_flg = True
+        self.reference_rng = reference_rng
+
+    def forward(self, xs):
+        xs = _dev(xs)
+        if not self.train_flg:
+            self.mask = None
+            return xs
+        scale = 1 / (1.0 - self.dropout_ratio)
+        if self.reference_rng:
+            keep = np.random.rand(*xs.shape) > self.dropout_ratio      # fp64 compare as in the reference :687
+            out, self.mask = D.dropout_fwd(xs, asarray(keep.astype(np.float32)), 0.5, scale)
+        else:
+            out, self.mask = D.dropout_fwd(xs, D.uniform(xs.shape), self.dropout_ratio, scale)
+        return out
+
+    def backward(self, dout):
+        if self.mask is None:                 # eval-mode forward: identity (the reference would fail on `dout * None`)
+            return dout
+        return D.binary(L.B_MUL, _dev(dout).contiguous(), self.mask)
+
+
+class Rnnlm:
+    """Two stacked stateful LSTMs between dropout layers with the output projection tied to the
+    embedding, `affine_W = embed_W.T` (reference layers.py:699-753).  The tied matrices are two views
+    of one buffer; `remove_duplicate` folds their gradients before the update.  Needs
+    wordvec_size == hidden_size, like the reference (second LSTM and the tied affine both consume H)."""
+
+    def __init__(self, vocab_size=10000, wordvec_size=100, hidden_size=100, weights=None, reference_rng=False):
+        V, Dm, H = vocab_size, wordvec_size, hidden_size
+        if weights is None:
+            rn = np.random.randn
+            embed_W = (rn(V, Dm) / 100).astype("f")
+            lstm_Wx = (rn(Dm, 4 * H) / np.sqrt(Dm)).astype("f")
+            lstm_Wh = (rn(H, 4 * H) / np.sqrt(H)).astype("f")
+            lstm_Wx2 = (rn(Dm, 4 * H) / np.sqrt(Dm)).astype("f")
+            lstm_Wh2 = (rn(H, 4 * H) / np.sqrt(H)).astype("f")
+            lstm_b = np.zeros(4 * H).astype("f")
+            lstm_b2 = np.zeros(4 * H).astype("f")
+            affine_b = np.zeros(V).astype("f")
+        else:
+            # parameter order of `params` (:731-734); the tied (Dm,V) view is rebuilt from the embedding
+            embed_W, lstm_Wx, lstm_Wh, lstm_b, lstm_Wx2, lstm_Wh2, lstm_b2 = weights[:7]
+            affine_b = weights[-1]
+        embed_W = _dev(embed_W)
+        affine_W = embed_W.T
+        self.layers = [
+            TimeEmbedding(embed_W),
+            TimeDropout(reference_rng=reference_rng),
+            TimeLSTM(lstm_Wx, lstm_Wh, lstm_b, stateful=True),
+            TimeDropout(reference_rng=reference_rng),
+            TimeLSTM(lstm_Wx2, lstm_Wh2, lstm_b2, stateful=True),
+            TimeDropout(reference_rng=reference_rng),
+            TimeAffine(affine_W, affine_b),
+        ]
+        self.loss_layer = TimeSoftmaxWithLoss()
+        self.lstm_layer = [self.layers[2], self.layers[4]]
+        self.drop_layers = [self.layers[1], self.layers[3], self.layers[5]]
+        self.params, self.grads = [], []
+        for layer in self.layers:
+            self.params += layer.weights
+            self.grads += layer.grads
+        self.weights = self.params
+
+    def train_mode(self, flag=True):
+        for layer in self.drop_layers:
+            layer.train_flg = flag
+
+    def predict(self, xs):
+        for layer in self.layers:
+            xs = layer.forward(xs)
+        return xs
+
+    def forward(self, xs, ts):
+        score = self.predict(xs)
+        return self.loss_layer.forward(score, ts)
+
+    def backward(self, dout=1):
+        dout = self.loss_layer.backward(dout)
+        for layer in reversed(self.layers):
+            dout = layer.backward(dout)
+        return dout
+
+    def reset_state(self):
+        for layer in self.lstm_layer:
+            layer.reset_state()
+
+
+class RnnlmTrainer:
+    """Truncated-BPTT trainer (reference layers.py:756-818): `batch_size` read heads spaced
+    len(x)//batch_size apart walk the corpus `time_size` tokens per iteration; each iteration is
+    forward, backward, remove_duplicate, optional clip_grads, optimizer.update; perplexity =
+    exp(mean loss since the last evaluation)."""
+
+    def __init__(self, model, optimizer):
+        self.model = model
+        self.optimizer = optimizer
+        self.time_idx = None
+        self.ppl_list = None
+        self.eval_interval = None
+        self.current_epoch = 0
+
+    def get_batch(self, x, t, batch_size, time_size):
+        x, t = np.asarray(x), np.asarray(t)
+        data_size = len(x)
+        jump = data_size // batch_size
+        # position of sample i at step k is (i*jump + time_idx + k) % data_size        :773-776
+        pos = (np.arange(batch_size)[:, None] * jump + self.time_idx + np.arange(time_size)[None, :]) % data_size
+        self.time_idx += time_size
+        return x[pos].astype("i"), t[pos].astype("i")
+
+    def fit(self, xs, ts, max_epoch=10, batch_size=20, time_size=35, max_grad=None, eval_interval=20):
+        data_size = len(xs)
+        max_iters = data_size // (batch_size * time_size)
+        self.time_idx = 0
+        self.ppl_list = []
+        self.eval_interval = eval_interval
+        model, optimizer = self.model, self.optimizer
+        total_loss, loss_count = 0, 0
+        for _ in range(max_epoch):
+            for iters in range(max_iters):
+                batch_x, batch_t = self.get_batch(xs, ts, batch_size, time_size)
+                loss = model.forward(batch_x, batch_t)
+                model.backward()
+                params, grads = remove_duplicate(model.params, model.grads)
+                if max_grad is not None:
+                    clip_grads(grads, max_grad)
+                optimizer.update(params, grads)
+                total_loss = loss + total_loss            # stays on the device until an evaluation point
+                loss_count += 1
+                if (eval_interval is not None) and not iters % eval_interval:
+                    self.ppl_list.append(float(np.exp(float(total_loss) / loss_count)))
+                    total_loss, loss_count = 0, 0
+            self.current_epoch += 1
+        return self.ppl_list
+
+    def save(self, prefix="weights"):
+        params, _ = remove_duplicate(self.model.params, self.model.grads)
+        for index, p in enumerate(params):
+            np.save("%s%d.npy" % (prefix, index), np.asarray(p))
+
+
 class TimeSoftmaxWithLoss:
     """Masked mean cross-entropy over (N,T,V) logits (reference layers.py:510-549).  `forward`
     returns the loss as a 0-d DeviceArray (float(loss) syncs; arithmetic on it stays on the device)."""

@@ -183,6 +183,10 @@ int b200ad_strided_copy(const float* in, float* out, int rank, const int64_t* sh
                         void* stream);
 int b200ad_fill(float* out, int64_t n, float value, void* stream);
 int b200ad_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream); /* y = a*x + b*y */
+/* TimeDropout.forward layers.py:685-692: mask = (u > ratio) * scale, y = x * mask, u = caller's uniform draws.
+ * Backward (:696-697) is binary_fwd(MUL, dout, mask). */
+int b200ad_dropout_fwd(const float* x, const float* u, float* mask, float* y, int64_t n, float ratio,
+                       float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contractions.   C[b0,b1] = alpha * op(A[b0,b1]) @ op(B[b0,b1]) + beta * C[b0,b1]

@@ -398,6 +398,58 @@ def gen_seq2seq(L):
     save("seq2seq", **out)
 
 
+def gen_rnnlm(L):
+    """Rnnlm + RnnlmTrainer (layers.py:699-818): two iterations of the trainer's inner loop (forward with dropout ON,
+    backward, remove_duplicate, clip_grads, SGD) on the tied-weight two-LSTM language model, an eval-mode forward, and
+    the trainer's batch walk over a corpus."""
+    np.random.seed(777)             # initial weights come from the global NumPy RNG (:702-712)
+    V, H = 23, 12
+    m = L.Rnnlm(V, H, H)
+    w0 = [np.array(w, dtype=np.float64) for w in m.params]
+    rng = np.random.default_rng(109)
+    N, T, steps, max_grad, lr = 3, 5, 2, 0.25, 0.5
+    xs = rng.integers(0, V, (steps, N, T))
+    ts = rng.integers(0, V, (steps, N, T))
+    out = dict(xs=xs, ts=ts, dims=np.array([V, H]), n=np.int64(len(w0)), max_grad=np.float64(max_grad), lr=np.float64(lr),
+               mask_seed=np.int64(4242))
+    for i, w in enumerate(w0):
+        out["w%d" % i] = w
+    opt = L.SGD(lr)
+    np.random.seed(4242)            # dropout masks: np.random.rand in layer order, every forward (:687)
+    losses = []
+    for it in range(steps):
+        loss = m.forward(xs[it], ts[it])
+        m.backward()
+        params, grads = L.remove_duplicate(m.params, m.grads)
+        if it == 0:
+            for i, g in enumerate(grads):
+                out["g%d" % i] = np.array(g, dtype=np.float64)       # merged, before clipping
+            out["n_merged"] = np.int64(len(grads))
+        L.clip_grads(grads, max_grad)
+        opt.update(params, grads)
+        losses.append(float(loss))
+    out["losses"] = np.array(losses)
+    params, _ = L.remove_duplicate(m.params, m.grads)
+    for i, p in enumerate(params):
+        out["p%d" % i] = np.array(p, dtype=np.float64)
+    # eval mode (dropout off), state carried on from the two training steps, then after reset_state
+    for layer in m.layers:
+        if hasattr(layer, "train_flg"):
+            layer.train_flg = False
+    out["eval_loss_stateful"] = np.float64(m.forward(xs[0], ts[0]))
+    m.reset_state()
+    out["eval_loss_reset"] = np.float64(m.forward(xs[0], ts[0]))
+    out["eval_score"] = np.array(m.predict(xs[1]), dtype=np.float64)
+    # the trainer's corpus walk (:765-777)
+    tr = L.RnnlmTrainer(m, opt)
+    tr.time_idx = 0
+    corpus = np.arange(50) * 3 % 23
+    bx1, bt1 = tr.get_batch(corpus[:-1], corpus[1:], 4, 5)
+    bx2, bt2 = tr.get_batch(corpus[:-1], corpus[1:], 4, 5)
+    out.update(corpus=corpus, bx1=bx1, bt1=bt1, bx2=bx2, bt2=bt2)
+    save("rnnlm", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found at %s" % ref_loader.REFERENCE_ROOT)
@@ -414,6 +466,7 @@ def main():
     gen_optim(L, U)
     gen_attention(L)
     gen_seq2seq(L)
+    gen_rnnlm(L)
 
 
 if __name__ == "__main__":

@@ -688,3 +688,49 @@ def attention_seq2seq_generate(question, weights, start_id, sample_size):       
         sid = int(np.argmax(score.flatten()))
         sampled.append(sid)
     return sampled
+
+
+# ------------------------------------------------------------------------------------------------------
+# Rnnlm (layers.py:699-753) and RnnlmTrainer.get_batch (:765-777)
+# ------------------------------------------------------------------------------------------------------
+def dropout_masks(shapes, ratio=0.5):                                             # TimeDropout.forward :685-689
+    """The masks one training forward draws from the global NumPy RNG, in layer order."""
+    scale = 1 / (1.0 - ratio)
+    return [(np.random.rand(*s) > ratio).astype(np.float32) * scale for s in shapes]
+
+
+def rnnlm_step(xs, ts, weights, masks=None, state=None):
+    """One forward + backward of Rnnlm.  weights = [embed_W, wx1, wh1, b1, wx2, wh2, b2, affine_b] (the list
+    remove_duplicate leaves: the tied affine_W = embed_W.T (:711) is folded into the embedding).  `masks` = three
+    dropout masks (N,T,H) or None for eval mode; `state` = (h1, c1, h2, c2) carried between calls (stateful=True
+    :718-720) or None.  Returns (loss, merged grads in the order of `weights`, new state, score)."""
+    emb, wx1, wh1, b1, wx2, wh2, b2, a_b = weights
+    m0, m1, m2 = masks if masks is not None else (1.0, 1.0, 1.0)
+    h1, c1, h2, c2 = state if state is not None else (None, None, None, None)
+    x0 = embedding_forward(emb, xs) * m0
+    hs1, caches1, h1, c1 = time_lstm_forward(x0, wx1, wh1, b1, h0=h1, c0=c1)
+    x1 = hs1 * m1
+    hs2, caches2, h2, c2 = time_lstm_forward(x1, wx2, wh2, b2, h0=h2, c0=c2)
+    x2 = hs2 * m2
+    score = time_affine_forward(x2, emb.T, a_b)
+    loss, lcache = time_softmax_with_loss_forward(score, ts)
+    dscore = time_softmax_with_loss_backward(lcache, 1)
+    dx2, g_aW, g_ab = time_affine_backward(x2, emb.T, dscore)
+    dx1, g2, _ = time_lstm_backward(caches2, wx2, wh2, dx2 * m2)
+    dx0, g1, _ = time_lstm_backward(caches1, wx1, wh1, dx1 * m1)
+    g_emb = time_embedding_backward(emb.shape, xs, dx0 * m0)
+    g_emb = g_emb + g_aW.T                                                         # remove_duplicate :96-98
+    return loss, [g_emb, g1[0], g1[1], g1[2], g2[0], g2[1], g2[2], g_ab], (h1, c1, h2, c2), score
+
+
+def rnnlm_get_batch(x, t, batch_size, time_size, time_idx):                        # RnnlmTrainer.get_batch :765-777
+    data_size = len(x)
+    jump = data_size // batch_size
+    bx = np.empty((batch_size, time_size), dtype=np.int32)
+    bt = np.empty((batch_size, time_size), dtype=np.int32)
+    for k in range(time_size):
+        for i in range(batch_size):
+            bx[i, k] = x[(i * jump + time_idx) % data_size]
+            bt[i, k] = t[(i * jump + time_idx) % data_size]
+        time_idx += 1
+    return bx, bt, time_idx

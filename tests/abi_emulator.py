@@ -312,6 +312,13 @@ class Emulator:
         yy[:] = a * _f32(x, n).astype(np.float64) + (b * yy.astype(np.float64) if b != 0 else 0.0)
         return 0
 
+    def b200ad_dropout_fwd(self, x, u, mask, y, n, ratio, scale, s):
+        self.launches += 1
+        m = np.where(_f32(u, n) > np.float32(ratio), np.float32(scale), np.float32(0.0))
+        _f32(mask, n)[:] = m
+        _f32(y, n)[:] = _f32(x, n) * m
+        return 0
+
     # ---- GEMM --------------------------------------------------------------------------------------
     def b200ad_gemm_workspace_bytes(self, d):
         return 0
