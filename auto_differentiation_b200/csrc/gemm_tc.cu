@@ -796,10 +796,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __shared__ uint64_t bars[3 * R + 4];
   __shared__ uint32_t tmem_base_smem;
   uint64_t* raw_full = bars;             // [R] TMA -> splitter (local)
-  uint64_t* conv_full = bars + R;        // [R] splitters of BOTH CTAs -> leader's MMA warp (512 arrivals)
+  uint64_t* conv_full = bars + R;        // [R] splitter warps of BOTH CTAs -> leader's MMA warp (8 arrivals)
   uint64_t* empty = bars + 2 * R;        // [R] MMA commit (multicast) -> TMA + splitter of both CTAs
   uint64_t* tmem_full = bars + 3 * R;    // [2: column half] MMA commit (multicast) -> epilogue of both CTAs
-  uint64_t* tmem_empty = tmem_full + 2;  // [2] that half's epilogue warps of both CTAs (256 arrivals) -> leader's MMA warp
+  uint64_t* tmem_empty = tmem_full + 2;  // [2] all epilogue warps of both CTAs (16 arrivals) -> leader's MMA warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -810,12 +810,12 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < R; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&conv_full[s], 2 * 128);
+      mbar_init(&conv_full[s], 2 * 4);
       mbar_init(&empty[s], 1);
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&tmem_full[h], 1);
-      mbar_init(&tmem_empty[h], 2 * 128);
+      mbar_init(&tmem_empty[h], 2 * 8);
     }
     fence_barrier_init();
   }
@@ -961,7 +961,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int btid = threadIdx.x - 128;                     // B part: 0..127
     uint32_t it = 0;
 #ifdef TC3_PROFILE
-    long long w_raw = 0; const long long t_start = clock64();
+    long long w_raw = 0, t_a = 0, t_b = 0, t_w = 0, t_f = 0, t_f1 = 0, t_f2 = 0, t_f3 = 0; const long long t_start = clock64();
 #endif
     for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
       int t = tile / (p.n_tiles * p.m_tiles);
@@ -977,6 +977,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(&raw_full[s], (it / R) & 1);
 #ifdef TC3_PROFILE
         w_raw += clock64() - q0;
+        const long long p0 = clock64();
 #endif
 
         const uint32_t sa = smem_u32(smem + (size_t)s * TC3_STAGE_BYTES);
@@ -1006,6 +1007,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tmem_st_32x32b_x32(ta, v);
           tmem_st_32x32b_x32(ta + 32, l);
         }
+#ifdef TC3_PROFILE
+        const long long p1 = clock64(); t_a += p1 - p0;
+#endif
         {
           const uint32_t sb = sa + A_BYTES + btid * 16;
 #pragma unroll
@@ -1019,23 +1023,44 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tc_sts128(sb + B_BYTES + i * 2048, lo);
           }
         }
+#ifdef TC3_PROFILE
+        const long long p2 = clock64(); t_b += p2 - p1;
+#endif
         tmem_st_wait();
+#ifdef TC3_PROFILE
+        const long long p3 = clock64(); t_w += p3 - p2;
+#endif
         tc_fence_before();
+#ifdef TC3_PROFILE
+        const long long p4 = clock64(); t_f1 += p4 - p3;
+#endif
         fence_proxy_async();
-        mbar_arrive_cluster(&conv_full[s], 0);     // the leader's barrier counts both CTAs' splitter threads
+#ifdef TC3_PROFILE
+        const long long p5 = clock64(); t_f2 += p5 - p4;
+#endif
+        __syncwarp();
+#ifdef TC3_PROFILE
+        const long long p6 = clock64(); t_f3 += p6 - p5;
+#endif
+        // one (cumulative) release per warp
+        if (lane == 0) mbar_arrive_cluster(&conv_full[s], 0);     // the leader's barrier counts both CTAs' splitter warps
+#ifdef TC3_PROFILE
+        t_f += clock64() - p3;
+#endif
       }
     }
 #ifdef TC3_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 128)
-      printf("[tc3] splitter: total %lld cycles, wait raw_full (TMA) %lld\n", clock64() - t_start, w_raw);
+      printf("[tc3] splitter: total %lld cycles, wait raw_full (TMA) %lld, A part %lld, B part %lld, st wait %lld, fences+arrive %lld (tcgen05 fence %lld, proxy fence %lld, syncwarp %lld)\n",
+             clock64() - t_start, w_raw, t_a, t_b, t_w, t_f, t_f1, t_f2, t_f3);
 #endif
   } else {
     // ===================================== epilogue (both CTAs, own 128 rows) =====================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     const int q = warp & 3;
-    const int hf = (warp - 8) >> 2;                         // column half of the 256-wide tile
+    const int hf = (warp - 8) >> 2;                         // which 64 columns of EACH 128-column half this warp folds
     const int row_in_tile = q * 32 + lane;
-    const uint32_t x_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hf * 128u;
+    const uint32_t x_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hf * 64u;
     uint32_t uit = 0;
 #ifdef TC3_PROFILE
     long long w_full = 0, t_fold = 0, t_store = 0; const long long t_start = clock64();
@@ -1056,30 +1081,38 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       float* crow;
       if (p.partial) crow = p.partial + (((int64_t)split * p.batches + batch) * p.m + gm) * p.n;
       else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
-      float y[128];                                          // running total of this thread's 128 columns
+      // running totals: y[0..63] = columns hf*64.. of half a, y[64..127] = the same columns of half b.  All eight warps
+      // fold every half (64 columns each), so a chunk sum leaves TMEM in half the time of a 4-warp fold and the
+      // tmem_empty round trip fits inside the two k-blocks the other half still has queued.
+      float y[128];
       for (int ch = 0; ch < nchunks; ++ch, ++uit) {
-#ifdef TC3_PROFILE
-        const long long q0 = clock64();
-#endif
-        mbar_wait(&tmem_full[hf], uit & 1);
-#ifdef TC3_PROFILE
-        const long long q1 = clock64(); w_full += q1 - q0;
-#endif
-        tc_fence_after();
-        // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation truncates)
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t x[16];
-          tmem_ld_32x32b_x16(x_addr + c0, x);
-          tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {
+#ifdef TC3_PROFILE
+          const long long q0 = clock64();
+#endif
+          mbar_wait(&tmem_full[h], uit & 1);
+#ifdef TC3_PROFILE
+          const long long q1 = clock64(); w_full += q1 - q0;
+#endif
+          tc_fence_after();
+          // fold the chunk sum into the running total with round-to-nearest adds (TMEM accumulation truncates)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) y[c0 + j] = (ch == 0) ? __uint_as_float(x[j]) : y[c0 + j] + __uint_as_float(x[j]);
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t x[16];
+            tmem_ld_32x32b_x16(x_addr + (uint32_t)(h * 128 + c0), x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              y[h * 64 + c0 + j] = (ch == 0) ? __uint_as_float(x[j]) : y[h * 64 + c0 + j] + __uint_as_float(x[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[h], 0);   // this half of X may be overwritten by the next chunk's MMAs
+#ifdef TC3_PROFILE
+          t_fold += clock64() - q1;
+#endif
         }
-        tc_fence_before();
-        mbar_arrive_cluster(&tmem_empty[hf], 0);             // this half of X may be overwritten by the next chunk's MMAs
-#ifdef TC3_PROFILE
-        t_fold += clock64() - q1;
-#endif
       }
 #ifdef TC3_PROFILE
       const long long q2 = clock64();
@@ -1101,7 +1134,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int sub_row = lane >> 3, chunk = lane & 7;
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int n_col0 = n_tile * BN + hf * 128 + c0;
+        const int n_col0 = n_tile * BN + (c0 >> 6) * 128 + hf * 64 + (c0 & 63);
         if (n_col0 < p.n && m_row0 < p.m && !(p.probe & 4)) {            // warp-uniform; probe bit 4 skips the stores
           if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free
           __syncwarp();

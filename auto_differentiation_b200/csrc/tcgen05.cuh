@@ -141,11 +141,15 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+// Arrive on a barrier of CTA `cta` of the cluster.  Default semantics (.release at .cta scope), as in CUTLASS's
+// ClusterBarrier::arrive: the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive and
+// costs ~1000 cycles per call (measured in the gen3 GEMM splitter: 978 of its 1513 cycles per k-block).  Callers order
+// their own TMEM / shared-memory writes first (tcgen05.wait::st + tcgen05.fence::before_thread_sync, fence.proxy.async).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }

@@ -69,8 +69,23 @@ def run_c2(args, torch, pk):
             ms_with_flush = _time(torch, fn_flushed, min_ms=100.0)
             ms_flush = _time(torch, lambda: flush.zero_(), min_ms=50.0) if n * 4 < (200 << 20) else 0.0
             ms = max(ms_with_flush - ms_flush, 1e-4)
-            table.setdefault(name, {})[str(n_req)] = {"ms": ms, "GBps": n * bpe / ms / 1e6,
-                                                      "frac_hbm": n * bpe / ms / 1e6 / pk["hbm"]}
+            row = {"ms": ms, "GBps": n * bpe / ms / 1e6, "frac_hbm": n * bpe / ms / 1e6 / pk["hbm"]}
+            if n * 4 < (200 << 20):
+                # the same pair replayed from a CUDA graph (8 flush+fwd+bwd iterations per replay): removes the host
+                # launch gaps that dominate the eager numbers below ~1e8 elements
+                from auto_differentiation_b200.graph import GraphedStep
+
+                def eight(f):
+                    def run():
+                        for _ in range(8):
+                            f()
+                    return run
+                g_fn = GraphedStep(eight(fn_flushed), warmup=1)
+                g_fl = GraphedStep(eight(lambda: flush.zero_()), warmup=1)
+                g_ms = max((_time(torch, g_fn, min_ms=50.0) - _time(torch, g_fl, min_ms=50.0)) / 8, 1e-4)
+                row.update(graph_ms=g_ms, graph_GBps=n * bpe / g_ms / 1e6, graph_frac_hbm=n * bpe / g_ms / 1e6 / pk["hbm"])
+                del g_fn, g_fl
+            table.setdefault(name, {})[str(n_req)] = row
         del a, g, b_full, x
         torch.cuda.empty_cache()
     big = str(sizes[-1])
