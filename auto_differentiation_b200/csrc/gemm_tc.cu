@@ -1081,6 +1081,12 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       float* crow;
       if (p.partial) crow = p.partial + (((int64_t)split * p.batches + batch) * p.m + gm) * p.n;
       else crow = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + gm * p.ldc;
+      // Tile epilogue.  Code size matters here: a fully unrolled alpha/beta/bias/activation epilogue over 128 register
+      // columns made this kernel 24 k instructions (390 KB) and the store phase instruction-fetch bound (~66 k cycles
+      // per tile, measured).  So the unrolled part only moves the registers into a per-warp 4 KB staging tile
+      // (32 rows x 32 columns, SWIZZLE_128B; every index into y[] is a compile-time constant), a ROLLED loop applies
+      // the epilogue math on row-contiguous segments, and the tile leaves either through cp.async.bulk.tensor stores
+      // (asynchronous; rows / columns beyond M / N are clipped by the tensor map) or through coalesced stores.
       // running totals: y[0..63] = columns hf*64.. of half a, y[64..127] = the same columns of half b.  All eight warps
       // fold every half (64 columns each), so a chunk sum leaves TMEM in half the time of a 4-warp fold and the
       // tmem_empty round trip fits inside the two k-blocks the other half still has queued.
@@ -1110,95 +1116,91 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tmem_empty[h], 0);   // this half of X may be overwritten by the next chunk's MMAs
 #ifdef TC3_PROFILE
-          t_fold += clock64() - q1;
+          const long long q2 = clock64(); t_fold += q2 - q1;
 #endif
-        }
-      }
-#ifdef TC3_PROFILE
-      const long long q2 = clock64();
-#endif
-      // Tile epilogue.  Code size matters here: a fully unrolled alpha/beta/bias/activation epilogue over 128 register
-      // columns made this kernel 24 k instructions (390 KB) and the store phase instruction-fetch bound (~66 k cycles
-      // per tile, measured).  So the unrolled part only moves the registers into a per-warp 4 KB staging tile
-      // (32 rows x 32 columns, SWIZZLE_128B; every index into y[] is a compile-time constant), a ROLLED loop applies
-      // the epilogue math on row-contiguous segments, and the tile leaves either through cp.async.bulk.tensor stores
-      // (asynchronous; rows / columns beyond M / N are clipped by the tensor map) or through coalesced stores.
-      const uint32_t stg = smem_u32(smem + (size_t)R * TC3_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
-      const int m_row0 = m_tile * 256 + (int)rank * TC_BM + q * 32;       // first row of this warp
-      const int c2 = p.partial ? batch : (int)b1, c3 = p.partial ? split : (int)b0;
-      const bool identity = p.partial || (p.alpha == 1.f && p.beta == 0.f && !p.bias && p.act == 0);
-      float* cwarp;
-      if (p.partial) cwarp = p.partial + (((int64_t)split * p.batches + batch) * p.m + m_row0) * p.n;
-      else cwarp = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + (int64_t)m_row0 * p.ldc;
-      const int64_t row_pitch = p.partial ? p.n : p.ldc;
-      const int sub_row = lane >> 3, chunk = lane & 7;
-#pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int n_col0 = n_tile * BN + (c0 >> 6) * 128 + hf * 64 + (c0 & 63);
-        if (n_col0 < p.n && m_row0 < p.m && !(p.probe & 4)) {            // warp-uniform; probe bit 4 skips the stores
-          if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 v4;
-            v4.x = __float_as_uint(y[c0 + 4 * c]); v4.y = __float_as_uint(y[c0 + 4 * c + 1]);
-            v4.z = __float_as_uint(y[c0 + 4 * c + 2]); v4.w = __float_as_uint(y[c0 + 4 * c + 3]);
-            tc_sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), v4);
-          }
-          __syncwarp();
-          if (!identity || !p.tma_store) {
-            const int gn0 = n_col0 + chunk * 4;
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-              const int rl = 4 * i + sub_row;
-              const uint32_t sa = stg + rl * 128 + ((chunk ^ (rl & 7)) << 4);
-              const uint4 v4 = tc_lds128(sa);
-              float v[4] = {__uint_as_float(v4.x), __uint_as_float(v4.y), __uint_as_float(v4.z), __uint_as_float(v4.w)};
-              float* dst = cwarp + (int64_t)rl * row_pitch + gn0;
-              const bool in_range = (m_row0 + rl < p.m) && (gn0 < p.n);
-              if (!p.partial) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  v[j] *= p.alpha;
-                  if (in_range && gn0 + j < p.n) {
-                    if (p.beta != 0.f) v[j] += p.beta * dst[j];
-                    if (p.bias) v[j] += __ldg(p.bias + gn0 + j);
+          // Last chunk: this half is final, so its 64 columns leave NOW: half a's stores run under half b's last
+          // two k-blocks of MMAs, half b's under the next tile's first chunk (the SM accepts ~32 B/clk of stores, so
+          // the 128 KB tile costs ~4-6 k cycles that must not sit between the folds).
+          if (ch == nchunks - 1) {
+            const uint32_t stg = smem_u32(smem + (size_t)R * TC3_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
+            const int m_row0 = m_tile * 256 + (int)rank * TC_BM + q * 32;       // first row of this warp
+            const int c2 = p.partial ? batch : (int)b1, c3 = p.partial ? split : (int)b0;
+            const bool identity = p.partial || (p.alpha == 1.f && p.beta == 0.f && !p.bias && p.act == 0);
+            float* cwarp;
+            if (p.partial) cwarp = p.partial + (((int64_t)split * p.batches + batch) * p.m + m_row0) * p.n;
+            else cwarp = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + (int64_t)m_row0 * p.ldc;
+            const int64_t row_pitch = p.partial ? p.n : p.ldc;
+            const int sub_row = lane >> 3, chunk = lane & 7;
+    #pragma unroll
+          for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 32) {
+            const int n_col0 = n_tile * BN + (c0 >> 6) * 128 + hf * 64 + (c0 & 63);
+            if (n_col0 < p.n && m_row0 < p.m && !(p.probe & 4)) {            // warp-uniform; probe bit 4 skips the stores
+              if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free
+              __syncwarp();
+    #pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4 v4;
+                v4.x = __float_as_uint(y[c0 + 4 * c]); v4.y = __float_as_uint(y[c0 + 4 * c + 1]);
+                v4.z = __float_as_uint(y[c0 + 4 * c + 2]); v4.w = __float_as_uint(y[c0 + 4 * c + 3]);
+                tc_sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), v4);
+              }
+              __syncwarp();
+              if (!identity || !p.tma_store) {
+                const int gn0 = n_col0 + chunk * 4;
+    #pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                  const int rl = 4 * i + sub_row;
+                  const uint32_t sa = stg + rl * 128 + ((chunk ^ (rl & 7)) << 4);
+                  const uint4 v4 = tc_lds128(sa);
+                  float v[4] = {__uint_as_float(v4.x), __uint_as_float(v4.y), __uint_as_float(v4.z), __uint_as_float(v4.w)};
+                  float* dst = cwarp + (int64_t)rl * row_pitch + gn0;
+                  const bool in_range = (m_row0 + rl < p.m) && (gn0 < p.n);
+                  if (!p.partial) {
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      v[j] *= p.alpha;
+                      if (in_range && gn0 + j < p.n) {
+                        if (p.beta != 0.f) v[j] += p.beta * dst[j];
+                        if (p.bias) v[j] += __ldg(p.bias + gn0 + j);
+                      }
+                      if (p.act == 1) v[j] = tc_act<1>(v[j]);
+                      else if (p.act == 2) v[j] = tc_act<2>(v[j]);
+                      else if (p.act == 3) v[j] = tc_act<3>(v[j]);
+                    }
                   }
-                  if (p.act == 1) v[j] = tc_act<1>(v[j]);
-                  else if (p.act == 2) v[j] = tc_act<2>(v[j]);
-                  else if (p.act == 3) v[j] = tc_act<3>(v[j]);
+                  if (p.tma_store) {
+                    uint4 o4;
+                    o4.x = __float_as_uint(v[0]); o4.y = __float_as_uint(v[1]); o4.z = __float_as_uint(v[2]); o4.w = __float_as_uint(v[3]);
+                    tc_sts128(sa, o4);
+                  } else if (in_range) {
+                    if (gn0 + 4 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+    #pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        if (gn0 + j < p.n) dst[j] = v[j];
+                    }
+                  }
                 }
               }
               if (p.tma_store) {
-                uint4 o4;
-                o4.x = __float_as_uint(v[0]); o4.y = __float_as_uint(v[1]); o4.z = __float_as_uint(v[2]); o4.w = __float_as_uint(v[3]);
-                tc_sts128(sa, o4);
-              } else if (in_range) {
-                if (gn0 + 4 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (gn0 + j < p.n) dst[j] = v[j];
+                fence_proxy_async();
+                __syncwarp();
+                if (elect_one()) {          // the same (lowest) lane every time: bulk groups are per thread
+                  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_c),
+                               "r"(stg), "r"(n_col0), "r"(m_row0), "r"(c2), "r"(c3)
+                               : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
               }
             }
           }
-          if (p.tma_store) {
-            fence_proxy_async();
-            __syncwarp();
-            if (elect_one()) {          // the same (lowest) lane every time: bulk groups are per thread
-              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_c),
-                           "r"(stg), "r"(n_col0), "r"(m_row0), "r"(c2), "r"(c3)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+#ifdef TC3_PROFILE
+            t_store += clock64() - q2;
+#endif
           }
         }
       }
-#ifdef TC3_PROFILE
-      t_store += clock64() - q2;
-#endif
     }
     if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every output tile has been written
 #ifdef TC3_PROFILE
