@@ -819,15 +819,16 @@ static int launch_pass_impl(const AttnTensor& a1, const AttnTensor& a2, const At
   return check_launch("attention(tcgen05)");
 }
 
-// Default: the 1-CTA passes.  B200AD_ATTN_PAIR=1 selects the CTA-pair variant (cta_group::2, each CTA stages half of every
-// B block).  Measured on B200 at the config-5 micro-batch: pair forward 1.01 ms vs 0.66 ms, backward 3.36 vs 2.62 ms —
-// parity-green but slower: the N = 64 MMAs of a pair and the cluster-scope hand-offs between the MMA warp and the row
-// owners cost more than the halved shared-memory traffic saves.
+// CTA pairs (cta_group::2: each CTA stages half of every B block, the pair shares one MMA stream) whenever the row tiles
+// of a (batch, head) come in pairs; otherwise the 1-CTA passes.  Measured on B200 at the config-5 micro-batch: pair
+// forward 0.586 ms vs 0.664 ms, backward 2.44 vs 2.59 ms.  (With `mbarrier.arrive.release.cluster` hand-offs the pair
+// variant had measured 1.01 / 3.36 ms: every such arrive carries a MEMBAR.ALL.GPU.)  B200AD_ATTN_PAIR=0 / 1 forces one.
 template <int MODE>
 static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTensor& b1, const AttnTensor& b2,
                        const AttnTensor& b3, AttnParams p, int64_t B, int64_t H, cudaStream_t s) {
   const char* e = getenv("B200AD_ATTN_PAIR");
-  if (e && atoi(e) == 1) return launch_pass_impl<MODE, true>(a1, a2, b1, b2, b3, p, B, H, s);
+  const bool pair = e ? atoi(e) == 1 : (ceil_div(p.R, AT_BM) % 2 == 0);
+  if (pair) return launch_pass_impl<MODE, true>(a1, a2, b1, b2, b3, p, B, H, s);
   return launch_pass_impl<MODE, false>(a1, a2, b1, b2, b3, p, B, H, s);
 }
 
