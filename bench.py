@@ -185,6 +185,8 @@ def run_c5(args):
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: the one JSON line is the contract
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import auto_differentiation_b200 as pkg
     from auto_differentiation_b200 import _lib as L, device as D
@@ -287,6 +289,14 @@ def run_c5(args):
         else:
             kname = "b200ad_gemm M=%d N=%d K=%d batches=%d transA=%d transB=%d precision=%d" % key
             traffic = NCU_TRAFFIC_BYTES.get(tuple(int(v) for v in key[:4]))
+        # tcgen05 kind::tf32 flops the kernel actually issues per algorithmic flop: three products per product
+        # (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, the fp32-faithful split), and for the backward attention passes the
+        # flash-style recomputation of S (dV pass) and of S and dP (dK and dQ passes): (2 + 3 + 3) x 3 / 5
+        if isinstance(key[0], str):
+            issued = 3.0 if key[0] == "attn_fwd" else 24.0 / 5.0
+        else:
+            issued = 3.0 if int(key[6]) in (1, 3) else 1.0       # b200ad_gemm_precision: TF32X3 / AUTO
+        tf32_peak = peak / 2.0
         # every timed tensor-core kernel family with its share of the step (the dominant one is `kernel`)
         fam = sorted(((("%s" % (k[0],)) if isinstance(k[0], str) else "gemm %dx%dx%d b%d %s%s" % (k[:4] + ("NT"[k[4]], "NT"[k[5]])), v[1])
                       for k, v in gemm.items()), key=lambda kv: -kv[1])
@@ -296,7 +306,11 @@ def run_c5(args):
                 "shares": {k: round(v / (ms_step * args.steps), 4) for k, v in fam[:8]},
                 "launches_timed": n, "avg_launch_ms": avg_ms,
                 "share_of_step": ms_tot / (ms_step * args.steps), "all_gemm_share_of_step": total_gemm_ms / (ms_step * args.steps),
-                "step_tflops": C5_FLOP_PER_SEQ * GLOBAL_BATCH / world / (ms_step * 1e-3) / 1e12}
+                "step_tflops": C5_FLOP_PER_SEQ * GLOBAL_BATCH / world / (ms_step * 1e-3) / 1e12,
+                "tensor_pipe": {"issued_tflops": achieved * issued, "issued_per_algorithmic_flop": issued,
+                                "tf32_peak": tf32_peak, "frac": achieved * issued / tf32_peak,
+                                "note": "kind::tf32 MMA flops issued (3xTF32 split; backward attention also recomputes "
+                                        "S / dP per pass) against the TF32 dense peak = half of the measured bf16 peak"}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, sec = cpu_reference_steps(2, 1, 4)
