@@ -136,50 +136,77 @@ __global__ void __cluster_dims__(SC_CL, 1, 1) __launch_bounds__(256) gemm_skinny
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int64_t k0 = kbeg; k0 < kbeg + kslice; k0 += SC_KC) {
-    // A chunk: 64 rows x 32 k (row-major source, k contiguous): 512 float4, 2 per thread -> As[k][row]
+  // The K-slice is walked in groups of up to four 32-deep chunks.  ALL global loads of a group are issued first (16
+  // independent float4 per thread), so one L2 round trip is exposed per group instead of one per chunk: at K = 1024
+  // (k-slice 128 = one group) the recurrent step pays a single load latency.
+  const int64_t kend = kbeg + kslice;
+  for (int64_t kg = kbeg; kg < kend; kg += 4 * SC_KC) {
+    float4 ra[4][2], rb[4][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int v = tid + i * 256;
-      const int row = v >> 3, kq = (v & 7) * 4;
-      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < M) a4 = __ldg(reinterpret_cast<const float4*>(g.a + (int64_t)row * g.lda + k0 + kq));
-      As[kq][row] = a4.x; As[kq + 1][row] = a4.y; As[kq + 2][row] = a4.z; As[kq + 3][row] = a4.w;
-    }
-    // B chunk: 32 k x 64 columns -> Bs[k][col]
-    if (!TRANS_B) {            // stored (K x N), columns contiguous: 512 float4, 2 per thread
+    for (int c = 0; c < 4; ++c) {
+      const int64_t k0 = kg + c * SC_KC;
+      if (k0 < kend) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int v = tid + i * 256;
-        const int kk = v >> 4, cq = (v & 15) * 4;
-        *reinterpret_cast<float4*>(&Bs[kk][cq]) = __ldg(reinterpret_cast<const float4*>(g.b + (k0 + kk) * g.ldb + n0 + cq));
+        for (int i = 0; i < 2; ++i) {
+          const int v = tid + i * 256;
+          {   // A chunk: 64 rows x 32 k (row-major source, k contiguous): 512 float4, 2 per thread
+            const int row = v >> 3, kq = (v & 7) * 4;
+            ra[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < M) ra[c][i] = __ldg(reinterpret_cast<const float4*>(g.a + (int64_t)row * g.lda + k0 + kq));
+          }
+          if (!TRANS_B) {   // B stored (K x N), columns contiguous
+            const int kk = v >> 4, cq = (v & 15) * 4;
+            rb[c][i] = __ldg(reinterpret_cast<const float4*>(g.b + (k0 + kk) * g.ldb + n0 + cq));
+          } else {          // B stored (N x K), k contiguous
+            const int col = v >> 3, kq = (v & 7) * 4;
+            rb[c][i] = __ldg(reinterpret_cast<const float4*>(g.b + (n0 + col) * g.ldb + k0 + kq));
+          }
+        }
       }
-    } else {                   // stored (N x K), k contiguous
+    }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int v = tid + i * 256;
-        const int col = v >> 3, kq = (v & 7) * 4;
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.b + (n0 + col) * g.ldb + k0 + kq));
-        Bs[kq][col] = b4.x; Bs[kq + 1][col] = b4.y; Bs[kq + 2][col] = b4.z; Bs[kq + 3][col] = b4.w;
+    for (int c = 0; c < 4; ++c) {
+      if (kg + c * SC_KC < kend) {        // block-uniform
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int v = tid + i * 256;
+          {
+            const int row = v >> 3, kq = (v & 7) * 4;
+            const float4 a4 = ra[c][i];
+            As[kq][row] = a4.x; As[kq + 1][row] = a4.y; As[kq + 2][row] = a4.z; As[kq + 3][row] = a4.w;
+          }
+          if (!TRANS_B) {
+            const int kk = v >> 4, cq = (v & 15) * 4;
+            *reinterpret_cast<float4*>(&Bs[kk][cq]) = rb[c][i];
+          } else {
+            const int col = v >> 3, kq = (v & 7) * 4;
+            const float4 b4 = rb[c][i];
+            Bs[kq][col] = b4.x; Bs[kq + 1][col] = b4.y; Bs[kq + 2][col] = b4.z; Bs[kq + 3][col] = b4.w;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SC_KC; ++kk) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < SC_KC; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(&part[ty * 4 + i][tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  cluster.sync();                                          // every CTA's partial is visible cluster-wide
+  // The partials live in SHARED memory, so CTA-scope completion of the stores is enough before the cluster barrier;
+  // `cluster.sync()` (arrive.release) would prepend MEMBAR.ALL.GPU + ERRBAR, ~1000 cycles of this ~5 us kernel.
+  __threadfence_block();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA's partial is visible cluster-wide
   // CTA `rank` reduces rows [8 rank, 8 rank + 8) x 64 columns over the 8 partials (fixed order) and applies the epilogue
   {
     const int row = rank * 8 + (tid >> 5), col = (tid & 31) * 2;
@@ -205,7 +232,8 @@ __global__ void __cluster_dims__(SC_CL, 1, 1) __launch_bounds__(256) gemm_skinny
       }
     }
   }
-  cluster.sync();                                          // peers may still be reading this CTA's partial
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // peers may still be reading this CTA's partial
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 static bool skinny_cluster_ok(const GemmArgs& g) {
