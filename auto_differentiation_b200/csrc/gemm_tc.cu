@@ -1316,6 +1316,12 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   TcPlan pl;
   pl.x3 = (precision == B200AD_GEMM_TF32X3);
   pl.bn = pick_bn(g.n);
+  // One row tile only (the M <= 128 recurrent steps of config 4): 64-column tiles (A in TMEM, 32-cycle MMAs) spread over
+  // the SMs by a deeper split-K.  Measured on the 64 x 1024 x 1024 step inside a CUDA graph: BN = 256 / 4 splits 19.3 us,
+  // BN = 64 / 8 splits 9.7 us, 16 splits 11.6 us (profiles/r1_summary.md, config 4).  A fused "last CTA sums the
+  // partials" epilogue was measured too: 38.8 us (one CTA's 128 threads are far slower than the grid-wide second pass).
+  const bool single_row_tile = pl.x3 && g.m <= TC_BM && g.n >= 256 && g.batch0 * g.batch1 == 1 && !getenv("B200AD_TC_BN");
+  if (single_row_tile) pl.bn = 64;
   // CTA-pair kernel: opt-in.  Measured on B200 (profiles/r1_gemm_tc_probe.md): +3..7 % on 4096^3 / 8192^3, but
   // -5 % on the (131072 x 512 x 512) projection shapes of config 5 (the chunk fold waits for two epilogues).
   const char* ep = getenv("B200AD_TC_PAIR");
@@ -1353,7 +1359,8 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   const int sms = pl.pair ? num_sms() / 2 : num_sms();   // schedulable units: CTAs or CTA pairs
   if (tiles < sms && pl.kblocks_total * TC_BK >= 512) {
     splits = (int)(sms / tiles);
-    const int max_by_k = pl.kblocks_total * TC_BK / 256;   // keep >= 256 K-elements per split
+    // keep >= 256 K-elements per split (one 128-K chunk when a single row tile has to fill the machine)
+    const int max_by_k = pl.kblocks_total * TC_BK / (single_row_tile ? 128 : 256);
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;

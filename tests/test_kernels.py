@@ -307,10 +307,13 @@ def test_gemm_skinny_recurrent_step(backend, M, N, K, tb, act, beta):
     out_full = D.asarray(C0.copy())                           # (the CPU emulation would alias the host array)
     out = out_full[:, 1, :]                                   # row stride 3N
     D.matmul(D.asarray(A), D.asarray(B), trans_b=tb, out=out, beta=beta, bias=D.asarray(bias), act=act)
-    ref = A.astype(np.float64) @ (B.T if tb else B).astype(np.float64) + beta * C0[:, 1, :].astype(np.float64) + bias
-    ref = {0: lambda v: v, 1: np.tanh, 2: lambda v: 1 / (1 + np.exp(-v)), 3: lambda v: np.maximum(v, 0)}[act](ref)
+    pre = A.astype(np.float64) @ (B.T if tb else B).astype(np.float64) + beta * C0[:, 1, :].astype(np.float64) + bias
+    ref = {0: lambda v: v, 1: np.tanh, 2: lambda v: 1 / (1 + np.exp(-v)), 3: lambda v: np.maximum(v, 0)}[act](pre)
     got = np.asarray(out_full)
-    assert_close(got[:, 1, :], ref, rtol=2e-5, atol=2e-6, what="skinny GEMM")
+    # absolute part relative to the magnitude of the accumulated pre-activation (every activation here is 1-Lipschitz):
+    # the small weight matrices run on the exact-fp32 kernels, N * K > 512 Ki on the 3xTF32 tensor-core path
+    scale = max(1.0, float(np.max(np.abs(pre)))) / max(1.0, float(np.max(np.abs(ref))))
+    assert_close(got[:, 1, :], ref, rtol=2e-5, atol=2e-6 * scale, what="skinny GEMM")
     assert np.array_equal(got[:, 0, :], C0[:, 0, :]) and np.array_equal(got[:, 2, :], C0[:, 2, :])
 
 
