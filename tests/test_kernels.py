@@ -452,3 +452,35 @@ def test_large_size_properties():
     # softmax rows sum to one; linearity of the GEMM in its first operand
     sm = D.softmax_lastaxis(x.reshape(n // 512, 512))
     assert abs(float(D.sum_axis(sm, None)) - n // 512) < 1e-5 * (n // 512)       # fp32 sum of ~2e5 row sums
+
+
+@pytest.mark.gpu
+def test_cluster_kernels_bitwise_repeatable():
+    """The CTA-pair kernels hand data between CTAs through mbarriers whose arrives are `.release.cta` (the
+    `.release.cluster` form costs a MEMBAR.ALL.GPU per call): a missed ordering would show up as run-to-run differences.
+    Thirty repetitions each of the gen3 projection / split-K weight-gradient GEMMs, the single-row-tile split-K step and
+    the pair attention passes must be bit-identical, with other kernels racing on the GPU in between."""
+    import torch
+    D, L = _D(), _Lc()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = D.DeviceArray(torch.randn((4096, 512), generator=g, device="cuda"))
+    W = D.DeviceArray(torch.randn((512, 512), generator=g, device="cuda"))
+    G = D.DeviceArray(torch.randn((4096, 512), generator=g, device="cuda"))
+    h = D.DeviceArray(torch.randn((64, 1024), generator=g, device="cuda") / 32)
+    Wh = D.DeviceArray(torch.randn((1024, 1024), generator=g, device="cuda"))
+    q, k, v, do = (D.DeviceArray(torch.randn((4, 512, 8, 64), generator=g, device="cuda")).transpose(0, 2, 1, 3) for _ in range(4))
+    noise = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+
+    def run():
+        y = D.matmul(A, W)                                   # gen3, projection shape
+        dw = D.matmul(A, G, trans_a=True)                    # gen3, split-K
+        s = D.matmul(h, Wh, bias=None, act=L.ACT_TANH)       # 1-CTA kernel, 64-column tiles, 8-way split-K
+        o, lse = D.attn_fwd(q, k, v, 0.125)                  # pair passes (512 rows = 4 row tiles)
+        dq, dk, dv = D.attn_bwd(q, k, v, o, do, lse, 0.125)
+        return [np.asarray(t.contiguous()) for t in (y, dw, s, o, lse, dq, dk, dv)]
+
+    first = run()
+    for rep in range(30):
+        noise.fill_(rep)                                     # unrelated traffic between repetitions
+        for a, b in zip(first, run()):
+            assert np.array_equal(a, b), "repetition %d differs" % rep
