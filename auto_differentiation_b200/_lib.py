@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 U_EXP, U_TANH, U_SIGMOID, U_RELU, U_LN, U_LOGB, U_SQRT, U_SQUARE, U_POW, U_ABS, U_NEG = range(11)
 U_SIN, U_COS, U_TAN, U_SEC, U_SINH, U_COSH, U_ARCSIN, U_ARCTAN, U_ARCOT, U_ARCSEC = range(11, 21)
 U_SCALE, U_ADDC, U_DIVC, U_RSUBC, U_RDIVC = range(21, 26)
+U_COT, U_CSC, U_ARCCOS = range(26, 29)
 # enum b200ad_binary_op / b200ad_bcast_mode
 B_ADD, B_SUB, B_MUL, B_DIV = range(4)
 FULL, ROW, COL, SCALAR = range(4)

@@ -324,6 +324,7 @@ _HOST_UNARY = {
     L.U_ABS: np.abs, L.U_SIN: np.sin, L.U_COS: np.cos, L.U_TAN: np.tan, L.U_SEC: lambda v: 1. / np.cos(v),
     L.U_SINH: np.sinh, L.U_COSH: np.cosh, L.U_ARCSIN: np.arcsin, L.U_ARCTAN: np.arctan,
     L.U_ARCOT: lambda v: np.arctan(1 / v), L.U_ARCSEC: lambda v: np.arccos(1. / v),
+    L.U_COT: lambda v: 1 / np.tan(v), L.U_CSC: lambda v: 1. / np.sin(v), L.U_ARCCOS: np.arccos,
 }
 
 
@@ -469,6 +470,49 @@ class arcot(_Unary):
 
 class arcsec(_Unary):
     _op = L.U_ARCSEC
+
+
+class cot(_Unary):
+    """1/tan(x) (reference :1632-1655).  The backward keeps the reference's expression `grad * csc(x)^2` (:1639),
+    i.e. without the derivative's minus sign."""
+    _op = L.U_COT
+
+
+class csc(_Unary):
+    """1/sin(x) (reference :1472-1495).  As shipped the backward calls the non-existent `np.csc` and raises; the
+    expression it spells, -grad * csc(x) * cot(x) (:1476), is what runs here."""
+    _op = L.U_CSC
+
+
+class arcos(_Unary):
+    """np.arccos (reference :1434-1456); backward as written there: grad * (-1 / sqrt(x + 1)) (:1438)."""
+    _op = L.U_ARCCOS
+
+
+class trace(Function):
+    """np.trace of a square matrix (reference :616-637); backward grad * identity."""
+
+    def __init__(self, x):
+        super().__init__(x)
+        self.x = x
+        self.shape = None
+
+    def result(self):
+        val = self.get_value(self.x)
+        assert val.ndim == 2, "trace: 2-D input expected"
+        n = min(val.shape)
+        diag = D.DeviceArray(val.t.diagonal()).contiguous()          # strided view of the diagonal -> (n,)
+        return D.reduce_mid(diag, 1, n, 1, 1.0).reshape(())
+
+    def get_grad(self, grad):
+        val = self.get_value(self.x)
+        assert val.shape[-2] == val.shape[-1], "input has to be square matrix"
+        n = val.shape[0]
+        self.shape = n
+        out = D.zeros((n, n))
+        g = D.broadcast_to(_to_device_grad(grad).reshape((1,)), (n,))
+        D.copy_into_(g, D.DeviceArray(out.t.diagonal()))
+        return check_shape(out, val)
 
 
 # --------------------------------------------------------------------------------------------------

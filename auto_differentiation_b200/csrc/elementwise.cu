@@ -36,6 +36,9 @@ __device__ __forceinline__ float u_fwd(float x, float p) {
   else if constexpr (OP == B200AD_U_ARCTAN) return atanf(x);
   else if constexpr (OP == B200AD_U_ARCOT) return atanf(1.f / x);
   else if constexpr (OP == B200AD_U_ARCSEC) return acosf(1.f / x);
+  else if constexpr (OP == B200AD_U_COT) return 1.f / tanf(x);
+  else if constexpr (OP == B200AD_U_CSC) return 1.f / sinf(x);
+  else if constexpr (OP == B200AD_U_ARCCOS) return acosf(x);
   else if constexpr (OP == B200AD_U_ADDC) return x + p;
   else if constexpr (OP == B200AD_U_DIVC) return x / p;
   else if constexpr (OP == B200AD_U_RSUBC) return p - x;
@@ -80,6 +83,9 @@ __device__ __forceinline__ float u_bwd(float g, float s, float p) {
   else if constexpr (OP == B200AD_U_ARCTAN) return g * (1.f / (1.f + s * s));       // :1559
   else if constexpr (OP == B200AD_U_ARCOT) return g * (-1.f / (1.f + s * s));       // :1683
   else if constexpr (OP == B200AD_U_ARCSEC) return g * (1.f / (fabsf(s) * sqrtf(s * s - 1.f)));  // :1247
+  else if constexpr (OP == B200AD_U_COT) { float sn = sinf(s); return g * (1.f / (sn * sn)); }   // :1639 (sign as written)
+  else if constexpr (OP == B200AD_U_CSC) { float sn = sinf(s); return -g * (1.f / sn) * (cosf(s) / sn); }   // :1476 (intent)
+  else if constexpr (OP == B200AD_U_ARCCOS) return g * (-1.f / sqrtf(s + 1.f));                 // :1438 (as written)
   else if constexpr (OP == B200AD_U_ADDC) return g;
   else if constexpr (OP == B200AD_U_DIVC) return g / (p + 1e-8f);                   // :1004
   else if constexpr (OP == B200AD_U_RSUBC) return -g;
@@ -172,7 +178,8 @@ __global__ void __launch_bounds__(256) unary_bwd_kernel(const float* __restrict_
   X(B200AD_U_LOGB) X(B200AD_U_SQRT) X(B200AD_U_SQUARE) X(B200AD_U_POW) X(B200AD_U_ABS)            \
   X(B200AD_U_NEG) X(B200AD_U_SIN) X(B200AD_U_COS) X(B200AD_U_TAN) X(B200AD_U_SEC) X(B200AD_U_SINH) \
   X(B200AD_U_COSH) X(B200AD_U_ARCSIN) X(B200AD_U_ARCTAN) X(B200AD_U_ARCOT) X(B200AD_U_ARCSEC)     \
-  X(B200AD_U_SCALE) X(B200AD_U_ADDC) X(B200AD_U_DIVC) X(B200AD_U_RSUBC) X(B200AD_U_RDIVC)
+  X(B200AD_U_SCALE) X(B200AD_U_ADDC) X(B200AD_U_DIVC) X(B200AD_U_RSUBC) X(B200AD_U_RDIVC)                \
+  X(B200AD_U_COT) X(B200AD_U_CSC) X(B200AD_U_ARCCOS)
 
 // ---------------------------------------------------------------------------------------------
 // Binary ops with collapsed broadcasting

@@ -45,7 +45,7 @@ int b200ad_device_info(char* name, int cap, int* cc_major, int* cc_minor);
  * Elementwise unary ops.  fwd: y = f(x, param).  bwd: gx = g * f'(.)
  *   replaces np.exp/np.tanh/... in  exp.result tgrad.py:1073-1075, tanh :1613-1615,
  *   Sigmoid :901-903, ln :1294-1297, log :1338-1341, sqrt :1784-1786, square :1741-1743,
- *   pow :1103-1105, Abs :1846-1848, sin/cos/tan/sec/sinh/cosh/arcsin/arctan/arcot/arcsec
+ *   pow :1103-1105, Abs :1846-1848, sin/cos/tan/sec/sinh/cosh/arcsin/arctan/arcot/arcsec/cot/csc/arcos
  *   (:1115-1713), layers.ReLU layers.py:1284-1290;  and their get_grad bodies
  *   (:1058-1060, :1596-1598, :887-888, :1280-1282, :1324-1326, :1769-1772, :1725-1728, :1091-1093,
  *    :1850-1853).
@@ -80,7 +80,10 @@ enum b200ad_unary_op {
                           bwd g/(param+1e-8) keeps the epsilon of tgrad.py:1004 */
   B200AD_U_RSUBC = 24, /* y = param - x */
   B200AD_U_RDIVC = 25, /* y = param / x ; bwd g*(-param/(x*x+1e-8)) tgrad.py:1005 */
-  B200AD_U_COUNT = 26
+  B200AD_U_COT = 26,   /* 1/tan(x); bwd +g*csc(x)^2: the sign of tgrad.py:1639-1641 (the derivative's sign is dropped there) */
+  B200AD_U_CSC = 27,   /* 1/sin(x); bwd -g*csc(x)*cot(x): the intent of :1476-1478 (as shipped it calls np.csc and raises) */
+  B200AD_U_ARCCOS = 28,/* arccos(x); bwd g*(-1/sqrt(x+1)) as written at :1438-1440 */
+  B200AD_U_COUNT = 29
 };
 int b200ad_unary_fwd(int op, const float* x, float* y, int64_t n, float param, void* stream);
 int b200ad_unary_bwd(int op, const float* g, const float* x, const float* y, float* gx, int64_t n,

@@ -75,6 +75,27 @@ def gen_unary(ad):
     save("unary", **out)
 
 
+def gen_unary_extra(ad):
+    """cot / arcos (backward quirks of :1639, :1438 included) and trace; csc is absent on purpose: its backward raises in
+    the reference (`np.csc`), only its forward is recorded."""
+    rng = np.random.default_rng(110)
+    out = {}
+    for name, ctor, kind in (("cot", "cot", "unit"), ("arcos", "arcos", "unit")):
+        x = domain(rng, kind, (5, 7))
+        g = rng.standard_normal((5, 7))
+        X = ad.Matrix(x)
+        node = getattr(ad, ctor)(X)
+        node.gradient(g)
+        out[name + "_x"], out[name + "_g"], out[name + "_y"], out[name + "_gx"] = x, g, node.val, X.grad
+    x = domain(rng, "unit", (5, 7))
+    out["csc_x"], out["csc_y"] = x, ad.csc(ad.Matrix(x)).val
+    x = rng.standard_normal((6, 6)); g = np.float64(rng.standard_normal())
+    X = ad.Matrix(x); node = ad.trace(X)
+    node.gradient(g)
+    out["trace_x"], out["trace_g"], out["trace_y"], out["trace_gx"] = x, g, np.float64(node.val), X.grad
+    save("unary_extra", **out)
+
+
 def gen_binary(ad):
     rng = np.random.default_rng(102)
     out = {}
@@ -458,6 +479,7 @@ def main():
     L = ref_loader.load_layers()
     U = ref_loader.load_utils()
     gen_unary(ad)
+    gen_unary_extra(ad)
     gen_binary(ad)
     gen_structural(ad)
     gen_mlp(ad, U)

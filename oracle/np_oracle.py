@@ -185,6 +185,8 @@ FWD = {
     "sec": lambda n, a: 1. / np.cos(a), "sinh": lambda n, a: np.sinh(a), "cosh": lambda n, a: np.cosh(a),
     "arcsin": lambda n, a: np.arcsin(a), "arctan": lambda n, a: np.arctan(a),
     "arcot": lambda n, a: np.arctan(1 / a), "arcsec": lambda n, a: np.arccos(1. / a),
+    "cot": lambda n, a: 1 / np.tan(a), "csc": lambda n, a: 1. / np.sin(a), "arcos": lambda n, a: np.arccos(a),   # :1654, :1493, :1455
+    "trace": lambda n, a: np.trace(a),                                           # :635-637
     "sum": lambda n, a: np.sum(a, axis=n.par["axis"], keepdims=n.par["keepdims"]),   # :720-721
     "mean": lambda n, a: np.mean(a),                                             # :991-993
     "repeat": lambda n, a: np.repeat(a, n.par["times"], axis=n.par["axis"]),     # :795-797
@@ -226,6 +228,10 @@ BWD = {
     "arcot": lambda n, g: (_cs(g * (-1 / (1 + np.square(value(n.ins[0])))), n.ins[0]),),   # :1682
     "arcsec": lambda n, g: (_cs(g * (1. / (np.abs(value(n.ins[0])) * np.sqrt(np.square(value(n.ins[0])) - 1.))),
                                 n.ins[0]),),                                     # :1246
+    "cot": lambda n, g: (_cs(g * np.square(1. / np.sin(value(n.ins[0]))), n.ins[0]),),       # :1639-1641 (sign as written)
+    "csc": lambda n, g: (_cs(-g * (1. / np.sin(value(n.ins[0]))) * (1. / np.tan(value(n.ins[0]))), n.ins[0]),),   # :1476 (intent; shipped code raises)
+    "arcos": lambda n, g: (_cs(g * (-1. / np.sqrt(value(n.ins[0]) + 1.)), n.ins[0]),),       # :1438-1440 (as written)
+    "trace": lambda n, g: (_cs(g * np.identity(np.shape(value(n.ins[0]))[0]), n.ins[0]),),   # :623-628
     "sum": _sum_bwd,
     "mean": lambda n, g: (np.full(np.shape(value(n.ins[0])), g / np.size(value(n.ins[0]))),),   # :986-989
     "repeat": lambda n, g: (_cs(np.sum(g, axis=n.par["axis"], keepdims=True), n.ins[0]),),      # :781-783

@@ -42,6 +42,7 @@ _U = {
     6: np.sqrt, 7: np.square, 9: np.abs, 10: np.negative, 11: np.sin, 12: np.cos, 13: np.tan,
     14: lambda x: 1 / np.cos(x), 15: np.sinh, 16: np.cosh, 17: np.arcsin, 18: np.arctan,
     19: lambda x: np.arctan(1 / x), 20: lambda x: np.arccos(1 / x),
+    26: lambda x: 1 / np.tan(x), 27: lambda x: 1 / np.sin(x), 28: np.arccos,
 }
 _USES = {0: 1, 1: 1, 2: 1, 3: 1, 6: 1, 10: 2, 21: 2, 22: 2, 23: 2, 24: 2}
 
@@ -112,6 +113,8 @@ class Emulator:
                 17: lambda: gg / np.sqrt(1 - sv * sv), 18: lambda: gg / (1 + sv * sv), 19: lambda: -gg / (1 + sv * sv),
                 20: lambda: gg / (np.abs(sv) * np.sqrt(sv * sv - 1)), 21: lambda: gg * p, 22: lambda: gg,
                 23: lambda: gg / (p + 1e-8), 24: lambda: -gg, 25: lambda: gg * (-p / (sv * sv + 1e-8)),
+                26: lambda: gg / np.sin(sv) ** 2, 27: lambda: -gg * np.cos(sv) / np.sin(sv) ** 2,
+                28: lambda: gg * (-1.0 / np.sqrt(sv + 1.0)),
             }[op]()
         _f32(gx, n)[:] = r
         return 0

@@ -35,6 +35,22 @@ def test_unary_ops():
         np.testing.assert_allclose(X.grad, g[name + "_gx"], err_msg=name, **TOL)
 
 
+def test_unary_extra_ops():
+    """cot / arcos (backward expressions as written in the reference), trace; csc forward (its reference backward raises)."""
+    g = golden("unary_extra")
+    for name in ("cot", "arcos", "trace"):
+        X = O.leaf(g[name + "_x"])
+        node = O.op(name, X)
+        O.backward(node, g[name + "_g"])
+        np.testing.assert_allclose(node.val, g[name + "_y"], err_msg=name, **TOL)
+        np.testing.assert_allclose(X.grad, g[name + "_gx"], err_msg=name, **TOL)
+    X = O.leaf(g["csc_x"])
+    node = O.op("csc", X)
+    np.testing.assert_allclose(node.val, g["csc_y"], **TOL)
+    O.backward(node, np.ones_like(g["csc_x"]))                  # d/dx (1/sin x) = -cos x / sin^2 x
+    np.testing.assert_allclose(X.grad, -np.cos(g["csc_x"]) / np.sin(g["csc_x"]) ** 2, **TOL)
+
+
 def test_binary_ops_all_broadcast_patterns():
     g = golden("binary")
     keys = sorted({k.rsplit("_", 1)[0] for k in g})

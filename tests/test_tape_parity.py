@@ -36,6 +36,28 @@ def test_unary_golden(backend):
         assert_close(X.grad, g[name + "_gx"], what=name + " bwd")
 
 
+def test_unary_extra_golden(backend):
+    """cot / arcos / trace against the reference's golden vectors; csc forward against them and backward against the
+    oracle (the reference's csc backward raises AttributeError: np.csc)."""
+    ad = _ad()
+    g = golden("unary_extra")
+    for name in ("cot", "arcos", "trace"):
+        X = ad.Matrix(g[name + "_x"])
+        node = getattr(ad, name)(X)
+        node.gradient(g[name + "_g"])
+        assert_close(node.val, g[name + "_y"], rtol=2e-5, atol=2e-6, what=name + " fwd")
+        assert_close(X.grad, g[name + "_gx"], rtol=2e-5, atol=2e-6, what=name + " bwd")
+    X = ad.Matrix(g["csc_x"])
+    node = ad.csc(X)
+    up = np.random.default_rng(3).standard_normal(g["csc_x"].shape)
+    node.gradient(up)
+    assert_close(node.val, g["csc_y"], rtol=2e-5, atol=2e-6, what="csc fwd")
+    Xo = O.leaf(g["csc_x"]); no = O.op("csc", Xo); O.backward(no, up)
+    assert_close(X.grad, Xo.grad, rtol=2e-5, atol=2e-6, what="csc bwd")
+    with pytest.raises(AssertionError):
+        ad.trace(ad.Matrix(np.ones((2, 3)))).gradient(np.float64(1.0))       # "input has to be square matrix" :625
+
+
 def test_binary_golden_all_broadcast_patterns(backend):
     ad = _ad()
     g = golden("binary")
