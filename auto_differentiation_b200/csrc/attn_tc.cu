@@ -477,7 +477,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       float ls_r = 0.f, d_r = 0.f;                             // DQ: per-row statistics
       if (MODE == AT_DQ && row_ok) {
         ls_r = __ldg(p.lse + (int64_t)bh * p.R + grow);
-        d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow);
+        d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow) * p.c;      // pre-scaled: Z = P (Y c - D c)
       }
       // fold this group's half of OUT_blk into the running total: run = run * a + OUT
       auto fold = [&](float a) {
@@ -508,7 +508,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         }
         if (MODE == AT_DKM && tid < 128) {
           const int col = c0 + tid - 64;
-          return (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) : 0.f;
+          return (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) * p.c : 0.f;   // pre-scaled: Z = P (Y c - D c)
         }
         return 0.f;
       };
@@ -586,11 +586,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           tmem_ld_32x32b_x32(xaddr, x);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -cs[cofs + c]));
-            const uint32_t hi = tf32_hi(__float_as_uint(pv));
-            lo[c] = tf32_lo(__float_as_uint(pv), hi);
-            x[c] = hi;
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c4 + i;
+              const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls[i]));
+              const uint32_t hi = tf32_hi(__float_as_uint(pv));
+              lo[c] = tf32_lo(__float_as_uint(pv), hi);
+              x[c] = hi;
+            }
           }
           tmem_st_32x32b_x32(xaddr, x);
           tmem_st_32x32b_x32(xaddr + 64, lo);
@@ -607,20 +613,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
           tmem_ld_32x32b_x32(lane_base + Y_COL + cofs, y);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float ls, dd;
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+            float ls[4], dd[4];
             if (MODE == AT_DQ) {
-              ls = (col0 + c < p.C) ? ls_r : INFINITY;
-              dd = d_r;
-            } else {
-              ls = cs[cofs + c];
-              dd = cs[64 + cofs + c];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                ls[i] = (col0 + c4 + i < p.C) ? ls_r : INFINITY;
+                dd[i] = d_r;
+              }
+            } else {                                  // per-column statistics: two 16-byte shared-memory reads per 4 columns
+              const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
+              const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cofs + c4);
+              ls[0] = l4.x; ls[1] = l4.y; ls[2] = l4.z; ls[3] = l4.w;
+              dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
             }
-            const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls));
-            const float z = pv * (__uint_as_float(y[c]) - dd) * p.c;
-            const uint32_t hi = tf32_hi(__float_as_uint(z));
-            y[c] = tf32_lo(__float_as_uint(z), hi);
-            x[c] = hi;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c4 + i;
+              const float pv = fast_exp2(fmaf(__uint_as_float(x[c]), p.c2, -ls[i]));
+              const float z = pv * fmaf(__uint_as_float(y[c]), p.c, -dd[i]);
+              const uint32_t hi = tf32_hi(__float_as_uint(z));
+              y[c] = tf32_lo(__float_as_uint(z), hi);
+              x[c] = hi;
+            }
           }
           tmem_st_32x32b_x32(xaddr, x);
           tmem_st_32x32b_x32(lane_base + Y_COL + cofs, y);
