@@ -177,6 +177,10 @@ def run_c3(args, torch, pk):
         layer.backward(dout)
     ms = _time(torch, step, min_ms=500.0)
     flops = 4831838208.0 * B
+    # the same forward + backward replayed from a CUDA graph (43 launches: the eager loop is partly host-bound at B = 16)
+    from auto_differentiation_b200.graph import GraphedStep
+    g = GraphedStep(step)
+    gms = _time(torch, g, min_ms=300.0)
     from oracle import np_oracle as O
     xs = rng.standard_normal((2, S, d))
     t0 = time.perf_counter()
@@ -187,6 +191,7 @@ def run_c3(args, torch, pk):
             "config": {"workload": "c3: MultiHeadAttention fwd+bwd, B=%d, S=512, d=512, 8 heads (3xTF32)" % B},
             "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": flops / ms / 1e9 / pk["bf16_sustained"], "peak_source": pk["src"] + " bf16 sustained"},
+            "cuda_graph": {"steps_per_s": 1e3 / gms, "ms_per_step": gms, "TFLOPs": flops / gms / 1e9},
             "cpu_baseline": {"value": 1.0 / (cpu_s / 2 * B), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "2 of %d sequences, fp64 tape twin, scaled linearly" % B}}
 
