@@ -111,8 +111,8 @@ NCU_TRAFFIC_BYTES = {
     (512, 64, 512, 2048): 2416e6 + 262e6,        # batched d_k=64 attention products (algorithmic: 2684 MB)
     (131072, 512, 512, 1): 269.6e6 + 224.9e6,    # projection, gemm_tc3_kernel (algorithmic: 537 MB)
     (512, 512, 131072, 1): 536.9e6 + 6.9e6,      # split-K weight gradient, gemm_tc3_kernel (algorithmic: 537 MB + partials in L2)
-    "attn_fwd": 805.4e6 + 254.2e6,               # fused attention forward: Q + K + V read, O written (algorithmic: 1074 MB)
-    "attn_bwd": 544.1e6 + 1061.0e6 + 1338.1e6 + 1335.8e6,   # dvec + dV + dK + dQ passes (algorithmic: 537 + 1074 + 1342 + 1342 MB)
+    "attn_fwd": 805.5e6 + 251.7e6,               # fused attention forward (CTA-pair pass): Q + K + V read, O written (algorithmic: 1074 MB)
+    "attn_bwd": 544.1e6 + 1056.9e6 + 1334.8e6 + 1336.9e6,   # dvec + dV + dK + dQ pair passes (algorithmic: 537 + 1074 + 1342 + 1342 MB)
 }
 
 
