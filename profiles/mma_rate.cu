@@ -103,12 +103,14 @@ __global__ void __launch_bounds__(160, 1) attn_stream_kernel(int variant, int gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bars[4];
   __shared__ uint64_t dummy[3];
+  __shared__ uint64_t hs[2];        // variant 17: "the other issuing warp has issued its group"
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     for (int i = 0; i < 3; ++i) mbar_init(&dummy[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&hs[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -117,6 +119,53 @@ __global__ void __launch_bounds__(160, 1) attn_stream_kernel(int variant, int gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (variant == 17 && warp <= 1) {
+    // TWO issuing warps alternate the groups (warp w issues groups g with (g & 1) == w): per group three waits on completed
+    // barriers + tcgen05.fence + 24 MMAs + 2 commits as in variant 8, plus a handshake so that group g is issued after
+    // group g - 1.  Question: does one warp's wait / fence round trip still drain the pipe when the OTHER warp's MMAs are
+    // queued behind it?
+    constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
+    if (warp == 0 && lane == 0) { mbar_arrive(&bars[1]); mbar_arrive(&bars[2]); mbar_arrive(&bars[3]); }
+    __syncwarp();
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int g = warp; g < groups; g += 2) {
+        const bool outg = (g & 1);
+        if (g >= 1) mbar_wait(&hs[g & 1], (warp == 1 ? ((g - 1) >> 1) : ((g >> 1) - 1)) & 1);
+        mbar_wait(&bars[1], 0); mbar_wait(&bars[2], 0); mbar_wait(&bars[3], 0);
+        tc_fence_after();
+        const uint32_t slot = smem_u32(smem) + (uint32_t)(g % 6) * 32768u;
+        const uint32_t xb = 128u + (uint32_t)((g >> 1) & 1) * 128u;
+        const uint32_t d = tmem_base + (outg ? 384u : xb);
+        const uint32_t a_hi = tmem_base + (outg ? xb : 0u), a_lo = a_hi + 64u;
+        const uint64_t d0 = outg ? make_smem_desc(slot, 4096, 512, 1) : make_smem_desc(slot, 16, 1024, 2);
+        const uint32_t kstep = outg ? 1024u : 32u;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_tf32_ts(d, (t == 0 ? a_lo : a_hi) + kk * 8,
+                         d0 + (uint64_t)(((t == 1 ? 16384u : 0u) + (kk >> 2) * 8192u + (kk & 3) * kstep) >> 4),
+                         outg ? IDESC_MN : IDESC_K, (t | kk) ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[g & 1])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[2])) : "memory");
+        mbar_arrive(&hs[(g + 1) & 1]);                       // the other warp may issue group g + 1
+        if (g == groups - 1) umma_commit(&bars[0]);
+      }
+      t1 = clock64();
+    }
+    __syncwarp();
+    if (warp == 0) {
+      mbar_wait(&bars[0], 0);
+      const long long t2 = clock64();
+      done_flag = 1;
+      if (lane == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+  } else
   if (warp == 0) {
     constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t IDESC_MN = IDESC_K | (1u << 16);
@@ -357,12 +406,13 @@ int main() {
   {
     cudaFuncSetAttribute(attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 197632);
     const int groups = 512;
-    const char* vn[17] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots",
+    const char* vn[18] = {"attention-like stream", "... without commits", "... no operand / accumulator switching", "... B rotating over 6 slots",
                          "... + 4 warps streaming tcgen05.ld", "... + 4 warps streaming tcgen05.st", "... + 4 warps streaming ld + st", "kernel-like role: warp loop, 3 waits + elect + syncwarp per group",
                          "one elected thread runs the role (3 waits per group)", "one elected thread, 1 wait per group",
                          "warp loop: 3 waits, no tcgen05.fence", "warp loop: fence only", "warp loop: next group's waits + fence before the last 8 MMAs",
-                         "one thread: 3 x test_wait + fence", "one thread: 3 x try_wait, no fence", "one thread: fence only", "one thread: 3 x test_wait, no fence"};
-    for (int v = 0; v < 17; ++v) {
+                         "one thread: 3 x test_wait + fence", "one thread: 3 x try_wait, no fence", "one thread: fence only", "one thread: 3 x test_wait, no fence",
+                         "TWO issuing warps alternate groups (3 waits + fence + handshake per group)"};
+    for (int v = 0; v < 18; ++v) {
       attn_stream_kernel<<<148, 160, 197632>>>(v, groups, d_out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("attn stream: %s\n", cudaGetErrorString(e)); return 1; }
