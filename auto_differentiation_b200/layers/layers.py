@@ -886,6 +886,102 @@ class Encoder:
         wordembed.backward(lstm.backward(dhs))
 
 
+class Decoder:
+    """"Peeky" decoder (reference layers.py:866-930): the encoder's last hidden state h is concatenated to every LSTM
+    input and to every affine input; TimeEmbedding -> concat(h, e_t) -> TimeLSTM (stateful, started from h) ->
+    concat(h, s_t) -> TimeAffine."""
+
+    def __init__(self, vocab_size=12, wordvec_size=100, hidden_size=100, weights=None):
+        V, Dm, H = vocab_size, wordvec_size, hidden_size
+        if weights is None:
+            rn = np.random.randn
+            weights = [rn(V, Dm) / 100, rn(Dm + H, 4 * H) / np.sqrt(Dm), rn(H, 4 * H) / np.sqrt(H), np.zeros(4 * H),
+                       rn(H * 2, V) / np.sqrt(H), np.zeros(V)]
+        w1, w2, w3, b, w4, b1 = weights
+        self.layers = [TimeEmbedding(w1), TimeLSTM(w2, w3, b, stateful=True), TimeAffine(w4, b1)]
+        self.loss_layer = [TimeSoftmaxWithLoss()]
+        self.weights, self.grads = [], []
+        self.hidden_size = hidden_size
+        for layer in self.layers:
+            self.weights += layer.weights
+            self.grads += layer.grads
+
+    def _peek(self, h, T):
+        """np.repeat(h, T, axis=0).reshape(N, T, H) (:893): h broadcast along time, materialised once."""
+        N, H = h.shape
+        return D.broadcast_to(h.reshape((N, 1, H)), (N, T, H))
+
+    def forward(self, xs, hidden_state):
+        h = _dev(hidden_state).contiguous()
+        embed, lstm, affine = self.layers
+        lstm.set_state(h)                                                        # :889
+        out = embed.forward(xs)
+        N, T = out.shape[:2]
+        hidden = self._peek(h, T)
+        out = lstm.forward(_concat_last(hidden, out))                             # :894-895
+        return affine.forward(_concat_last(hidden, out))                          # :896-897
+
+    def backward(self, dout):
+        embed, lstm, affine = self.layers
+        H = self.hidden_size
+        dout = affine.backward(dout)
+        dhs0, dout = dout[:, :, :H], dout[:, :, H:]                                # :903
+        dout = lstm.backward(dout.contiguous())
+        dhs1, dout = dout[:, :, :H], dout[:, :, H:]                                # :905
+        embed.backward(dout)
+        dhs = D.binary(L.B_ADD, dhs0.contiguous(), dhs1.contiguous())
+        return D.binary(L.B_ADD, lstm.dh, D.sum_axis(dhs, 1, False))              # lstm.dh + sum_t dhs   :908
+
+    def generate(self, h, xs, size):
+        h = _dev(h).contiguous()
+        embed, lstm, affine = self.layers
+        lstm.set_state(h)
+        N, T = np.asarray(xs).shape
+        hidden = h.reshape((N, T, self.hidden_size))                              # :918 (N = T = 1)
+        sampled, ids = [], np.asarray(xs)
+        for _ in range(size):
+            out = lstm.forward(_concat_last(hidden, embed.forward(ids)))
+            score = affine.forward(_concat_last(hidden, out))
+            sample_id = int(D.argext_flat(score.reshape(-1)))                     # np.argmax(score, axis=2) with N = T = 1
+            ids = np.array([[sample_id]])
+            sampled.append(sample_id)
+        return sampled
+
+
+class Seq2Seq:
+    """Encoder + peeky Decoder (reference layers.py:933-961)."""
+
+    def __init__(self, word_id, vocab_size, wordvec_size=100, hidden_size=100, weights=None):
+        ew = dw = None
+        if weights is not None:
+            ew, dw = list(weights[:4]), list(weights[4:])
+        self.encoder = Encoder(vocab_size, wordvec_size, hidden_size, weights=ew)
+        self.decoder = Decoder(vocab_size, wordvec_size, hidden_size, weights=dw)
+        self.loss_layer = TimeSoftmaxWithLoss()
+        self.word_id = word_id
+        self.weights = self.encoder.weights + self.decoder.weights
+        self.grads = self.encoder.grads + self.decoder.grads
+
+    def forward(self, xs, ts):
+        ts = np.asarray(ts)
+        decoder_input, decoder_target = ts[:, :-1], ts[:, 1:]
+        h = self.encoder.forward(np.asarray(xs))
+        score = self.decoder.forward(decoder_input, h)
+        return self.loss_layer.forward(score, decoder_target)
+
+    def backward(self, dout=1):
+        dout = self.loss_layer.backward(dout)
+        dh = self.decoder.backward(dout)
+        self.encoder.backward(dh)
+
+    def generate(self, question, word_id, size):
+        h = self.encoder.forward(np.asarray(question))
+        return self.decoder.generate(h, np.array(word_id["_"]).reshape(1, 1), size)
+
+    def reset_state(self):
+        self.decoder.layers[1].reset_state()
+
+
 class AttentionEncoder(Encoder):
     """Returns every hidden state (reference layers.py:1159-1168)."""
 

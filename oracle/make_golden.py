@@ -471,6 +471,27 @@ def gen_rnnlm(L):
     save("rnnlm", **out)
 
 
+def gen_peeky_seq2seq(L):
+    """Seq2Seq with the peeky Decoder (layers.py:866-958): the encoder's last state is concatenated to every decoder LSTM
+    input and to every affine input.  One forward + backward, and greedy decoding."""
+    np.random.seed(2468)
+    V, Dm, H = 11, 6, 10
+    m = L.Seq2Seq({"_": 4}, V, Dm, H)
+    w0 = [np.array(w, dtype=np.float64) for w in m.weights]
+    rng = np.random.default_rng(111)
+    N, Te, Td = 3, 6, 4
+    xs = rng.integers(0, V, (N, Te))
+    ts = rng.integers(0, V, (N, Td + 1))
+    loss = m.forward(xs, ts)
+    m.backward()
+    out = dict(xs=xs, ts=ts, loss=np.float64(loss), n=np.int64(len(w0)), dims=np.array([V, Dm, H]))
+    for i, (w, g) in enumerate(zip(w0, m.grads)):
+        out["w%d" % i] = w
+        out["g%d" % i] = np.array(g, dtype=np.float64)
+    out["generated"] = np.array(m.generate(xs[:1], {"_": 4}, 5), dtype=np.int64)
+    save("peeky_seq2seq", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found at %s" % ref_loader.REFERENCE_ROOT)
@@ -489,6 +510,7 @@ def main():
     gen_attention(L)
     gen_seq2seq(L)
     gen_rnnlm(L)
+    gen_peeky_seq2seq(L)
 
 
 if __name__ == "__main__":

@@ -740,3 +740,50 @@ def rnnlm_get_batch(x, t, batch_size, time_size, time_idx):                     
             bt[i, k] = t[(i * jump + time_idx) % data_size]
         time_idx += 1
     return bx, bt, time_idx
+
+
+# ------------------------------------------------------------------------------------------------------
+# Seq2Seq with the peeky Decoder (layers.py:866-958)
+# ------------------------------------------------------------------------------------------------------
+def peeky_seq2seq_step(xs, ts, weights):
+    """One forward + backward.  weights = [enc_embed, enc_wx, enc_wh, enc_b, dec_embed, dec_wx (D+H, 4H), dec_wh, dec_b,
+    affine_W (2H, V), affine_b] (the order of model.weights :939).  Returns (loss, grads in the same order)."""
+    e_emb, e_wx, e_wh, e_b, d_emb, d_wx, d_wh, d_b, a_W, a_b = weights
+    dec_in, dec_tgt = ts[:, :-1], ts[:, 1:]                                        # :943
+    enc_hs, e_caches, _, _ = time_lstm_forward(embedding_forward(e_emb, xs), e_wx, e_wh, e_b)
+    h = enc_hs[:, -1, :]                                                           # Encoder.forward :855
+    N, T = dec_in.shape
+    H = h.shape[1]
+    hidden = np.repeat(h, T, axis=0).reshape(N, T, H)                              # :893
+    d_x = np.concatenate((hidden, embedding_forward(d_emb, dec_in)), axis=-1)      # :894
+    dec_hs, d_caches, _, _ = time_lstm_forward(d_x, d_wx, d_wh, d_b, h0=h)         # set_state(h) :889
+    cat = np.concatenate((hidden, dec_hs), axis=-1)                                # :896
+    score = time_affine_forward(cat, a_W, a_b)
+    loss, lcache = time_softmax_with_loss_forward(score, dec_tgt)
+    dscore = time_softmax_with_loss_backward(lcache, 1)
+    dcat, g_aW, g_ab = time_affine_backward(cat, a_W, dscore)
+    dhs0, ddec = dcat[:, :, :H], dcat[:, :, H:]                                    # :903
+    d_dx, d_grads, dh_lstm = time_lstm_backward(d_caches, d_wx, d_wh, ddec)
+    dhs1, demb = d_dx[:, :, :H], d_dx[:, :, H:]                                    # :905
+    g_demb = time_embedding_backward(d_emb.shape, dec_in, demb)
+    dh = dh_lstm + np.sum(dhs0 + dhs1, axis=1)                                     # :907-908
+    denc = np.zeros_like(enc_hs)
+    denc[:, -1, :] = dh                                                            # Encoder.backward :858-859
+    e_dx, e_grads, _ = time_lstm_backward(e_caches, e_wx, e_wh, denc)
+    g_eemb = time_embedding_backward(e_emb.shape, xs, e_dx)
+    return loss, [g_eemb, e_grads[0], e_grads[1], e_grads[2], g_demb, d_grads[0], d_grads[1], d_grads[2], g_aW, g_ab]
+
+
+def peeky_seq2seq_generate(question, weights, start_id, size):                    # :955-958 + Decoder.generate :911-930
+    e_emb, e_wx, e_wh, e_b, d_emb, d_wx, d_wh, d_b, a_W, a_b = weights
+    enc_hs, _, _, _ = time_lstm_forward(embedding_forward(e_emb, question), e_wx, e_wh, e_b)
+    h0 = enc_hs[:, -1, :]
+    hidden = h0.reshape(1, 1, -1)
+    h, cst, sid, sampled = h0, None, start_id, []
+    for _ in range(size):
+        x = np.concatenate((hidden, embedding_forward(d_emb, np.array([[sid]]))), axis=-1)
+        out, _, h, cst = time_lstm_forward(x, d_wx, d_wh, d_b, h0=h, c0=cst)
+        score = time_affine_forward(np.concatenate((hidden, out), axis=-1), a_W, a_b)
+        sid = int(np.argmax(score, axis=2).reshape(-1)[0])
+        sampled.append(sid)
+    return sampled

@@ -65,3 +65,31 @@ def test_seq2seq_fit_matches_oracle_loop(backend):
     assert np.allclose(hist, ref_hist, rtol=2e-5, atol=2e-6), (hist, ref_hist)
     for i, (w, ref) in enumerate(zip(m.weights, ws)):
         assert_close(np.asarray(w).reshape(ref.shape), ref, rtol=5e-5, atol=5e-6, what="weight %d after fit" % i)
+
+
+# ---- Seq2Seq with the peeky Decoder (reference layers.py:866-958) --------------------------------------------------
+def test_oracle_peeky_seq2seq_matches_reference_golden():
+    g = golden("peeky_seq2seq")
+    ws = _weights(g)
+    loss, grads = O.peeky_seq2seq_step(g["xs"], g["ts"], ws)
+    assert abs(loss - float(g["loss"])) < 1e-9
+    for i, gr in enumerate(grads):
+        ref = g["g%d" % i]
+        assert_close(gr.reshape(ref.shape), ref, rtol=1e-5, atol=1e-6, what="grad %d" % i)
+    assert O.peeky_seq2seq_generate(g["xs"][:1], ws, 4, 5) == [int(v) for v in g["generated"]]
+
+
+def test_peeky_seq2seq_forward_backward_generate_golden(backend):
+    from auto_differentiation_b200.layers import layers as Ls
+    g = golden("peeky_seq2seq")
+    V, Dm, H = (int(v) for v in g["dims"])
+    m = Ls.Seq2Seq({"_": 4}, V, Dm, H, weights=_weights(g))
+    loss = m.forward(g["xs"], g["ts"])
+    m.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-5
+    for i, gr in enumerate(m.grads):
+        ref = g["g%d" % i]
+        assert_close(np.asarray(gr).reshape(ref.shape), ref, rtol=2e-5, atol=2e-6, what="grad %d" % i)
+    assert m.generate(g["xs"][:1], {"_": 4}, 5) == [int(v) for v in g["generated"]]      # integer outputs, bit-exact
+    m.reset_state()
+    assert m.decoder.layers[1].h is None
