@@ -47,6 +47,19 @@ class SGD(SGDCore):
     """SGD (reference layers.py:821-831)."""
 
 
+class Repeat:
+    """np.repeat of a 2-D offset along rows ('y') or columns ('x'), kept in `.repeated` (reference layers.py:113-121)."""
+
+    def __init__(self, offset_var, repeat_num, axis: str):
+        axis = axis.lower()
+        if axis == "y":
+            self.repeated = D.repeat_axis(_dev(offset_var), repeat_num, 0)
+        elif axis == "x":
+            self.repeated = D.repeat_axis(_dev(offset_var), repeat_num, 1)
+        else:
+            raise ValueError("axis should be x or y")
+
+
 class Sum:
     def forward(self, x):
         return D.sum_axis(_dev(x), 0, True)

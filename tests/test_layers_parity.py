@@ -245,3 +245,19 @@ def test_remove_duplicate_and_trainer_contract(backend):
     tr = Trainer(Model(), Adam(lr=0.05))
     tr.fit(x, t, np.zeros(64), max_epoch=6, batch_size=16, eval_interval=1, verbose=False)
     assert tr.loss_list[-1] < tr.loss_list[0] * 0.7
+
+
+def test_repeat_and_sum_helpers(backend):
+    """`Repeat` (layers.py:113-121) and `Sum` (:124-129): np.repeat along rows / columns, column sums and their backward."""
+    L = _L()
+    rng = np.random.default_rng(8)
+    b = rng.standard_normal((2, 5))
+    np.testing.assert_array_equal(np.asarray(L.Repeat(b, 3, "Y").repeated), np.repeat(b.astype(np.float32), 3, axis=0))
+    np.testing.assert_array_equal(np.asarray(L.Repeat(b, 4, "x").repeated), np.repeat(b.astype(np.float32), 4, axis=1))
+    with pytest.raises(ValueError):
+        L.Repeat(b, 2, "z")
+    x = rng.standard_normal((7, 5))
+    sm = L.Sum()
+    assert_close(sm.forward(x), np.sum(x, axis=0, keepdims=True), what="Sum fwd")
+    dy = rng.standard_normal((1, 5))
+    np.testing.assert_array_equal(np.asarray(sm.backward(dy, 7)), np.repeat(dy.astype(np.float32), 7, axis=0))
