@@ -885,6 +885,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       uint32_t it = 0, uit = 0;
 #ifdef TC3_PROFILE
       long long w_conv = 0, w_empty = 0; const long long t_start = clock64();
+      long long w_conv_kb[16] = {0}, w_empty_ch[8] = {0};     // by k-block / chunk index inside the tile (first 16 / 4)
 #endif
       for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
         int t = tile / (p.n_tiles * p.m_tiles);
@@ -905,7 +906,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #endif
                 mbar_wait(&tmem_empty[h], (uit & 1) ^ 1);     // that half's epilogues have read the previous chunk sum
 #ifdef TC3_PROFILE
-                w_empty += clock64() - q0;
+                { const long long dq = clock64() - q0; w_empty += dq; const int ci = (cb0 - kb0) / p.chunk_kb; if (ci < 4) w_empty_ch[ci * 2 + h] += dq; }
 #endif
                 tc_fence_after();
               }
@@ -918,7 +919,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #endif
                   mbar_wait(&conv_full[s], (its / R) & 1);    // both CTAs: A hi/lo in TMEM, B lo tile in smem
 #ifdef TC3_PROFILE
-                  w_conv += clock64() - q0;
+                  { const long long dq = clock64() - q0; w_conv += dq; if (kb - kb0 < 16) w_conv_kb[kb - kb0] += dq; }
 #endif
                   tc_fence_after();
                 }
@@ -950,7 +951,14 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
 #ifdef TC3_PROFILE
       if (blockIdx.x == 0 && lane == 0)
+      {
         printf("[tc3] MMA warp: total %lld cycles, k-blocks %u, wait conv %lld, wait tmem_empty %lld\n", clock64() - t_start, it, w_conv, w_empty);
+        printf("[tc3]   wait conv by k-block in tile:");
+        for (int i = 0; i < 16; ++i) printf(" %lld", w_conv_kb[i]);
+        printf("\n[tc3]   wait tmem_empty by (chunk, half):");
+        for (int i = 0; i < 8; ++i) printf(" %lld", w_empty_ch[i]);
+        printf("\n");
+      }
 #endif
     }
   } else if (warp < 8) {
@@ -1119,8 +1127,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const long long q2 = clock64(); t_fold += q2 - q1;
 #endif
           // Last chunk: this half is final, so its 64 columns leave NOW: half a's stores run under half b's last
-          // two k-blocks of MMAs, half b's under the next tile's first chunk (the SM accepts ~32 B/clk of stores, so
-          // the 128 KB tile costs ~4-6 k cycles that must not sit between the folds).
+          // two k-blocks of MMAs, half b's under the next tile's first chunk (the SM accepts ~21-32 B/clk of stores, so
+          // the 128 KB tile costs ~5 k cycles of the epilogue warps' time; what cannot be hidden between the folds shows
+          // up as a ~1.1 k-cycle tmem_empty stall per tile, whichever way the four segments are ordered - measured).
           if (ch == nchunks - 1) {
             const uint32_t stg = smem_u32(smem + (size_t)R * TC3_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
             const int m_row0 = m_tile * 256 + (int)rank * TC_BM + q * 32;       // first row of this warp
