@@ -175,6 +175,30 @@ def workload_config(n_gpus, micro_batch):
 # ---------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(torch, index):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the CPUs of the NUMA node its
+    GPU hangs off: with one rank per GPU the eight host->device input streams otherwise cross the socket
+    interconnect.  Best effort: silently does nothing when sysfs does not expose the topology."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_c5(args):
     import torch
     import torch.distributed as dist
@@ -184,6 +208,7 @@ def run_c5(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa(torch, local_rank) if world > 1 else 0
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: the one JSON line is the contract
@@ -265,7 +290,8 @@ def run_c5(args):
         ms_e2e, _, _, _ = timed(x_host, t_host, e2e_steps, 1, True)
         e2e = {"value": 1e3 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(b_local * SEQ * DMODEL * 4 + b_local * 8), "d2h_bytes_per_step": 4,
-               "steps": e2e_steps, "api": "AttentionClassifier.forward(x_host, t) / backward() / Adam.update"}
+               "steps": e2e_steps, "api": "AttentionClassifier.forward(x_host, t) / backward() / Adam.update",
+               "host_cpus_bound": numa_cpus}
 
     if rank != 0:
         if world > 1:
