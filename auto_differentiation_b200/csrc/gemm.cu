@@ -46,7 +46,7 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d) {
   if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32) return 0;
   if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_workspace_bytes(g);
-  if (d->precision == B200AD_GEMM_AUTO && gemm_skinny_supported(g)) {
+  if (d->precision == B200AD_GEMM_AUTO && gemm_skinny_supported(g, false)) {
     // skinny recurrent-step kernels need no workspace.  (Pointer alignment is part of the check; with the null pointers
     // of this query it passes, and a misaligned operand at launch time falls back to an un-split tensor-core launch.)
     return 0;
@@ -64,7 +64,12 @@ int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float
   B200AD_REQUIRE(c && (g.k == 0 || (a && b)), "gemm: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   int prec = d->precision;
-  if (prec == B200AD_GEMM_AUTO && g.k > 0 && gemm_skinny_supported(g)) return gemm_skinny_launch(g, s);
+  if (prec == B200AD_GEMM_AUTO && g.k > 0) {
+    // inside a stream capture the host cost is paid once and device time decides; eagerly the recurrent step is host-bound
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+    if (gemm_skinny_supported(g, !capturing)) return gemm_skinny_launch(g, s);
+  }
   if (prec == B200AD_GEMM_AUTO) {
     const char* why = nullptr;
     prec = gemm_tc_supported(g, B200AD_GEMM_TF32X3, &why) ? B200AD_GEMM_TF32X3 : B200AD_GEMM_FP32;

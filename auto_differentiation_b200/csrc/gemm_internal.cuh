@@ -25,7 +25,7 @@ int64_t gemm_tc_workspace_bytes(const GemmArgs& p, int precision);
 int gemm_tc_launch(const GemmArgs& p, int precision, void* ws, int64_t ws_bytes, cudaStream_t s);
 
 // skinny fp32 kernel for the recurrent time steps, M <= 64 (gemm_skinny.cu)
-bool gemm_skinny_supported(const GemmArgs& p);
+bool gemm_skinny_supported(const GemmArgs& p, bool host_bound);
 int gemm_skinny_launch(const GemmArgs& p, cudaStream_t s);
 
 // bf16 variant (gemm_bf16.cu): conversion pre-pass + cta_group::2 kind::f16 kernel

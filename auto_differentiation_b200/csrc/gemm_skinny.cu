@@ -238,22 +238,25 @@ __global__ void __cluster_dims__(SC_CL, 1, 1) __launch_bounds__(256) gemm_skinny
 
 // Measured crossover against the tcgen05 path with 64-column tiles + split-K (profiles/recurrent_shapes_probe.py, us per
 // dependent step in a CUDA graph, M = 64): 256 x 256: 3.8 vs 16.0, 512 x 512: 5.1 vs 9.2, 1024 x 256: 5.5 vs 16.0,
-// 1024 x 1024: 12.7 vs 9.6, 2048 x 2048: 23.2 vs 18.1 -> the exact-fp32 kernels keep the small weight matrices.
+// 1024 x 1024: 12.7 vs 9.6, 2048 x 2048: 23.2 vs 18.1 -> the exact-fp32 kernels keep the small weight matrices when DEVICE
+// time decides (the launch stream is being captured into a CUDA graph).  Launched eagerly from Python the same step is
+// host-bound (one kernel here against two kernels + two tensor-map encodes there: config 4 measured 15.5 vs 21.3 ms per
+// step), so outside a capture the single-launch kernels keep every shape up to N, K <= 2048.
 constexpr int64_t SKINNY_MAX_NK = 512 * 1024;
 
-static bool skinny_cluster_ok(const GemmArgs& g) {
+static bool skinny_cluster_ok(const GemmArgs& g, bool host_bound) {
   if (getenv("B200AD_NO_SKINNY_CLUSTER")) return false;
   // measured crossover against the tensor-core path (profiles/skinny_probe.py): wins for the H = 1024 tanh-RNN step
   // (one wave of 128 CTAs), loses beyond ~2 waves or K > 2048 (the LSTM's 4H-wide / 4H-deep products)
-  if (g.n * g.k > SKINNY_MAX_NK) return false;
+  if (!host_bound && g.n * g.k > SKINNY_MAX_NK) return false;
   return g.m >= 1 && g.m <= 64 && g.batch0 * g.batch1 == 1 && !g.trans_a && g.k >= 256 && g.k <= 2048 &&
          (g.k % (SC_CL * SC_KC)) == 0 && g.n >= 64 && g.n <= 2048 && (g.n % SC_BN) == 0 && (g.lda & 3) == 0 && (g.ldb & 3) == 0 && aligned16(g.a) && aligned16(g.b);
 }
 
-bool gemm_skinny_supported(const GemmArgs& g) {
-  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g)) return true;
+bool gemm_skinny_supported(const GemmArgs& g, bool host_bound) {
+  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g, host_bound)) return true;
   if (getenv("B200AD_NO_SKINNY")) return false;
-  if (g.m < 1 || g.m > 64 || g.batch0 * g.batch1 != 1 || g.trans_a || g.n * g.k > SKINNY_MAX_NK) return false;
+  if (g.m < 1 || g.m > 64 || g.batch0 * g.batch1 != 1 || g.trans_a || (!host_bound && g.n * g.k > SKINNY_MAX_NK)) return false;
   // N <= 2048: every CTA re-reads the whole A panel (M x K) from L2, which stops paying beyond ~256 CTAs (the LSTM's
   // 4H = 4096 columns run faster on the tensor-core path: measured 14.7 vs 30.7 ms per graph-captured step)
   // ... and K <= 2048: the A panel (M x K) is re-read by every CTA (measured: 64 x 1024 x 4096 takes 52 us here, 23 us on
@@ -264,7 +267,7 @@ bool gemm_skinny_supported(const GemmArgs& g) {
 }
 
 int gemm_skinny_launch(const GemmArgs& g, cudaStream_t s) {
-  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g)) {
+  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g, true)) {
     const int grid_c = (int)(g.n / SC_BN) * SC_CL;
     if (g.trans_b) gemm_skinny_cluster_kernel<true><<<grid_c, 256, 0, s>>>(g);
     else gemm_skinny_cluster_kernel<false><<<grid_c, 256, 0, s>>>(g);
