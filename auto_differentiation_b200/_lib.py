@@ -87,6 +87,7 @@ SIGNATURES = {
     "b200ad_gemm": (c_int, [POINTER(GemmDesc), P, P, P, P, P, I64, P]),
     "b200ad_gemm_supported": (c_int, [POINTER(GemmDesc), P, P, P]),
     "b200ad_gemm_workspace_bytes": (c_int64, [POINTER(GemmDesc)]),
+    "b200ad_gemm_set_recurrent_dispatch": (c_int, [c_int]),
     "b200ad_attn_supported": (c_int, [POINTER(AttnDesc)]),
     "b200ad_attn_fwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P]),
     "b200ad_attn_bwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),

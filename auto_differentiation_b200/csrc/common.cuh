@@ -47,6 +47,16 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                : "l"(p));
   return v;
 }
+// Coherent variant for kernels that may run IN PLACE (output aliasing an input): ld.global.nc on memory the same
+// kernel writes is undefined, so the aliasing-tolerant backward kernels use this one.
+__device__ __forceinline__ float4 ld_stream_coherent(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)

@@ -4,6 +4,7 @@
 // :1252,:1263,:1266, MultiHeadAttention :1347-1360.
 #include "common.cuh"
 #include "gemm_internal.cuh"
+#include <atomic>
 
 using namespace b200ad;
 
@@ -30,7 +31,15 @@ static int fill_args(const b200ad_gemm_desc* d, const float* a, const float* b, 
   return B200AD_OK;
 }
 
+// 0 = by capture state (default), 1 = device time decides (the captured behaviour), 2 = single launch (the eager behaviour)
+static std::atomic<int> g_recurrent_dispatch{0};
+
 extern "C" {
+
+int b200ad_gemm_set_recurrent_dispatch(int mode) {
+  if (mode < 0 || mode > 2) return set_error(B200AD_ERR_INVALID, "gemm_set_recurrent_dispatch: mode %d not in 0..2", mode);
+  return g_recurrent_dispatch.exchange(mode);
+}
 
 int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float* b, const float* c) {
   GemmArgs g;
@@ -65,10 +74,16 @@ int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float
   cudaStream_t s = (cudaStream_t)stream;
   int prec = d->precision;
   if (prec == B200AD_GEMM_AUTO && g.k > 0) {
-    // inside a stream capture the host cost is paid once and device time decides; eagerly the recurrent step is host-bound
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
-    if (gemm_skinny_supported(g, !capturing)) return gemm_skinny_launch(g, s);
+    // inside a stream capture the host cost is paid once and device time decides; eagerly the recurrent step is host-bound.
+    // The two branches differ by ~1e-6 relative (both inside the parity tolerance, tests/test_config_parity.py pins each);
+    // b200ad_gemm_set_recurrent_dispatch(1 | 2) fixes one of them regardless of the capture state.
+    const int mode = g_recurrent_dispatch.load(std::memory_order_relaxed);
+    bool device_time = (mode == 1);
+    if (mode == 0) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      device_time = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+    }
+    if (gemm_skinny_supported(g, !device_time)) return gemm_skinny_launch(g, s);
   }
   if (prec == B200AD_GEMM_AUTO) {
     const char* why = nullptr;

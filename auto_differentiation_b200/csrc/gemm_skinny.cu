@@ -244,8 +244,12 @@ __global__ void __cluster_dims__(SC_CL, 1, 1) __launch_bounds__(256) gemm_skinny
 // step), so outside a capture the single-launch kernels keep every shape up to N, K <= 2048.
 constexpr int64_t SKINNY_MAX_NK = 512 * 1024;
 
+// environment switches are read once (the dispatcher runs per GEMM call)
+static bool env_no_skinny() { static const bool v = getenv("B200AD_NO_SKINNY") != nullptr; return v; }
+static bool env_no_skinny_cluster() { static const bool v = getenv("B200AD_NO_SKINNY_CLUSTER") != nullptr; return v; }
+
 static bool skinny_cluster_ok(const GemmArgs& g, bool host_bound) {
-  if (getenv("B200AD_NO_SKINNY_CLUSTER")) return false;
+  if (env_no_skinny_cluster()) return false;
   // measured crossover against the tensor-core path (profiles/skinny_probe.py): wins for the H = 1024 tanh-RNN step
   // (one wave of 128 CTAs), loses beyond ~2 waves or K > 2048 (the LSTM's 4H-wide / 4H-deep products)
   if (!host_bound && g.n * g.k > SKINNY_MAX_NK) return false;
@@ -254,8 +258,8 @@ static bool skinny_cluster_ok(const GemmArgs& g, bool host_bound) {
 }
 
 bool gemm_skinny_supported(const GemmArgs& g, bool host_bound) {
-  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g, host_bound)) return true;
-  if (getenv("B200AD_NO_SKINNY")) return false;
+  if (env_no_skinny()) return false;
+  if (skinny_cluster_ok(g, host_bound)) return true;
   if (g.m < 1 || g.m > 64 || g.batch0 * g.batch1 != 1 || g.trans_a || (!host_bound && g.n * g.k > SKINNY_MAX_NK)) return false;
   // N <= 2048: every CTA re-reads the whole A panel (M x K) from L2, which stops paying beyond ~256 CTAs (the LSTM's
   // 4H = 4096 columns run faster on the tensor-core path: measured 14.7 vs 30.7 ms per graph-captured step)
@@ -267,7 +271,7 @@ bool gemm_skinny_supported(const GemmArgs& g, bool host_bound) {
 }
 
 int gemm_skinny_launch(const GemmArgs& g, cudaStream_t s) {
-  if (!getenv("B200AD_NO_SKINNY") && skinny_cluster_ok(g, true)) {
+  if (!env_no_skinny() && skinny_cluster_ok(g, true)) {
     const int grid_c = (int)(g.n / SC_BN) * SC_CL;
     if (g.trans_b) gemm_skinny_cluster_kernel<true><<<grid_c, 256, 0, s>>>(g);
     else gemm_skinny_cluster_kernel<false><<<grid_c, 256, 0, s>>>(g);

@@ -37,7 +37,28 @@ struct WarpRow {
       }
     }
   }
-  __device__ __forceinline__ void store(float* __restrict__ row, int cols, int lane) const {
+  // same as load(), through coherent loads and without __restrict__: `row` may alias the kernel's output
+  __device__ __forceinline__ void load_aliasable(const float* row, int cols, int lane, float fill) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        if (c < cols) {
+          float4 t = ld_stream_coherent(reinterpret_cast<const float4*>(row + c));
+          v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        } else {
+          v[4 * j] = v[4 * j + 1] = v[4 * j + 2] = v[4 * j + 3] = fill;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int c = lane + 32 * j;
+        v[j] = c < cols ? row[c] : fill;
+      }
+    }
+  }
+  __device__ __forceinline__ void store(float* row, int cols, int lane) const {
     if constexpr (VEC) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
@@ -82,16 +103,17 @@ __global__ void __launch_bounds__(256) softmax_fwd_warp(const float* __restrict_
   }
 }
 
+// gx may alias g or y (MultiHeadAttention.backward writes dS over dP): a warp holds its whole row in registers before
+// it stores, rows are private to a warp, and the loads are coherent and not __restrict__.
 template <int N, bool VEC>
-__global__ void __launch_bounds__(256) softmax_bwd_warp(const float* __restrict__ g, const float* __restrict__ y,
-                                                        float* __restrict__ gx, int64_t rows, int cols,
+__global__ void __launch_bounds__(256) softmax_bwd_warp(const float* g, const float* y, float* gx, int64_t rows, int cols,
                                                         float out_scale, int diag_only) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
     WarpRow<N, VEC> wy, wg;
-    wy.load(y + r * cols, cols, lane, 0.f);
-    wg.load(g + r * cols, cols, lane, 0.f);
+    wy.load_aliasable(y + r * cols, cols, lane, 0.f);
+    wg.load_aliasable(g + r * cols, cols, lane, 0.f);
     if (diag_only) {  // SoftmaxWithLoss.get_grad as shipped: g*y*(1-y)   tgrad.py:919
 #pragma unroll
       for (int e = 0; e < wy.kElems; ++e) wg.v[e] = out_scale * wg.v[e] * wy.v[e] * (1.f - wy.v[e]);
@@ -129,9 +151,10 @@ __global__ void __launch_bounds__(256) softmax_fwd_block(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) softmax_bwd_block(const float* __restrict__ g, const float* __restrict__ y,
-                                                         float* __restrict__ gx, int64_t rows, int64_t cols,
-                                                         float out_scale, int diag_only) {
+// gx may alias g or y: pass 1 only reads, the block-wide reduction orders it before pass 2, where every thread reads
+// exactly the elements it then writes (coherent loads, no __restrict__).
+__global__ void __launch_bounds__(256) softmax_bwd_block(const float* g, const float* y, float* gx, int64_t rows,
+                                                         int64_t cols, float out_scale, int diag_only) {
   __shared__ float red[32];
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* gr = g + r * cols;
@@ -139,11 +162,11 @@ __global__ void __launch_bounds__(256) softmax_bwd_block(const float* __restrict
     float* o = gx + r * cols;
     float d = 0.f;
     if (!diag_only) {
-      for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) d += __ldg(gr + c) * __ldg(yr + c);
+      for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) d += gr[c] * yr[c];
       d = block_sum(d, red);
     }
     for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
-      const float yy = __ldg(yr + c), gg = __ldg(gr + c);
+      const float yy = yr[c], gg = gr[c];
       o[c] = diag_only ? out_scale * gg * yy * (1.f - yy) : out_scale * (gg * yy - yy * d);
     }
   }
@@ -263,8 +286,10 @@ __global__ void __launch_bounds__(1024) xent_finalize(const float* __restrict__ 
 }
 
 // dx = (p - onehot) * dout / denom * mask     (TimeSoftmaxWithLoss.backward layers.py:538-549)
-__global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__ probs, const int64_t* __restrict__ labels,
-                                                       const float* __restrict__ loss_and_count, float* __restrict__ dx,
+// dx may alias probs (TimeSoftmaxWithLoss.backward works in place on the cached probabilities, layers.py:541-545):
+// every thread reads an element (coherent load, no __restrict__ on the pair) and then writes the same element.
+__global__ void __launch_bounds__(256) xent_bwd_kernel(const float* probs, const int64_t* __restrict__ labels,
+                                                       const float* __restrict__ loss_and_count, float* dx,
                                                        int64_t rows, int64_t cols, int64_t ignore_label, float dout,
                                                        int vec_ok) {
   const float k = dout / loss_and_count[1];
@@ -276,7 +301,7 @@ __global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__
       const int64_t r = i / c4, c = (i - r * c4) << 2;
       const int64_t t_raw = labels[r];
       const int64_t t = wrap_label(t_raw, cols);
-      float4 p = ldg_stream(reinterpret_cast<const float4*>(probs) + i);
+      float4 p = ld_stream_coherent(reinterpret_cast<const float4*>(probs) + i);
       if (t_raw == ignore_label) {
         p = make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__
       const int64_t r = i / cols, c = i - r * cols;
       const int64_t t_raw = labels[r];
       const int64_t t = wrap_label(t_raw, cols);
-      float p = __ldg(probs + i);
+      float p = probs[i];
       dx[i] = (t_raw == ignore_label) ? 0.f : (p - (t == c ? 1.f : 0.f)) * k;
     }
   }

@@ -60,3 +60,45 @@ class GradientReducer:
                     w.wait()
         self._pending = []
         self._done = set()
+
+
+def dp_parity(make_model, x_global, t_global, group=None):
+    """SURVEY §8(e) parity check, run by every rank: the sum-all-reduced gradients of the W ranks (rows sharded by
+    `shard_rows`) against ONE rank running the same global batch alone.  `make_model()` must build identical models
+    (shared seed) exposing forward / backward / grads / flat_grads / bucket_slices / global_batch / reducer.
+    Returns {"max_err_over_scale", "max_rel_err", ...} on rank 0 (None elsewhere); raises nothing — callers assert."""
+    import numpy as np
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = len(x_global)
+    lo, hi = shard_rows(n, rank, world)
+    m = make_model()
+    m.global_batch = n
+    m.reducer = GradientReducer(m.flat_grads.t, m.bucket_slices(), group) if world > 1 else None
+    loss = m.forward(x_global[lo:hi], t_global[lo:hi])
+    m.backward()
+    lt = loss.t.detach().clone().reshape(1)
+    if world > 1:
+        dist.all_reduce(lt, group=group)
+    sharded = [np.asarray(g, dtype=np.float64) for g in m.grads]
+    if rank != 0:
+        return None
+    single = make_model()
+    single.global_batch = n
+    single.reducer = None
+    loss1 = single.forward(x_global, t_global)
+    single.backward()
+    worst_scaled, worst_rel, per = 0.0, 0.0, []
+    for a, g in zip(sharded, single.grads):
+        b = np.asarray(g, dtype=np.float64)
+        scale = max(float(np.abs(b).max()), 1e-30)
+        err = np.abs(a - b)
+        # elementwise |a-b| <= atol*scale + rtol*|b| with rtol 1e-5, atol 1e-6 (summation order differs between W and 1)
+        ratio = float(np.max(err / (1e-6 * scale + 1e-5 * np.abs(b))))
+        per.append(ratio)
+        worst_scaled = max(worst_scaled, float(err.max()) / scale)
+        worst_rel = max(worst_rel, ratio)
+    return {"world": world, "global_batch": int(n), "rtol": 1e-5, "atol_of_scale": 1e-6,
+            "max_err_over_scale": worst_scaled, "worst_err_over_tol": worst_rel,
+            "loss_sharded": float(lt.item()), "loss_single": float(loss1),
+            "ok": bool(worst_rel <= 1.0 and abs(float(lt.item()) - float(loss1)) <= 1e-5 * max(1.0, abs(float(loss1))))}

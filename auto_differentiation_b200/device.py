@@ -202,6 +202,18 @@ class DeviceArray:
         return out
 
     def astype(self, dtype, copy=True):
+        """Only the dtype the array already has is accepted (fp32 data / int64 indices; float64 maps to fp32 like every
+        upload does): a silent no-op conversion would hand back the wrong type."""
+        want = np.dtype(dtype) if not isinstance(dtype, torch.dtype) else None
+        if isinstance(dtype, torch.dtype):
+            same = dtype == self.t.dtype
+        elif self.t.dtype == _F32:
+            same = want.kind == "f"
+        else:
+            same = want == np.dtype(np.int64)
+        if not same:
+            raise TypeError("DeviceArray.astype(%s): device arrays are fp32 (data) or int64 (indices) only; this one is %s"
+                            % (dtype, self.t.dtype))
         return self.copy() if copy else self
 
     def __getitem__(self, idx):

@@ -29,52 +29,84 @@ def _flatten_into(arrays):
     return flat, views
 
 
-class _ChunkFeeder:
-    """Double-buffered host->device streaming of row chunks of a host array (copy stream + events).
-    On a CPU-only test backend it degenerates to synchronous per-chunk uploads."""
+def chunk_plan(n_rows, max_rows, first=32, growth=1.3, taper=3):
+    """Row counts of the micro-batches a HOST-resident batch is streamed in.  The first chunk is small (its copy is the
+    only one nothing overlaps), the sizes then grow geometrically (a chunk's copy must fit under the previous chunk's
+    compute: growth < copy rate / compute rate) up to `max_rows`, and shrink again towards the end (each chunk at most
+    1/taper of what remains) so that little compute is left once the last copy has landed — that tail is what a
+    copy-bound rank (8 ranks sharing the host fabric) otherwise pays on top of its transfer time."""
+    sizes, remaining, grow = [], int(n_rows), float(first)
+    while remaining > 0:
+        size = min(int(max_rows), int(grow) // 8 * 8 or int(grow), max(int(first), -(-remaining // taper)))
+        size = max(1, min(size, remaining))
+        sizes.append(size)
+        remaining -= size
+        grow = grow * growth
+    return sizes
 
-    def __init__(self, x, mb):
+
+class _InputStreamer:
+    """Host -> device streaming of row chunks of a host array, owned by the model and reused by every `forward`
+    (nothing is allocated per step).  Each chunk is copied as sub-copies of <= `piece` rows spread over `n_streams`
+    copy streams into a ring of `depth` staging buffers; compute waits on the chunk's events, the copy streams wait
+    on the event that says the kernels of the chunk that last used the buffer are done.  On a CPU-only test backend
+    it degenerates to synchronous per-chunk uploads."""
+
+    def __init__(self, max_rows, row_shape, depth=3):
+        import os
         import torch
         self.torch = torch
-        self.x = x
-        self.mb = mb
-        self.n = len(x)
-        self.async_ok = (D._DEVICE == "cuda" and isinstance(x, np.ndarray) and x.dtype == np.float32
-                         and x.flags.c_contiguous)
-        if self.async_ok:
-            self.src = torch.from_numpy(x)
-            self.stream = torch.cuda.Stream()
-            self.bufs = [torch.empty((mb,) + tuple(x.shape[1:]), dtype=torch.float32, device="cuda") for _ in range(2)]
-            self.ready = [None, None]
-            self.free = [None, None]
-            self._issue(0)
+        self.max_rows, self.row_shape, self.depth = int(max_rows), tuple(row_shape), depth
+        self.piece = max(1, int(os.environ.get("B200AD_H2D_PIECE_ROWS", "32")))
+        n_streams = max(1, int(os.environ.get("B200AD_H2D_STREAMS", "2")))
+        self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        self.bufs = [torch.empty((self.max_rows,) + self.row_shape, dtype=torch.float32, device="cuda")
+                     for _ in range(depth)]
+        self.free = [None] * depth
+        self.ready = {}
+        self.src = None
+        self.bounds = None
+
+    def begin(self, x, bounds):
+        """x: C-contiguous float32 host array (page-locked memory makes the copies asynchronous); bounds: [(lo, hi)]."""
+        self.src = self.torch.from_numpy(x)
+        self.bounds = bounds
+        self.ready = {}
+        self._issue(0)
+        self._issue(1)
 
     def _issue(self, c):
-        lo, hi = c * self.mb, min(self.n, (c + 1) * self.mb)
-        if lo >= self.n:
+        if c >= len(self.bounds) or c in self.ready:
             return
-        torch, slot = self.torch, c & 1
-        with torch.cuda.stream(self.stream):
-            if self.free[slot] is not None:
-                self.stream.wait_event(self.free[slot])         # the kernels of chunk c-2 are done with it
-            self.bufs[slot][:hi - lo].copy_(self.src[lo:hi], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-            self.ready[slot] = ev
+        torch, slot = self.torch, c % self.depth
+        lo, hi = self.bounds[c]
+        buf = self.bufs[slot]
+        events = []
+        for i, st in enumerate(self.streams):
+            with torch.cuda.stream(st):
+                if self.free[slot] is not None:
+                    st.wait_event(self.free[slot])          # the kernels of chunk c-depth are done with this buffer
+                for p0 in range(lo + i * self.piece, hi, self.piece * len(self.streams)):
+                    p1 = min(hi, p0 + self.piece)
+                    buf[p0 - lo:p1 - lo].copy_(self.src[p0:p1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events.append(ev)
+        self.ready[c] = events
 
     def get(self, c):
-        lo, hi = c * self.mb, min(self.n, (c + 1) * self.mb)
-        if not self.async_ok:
-            return asarray(np.asarray(self.x[lo:hi]))
         self._issue(c + 1)
-        self.torch.cuda.current_stream().wait_event(self.ready[c & 1])
-        return DeviceArray(self.bufs[c & 1][:hi - lo])
+        self._issue(c + 2)
+        cur = self.torch.cuda.current_stream()
+        for ev in self.ready.pop(c):
+            cur.wait_event(ev)
+        lo, hi = self.bounds[c]
+        return DeviceArray(self.bufs[c % self.depth][:hi - lo])
 
     def release(self, c):
-        if self.async_ok:
-            ev = self.torch.cuda.Event()
-            ev.record(self.torch.cuda.current_stream())
-            self.free[c & 1] = ev
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream())
+        self.free[c % self.depth] = ev
 
 
 class TapeMLP:
@@ -190,6 +222,7 @@ class AttentionClassifier:
         self.global_batch = None
         self.loss_buf = D.zeros((1,))
         self.last_logits = None
+        self._streamer, self._streamer_key = None, None
 
     # gradient buckets in the order they become final during the LAST micro-batch's backward
     def bucket_slices(self):
@@ -235,15 +268,36 @@ class AttentionClassifier:
         host->device copy of micro-batch c+1 runs on a copy stream while micro-batch c computes."""
         B = len(x)
         gb = self.global_batch or B
-        mb = min(self.micro_batch, B)
         self.zero_grads()
+        if B == 0:
+            # a rank whose row shard is empty (global batch < world size) contributes zero gradients and zero loss, and
+            # still joins every all-reduce in `backward()` — the other ranks would otherwise hang there
+            return self.loss_buf.reshape(())
+        mb = min(self.micro_batch, B)
         t_dev = D.as_index(t)
-        nchunks = (B + mb - 1) // mb
-        feeder = None if isinstance(x, DeviceArray) else _ChunkFeeder(x, mb)
-        for c in range(nchunks):
-            lo, hi = c * mb, min(B, (c + 1) * mb)
-            xc = x[lo:hi] if feeder is None else feeder.get(c)
-            last = (c == nchunks - 1)
+        streamed = (D._DEVICE == "cuda" and isinstance(x, np.ndarray) and x.dtype == np.float32
+                    and x.flags.c_contiguous)
+        if streamed:
+            sizes = chunk_plan(B, mb)
+        else:
+            sizes = [mb] * (B // mb) + ([B % mb] if B % mb else [])
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        bounds = [(int(offs[i]), int(offs[i + 1])) for i in range(len(sizes))]
+        feeder = None
+        if streamed:
+            key = (mb, tuple(x.shape[1:]))
+            if self._streamer is None or self._streamer_key != key:
+                self._streamer, self._streamer_key = _InputStreamer(mb, x.shape[1:]), key
+            feeder = self._streamer
+            feeder.begin(x, bounds)
+        for c, (lo, hi) in enumerate(bounds):
+            if feeder is not None:
+                xc = feeder.get(c)
+            elif isinstance(x, DeviceArray):
+                xc = x[lo:hi]
+            else:
+                xc = asarray(np.asarray(x[lo:hi]))
+            last = (c == len(bounds) - 1)
             notify = self.reducer.bucket_ready if (last and self.reducer is not None) else None
             self.chunk_step(xc, t_dev[lo:hi], (hi - lo) / gb, notify)
             if feeder is not None:

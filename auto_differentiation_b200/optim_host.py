@@ -75,6 +75,19 @@ class AdamCore:
         self._iter_dev = None
         self._lr_dev = None
 
+    def step_count(self):
+        """Number of updates applied so far.  With `capturable` the authoritative counter is the device scalar
+        (graph replays advance it without touching the host attribute); reading it synchronises."""
+        if self.capturable and self._iter_dev is not None:
+            return int(self._iter_dev.t.item())
+        return int(self.iter)
+
+    def set_step_count(self, n):
+        """Restore the step counter (checkpoint load): host attribute and, when it exists, the device scalar."""
+        self.iter = int(n)
+        if self._iter_dev is not None:
+            self._iter_dev.t.fill_(int(n))
+
     def update(self, params, grads):
         if self.m is None:
             self.m, self.v = [], []
@@ -132,6 +145,21 @@ def clip_grads(grads, max_norm):
     return norm_sq
 
 
+def _same_storage_transposed(pi, pj):
+    return (isinstance(pi, DeviceArray) and isinstance(pj, DeviceArray) and pi.ndim == 2 and pj.ndim == 2
+            and pi.ptr == pj.ptr and pi.T.shape == pj.shape and pi.t.stride() == pj.t.stride()[::-1])
+
+
+def unique_params(params):
+    """The parameters `remove_duplicate` would keep, WITHOUT touching any gradient buffer (checkpoint save / load
+    must not fold tied gradients a second time)."""
+    kept = []
+    for p in params:
+        if not any(p is q or _same_storage_transposed(q, p) for q in kept):
+            kept.append(p)
+    return kept
+
+
 def remove_duplicate(params, grads):
     """Merge shared weights (reference layers.py:76-110 / utils/useful_func.py:24-47): identical
     objects, and transposed-view weight tying (`affine_W = embed_W.T`, layers.py:711), detected by
@@ -146,8 +174,7 @@ def remove_duplicate(params, grads):
                 if pi is pj:
                     grads[i] += grads[j]
                     find_flg = True
-                elif (isinstance(pi, DeviceArray) and isinstance(pj, DeviceArray) and pi.ndim == 2 and pj.ndim == 2
-                      and pi.ptr == pj.ptr and pi.T.shape == pj.shape and pi.t.stride() == pj.t.stride()[::-1]):
+                elif _same_storage_transposed(pi, pj):
                     grads[i] += grads[j].T
                     find_flg = True
                 if find_flg:

@@ -229,6 +229,11 @@ int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float
                 const float* bias, void* workspace, int64_t workspace_bytes, void* stream);
 int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float* b, const float* c);
 int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d);
+/* B200AD_GEMM_AUTO has two implementations of the M <= 64 recurrent-step product (h_{t-1} @ Wh, dA_t @ Wh^T;
+ * reference time loops layers/layers.py:203-207, :573-576, :588-596): tcgen05 64-column tiles + split-K, and a
+ * single-launch exact-fp32 cluster kernel.  mode 0 (default) picks by whether `stream` is being captured into a
+ * CUDA graph (device time vs host launch cost), 1 pins the first, 2 the second.  Returns the previous mode. */
+int b200ad_gemm_set_recurrent_dispatch(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention core (tcgen05, fp32-faithful 3xTF32; scores never leave the SM).

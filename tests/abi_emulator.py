@@ -329,6 +329,9 @@ class Emulator:
     def b200ad_gemm_supported(self, d, a, b, c):
         return 1
 
+    def b200ad_gemm_set_recurrent_dispatch(self, mode):
+        return 0
+
     def b200ad_gemm(self, dref, a, b, c, bias, ws, ws_bytes, s):
         self.launches += 1
         d = dref._obj if hasattr(dref, "_obj") else dref

@@ -82,3 +82,49 @@ def test_checkpoint_roundtrip(backend, tmp_path):
     opt2.update(params, grads)                                              # resumed run == uninterrupted run
     for p, a in zip(params, after_one_more):
         assert_close(p, a, rtol=1e-6, atol=1e-7, what="resume")
+
+
+def test_checkpoint_capturable_adam_counter_and_tied_grads(backend, tmp_path):
+    """(1) a capturable Adam's real step counter is the DEVICE scalar (graph replays never touch the host
+    attribute): save() must read it, load() must write it back into a live optimizer; (2) save()/load() must not fold
+    the gradients of tied weights (they only select parameters)."""
+    import auto_differentiation_b200 as pkg
+    from auto_differentiation_b200.utils import checkpoint
+    from auto_differentiation_b200.utils.optimizer import Adam
+    rng = np.random.default_rng(10)
+    params = [pkg.asarray(rng.standard_normal((6, 4))), pkg.asarray(rng.standard_normal((4,)))]
+    grads = [pkg.asarray(rng.standard_normal((6, 4))), pkg.asarray(rng.standard_normal((4,)))]
+    opt = Adam(lr=0.01, capturable=True)
+    for _ in range(5):
+        opt.update(params, grads)
+    opt.iter = 2                                   # what the host attribute looks like after graph REPLAYS: stale
+    assert opt.step_count() == 5
+    checkpoint.save(params, grads, directory=str(tmp_path), optimizer=opt)
+    assert int(np.load(tmp_path / "adam_state.npz")["iter"]) == 5
+    ref = Adam(lr=0.01, capturable=True)           # uninterrupted run: 6 updates
+    p_ref = [pkg.asarray(np.asarray(p)) for p in params]
+    # rebuild the same state by restoring into a fresh optimizer and stepping once; compare with stepping the live one
+    m_ids = [id(m) for m in opt.m]
+    opt.update(params, grads)
+    expected = [np.asarray(p).copy() for p in params]
+    for _ in range(3):
+        opt.update(params, grads)                  # diverge the live optimizer (counter 9, m/v moved on) ...
+    checkpoint.load(params, grads, directory=str(tmp_path), optimizer=opt)     # ... and restore it IN PLACE
+    assert opt.step_count() == 5 and m_ids == [id(m) for m in opt.m]
+    opt.update(params, grads)
+    for p, e in zip(params, expected):
+        assert_close(p, e, rtol=1e-6, atol=1e-7, what="live capturable resume")
+    fresh = Adam(lr=0.01, capturable=True)
+    checkpoint.load(p_ref, None, directory=str(tmp_path), optimizer=fresh)
+    fresh.update(p_ref, grads)
+    assert fresh.step_count() == 6
+    for p, e in zip(p_ref, expected):
+        assert_close(p, e, rtol=1e-6, atol=1e-7, what="fresh capturable resume")
+    # tied weights: W and W.T share storage; checkpointing between backward() and update() leaves both gradients alone
+    w = pkg.asarray(rng.standard_normal((3, 5)))
+    g1, g2 = pkg.asarray(np.ones((3, 5))), pkg.asarray(np.full((5, 3), 2.0))
+    d2 = tmp_path / "tied"
+    assert checkpoint.save([w, w.T], [g1, g2], directory=str(d2)) == 1
+    checkpoint.load([w, w.T], [g1, g2], directory=str(d2))
+    np.testing.assert_array_equal(np.asarray(g1), np.ones((3, 5)))
+    np.testing.assert_array_equal(np.asarray(g2), np.full((5, 3), 2.0))
