@@ -947,7 +947,9 @@ def attn_bwd(q, k, v, o, dout, lse, scale):
         dq, dk_, dv = empty(q.shape), empty(k.shape), empty(v.shape)
     ws = empty((int(_lib().b200ad_attn_bwd_ws_floats(ctypes.byref(d))),))
     s = stream_ptr()
-    _timed(("attn_bwd", B, H, Sq, Skv, dk), 10.0 * B * H * Sq * Skv * dk,
+    # algorithmic flops: backward = 2 x forward = 8 Sq Skv dk per (batch, head); the S / dP recomputation
+    # the passes do is issued work, not algorithmic work
+    _timed(("attn_bwd", B, H, Sq, Skv, dk), 8.0 * B * H * Sq * Skv * dk,
            lambda: L.check(_lib().b200ad_attn_bwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr,
                                                   dq.ptr, dk_.ptr, dv.ptr, ws.ptr, s)))
     return dq, dk_, dv

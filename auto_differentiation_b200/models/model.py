@@ -123,6 +123,7 @@ class TapeMLP:
         self.weights = [m.val for m in self.leaves]
         self.grads = [D.zeros(w.shape) for w in self.weights]
         self.d_out = d_out
+        self._eye = None
         self._loss_node = None
         self.y = None
 
@@ -131,6 +132,11 @@ class TapeMLP:
         X = ad.Matrix(x, requires_grad=False)
         if isinstance(t, DeviceArray) and t.ndim == 2:
             onehot = t                                                           # device-resident one-hot (graph capture)
+        elif isinstance(t, DeviceArray):
+            # device-resident integer labels (Trainer.fit(graph=True)): rows of the identity = the exact one-hot
+            if self._eye is None:
+                self._eye = asarray(np.eye(self.d_out, dtype=np.float32))
+            onehot = D.embedding_gather(self._eye, D.as_index(t).reshape(n))
         else:
             onehot = np.zeros((n, self.d_out), dtype=np.float32)
             onehot[np.arange(n), np.asarray(t).astype(np.int64)] = 1.0           # exact one-hot (host, 64x10)

@@ -107,6 +107,7 @@ def c5_params_np(seed=1239, dtype=np.float64):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r1_summary.md §3), keyed by the GEMM shape bench.py reports as the dominant kernel.
+# (labelled: a table captured under ncu on a separate run, profiles/r1_summary.md — not measured inside this run)
 NCU_TRAFFIC_BYTES = {
     (512, 64, 512, 2048): 2416e6 + 262e6,        # batched d_k=64 attention products (algorithmic: 2684 MB)
     (131072, 512, 512, 1): 269.6e6 + 224.9e6,    # projection, gemm_tc3_kernel (algorithmic: 537 MB)
@@ -116,11 +117,13 @@ NCU_TRAFFIC_BYTES = {
 }
 
 
-def cpu_reference_steps(steps, warmup, sample_seqs=4):
-    """Times the oracle's config-5 step (tape-twin MHA with the reference's per-path DFS backward + head +
-    Adam, fp64 like the reference's default) on `sample_seqs` sequences; returns (steps/s scaled to the
-    full 8192-sequence step, seconds per sampled step).  BLAS threads = all host cores (torchrun exports
-    OMP_NUM_THREADS=1, which would otherwise throttle the reference arm)."""
+def cpu_reference_steps(steps, warmup, sample_seqs=64, micro=16, budget_s=150.0):
+    """Times the oracle's config-5 step (tape-twin MHA with the reference's per-path DFS backward + head + Adam, fp64
+    like the reference's default) on a SAMPLE of the 8192-sequence step: `sample_seqs` sequences processed in
+    micro-batches of `micro` (16 x 512 = 8192-row GEMMs, enough to load every BLAS thread; memory stays ~3 GB), the
+    gradients accumulated like the GPU arm does.  The sample is halved until steps x sample fits `budget_s`.
+    Returns (steps/s EXTRAPOLATED linearly to 8192 sequences, seconds per sampled step, sequences per sampled step).
+    BLAS threads = all host cores (torchrun exports OMP_NUM_THREADS=1, which would otherwise throttle this arm)."""
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=os.cpu_count() or 1)
@@ -129,36 +132,54 @@ def cpu_reference_steps(steps, warmup, sample_seqs=4):
     from oracle import np_oracle as O
     rng = np.random.default_rng(1239)
     params = c5_params_np()
+    opt = O.Adam(lr=1e-3)
     x = rng.standard_normal((sample_seqs, SEQ, DMODEL))
     t = rng.integers(0, CLASSES, sample_seqs)
-    opt = O.Adam(lr=1e-3)
+
+    def one_step(n_seqs):
+        acc = None
+        for lo in range(0, n_seqs, micro):
+            hi = min(n_seqs, lo + micro)
+            _, grads, _ = O.c5_model_step(x[lo:hi], t[lo:hi], params, heads=HEADS)
+            w = (hi - lo) / float(n_seqs)
+            acc = [g * w for g in grads] if acc is None else [a + g * w for a, g in zip(acc, grads)]
+        opt.update(params, [g.reshape(p.shape) for g, p in zip(acc, params)])
+
+    t0 = time.perf_counter()
+    one_step(min(micro, sample_seqs))                         # warm-up (BLAS thread pool, page faults) + cost estimate
+    per_seq = (time.perf_counter() - t0) / min(micro, sample_seqs)
+    n = sample_seqs
+    while n > micro and per_seq * n * (steps + max(0, warmup - 1)) > budget_s:
+        n //= 2
     times = []
-    for i in range(warmup + steps):
+    for i in range(max(0, warmup - 1) + steps):
         t0 = time.perf_counter()
-        loss, grads, _ = O.c5_model_step(x, t, params, heads=HEADS)
-        opt.update(params, [g.reshape(p.shape) for g, p in zip(grads, params)])
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+        one_step(n)
+        if i >= max(0, warmup - 1):
+            times.append(time.perf_counter() - t0)
     sec = float(np.median(times))
-    return (sample_seqs / sec) / GLOBAL_BATCH, sec
+    return (n / sec) / GLOBAL_BATCH, sec, n
+
+
+def _cpu_sample_text(n, sec):
+    return ("%d of %d sequences per step in micro-batches of 16 (S=512, d=512, 8 heads), fp64 NumPy port of the reference "
+            "tape + Adam, %.2f s per sampled step, extrapolated linearly to %d sequences" % (n, GLOBAL_BATCH, sec, GLOBAL_BATCH))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
-    value, sec = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 1)), sample)
+    value, sec, n = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 2)))
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "fwd+bwd+update steps/sec", "value": value, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "extrapolated": True, "sampled_ms_per_step": sec * 1e3, "sampled_sequences_per_step": n,
         "config": workload_config(args.gpus, args.micro_batch),
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d of %d sequences per step (S=512, d=512, 8 heads), fp64 NumPy port of the "
-                                   "reference tape + Adam, %.3f s per sample, scaled linearly" % (sample, GLOBAL_BATCH, sec)},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "extrapolated": True,
+                         "sample": _cpu_sample_text(n, sec)},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -175,28 +196,74 @@ def workload_config(n_gpus, micro_batch):
 # ---------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------------------
-def bind_to_gpu_numa(torch, index):
-    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the CPUs of the NUMA node its
-    GPU hangs off: with one rank per GPU the eight host->device input streams otherwise cross the socket
-    interconnect.  Best effort: silently does nothing when sysfs does not expose the topology."""
+def _parse_cpulist(spec):
+    cpus = set()
+    for part in spec.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def host_topology(torch):
+    """{"nodes": {node: cpus}, "gpu_cpus": [cpus of the NUMA node each visible GPU hangs off]} from sysfs (best effort)."""
+    import glob
+    nodes = {}
+    for path in glob.glob("/sys/devices/system/node/node[0-9]*/cpulist"):
+        try:
+            nodes[int(path.split("node")[-1].split("/")[0])] = _parse_cpulist(open(path).read())
+        except Exception:
+            pass
+    gpu_cpus = []
+    for i in range(torch.cuda.device_count()):
+        try:
+            props = torch.cuda.get_device_properties(i)
+            bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+            gpu_cpus.append(_parse_cpulist(open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read()))
+        except Exception:
+            gpu_cpus.append(set())
+    return {"nodes": nodes, "gpu_cpus": gpu_cpus}
+
+
+def bind_to_gpu_numa(torch, index, world):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) near its GPU so that the N
+    host->device input streams do not all read one memory node.  If sysfs gives each GPU its own CPU list, use it.
+    If every GPU reports the SAME list (a VM that hides the topology — what round 1 ran into: all 8 ranks ended up on
+    `0-31`), spread the ranks round-robin over the NUMA nodes that exist instead of piling onto one; with a single node
+    there is nothing to choose and the affinity is left alone.  Returns a short description for the JSON line."""
     try:
-        props = torch.cuda.get_device_properties(index)
-        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
-        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-        return len(cpus)
-    except Exception:
-        return 0
+        topo = host_topology(torch)
+        allowed = os.sched_getaffinity(0)
+        mine = topo["gpu_cpus"][index] & allowed if index < len(topo["gpu_cpus"]) else set()
+        distinct = {frozenset(c) for c in topo["gpu_cpus"] if c}
+        nodes = {k: v & allowed for k, v in topo["nodes"].items() if v & allowed}
+        if mine and len(distinct) > 1:
+            os.sched_setaffinity(0, mine)
+            return "gpu-local cpus (%d)" % len(mine)
+        if len(nodes) > 1 and world > 1:
+            order = sorted(nodes)
+            node = order[index % len(order)]
+            os.sched_setaffinity(0, nodes[node])
+            return "round-robin numa node %d of %d (%d cpus; sysfs reports one cpu list for every GPU)" % (
+                node, len(order), len(nodes[node]))
+        return "unbound (%d numa node%s visible)" % (len(nodes), "" if len(nodes) == 1 else "s")
+    except Exception as e:                                   # noqa: BLE001 - best effort
+        return "unbound (%s)" % type(e).__name__
+
+
+def synthetic_rows(torch, lo, hi, block=256):
+    """Rows [lo, hi) of THE global synthetic input tensor (8192, 512, 512): generated on the device in blocks of 256
+    rows seeded by the block index, so every world size sees the same global batch (losses are comparable across N)."""
+    import math
+    block = math.gcd(block, math.gcd(lo, hi - lo)) or block    # 256 at every benchmarked size; smaller only for odd --global-batch
+    out = torch.empty((hi - lo, SEQ, DMODEL), dtype=torch.float32, device="cuda")
+    gen = torch.Generator(device="cuda")
+    for b in range(lo // block, hi // block):
+        gen.manual_seed(1239 + b)
+        out[(b * block - lo):((b + 1) * block - lo)].normal_(generator=gen)
+    return out
 
 
 def run_c5(args):
@@ -208,7 +275,7 @@ def run_c5(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local_rank)
-    numa_cpus = bind_to_gpu_numa(torch, local_rank) if world > 1 else 0
+    numa_binding = bind_to_gpu_numa(torch, local_rank, world) if world > 1 else "single rank: unbound"
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: the one JSON line is the contract
@@ -216,7 +283,7 @@ def run_c5(args):
     import auto_differentiation_b200 as pkg
     from auto_differentiation_b200 import _lib as L, device as D
     from auto_differentiation_b200.data_parallel import GradientReducer, shard_rows
-    from auto_differentiation_b200.models.model import AttentionClassifier
+    from auto_differentiation_b200.models.model import AttentionClassifier, chunk_plan
     from auto_differentiation_b200.utils.optimizer import Adam
 
     pkg.set_gemm_precision(args.precision)
@@ -227,9 +294,8 @@ def run_c5(args):
     model.reducer = GradientReducer(model.flat_grads.t, model.bucket_slices()) if world > 1 else None
     opt = Adam(lr=1e-3)
 
-    gen = torch.Generator(device="cuda").manual_seed(1239 + rank)
-    x_dev = D.DeviceArray(torch.randn((b_local, SEQ, DMODEL), generator=gen, device="cuda"))   # synthetic inputs
-    t_host = np.random.default_rng(1239 + rank).integers(0, CLASSES, b_local)
+    x_dev = D.DeviceArray(synthetic_rows(torch, lo, hi))                                       # synthetic inputs
+    t_host = np.random.default_rng(1239).integers(0, CLASSES, GLOBAL_BATCH)[lo:hi]
     t_dev = D.as_index(t_host)
 
     def step(x, t):
@@ -291,7 +357,23 @@ def run_c5(args):
         e2e = {"value": 1e3 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(b_local * SEQ * DMODEL * 4 + b_local * 8), "d2h_bytes_per_step": 4,
                "steps": e2e_steps, "api": "AttentionClassifier.forward(x_host, t) / backward() / Adam.update",
-               "host_cpus_bound": numa_cpus}
+               "host_binding": numa_binding, "input_chunks": len(chunk_plan(b_local, args.micro_batch)),
+               "h2d_streams": int(os.environ.get("B200AD_H2D_STREAMS", "2"))}
+
+    # ---- data-parallel parity: reduced gradients of `world` ranks == one rank on the same global batch ----
+    dp_par = None
+    if world > 1 and not args.no_dp_parity:
+        from auto_differentiation_b200.data_parallel import dp_parity
+        rng = np.random.default_rng(77)
+        nb = 16 * world + 3                                           # uneven shards on purpose
+        xg = rng.standard_normal((nb, SEQ, DMODEL)).astype(np.float32)
+        tg = rng.integers(0, CLASSES, nb)
+        dp_par = dp_parity(lambda: AttentionClassifier(DMODEL, HEADS, HIDDEN, CLASSES, seed=1239, micro_batch=8), xg, tg)
+    if world > 1:
+        lt = torch.tensor([loss_val], device="cuda", dtype=torch.float64)
+        dist.all_reduce(lt)
+        loss_val = float(lt.item())                                   # global mean loss (each rank holds its share)
+        dist.barrier()
 
     if rank != 0:
         if world > 1:
@@ -299,6 +381,7 @@ def run_c5(args):
         return
 
     pk = peaks()
+    attn_bwd_units = float(os.environ.get("B200AD_ATTN_BWD_UNITS", "8"))    # GEMM units the backward passes issue (dV 2 + dK 3 + dQ 3)
     # dominant kernel = the GEMM shape with the largest accumulated device time in the timed region
     roof = None
     if gemm:
@@ -317,9 +400,10 @@ def run_c5(args):
             traffic = NCU_TRAFFIC_BYTES.get(tuple(int(v) for v in key[:4]))
         # tcgen05 kind::tf32 flops the kernel actually issues per algorithmic flop: three products per product
         # (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, the fp32-faithful split), and for the backward attention passes the
-        # flash-style recomputation of S (dV pass) and of S and dP (dK and dQ passes): (2 + 3 + 3) x 3 / 5
+        # flash-style recomputation of S (dV pass) and of S and dP (dK and dQ passes): (2 + 3 + 3) x 3 GEMM units issued
+        # per 4 algorithmic ones (backward = 2 x (QK^T + PV) = 8 S^2 d_k flops per (batch, head))
         if isinstance(key[0], str):
-            issued = 3.0 if key[0] == "attn_fwd" else 24.0 / 5.0
+            issued = 3.0 if key[0] == "attn_fwd" else attn_bwd_units * 3.0 / 4.0
         else:
             issued = 3.0 if int(key[6]) in (1, 3) else 1.0       # b200ad_gemm_precision: TF32X3 / AUTO
         tf32_peak = peak / 2.0
@@ -329,6 +413,8 @@ def run_c5(args):
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % pk["src"],
                 "kernel": kname,
+                "flop_basis": "SURVEY 8(d): 2MNK per mathematically required product once (attention fwd 4 S^2 d_k, bwd 8 S^2 d_k "
+                              "per (batch, head); recomputation inside the kernels is NOT counted)",
                 "shares": {k: round(v / (ms_step * args.steps), 4) for k, v in fam[:8]},
                 "launches_timed": n, "avg_launch_ms": avg_ms,
                 "share_of_step": ms_tot / (ms_step * args.steps), "all_gemm_share_of_step": total_gemm_ms / (ms_step * args.steps),
@@ -339,10 +425,9 @@ def run_c5(args):
                                         "S / dP per pass) against the TF32 dense peak = half of the measured bf16 peak"}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec = cpu_reference_steps(2, 1, 4)
-        cpu = {"value": v, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "4 of %d sequences per step (S=512, d=512, 8 heads), fp64 NumPy port of the reference tape + "
-                         "Adam, %.3f s per sample, scaled linearly" % (GLOBAL_BATCH, sec)}
+        v, sec, n = cpu_reference_steps(2, 1, 64, budget_s=25.0)
+        cpu = {"value": v, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port", "extrapolated": True,
+               "sample": _cpu_sample_text(n, sec)}
     line = {
         "metric": "fwd+bwd+update steps/sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -352,6 +437,14 @@ def run_c5(args):
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "loss": loss_val,
         "gemm_precision": args.precision,
     }
+    if dp_par is not None:
+        line["dp_parity"] = dp_par
+    if world == 1 and not args.no_workloads:
+        # BASELINE configs[0..3] next to the headline (each with its own clocks / roofline / through-the-API number)
+        del model, opt, x_dev
+        torch.cuda.empty_cache()
+        from profiles import workloads
+        line["workloads"] = workloads.run_all(args, torch, pk, ClockSampler)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -370,6 +463,8 @@ def main():
                          "four host->device chunks per step so the input stream overlaps the compute)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the configs 1-4 block of the --gpus 1 line")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the data-parallel gradient parity check (N > 1)")
     ap.add_argument("--max-elems", type=int, default=0, help="c2 sweep: largest size (default 1e9)")
     ap.add_argument("--c3-batch", type=int, default=16)
     ap.add_argument("--global-batch", type=int, default=8192,

@@ -34,8 +34,17 @@ def run_c2(args, torch, pk):
     sizes = [10 ** e for e in range(3, 10)]
     if args.max_elems:
         sizes = [s for s in sizes if s <= args.max_elems]
-    ops = {"add_bcast": 16, "mul_bcast": 20, "add_same": 24, "mul_same": 32, "exp": 20, "tanh": 20, "sigmoid": 20,
+    if getattr(args, "c2_sizes", None):
+        sizes = list(args.c2_sizes)
+    # bytes per element the B200 path MOVES (fwd + bwd) — the basis of GBps / frac_hbm below.  For mul and the unary ops
+    # this equals SURVEY 8(d)'s out-of-place count (32 / 20 / 20).  Add differs: the reference's backward writes two
+    # copies of g (24 B/elem same-shape, 16 broadcast), this path returns g itself for a same-shape operand and only
+    # reads g once for the broadcast operand's column sum, so it moves 12 B/elem in both variants; quoting the
+    # reference's byte count over this path's time would overstate the bandwidth (the 182 % of round 1).
+    ops = {"add_bcast": 12, "mul_bcast": 20, "add_same": 12, "mul_same": 32, "exp": 20, "tanh": 20, "sigmoid": 20,
            "relu": 20}
+    ref_bytes = {"add_bcast": 16, "mul_bcast": 20, "add_same": 24, "mul_same": 32, "exp": 20, "tanh": 20, "sigmoid": 20,
+                 "relu": 20}
     table = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
     for n_req in sizes:
@@ -69,8 +78,9 @@ def run_c2(args, torch, pk):
             ms_with_flush = _time(torch, fn_flushed, min_ms=100.0)
             ms_flush = _time(torch, lambda: flush.zero_(), min_ms=50.0) if n * 4 < (200 << 20) else 0.0
             ms = max(ms_with_flush - ms_flush, 1e-4)
-            row = {"ms": ms, "GBps": n * bpe / ms / 1e6, "frac_hbm": n * bpe / ms / 1e6 / pk["hbm"]}
-            if n * 4 < (200 << 20):
+            row = {"ms": ms, "GBps": n * bpe / ms / 1e6, "frac_hbm": n * bpe / ms / 1e6 / pk["hbm"],
+                   "bytes_per_elem_moved": bpe, "bytes_per_elem_reference": ref_bytes[name]}
+            if n * 4 < (200 << 20) and not getattr(args, "c2_no_graph", False):
                 # the same pair replayed from a CUDA graph (8 flush+fwd+bwd iterations per replay): removes the host
                 # launch gaps that dominate the eager numbers below ~1e8 elements
                 from auto_differentiation_b200.graph import GraphedStep
@@ -91,9 +101,12 @@ def run_c2(args, torch, pk):
     big = str(sizes[-1])
     best = {k: v[big]["frac_hbm"] for k, v in table.items()}
     return {"metric": "elementwise fwd+bwd algorithmic GB/s", "unit": "GB/s", "value": float(np.mean([v[big]["GBps"] for v in table.values()])),
-            "config": {"workload": "c2: elementwise+activation gradient sweep, fp32, 1e3..%s elements" % big,
+            "config": {"workload": "c2: elementwise+activation gradient sweep, fp32, %s..%s elements" % (sizes[0], big),
                        "l2": "L2 flushed (256 MB write) between iterations when the working set is < 200 MB"},
-            "roofline": {"bound": "hbm", "peak": pk["hbm"], "unit": "GB/s", "frac_at_largest": best, "peak_source": pk["src"]},
+            "roofline": {"bound": "hbm", "peak": pk["hbm"], "unit": "GB/s", "frac_at_largest": best, "peak_source": pk["src"],
+                         "frac": float(np.mean(list(best.values()))), "achieved": float(np.mean([v[big]["GBps"] for v in table.values()])),
+                         "byte_basis": "bytes this path moves per element (fwd+bwd): add 12, mul same-shape 32 / broadcast 20, "
+                                       "unary 20; equal to SURVEY 8(d) except add (reference: 24 / 16, it copies g twice)"},
             "table": table}
 
 
@@ -153,8 +166,30 @@ def run_c1(args, torch, pk):
         ropt.update([W1, b1, W2, b2], grads)
         ts.append(time.perf_counter() - t0)
     cpu_ms = float(np.median(ts[5:])) * 1e3
-    return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / wall_ms, "ms_per_step": wall_ms,
+    # through the reference's own training entry point: Trainer.fit (utils/Train.py:15-64), eager and graph=True
+    from auto_differentiation_b200.utils.Train import Trainer
+    xs = rng.standard_normal((64 * 64, 784)).astype(np.float32)
+    ts = rng.integers(0, 10, 64 * 64)
+    api = {}
+    for mode, epochs in (("eager", 4), ("graph", 40)):
+        tr = Trainer(TapeMLP(), Adam(lr=1e-3))
+        tr.fit(xs[:64 * 8], ts[:64 * 8], max_epoch=1, batch_size=64, eval_interval=10 ** 9, verbose=False, graph=(mode == "graph"))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.fit(xs, ts, max_epoch=epochs, batch_size=64, eval_interval=10 ** 9, verbose=False, graph=(mode == "graph"))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        api[mode] = {"steps_per_s": 64 * epochs / dt, "iterations": 64 * epochs, "final_loss": tr.loss_list[-1]}
+    flops = 78053376.0
+    return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": api["graph"]["steps_per_s"],
+            "ms_per_step": 1e3 / api["graph"]["steps_per_s"],
+            "through_api": {"call": "Trainer(TapeMLP(), Adam()).fit(x, t, batch_size=64, graph=True) — wall clock incl. the per-batch "
+                                    "input copy, one loss read-back per epoch", "trainer_fit_graph": api["graph"],
+                            "trainer_fit_eager": api["eager"], "manual_step_eager_steps_per_s": 1e3 / wall_ms},
             "device_ms_per_step": ms, "gpu_launches_per_step": int(per_step),
+            "roofline": {"bound": "launch latency (78 MFLOP/step: < 1 us of tensor time; SURVEY 8d says to report steps/s)",
+                         "achieved": flops * api["graph"]["steps_per_s"] / 1e12, "unit": "TFLOP/s", "peak": pk["bf16_sustained"],
+                         "frac": flops * api["graph"]["steps_per_s"] / 1e12 / pk["bf16_sustained"]},
             "cuda_graph": {"steps_per_s": 1e3 / graph_ms, "ms_per_step": graph_ms, "loss_after_523_steps": graph_loss},
             "config": {"workload": "c1: tape MLP 784-256-10, batch 64, Adam (eager, launch-latency bound: 78 MFLOP/step)"},
             "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
@@ -188,6 +223,9 @@ def run_c3(args, torch, pk):
     O.backward(out, np.ones_like(out.val))
     cpu_s = time.perf_counter() - t0
     return {"metric": "MHA fwd+bwd steps/sec", "unit": "steps/s", "value": 1e3 / ms, "ms_per_step": ms,
+            "through_api": {"call": "layer.forward(x, x, x); layer.backward(dout) (eager, device-timed)", "steps_per_s": 1e3 / ms,
+                            "graphed_call": "GraphedStep(lambda: (layer.forward(x, x, x), layer.backward(dout)))()",
+                            "graphed_steps_per_s": 1e3 / gms},
             "config": {"workload": "c3: MultiHeadAttention fwd+bwd, B=%d, S=512, d=512, 8 heads (3xTF32)" % B},
             "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": flops / ms / 1e9 / pk["bf16_sustained"], "peak_source": pk["src"] + " bf16 sustained"},
@@ -197,61 +235,81 @@ def run_c3(args, torch, pk):
 
 
 def run_c4(args, torch, pk):
+    """Config 4 through the reference's training entry point: `Trainer.fit` on RnnLM (TimeEmbedding -> TimeRNN / TimeLSTM
+    -> TimeAffine -> TimeSoftmaxWithLoss), eager and graph=True; one step = forward + backward + Adam over N=64, T=256."""
     from auto_differentiation_b200.models.model import RnnLM
     from auto_differentiation_b200.utils.optimizer import Adam
+    from auto_differentiation_b200.utils.Train import Trainer
     from auto_differentiation_b200 import _lib as L
     out = {}
     rng = np.random.default_rng(1238)
     N, T, V = 64, 256, 1000
-    xs = rng.integers(0, V, (N, T))
+    n_batches = 4
+    xs = rng.integers(0, V, (N * n_batches, T))
     ts = np.roll(xs, -1, axis=1)
-    from auto_differentiation_b200 import device as D
-    from auto_differentiation_b200.graph import GraphedStep
-    xs_d, ts_d = D.as_index(xs), D.as_index(ts)
-    for cell in ("rnn", "lstm"):
+    cells = getattr(args, "c4_cells", None) or ("rnn", "lstm")
+    for cell in cells:
         m, opt = RnnLM(vocab=V, wordvec=256, hidden=1024, cell=cell), Adam(lr=1e-3)
 
         def step():
-            m.forward(xs, ts)
+            m.forward(xs[:N], ts[:N])
             m.backward()
             opt.update(m.weights, m.grads)
+        step()
         n0 = L.launch_count()
         step()
         launches = L.launch_count() - n0
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        reps = 5
-        for _ in range(reps):
-            step()
-        torch.cuda.synchronize()
-        out[cell] = {"ms_per_step": (time.perf_counter() - t0) / reps * 1e3, "gpu_launches_per_step": int(launches)}
-        m2, opt2 = RnnLM(vocab=V, wordvec=256, hidden=1024, cell=cell), Adam(lr=1e-3, capturable=True)
-
-        def gstep():
-            loss = m2.forward(xs_d, ts_d)
-            m2.backward()
-            opt2.update(m2.weights, m2.grads)
-            return loss
-        g = GraphedStep(gstep, warmup=2)
-        g(); g()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(10):
-            g()
-        torch.cuda.synchronize()
-        out[cell]["cuda_graph_ms_per_step"] = (time.perf_counter() - t0) / 10 * 1e3
-        out[cell]["loss_after_graph_steps"] = float(g.result)
+        res = {"gpu_launches_per_step": int(launches)}
+        for mode, epochs in (("eager", 2), ("graph", 4)):
+            tr = Trainer(RnnLM(vocab=V, wordvec=256, hidden=1024, cell=cell), Adam(lr=1e-3))
+            tr.fit(xs, ts, max_epoch=1, batch_size=N, eval_interval=10 ** 9, verbose=False, graph=(mode == "graph"))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tr.fit(xs, ts, max_epoch=epochs, batch_size=N, eval_interval=10 ** 9, verbose=False, graph=(mode == "graph"))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            res["trainer_fit_%s_ms_per_step" % mode] = dt / (epochs * n_batches) * 1e3
+            res["trainer_fit_%s_final_loss" % mode] = tr.loss_list[-1]
+        out[cell] = res
     flops = 229512314880.0
-    # headline = the whole step replayed from one CUDA graph (auto_differentiation_b200.graph.GraphedStep): the recurrence is
-    # 768 dependent small launches, which an eager Python loop cannot issue fast enough (eager numbers stay in `cells`)
-    gms = out["rnn"]["cuda_graph_ms_per_step"]
-    return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / gms, "ms_per_step": gms,
-            "eager_ms_per_step": out["rnn"]["ms_per_step"],
-            "config": {"workload": "c4: RNN LM V=1000 D=256 H=1024 T=256 N=64 (tanh cell; LSTM variant in `cells`)",
-                       "mode": "CUDA-graph replay of forward + backward + Adam (capturable, device-side step scalar)"},
+    first = out[cells[0]]
+    best_ms = min(first["trainer_fit_eager_ms_per_step"], first["trainer_fit_graph_ms_per_step"])
+    return {"metric": "fwd+bwd+update steps/sec", "unit": "steps/s", "value": 1e3 / best_ms, "ms_per_step": best_ms,
+            "through_api": {"call": "Trainer(RnnLM(hidden=1024), Adam()).fit(xs, ts, batch_size=64[, graph=True]) — wall clock incl. "
+                                    "the per-batch input copy", "cells": out},
+            "config": {"workload": "c4: RNN LM V=1000 D=256 H=1024 T=256 N=64 (tanh cell; LSTM variant in `cells`)"},
             "cells": out,
-            "roofline": {"bound": "tensor", "achieved": flops / gms / 1e9, "unit": "TFLOP/s",
-                         "peak": pk["bf16_sustained"], "note": "sequential M=64 recurrent GEMMs are latency bound"}}
+            "roofline": {"bound": "tensor", "achieved": flops / best_ms / 1e9, "unit": "TFLOP/s",
+                         "peak": pk["bf16_sustained"], "frac": flops / best_ms / 1e9 / pk["bf16_sustained"],
+                         "note": "229.5 GFLOP/step (SURVEY 8d); the M=64 recurrence is a latency-bound dependent chain, "
+                                 "the input projection / affine / weight-gradient GEMMs run on tcgen05 (3xTF32)"}}
+
+
+def run_all(args, torch, pk, ClockSampler):
+    """BASELINE configs[0..3] in one pass for the `workloads` block of the `bench.py --gpus 1` line: each entry carries
+    its own clocks record (nvidia-smi sampled while it runs), roofline fraction and through-the-API number."""
+    import copy
+    out = {}
+    a = copy.copy(args)
+    a.c2_sizes, a.c2_no_graph, a.c3_batch = (10 ** 8, 10 ** 9), True, 16
+    for name, fn in (("c1", run_c1), ("c2", run_c2), ("c3", run_c3), ("c4", run_c4)):
+        sampler = ClockSampler(torch.cuda.current_device())
+        sampler.start()
+        t0 = time.perf_counter()
+        try:
+            line = fn(a, torch, pk)
+        except Exception as e:                        # noqa: BLE001 - one failing side workload must not lose the headline
+            line = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.synchronize()
+        line["clocks"] = sampler.stop()
+        line["wall_s"] = time.perf_counter() - t0
+        if name == "c2" and "table" in line:           # keep the line small: the per-op fractions are in roofline
+            line["table"] = {k: {sz: {kk: round(vv, 4) if isinstance(vv, float) else vv for kk, vv in r.items()}
+                                 for sz, r in v.items()} for k, v in line["table"].items()}
+        out[name] = line
+        torch.cuda.empty_cache()
+    return out
 
 
 def run(args):
@@ -266,6 +324,11 @@ def run(args):
     pkg.set_gemm_precision(args.precision)
     pk = peaks()
     fn = {"c1": run_c1, "c2": run_c2, "c3": run_c3, "c4": run_c4}[args.workload]
+    from bench import ClockSampler
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
     line = fn(args, torch, pk)
+    torch.cuda.synchronize()
+    line["clocks"] = sampler.stop()
     line.update({"n_gpus": 1, "dtype": "f32", "data": "synthetic", "gemm_precision": args.precision})
     print(json.dumps(line))
