@@ -986,3 +986,52 @@ def act_bwd(g, y, act, out=None):
     po, ldo, _, _ = _rows_ld(out)
     L.check(_lib().b200ad_act_bwd(pg, ldg, py, ldy, po, ldo, rows, cols, act, stream_ptr()))
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# persistent recurrent time loops (csrc/rnn_seq.cu)
+# --------------------------------------------------------------------------------------------------
+_rnn_seq_ok = {}
+_persistent_recurrence = [True]
+
+
+def set_persistent_recurrence(flag):
+    """False forces the per-step loop over b200ad_gemm (the reference's own loop structure; used by parity tests)."""
+    _persistent_recurrence[0] = bool(flag)
+
+
+def rnn_seq_supported(batch, hidden):
+    if not _persistent_recurrence[0]:
+        return False
+    key = (int(batch), int(hidden))
+    if key not in _rnn_seq_ok:
+        _rnn_seq_ok[key] = bool(_lib().b200ad_rnn_seq_supported(key[0], key[1]))
+    return _rnn_seq_ok[key]
+
+
+def _rnn_seq_ws():
+    return raw_bytes(int(_lib().b200ad_rnn_seq_ws_bytes()))
+
+
+def rnn_tanh_seq_fwd_(hs_ext, wh):
+    """hs_ext (T+1, N, H) contiguous: hs_ext[t+1] = tanh(hs_ext[t+1] + hs_ext[t] @ wh) for all t, in ONE launch."""
+    T1, N, H = hs_ext.shape
+    wh = wh.contiguous()
+    ws = _rnn_seq_ws()
+    L.check(_lib().b200ad_rnn_tanh_seq_fwd(hs_ext.ptr, wh.ptr, T1 - 1, N, H, ws.data_ptr(), stream_ptr()))
+    return hs_ext
+
+
+def rnn_tanh_seq_bwd(dhs, hs_ext, wh):
+    """BPTT of the tanh recurrence in ONE launch.  dhs: (N, T, H) view with a contiguous last axis.  Returns
+    (dA (T, N, H), dh0 (N, H))."""
+    T1, N, H = hs_ext.shape
+    T = T1 - 1
+    wh = wh.contiguous()
+    if dhs.t.stride(2) != 1 or (dhs.t.stride(0) & 3) or (dhs.t.stride(1) & 3) or (dhs.ptr & 15):
+        dhs = dhs.copy()
+    dA, dh0 = empty((T, N, H)), empty((N, H))
+    ws = _rnn_seq_ws()
+    L.check(_lib().b200ad_rnn_tanh_seq_bwd(dhs.ptr, dhs.t.stride(0), dhs.t.stride(1), hs_ext.ptr, wh.ptr, dA.ptr, dh0.ptr,
+                                           T, N, H, ws.data_ptr(), stream_ptr()))
+    return dA, dh0

@@ -301,8 +301,11 @@ class TimeRNN(_TimeRecurrent):
         # place: hs_ext[t+1] = tanh(hs_ext[t+1] + h_{t-1} @ Wh) — one launch per step (fused beta / tanh epilogue)
         xs_tm = xs.transpose(1, 0, 2).contiguous()
         D.matmul(xs_tm.reshape(T * N, Dm), wx, bias=b.reshape(-1), out=hs_ext[1:].reshape(T * N, H))
-        for t in range(T):
-            D.matmul(hs_ext[t], wh, out=hs_ext[t + 1], beta=1.0, act=L.ACT_TANH)
+        if D.rnn_seq_supported(N, H):
+            D.rnn_tanh_seq_fwd_(hs_ext, wh)          # the whole time loop in ONE persistent launch (csrc/rnn_seq.cu)
+        else:
+            for t in range(T):
+                D.matmul(hs_ext[t], wh, out=hs_ext[t + 1], beta=1.0, act=L.ACT_TANH)
         self.h = hs_ext[T]
         self._cache = (xs_tm, hs_ext)
         return hs_ext[1:].transpose(1, 0, 2)
@@ -313,16 +316,19 @@ class TimeRNN(_TimeRecurrent):
         T, N, Dm = xs_tm.shape
         H = wh.shape[0]
         dhs = _last_contig(_dev(dhs))
-        dA = D.empty((T, N, H))
-        dh = None
-        lib = L.load()
-        for t in reversed(range(T)):
-            pa, lda = _row_view(dhs[:, t, :])
-            pb, ldb = _row_view(dh) if dh is not None else (None, 0)
-            ph, ldh = _row_view(hs_ext[t + 1])
-            pd, ldd = _row_view(dA[t])
-            _cell_call(lib.b200ad_rnn_cell_bwd, pa, lda, pb, ldb, ph, ldh, pd, ldd, N, H)
-            dh = D.matmul(dA[t], wh, trans_b=True)
+        if D.rnn_seq_supported(N, H):
+            dA, dh = D.rnn_tanh_seq_bwd(dhs, hs_ext, wh)     # all T + 1 BPTT phases in ONE persistent launch
+        else:
+            dA = D.empty((T, N, H))
+            dh = None
+            lib = L.load()
+            for t in reversed(range(T)):
+                pa, lda = _row_view(dhs[:, t, :])
+                pb, ldb = _row_view(dh) if dh is not None else (None, 0)
+                ph, ldh = _row_view(hs_ext[t + 1])
+                pd, ldd = _row_view(dA[t])
+                _cell_call(lib.b200ad_rnn_cell_bwd, pa, lda, pb, ldb, ph, ldh, pd, ldd, N, H)
+                dh = D.matmul(dA[t], wh, trans_b=True)
         self.dh = dh
         return self._weight_grads(xs_tm, hs_ext[:T], dA)
 

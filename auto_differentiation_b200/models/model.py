@@ -29,7 +29,7 @@ def _flatten_into(arrays):
     return flat, views
 
 
-def chunk_plan(n_rows, max_rows, first=32, growth=1.3, taper=3):
+def chunk_plan(n_rows, max_rows, first=32, growth=1.3, taper=2):
     """Row counts of the micro-batches a HOST-resident batch is streamed in.  The first chunk is small (its copy is the
     only one nothing overlaps), the sizes then grow geometrically (a chunk's copy must fit under the previous chunk's
     compute: growth < copy rate / compute rate) up to `max_rows`, and shrink again towards the end (each chunk at most

@@ -48,7 +48,8 @@ class _GraphedIteration:
         from .. import device as D
         self.torch, self.D = torch, D
         self.on_gpu = D._DEVICE == "cuda"
-        self.x_buf = D.empty((batch_size,) + tuple(x.shape[1:]))
+        self.x_is_index = np.asarray(x).dtype.kind in "iu"            # token ids (config 4) stay int64 on the device
+        self.x_buf = D.empty((batch_size,) + tuple(x.shape[1:]), torch.int64 if self.x_is_index else torch.float32)
         t = np.asarray(t)
         self.t_is_index = t.dtype.kind in "iu"
         self.t_buf = D.empty((batch_size,) + tuple(t.shape[1:]), torch.int64 if self.t_is_index else torch.float32)
@@ -64,6 +65,9 @@ class _GraphedIteration:
             trainer.optimizer.capturable = True
         self.epoch_x = self.epoch_t = self.epoch_extra = None
 
+    def _x_dtype(self):
+        return np.int64 if self.x_is_index else np.float32
+
     def _iteration(self):
         loss = self.trainer._train_step(self.x_buf, self.t_buf, self.third, self.max_grad)
         self.D.axpby_(loss.reshape(1), self.loss_sum, 1.0, 1.0)
@@ -74,13 +78,13 @@ class _GraphedIteration:
         torch = self.torch
         if x.nbytes + np.asarray(t).nbytes <= (2 << 30):
             dev = self.x_buf.t.device
-            self.epoch_x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev, non_blocking=True)
+            self.epoch_x = torch.from_numpy(np.ascontiguousarray(x, dtype=self._x_dtype())).to(dev, non_blocking=True)
             tt = np.ascontiguousarray(t, dtype=np.int64 if self.t_is_index else np.float32)
             self.epoch_t = torch.from_numpy(tt).to(dev, non_blocking=True)
             if self.extra_buf is not None:
                 self.epoch_extra = torch.from_numpy(np.ascontiguousarray(extra, dtype=np.float32)).to(dev, non_blocking=True)
         else:
-            self.epoch_x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            self.epoch_x = torch.from_numpy(np.ascontiguousarray(x, dtype=self._x_dtype()))
             self.epoch_t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.int64 if self.t_is_index else np.float32))
             if self.extra_buf is not None:
                 self.epoch_extra = torch.from_numpy(np.ascontiguousarray(extra, dtype=np.float32))

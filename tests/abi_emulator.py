@@ -468,6 +468,35 @@ class Emulator:
         _rows(dt, lddt, n, h)[...] = self._actb(d, _rows(h_next, ldh, n, h).astype(np.float64), 1)
         return 0
 
+    def b200ad_rnn_seq_supported(self, batch, hidden):
+        return 1 if (1 <= batch <= 64 and hidden in (256, 512, 1024)) else 0
+
+    def b200ad_rnn_seq_ws_bytes(self):
+        return 256
+
+    def b200ad_rnn_tanh_seq_fwd(self, hs_ext, wh, T, N, H, ws, s):
+        self.launches += 1
+        hs = _f32(hs_ext, (T + 1) * N * H).reshape(T + 1, N, H)
+        w = _f32(wh, H * H).reshape(H, H).astype(np.float64)
+        for t in range(T):
+            hs[t + 1] = np.tanh(hs[t + 1].astype(np.float64) + hs[t].astype(np.float64) @ w)
+        return 0
+
+    def b200ad_rnn_tanh_seq_bwd(self, dhs, sn, st, hs_ext, wh, dA, dh0, T, N, H, ws, s):
+        self.launches += 1
+        hs = _f32(hs_ext, (T + 1) * N * H).reshape(T + 1, N, H)
+        w = _f32(wh, H * H).reshape(H, H).astype(np.float64)
+        da = _f32(dA, T * N * H).reshape(T, N, H)
+        span = (N - 1) * sn + (T - 1) * st + H
+        g = np.lib.stride_tricks.as_strided(_f32(dhs, span), shape=(N, T, H), strides=(4 * sn, 4 * st, 4))
+        dh = np.zeros((N, H))
+        for t in reversed(range(T)):
+            da[t] = (g[:, t, :].astype(np.float64) + dh) * (1.0 - hs[t + 1].astype(np.float64) ** 2)
+            dh = da[t].astype(np.float64) @ w.T
+        if dh0:
+            _f32(dh0, N * H).reshape(N, H)[...] = dh
+        return 0
+
     def b200ad_act_bwd(self, g, ldg, y, ldy, gx, ldgx, rows, cols, act, s):
         self.launches += 1
         _rows(gx, ldgx, rows, cols)[...] = self._actb(_rows(g, ldg, rows, cols).astype(np.float64),

@@ -104,13 +104,20 @@ def test_recurrent_gemm_dispatch_branches_pinned(mode):
     h = rng.standard_normal((64, 1024))
     w = rng.standard_normal((1024, 1024)) / 32.0
     pre = rng.standard_normal((64, 1024))
-    ref = np.tanh(pre + h @ w)
+    z = pre + h @ w
     lib = L.load()
     prev = lib.b200ad_gemm_set_recurrent_dispatch({"device_time": 1, "single_launch": 2}[mode])
     try:
+        # the product itself, to rtol 1e-5 / atol 1e-6 of ITS scale (max |z| ~ 6): the tcgen05 branch sits at ~0.6e-6 of
+        # that scale (fp32 accumulation inside the tensor core truncates; chains are folded every 128 K-elements)
+        lin = pkg.asarray(pre).copy()
+        D.matmul(pkg.asarray(h), pkg.asarray(w), out=lin, beta=1.0)
+        assert_close(lin, z, rtol=1e-5, atol=1e-6, what="recurrent step pre-activation (%s)" % mode)
+        # with the fused tanh: tanh is 1-Lipschitz, so the same ABSOLUTE error bound carries over (atol stated in units
+        # of the pre-activation scale, not of tanh's unit range)
         out = pkg.asarray(pre).copy()
         D.matmul(pkg.asarray(h), pkg.asarray(w), out=out, beta=1.0, act=L.ACT_TANH)
-        assert_close(out, ref, rtol=1e-5, atol=1e-6, what="recurrent step (%s)" % mode)
+        assert_close(out, np.tanh(z), rtol=1e-5, atol=1e-6 * float(np.abs(z).max()), what="recurrent step (%s)" % mode)
         outT = D.matmul(pkg.asarray(h), pkg.asarray(w), trans_b=True)
         assert_close(outT, h @ w.T, rtol=1e-5, atol=1e-6, what="BPTT step (%s)" % mode)
     finally:
