@@ -97,9 +97,8 @@ SIGNATURES = {
                                      I64, I64, P]),
     "b200ad_rnn_cell_bwd": (c_int, [P, I64, P, I64, P, I64, P, I64, I64, I64, P]),
     "b200ad_rnn_seq_supported": (c_int, [I64, I64]),
-    "b200ad_rnn_seq_ws_bytes": (c_int64, []),
-    "b200ad_rnn_tanh_seq_fwd": (c_int, [P, P, I64, I64, I64, P, P]),
-    "b200ad_rnn_tanh_seq_bwd": (c_int, [P, I64, I64, P, P, P, P, I64, I64, I64, P, P]),
+    "b200ad_rnn_tanh_seq_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
+    "b200ad_rnn_tanh_seq_bwd": (c_int, [P, I64, I64, P, P, P, P, I64, I64, I64, P]),
     "b200ad_bias_act_fwd": (c_int, [P, I64, P, P, I64, I64, I64, c_int, P]),
     "b200ad_act_bwd": (c_int, [P, I64, P, I64, P, I64, I64, I64, c_int, P]),
     "b200ad_adam_multi": (c_int, [P, c_int, I64, P, P, c_float, c_float, c_float, c_float, c_float, P, P]),

@@ -2,7 +2,7 @@
 //
 // Reference loops replaced: TimeRNN.forward layers/layers.py:203-207 (h_t = tanh(x_t Wx + h_{t-1} Wh + b), the x_t Wx + b
 // part hoisted into one big GEMM by the caller) and TimeRNN.backward :210-225 in its intended form:
-//   forward  phase t      : hs[t+1] = tanh(hs[t+1] + hs[t] @ Wh)                                   t = 0 .. T-1
+//   forward  phase t      : hs[t+1] = tanh(pre[t] + hs[t] @ Wh)                                    t = 0 .. T-1
 //   backward phase p      : dA[t]   = (dhs[:, t, :] + dA[t+1] @ Wh^T) * (1 - hs[t+1]^2)            t = T-1-p, p = 0 .. T-1
 //            phase T      : dh0     = dA[0] @ Wh^T
 // Every phase is one dependent (N <= 64) x H x H product.  Launched step by step it costs ~10 us per step at H = 1024 (512
@@ -15,16 +15,21 @@
 //     MEMORY for the whole launch as the TS-mode A operand (lane = output column, TMEM column = k);
 //   * per phase it loads its (rows x H/8) slice of the previous state from L2 (ld.global.cg), splits it into hi / lo
 //     SWIZZLE_128B K-major tiles in shared memory (the B operand) and issues 3 x (H/8)/8 tcgen05.mma kind::tf32
-//     (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi: the same fp32-faithful 3xTF32 scheme as gemm_tc.cu, one <= 128-deep chain);
-//   * the 8 K-partials of a cluster are summed through distributed shared memory in a fixed order (bit-reproducible):
-//     CTA j of the cluster finalises rows [j*rows/8, (j+1)*rows/8) of the 128-column slice, applies the fused epilogue
-//     (+ pre-activation, tanh / BPTT product) and writes the new state to global memory;
-//   * dependent phases are ordered by per-slice arrival counters in global memory (release: __syncthreads +
-//     __threadfence + red.release.gpu by one thread; acquire: one thread spins on ld.acquire.gpu, then __syncthreads):
-//     a consumer only waits for the ONE cluster that produces its K-slice, never for the whole grid.
+//     (cross terms first, hi.hi last: the same fp32-faithful 3xTF32 scheme as gemm_tc.cu, one <= 128-deep chain);
+//   * the 8 K-partials of a cluster are exchanged by PUSH: every CTA sends the rows of its partial straight from
+//     registers into the shared memory of the CTA that finalises them (st.async ... mbarrier::complete_tx::bytes through
+//     distributed shared memory), the owner waits on a LOCAL mbarrier for the 8 x rows x 128 x 4 bytes and sums the
+//     eight partials in a fixed order (bit-reproducible), applies the fused epilogue (+ pre-activation, tanh / BPTT
+//     product) and writes the new state to global memory.  No cluster barrier and no fence on the dependent path;
+//   * dependent phases are ordered THROUGH THE DATA: the output buffers are filled with a sentinel (0xFFFFFFFF, a NaN
+//     pattern the epilogue never stores) before the launch, and a consumer simply re-loads its slice of the state from
+//     L2 until no word carries the sentinel — one L2 round trip instead of store -> fence -> flag -> poll -> load
+//     (measured: 2.0k + 1.5k cycles of an 11.5k-cycle phase went into fence + flag).  A consumer only ever waits for the
+//     ONE cluster that produces its K-slice, never for the whole grid.
 // All waits are bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include <vector>
 
 namespace b200ad {
 
@@ -32,48 +37,53 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_CL = 8;            // CTAs per cluster = K-slices
 constexpr int RS_BM = 128;          // output columns per cluster (= TMEM lanes)
 constexpr uint32_t RS_ACC_COLS = 64;   // TMEM columns reserved for the accumulator (<= 64 batch rows)
+constexpr uint32_t RS_SENTINEL = 0xffffffffu;
 
 struct RnnSeqParams {
   const float* w;        // Wh, (H, H) row-major
   int64_t ldw;
-  float* hs;             // (T+1, N, H): fwd reads hs[t] and completes hs[t+1] in place; bwd reads hs[t+1]
+  float* hs;             // (T+1, N, H): fwd reads hs[t] and writes hs[t+1] (sentinel-filled at launch); bwd reads hs[t+1]
+  const float* pre;      // fwd: (T, N, H) pre-activations x_t Wx + b
   const float* dhs;      // bwd: upstream gradient of the outputs, element (n, t, c) at dhs[n*dhs_sn + t*dhs_st + c]
   int64_t dhs_sn, dhs_st;
-  float* dA;             // bwd: (T, N, H) pre-activation gradients (output, also the next phase's operand)
+  float* dA;             // bwd: (T, N, H) pre-activation gradients (output, sentinel-filled at launch; also the next operand)
   float* dh0;            // bwd: (N, H) gradient of the initial state (may be null)
-  unsigned int* flags;   // [H/128 * n_split] arrival counters, zero at launch
   int32_t T, N, H;
   int32_t ks;            // K elements per CTA = H / 8  (32, 64 or 128)
   int32_t n_split;       // batch halves (1 or 2)
   int32_t bwd;
+  long long* prof;       // debugging aid (B200AD_RNN_SEQ_PROF=1): per-CTA cycle counters of the phase segments, or null
 };
+constexpr int RS_PROF_SEGS = 8;
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// (the memory clobber keeps the load behind whatever precedes it; callers issue all loads of a batch before the first use
+// so that they are in flight together)
+__device__ __forceinline__ uint4 ld_cg_u4(const float* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// (the memory clobber keeps the load behind the acquire / barrier that precedes it; callers issue all loads of a batch
-// before the first use so that they are in flight together)
 __device__ __forceinline__ float4 ld_cg_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
+  const uint4 v = ld_cg_u4(p);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta) {
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
   uint32_t ra;
-  float4 v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(cta));
-  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
-  return v;
+  return ra;
+}
+// remote (or local) shared-memory store that completes `4` bytes on the mbarrier of the SAME destination CTA
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, uint32_t value, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(value),
+               "r"(remote_bar)
+               : "memory");
 }
 __device__ __forceinline__ uint32_t tf32_hi(uint32_t x) { return x & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(uint32_t x) {
   return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xffffe000u)) & 0xffffe000u;
 }
+// the sentinel pattern is never stored as data (it is a NaN; a NaN result is stored with the canonical payload)
+__device__ __forceinline__ float rs_clean(float v) { return __float_as_uint(v) == RS_SENTINEL ? __uint_as_float(0x7fffffffu) : v; }
 
 // NB: batch rows per cluster (32 or 64) = the MMA N dimension.
 template <int NB>
@@ -81,13 +91,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_seq_kernel(const RnnSeqPara
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KS = p.ks;
+  constexpr int ROWS = NB / RS_CL;                       // rows of the cluster's tile this CTA finalises
   const uint32_t KB_BYTES = NB * 128;                    // one 32-deep k-block of the B tile: NB rows x 128 B
   const uint32_t B_BYTES = (uint32_t)(KS / 32) * KB_BYTES;
+  constexpr uint32_t RECV_BYTES = RS_CL * ROWS * RS_BM * 4;   // one receive buffer: [src CTA 8][ROWS][128] floats
   uint8_t* b_hi = smem;                                  // [KS/32][NB][128 B] SWIZZLE_128B, K-major
   uint8_t* b_lo = smem + B_BYTES;
-  float* part = reinterpret_cast<float*>(smem + 2 * B_BYTES);          // [2][NB][128] this CTA's K-partials (double buffered)
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 2 * B_BYTES + 2 * NB * RS_BM * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* recv = reinterpret_cast<float*>(smem + 2 * B_BYTES);           // [2][8][ROWS][128] K-partials pushed by the peers
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 2 * B_BYTES + 2 * RECV_BYTES);
+  uint64_t* recv_bar = mma_bar + 1;                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();               // K-slice of this CTA
@@ -98,6 +111,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_seq_kernel(const RnnSeqPara
 
   if (tid == 0) {
     mbar_init(mma_bar, 1);
+    mbar_init(&recv_bar[0], 1);
+    mbar_init(&recv_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
@@ -132,40 +147,47 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_seq_kernel(const RnnSeqPara
     tmem_st_wait();
     tc_fence_before();
   }
-  __syncthreads();
+  // every CTA's mbarriers are initialised before any peer pushes into it
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
 
   // instruction descriptor: D = f32, A = B = tf32, both K-major, N = NB, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(RS_BM >> 4) << 24);
   const uint32_t sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
-  const uint32_t part_addr = smem_u32(part);
+  const uint32_t recv_addr = smem_u32(recv);
 
-  // the rows this thread finalises after the cluster reduction: NB/8 rows x 32 float4 per CTA
-  const bool fin = tid < NB * 4;
-  const int fin_row = (int)rank * (NB / 8) + (tid >> 5);        // row inside the cluster's NB rows
-  const int fin_n = n0 + fin_row;                                // batch row
+  // the rows this thread finalises after the exchange: ROWS rows x 32 float4 per CTA
+  const bool fin = tid < ROWS * 32;
+  const int fin_r = tid >> 5;                                    // row inside this CTA's ROWS rows
+  const int fin_n = n0 + (int)rank * ROWS + fin_r;               // batch row
   const int fin_c = c0 + (tid & 31) * 4;                         // first of 4 output columns
   const bool fin_live = fin && fin_n < p.N;
   const int64_t NH = (int64_t)p.N * p.H;
 
-  // which cluster produces this CTA's K-slice of the state, and its counter
-  const unsigned int* wait_flag = p.flags + ((k0 / RS_BM) * p.n_split + ns);
-  unsigned int* my_flag = p.flags + (cs * p.n_split + ns);
-
   const int phases = p.bwd ? p.T + 1 : p.T;
   uint32_t mma_phase = 0;
+  long long prof[RS_PROF_SEGS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tick = p.prof ? clock64() : 0;
+#define RS_TICK(seg)                                   \
+  if (p.prof) {                                        \
+    const long long now_ = clock64();                  \
+    prof[seg] += now_ - tick;                          \
+    tick = now_;                                       \
+  }
   for (int ph = 0; ph < phases; ++ph) {
     // ---- operand / epilogue pointers of this phase
     const float* src;            // (N, H) state consumed by the product (nullptr: no product, acc = 0)
     const int t = p.bwd ? p.T - 1 - ph : ph;
     if (!p.bwd) src = p.hs + (int64_t)ph * NH;
     else src = ph == 0 ? nullptr : p.dA + (int64_t)(p.T - ph) * NH;
+    const bool produced_here = p.bwd ? true : ph > 0;     // the operand is an output of this launch (sentinel protocol)
 
     // ---- epilogue operands do not depend on the recurrence: fetch them before waiting
     float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
     if (fin_live) {
       if (!p.bwd) {
-        e0 = ld_cg_f4(p.hs + (int64_t)(ph + 1) * NH + (int64_t)fin_n * p.H + fin_c);          // x_t Wx + b (pre-activation)
+        e0 = ld_cg_f4(p.pre + (int64_t)ph * NH + (int64_t)fin_n * p.H + fin_c);               // x_t Wx + b (pre-activation)
       } else if (ph < p.T) {
         e0 = ld_cg_f4(p.dhs + (int64_t)fin_n * p.dhs_sn + (int64_t)t * p.dhs_st + fin_c);     // upstream dh_t
         e1 = ld_cg_f4(p.hs + (int64_t)(t + 1) * NH + (int64_t)fin_n * p.H + fin_c);           // h_t
@@ -174,65 +196,88 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_seq_kernel(const RnnSeqPara
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (src != nullptr) {
-      // ---- wait until the producing cluster has published the previous phase (8 CTAs x ph arrivals)
-      if (ph > 0) {
-        if (tid == 0) {
-          const unsigned int need = (unsigned int)RS_CL * (unsigned int)ph;
-          if (ld_acquire_gpu_u32(wait_flag) < need) {
-            const long long t0 = clock64();
-            uint32_t spins = 0;
-            while (ld_acquire_gpu_u32(wait_flag) < need) {
-              if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();
-            }
-          }
-        }
-        __syncthreads();
-      }
-      // ---- B operand: rows [n0, n0+NB) x k [k0, k0+KS) of the state -> hi / lo SWIZZLE_128B tiles
+      const uint32_t buf = mma_phase & 1u;
+      if (tid == 0) mbar_expect_tx(&recv_bar[buf], RECV_BYTES);   // 8 senders x ROWS rows x 128 floats will land here
+      // ---- B operand: rows [n0, n0+NB) x k [k0, k0+KS) of the state -> hi / lo SWIZZLE_128B tiles.
+      // All loads of the slice are issued before the first one is consumed (one L2 round trip); words still carrying
+      // the sentinel have not been produced yet -> reload them.
       {
-        // all loads of the slice are issued before the first one is consumed: ONE L2 round trip per phase
         const int vec_per_row = KS / 4, total = NB * vec_per_row;
         constexpr int MAX_IT = NB / 8;                       // NB * (128 / 4) / 256 at the largest K-slice
-        float4 xs[MAX_IT];
+        uint4 xs[MAX_IT];
+        uint32_t pending = 0;
 #pragma unroll
         for (int i = 0; i < MAX_IT; ++i) {
           const int idx = tid + i * RS_THREADS;
-          const int row = idx / vec_per_row, c16 = idx - row * vec_per_row;
-          xs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < total && n0 + row < p.N) xs[i] = ld_cg_f4(src + (int64_t)(n0 + row) * p.H + k0 + c16 * 4);
+          const int row = idx / vec_per_row;
+          xs[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (idx < total && n0 + row < p.N) pending |= 1u << i;
         }
+        long long t0 = 0;
+        uint32_t spins = 0;
+        while (pending) {
+#pragma unroll
+          for (int i = 0; i < MAX_IT; ++i) {
+            if (pending & (1u << i)) {
+              const int idx = tid + i * RS_THREADS;
+              const int row = idx / vec_per_row, c16 = idx - row * vec_per_row;
+              xs[i] = ld_cg_u4(src + (int64_t)(n0 + row) * p.H + k0 + c16 * 4);
+            }
+          }
+          if (!produced_here) break;
+#pragma unroll
+          for (int i = 0; i < MAX_IT; ++i) {
+            if ((pending & (1u << i)) && xs[i].x != RS_SENTINEL && xs[i].y != RS_SENTINEL && xs[i].z != RS_SENTINEL &&
+                xs[i].w != RS_SENTINEL)
+              pending &= ~(1u << i);
+          }
+          if (pending) {
+            if (spins == 0) t0 = clock64();
+            if ((++spins & 63u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+          }
+        }
+        RS_TICK(0)      // operand available (poll + load)
 #pragma unroll
         for (int i = 0; i < MAX_IT; ++i) {
           const int idx = tid + i * RS_THREADS;
           if (idx >= total) break;
           const int row = idx / vec_per_row, c16 = idx - row * vec_per_row;
-          const float4 x = xs[i];
+          const uint4 x = xs[i];
           const uint32_t off = (uint32_t)(c16 >> 3) * KB_BYTES + (uint32_t)row * 128u + (uint32_t)(((c16 & 7) ^ (row & 7)) << 4);
           uint4 h, l;
-          h.x = tf32_hi(__float_as_uint(x.x)); h.y = tf32_hi(__float_as_uint(x.y));
-          h.z = tf32_hi(__float_as_uint(x.z)); h.w = tf32_hi(__float_as_uint(x.w));
-          l.x = tf32_lo(__float_as_uint(x.x)); l.y = tf32_lo(__float_as_uint(x.y));
-          l.z = tf32_lo(__float_as_uint(x.z)); l.w = tf32_lo(__float_as_uint(x.w));
+          h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+          l.x = tf32_lo(x.x); l.y = tf32_lo(x.y); l.z = tf32_lo(x.z); l.w = tf32_lo(x.w);
           *reinterpret_cast<uint4*>(b_hi + off) = h;
           *reinterpret_cast<uint4*>(b_lo + off) = l;
         }
         fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
       }
+      tc_fence_before();                // (orders the previous phase's tcgen05.ld before the MMAs that overwrite the accumulator)
       __syncthreads();
+      RS_TICK(1)      // split + barrier
       // ---- 3 x KS/8 MMAs (one elected thread), accumulator = TMEM columns [0, NB)
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
+          // The accumulator truncates on every MMA (measured): the 2 x KS/8 cross-term MMAs go FIRST, while
+          // the accumulator is ~2^-11 of its final size (their truncation error is negligible), the KS/8 hi.hi MMAs last
+          // -> a third of the truncations at full magnitude compared with interleaving the three terms per k-step.
           for (int kb = 0; kb < KS / 32; ++kb) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint32_t koff = (uint32_t)kb * KB_BYTES + (uint32_t)kk * 32u;
               const uint32_t acol = (uint32_t)kb * 32u + (uint32_t)kk * 8u;
-              const uint64_t dh = make_smem_desc(sb_hi + koff, 16u, 1024u, 2u);
-              const uint64_t dl = make_smem_desc(sb_lo + koff, 16u, 1024u, 2u);
-              umma_tf32_ts(tmem_base, a_lo + acol, dh, idesc, (kb == 0 && kk == 0) ? 0u : 1u);
-              umma_tf32_ts(tmem_base, a_hi + acol, dl, idesc, 1u);
-              umma_tf32_ts(tmem_base, a_hi + acol, dh, idesc, 1u);
+              umma_tf32_ts(tmem_base, a_lo + acol, make_smem_desc(sb_hi + koff, 16u, 1024u, 2u), idesc,
+                           (kb == 0 && kk == 0) ? 0u : 1u);
+              umma_tf32_ts(tmem_base, a_hi + acol, make_smem_desc(sb_lo + koff, 16u, 1024u, 2u), idesc, 1u);
+            }
+          }
+          for (int kb = 0; kb < KS / 32; ++kb) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t koff = (uint32_t)kb * KB_BYTES + (uint32_t)kk * 32u;
+              const uint32_t acol = (uint32_t)kb * 32u + (uint32_t)kk * 8u;
+              umma_tf32_ts(tmem_base, a_hi + acol, make_smem_desc(sb_hi + koff, 16u, 1024u, 2u), idesc, 1u);
             }
           }
           umma_commit(mma_bar);
@@ -240,66 +285,67 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_seq_kernel(const RnnSeqPara
         __syncwarp();
       }
       mbar_wait(mma_bar, mma_phase & 1);
-      ++mma_phase;
       tc_fence_after();
-      // ---- accumulator (lane = column c, TMEM column = row n) -> part[ph & 1][n][c]
+      RS_TICK(2)      // MMA issue + completion
+      // ---- accumulator (lane = column c, TMEM column = row n) -> pushed to the CTA that finalises row n:
+      //      recv[buf][this CTA's rank][n % ROWS][c] in CTA n / ROWS of the cluster
       {
         const int q = warp & 3, half = warp >> 2;
-        float* dst = part + (size_t)(ph & 1) * NB * RS_BM + (q * 32 + lane);
-        if constexpr (NB == 32) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 16u, r);
-          tmem_ld_wait();
+        const int c = q * 32 + lane;
+        constexpr int HALF_ROWS = NB / 2;
+        uint32_t r[HALF_ROWS];
+        if constexpr (NB == 32) tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 16u, r);
+        else tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 32u, r);
+        tmem_ld_wait();
+        const uint32_t slot = recv_addr + buf * RECV_BYTES + (uint32_t)(rank * ROWS * RS_BM + c) * 4u;
+        const uint32_t bar_local = smem_u32(&recv_bar[buf]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dst[(size_t)(half * 16 + j) * RS_BM] = __uint_as_float(r[j]);
-        } else {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 32u, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dst[(size_t)(half * 32 + j) * RS_BM] = __uint_as_float(r[j]);
+        for (int j = 0; j < HALF_ROWS; ++j) {
+          const int n = half * HALF_ROWS + j;              // row inside the cluster's NB rows
+          const uint32_t owner = (uint32_t)(n / ROWS);
+          st_async_f32(mapa_u32(slot + (uint32_t)((n % ROWS) * RS_BM) * 4u, owner), r[j], mapa_u32(bar_local, owner));
         }
-        tc_fence_before();
       }
-      // ---- all 8 K-partials of the cluster are in shared memory after this barrier
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      RS_TICK(3)      // TMEM -> registers -> pushed
+      mbar_wait(&recv_bar[buf], (mma_phase >> 1) & 1);
+      ++mma_phase;
+      RS_TICK(4)      // all 8 partials of my rows have landed
       if (fin) {
-        const uint32_t a = part_addr + (uint32_t)((ph & 1) * NB * RS_BM + fin_row * RS_BM + (tid & 31) * 4) * 4u;
-        float4 pv[RS_CL];
-#pragma unroll
-        for (uint32_t peer = 0; peer < (uint32_t)RS_CL; ++peer) pv[peer] = ld_dsmem_f4(a, peer);   // 8 loads in flight
+        const float4* mine = reinterpret_cast<const float4*>(recv) + (size_t)buf * (RECV_BYTES / 16) + fin_r * (RS_BM / 4) + (tid & 31);
 #pragma unroll
         for (int peer = 0; peer < RS_CL; ++peer) {                     // fixed order: bit-reproducible
-          acc.x += pv[peer].x; acc.y += pv[peer].y; acc.z += pv[peer].z; acc.w += pv[peer].w;
+          const float4 v = mine[(size_t)peer * ROWS * (RS_BM / 4)];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
       }
+      RS_TICK(5)      // local reduction
     }
 
-    // ---- fused epilogue + store of the new state
+    // ---- fused epilogue + store of the new state (plain stores: consumers poll the data itself)
     if (fin_live) {
       if (!p.bwd) {
         float4 o;
-        o.x = tanhf(e0.x + acc.x); o.y = tanhf(e0.y + acc.y); o.z = tanhf(e0.z + acc.z); o.w = tanhf(e0.w + acc.w);
+        o.x = rs_clean(tanhf(e0.x + acc.x)); o.y = rs_clean(tanhf(e0.y + acc.y));
+        o.z = rs_clean(tanhf(e0.z + acc.z)); o.w = rs_clean(tanhf(e0.w + acc.w));
         *reinterpret_cast<float4*>(p.hs + (int64_t)(ph + 1) * NH + (int64_t)fin_n * p.H + fin_c) = o;
       } else if (ph < p.T) {
         float4 o;
-        o.x = (e0.x + acc.x) * (1.f - e1.x * e1.x); o.y = (e0.y + acc.y) * (1.f - e1.y * e1.y);
-        o.z = (e0.z + acc.z) * (1.f - e1.z * e1.z); o.w = (e0.w + acc.w) * (1.f - e1.w * e1.w);
+        o.x = rs_clean((e0.x + acc.x) * (1.f - e1.x * e1.x)); o.y = rs_clean((e0.y + acc.y) * (1.f - e1.y * e1.y));
+        o.z = rs_clean((e0.z + acc.z) * (1.f - e1.z * e1.z)); o.w = rs_clean((e0.w + acc.w) * (1.f - e1.w * e1.w));
         *reinterpret_cast<float4*>(p.dA + (int64_t)t * NH + (int64_t)fin_n * p.H + fin_c) = o;
       } else if (p.dh0 != nullptr) {
         *reinterpret_cast<float4*>(p.dh0 + (int64_t)fin_n * p.H + fin_c) = acc;
       }
     }
-    // ---- publish: every store of this CTA happens-before the counter increment
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      red_release_gpu_add(my_flag, 1u);
-    }
+    RS_TICK(6)        // epilogue + store
+  }
+#undef RS_TICK
+  if (p.prof && tid == 0) {
+#pragma unroll
+    for (int i = 0; i < RS_PROF_SEGS; ++i) p.prof[(size_t)blockIdx.x * RS_PROF_SEGS + i] = prof[i];
   }
 
-  // peers may still be reading this CTA's last partial through DSMEM: leave together
+  // no CTA leaves while a peer may still push into its shared memory
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_before();
@@ -311,7 +357,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_seq_kernel(const RnnSeqPara
 // host side
 // ---------------------------------------------------------------------------------------------------------
 static size_t rs_smem_bytes(int nb, int ks) {
-  return 1024 + 2 * (size_t)(ks / 32) * nb * 128 + 2 * (size_t)nb * RS_BM * 4 + 64;
+  return 1024 + 2 * (size_t)(ks / 32) * nb * 128 + 2 * (size_t)nb * RS_BM * 4 + 64;    // B hi/lo tiles + 2 receive buffers + barriers
 }
 
 template <int NB>
@@ -354,10 +400,11 @@ static RsPlan rs_plan(int64_t N, int64_t H) {
   const int slot = pl.ks == 32 ? 0 : (pl.ks == 64 ? 1 : 2);
   if (max32[slot] < 0) max32[slot] = rs_max_clusters<32>(pl.ks);
   if (max64[slot] < 0) max64[slot] = rs_max_clusters<64>(pl.ks);
+  static const int force_split = getenv("B200AD_RNN_SEQ_NSPLIT") ? atoi(getenv("B200AD_RNN_SEQ_NSPLIT")) : 0;   // probe knob
   if (N <= 32) {
     pl.nb = 32; pl.n_split = 1;
     pl.ok = max32[slot] >= slices;
-  } else if (max32[slot] >= 2 * slices) {
+  } else if (max32[slot] >= 2 * slices && force_split != 1) {
     pl.nb = 32; pl.n_split = 2; pl.ok = true;
   } else {
     pl.nb = 64; pl.n_split = 1;
@@ -367,8 +414,15 @@ static RsPlan rs_plan(int64_t N, int64_t H) {
   return pl;
 }
 
-static int rs_launch(const RnnSeqParams& prm, const RsPlan& pl, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(prm.flags, 0, sizeof(unsigned int) * 64, s);
+static int rs_launch(const RnnSeqParams& prm_in, const RsPlan& pl, cudaStream_t s) {
+  RnnSeqParams prm = prm_in;
+  static const bool want_prof = getenv("B200AD_RNN_SEQ_PROF") != nullptr;
+  static long long* prof_dev = nullptr;
+  if (want_prof && !prof_dev) cudaMalloc(&prof_dev, sizeof(long long) * RS_PROF_SEGS * 256);
+  prm.prof = want_prof ? prof_dev : nullptr;
+  // the outputs double as "not produced yet" markers: fill them with the sentinel before the launch
+  cudaError_t e = prm.bwd ? cudaMemsetAsync(prm.dA, 0xff, sizeof(float) * (size_t)prm.T * prm.N * prm.H, s)
+                          : cudaMemsetAsync(prm.hs + (size_t)prm.N * prm.H, 0xff, sizeof(float) * (size_t)prm.T * prm.N * prm.H, s);
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "rnn_seq: memset: %s", cudaGetErrorString(e));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(RS_CL * pl.clusters);
@@ -382,6 +436,26 @@ static int rs_launch(const RnnSeqParams& prm, const RsPlan& pl, cudaStream_t s) 
   e = pl.nb == 32 ? cudaLaunchKernelEx(&cfg, rnn_seq_kernel<32>, prm) : cudaLaunchKernelEx(&cfg, rnn_seq_kernel<64>, prm);
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "rnn_seq: launch: %s", cudaGetErrorString(e));
   count_launch();
+  if (want_prof && prof_dev) {      // debugging aid: synchronous read-back of the per-segment cycle counters
+    const int ctas = RS_CL * pl.clusters;
+    std::vector<long long> h((size_t)ctas * RS_PROF_SEGS);
+    if (cudaStreamSynchronize(s) == cudaSuccess &&
+        cudaMemcpy(h.data(), prof_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char* names[RS_PROF_SEGS] = {"poll+load", "split+bar", "mma", "tmem->push", "recv-wait", "local-reduce",
+                                                "epilogue+store", "-"};
+      const int phases = prm.bwd ? prm.T + 1 : prm.T;
+      fprintf(stderr, "[rnn_seq prof] %s T=%d N=%d H=%d nb=%d n_split=%d ctas=%d: cycles per phase (mean over CTAs | max CTA)\n",
+              prm.bwd ? "bwd" : "fwd", prm.T, prm.N, prm.H, pl.nb, pl.n_split, ctas);
+      double total = 0;
+      for (int i = 0; i < RS_PROF_SEGS; ++i) {
+        double sum = 0, mx = 0;
+        for (int c = 0; c < ctas; ++c) { const double v = (double)h[(size_t)c * RS_PROF_SEGS + i]; sum += v; if (v > mx) mx = v; }
+        fprintf(stderr, "    %-14s %9.0f | %9.0f\n", names[i], sum / ctas / phases, mx / phases);
+        total += sum / ctas / phases;
+      }
+      fprintf(stderr, "    %-14s %9.0f\n", "total", total);
+    }
+  }
   return check_launch("rnn_seq");
 }
 
@@ -393,28 +467,26 @@ extern "C" {
 
 int b200ad_rnn_seq_supported(int64_t batch, int64_t hidden) { return rs_plan(batch, hidden).ok ? 1 : 0; }
 
-int64_t b200ad_rnn_seq_ws_bytes(void) { return 64 * (int64_t)sizeof(unsigned int); }
-
-int b200ad_rnn_tanh_seq_fwd(float* hs_ext, const float* wh, int64_t T, int64_t N, int64_t H, void* ws, void* stream) {
+int b200ad_rnn_tanh_seq_fwd(float* hs_ext, const float* pre, const float* wh, int64_t T, int64_t N, int64_t H,
+                            void* stream) {
   B200AD_REQUIRE(T >= 0 && N >= 1 && H >= 1, "rnn_tanh_seq_fwd: bad shape");
   if (T == 0) return B200AD_OK;
-  B200AD_REQUIRE(hs_ext && wh && ws, "rnn_tanh_seq_fwd: null pointer");
-  B200AD_REQUIRE(aligned16(hs_ext) && aligned16(wh), "rnn_tanh_seq_fwd: operands must be 16-byte aligned");
+  B200AD_REQUIRE(hs_ext && pre && wh, "rnn_tanh_seq_fwd: null pointer");
+  B200AD_REQUIRE(aligned16(hs_ext) && aligned16(pre) && aligned16(wh), "rnn_tanh_seq_fwd: operands must be 16-byte aligned");
   const RsPlan pl = rs_plan(N, H);
   if (!pl.ok) return set_error(B200AD_ERR_UNSUPPORTED, "rnn_tanh_seq_fwd: N=%lld H=%lld not supported by the persistent kernel "
                                "(N <= 64, H in {256, 512, 1024}, all clusters co-resident)", (long long)N, (long long)H);
   RnnSeqParams prm{};
-  prm.w = wh; prm.ldw = H; prm.hs = hs_ext; prm.flags = static_cast<unsigned int*>(ws);
+  prm.w = wh; prm.ldw = H; prm.hs = hs_ext; prm.pre = pre;
   prm.T = (int32_t)T; prm.N = (int32_t)N; prm.H = (int32_t)H; prm.ks = pl.ks; prm.n_split = pl.n_split; prm.bwd = 0;
   return rs_launch(prm, pl, (cudaStream_t)stream);
 }
 
 int b200ad_rnn_tanh_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_stride_t, const float* hs_ext,
-                            const float* wh, float* dA, float* dh0, int64_t T, int64_t N, int64_t H, void* ws,
-                            void* stream) {
+                            const float* wh, float* dA, float* dh0, int64_t T, int64_t N, int64_t H, void* stream) {
   B200AD_REQUIRE(T >= 0 && N >= 1 && H >= 1, "rnn_tanh_seq_bwd: bad shape");
   if (T == 0) return B200AD_OK;
-  B200AD_REQUIRE(dhs && hs_ext && wh && dA && ws, "rnn_tanh_seq_bwd: null pointer");
+  B200AD_REQUIRE(dhs && hs_ext && wh && dA, "rnn_tanh_seq_bwd: null pointer");
   B200AD_REQUIRE(aligned16(dhs) && aligned16(hs_ext) && aligned16(wh) && aligned16(dA) && (!dh0 || aligned16(dh0)) &&
                  (dhs_stride_n & 3) == 0 && (dhs_stride_t & 3) == 0,
                  "rnn_tanh_seq_bwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
@@ -423,7 +495,7 @@ int b200ad_rnn_tanh_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_
                                (long long)N, (long long)H);
   RnnSeqParams prm{};
   prm.w = wh; prm.ldw = H; prm.hs = const_cast<float*>(hs_ext); prm.dhs = dhs; prm.dhs_sn = dhs_stride_n;
-  prm.dhs_st = dhs_stride_t; prm.dA = dA; prm.dh0 = dh0; prm.flags = static_cast<unsigned int*>(ws);
+  prm.dhs_st = dhs_stride_t; prm.dA = dA; prm.dh0 = dh0;
   prm.T = (int32_t)T; prm.N = (int32_t)N; prm.H = (int32_t)H; prm.ks = pl.ks; prm.n_split = pl.n_split; prm.bwd = 1;
   return rs_launch(prm, pl, (cudaStream_t)stream);
 }

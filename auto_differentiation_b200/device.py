@@ -1009,16 +1009,12 @@ def rnn_seq_supported(batch, hidden):
     return _rnn_seq_ok[key]
 
 
-def _rnn_seq_ws():
-    return raw_bytes(int(_lib().b200ad_rnn_seq_ws_bytes()))
-
-
-def rnn_tanh_seq_fwd_(hs_ext, wh):
-    """hs_ext (T+1, N, H) contiguous: hs_ext[t+1] = tanh(hs_ext[t+1] + hs_ext[t] @ wh) for all t, in ONE launch."""
+def rnn_tanh_seq_fwd_(hs_ext, pre, wh):
+    """hs_ext (T+1, N, H) contiguous with hs_ext[0] = h_0; pre (T, N, H): hs_ext[t+1] = tanh(pre[t] + hs_ext[t] @ wh)
+    for all t, in ONE launch."""
     T1, N, H = hs_ext.shape
-    wh = wh.contiguous()
-    ws = _rnn_seq_ws()
-    L.check(_lib().b200ad_rnn_tanh_seq_fwd(hs_ext.ptr, wh.ptr, T1 - 1, N, H, ws.data_ptr(), stream_ptr()))
+    wh, pre = wh.contiguous(), pre.contiguous()
+    L.check(_lib().b200ad_rnn_tanh_seq_fwd(hs_ext.ptr, pre.ptr, wh.ptr, T1 - 1, N, H, stream_ptr()))
     return hs_ext
 
 
@@ -1031,7 +1027,6 @@ def rnn_tanh_seq_bwd(dhs, hs_ext, wh):
     if dhs.t.stride(2) != 1 or (dhs.t.stride(0) & 3) or (dhs.t.stride(1) & 3) or (dhs.ptr & 15):
         dhs = dhs.copy()
     dA, dh0 = empty((T, N, H)), empty((N, H))
-    ws = _rnn_seq_ws()
     L.check(_lib().b200ad_rnn_tanh_seq_bwd(dhs.ptr, dhs.t.stride(0), dhs.t.stride(1), hs_ext.ptr, wh.ptr, dA.ptr, dh0.ptr,
-                                           T, N, H, ws.data_ptr(), stream_ptr()))
+                                           T, N, H, stream_ptr()))
     return dA, dh0

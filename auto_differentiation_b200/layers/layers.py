@@ -297,13 +297,15 @@ class TimeRNN(_TimeRecurrent):
             self.h = D.zeros((N, H))
         hs_ext = D.empty((T + 1, N, H))       # hs_ext[t] = h_{t-1}; hs_ext[0] = initial state
         D.copy_into_(self.h, hs_ext[0])
-        # x@Wx + b for all steps in ONE GEMM, written straight into hs_ext[1:]; each step then completes its slice in
-        # place: hs_ext[t+1] = tanh(hs_ext[t+1] + h_{t-1} @ Wh) — one launch per step (fused beta / tanh epilogue)
         xs_tm = xs.transpose(1, 0, 2).contiguous()
-        D.matmul(xs_tm.reshape(T * N, Dm), wx, bias=b.reshape(-1), out=hs_ext[1:].reshape(T * N, H))
         if D.rnn_seq_supported(N, H):
-            D.rnn_tanh_seq_fwd_(hs_ext, wh)          # the whole time loop in ONE persistent launch (csrc/rnn_seq.cu)
+            # x@Wx + b for all steps in ONE GEMM, then the whole time loop in ONE persistent launch (csrc/rnn_seq.cu)
+            pre = D.matmul(xs_tm.reshape(T * N, Dm), wx, bias=b.reshape(-1)).reshape(T, N, H)
+            D.rnn_tanh_seq_fwd_(hs_ext, pre, wh)
         else:
+            # the same GEMM written straight into hs_ext[1:]; each step then completes its slice in place:
+            # hs_ext[t+1] = tanh(hs_ext[t+1] + h_{t-1} @ Wh) — one launch per step (fused beta / tanh epilogue)
+            D.matmul(xs_tm.reshape(T * N, Dm), wx, bias=b.reshape(-1), out=hs_ext[1:].reshape(T * N, H))
             for t in range(T):
                 D.matmul(hs_ext[t], wh, out=hs_ext[t + 1], beta=1.0, act=L.ACT_TANH)
         self.h = hs_ext[T]

@@ -123,6 +123,7 @@ class Trainer:
         self.loss_list = []
         self.eval_interval = None
         self.current_epoch = 0
+        self.graphed, self._graphed_key = None, None
 
     def _train_step(self, bx, bt, third, max_grad):
         loss = self.model.forward(bx, bt, third)
@@ -145,7 +146,14 @@ class Trainer:
         n_iterations = n_rows // batch_size
         self.eval_interval = eval_interval
         extra = args[0] if args else None
-        graphed = _GraphedIteration(self, x, t, extra, batch_size, max_grad) if graph else None
+        graphed = None
+        if graph:
+            # the captured iteration is kept across fit() calls of the same batch geometry (capture costs tens of ms)
+            key = (batch_size, tuple(np.shape(x)[1:]), np.asarray(x).dtype.kind, tuple(np.shape(t)[1:]),
+                   np.asarray(t).dtype.kind, None if extra is None else tuple(np.shape(extra)[1:]), max_grad)
+            if getattr(self, "_graphed_key", None) != key:
+                self.graphed, self._graphed_key = _GraphedIteration(self, x, t, extra, batch_size, max_grad), key
+            graphed = self.graphed
         meter = graphed if graphed is not None else _RunningLoss()
         began = time()
         for _ in range(max_epoch):
@@ -163,4 +171,3 @@ class Trainer:
                 if eval_interval is not None and it % eval_interval == 0:
                     self._report(meter.pop_mean(), it, n_iterations, time() - began, verbose)
             self.current_epoch += 1
-        self.graphed = graphed

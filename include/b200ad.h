@@ -291,19 +291,17 @@ int b200ad_rnn_cell_bwd(const float* dh_a, int64_t ld_dha, const float* dh_b, in
 /* Persistent tanh-RNN time loop: ONE launch runs all T dependent steps (forward) / all T+1 BPTT phases (backward) with
  * the recurrent weight resident in tensor memory (csrc/rnn_seq.cu).  Replaces the Python time loops
  * TimeRNN.forward layers/layers.py:203-207 and TimeRNN.backward :210-225 (intended math).
- *   fwd: hs_ext is (T+1, N, H) time-major; on entry hs_ext[0] = h_0 and hs_ext[t+1] = x_t Wx + b (one big GEMM by the
- *        caller); on exit hs_ext[t+1] = tanh(hs_ext[t+1] + hs_ext[t] @ Wh).
+ *   fwd: hs_ext is (T+1, N, H) time-major with hs_ext[0] = h_0 on entry; pre is (T, N, H) = x_t Wx + b (one big GEMM by
+ *        the caller); on exit hs_ext[t+1] = tanh(pre[t] + hs_ext[t] @ Wh).  hs_ext[1:] is overwritten.
  *   bwd: dA[t] = (dhs[n,t,:] + dA[t+1] @ Wh^T) * (1 - hs_ext[t+1]^2) for t = T-1..0 (dA is (T, N, H) time-major),
  *        dh0 = dA[0] @ Wh^T (may be NULL).  dhs element (n, t, c) sits at dhs[n*stride_n + t*stride_t + c].
- *   ws: b200ad_rnn_seq_ws_bytes() bytes of device scratch (phase counters).  b200ad_rnn_seq_supported(batch, hidden)
- *   is 1 when this device can keep all clusters co-resident for the shape (batch <= 64, hidden in {256, 512, 1024});
- *   otherwise callers run the per-step loop over b200ad_gemm. */
+ *   b200ad_rnn_seq_supported(batch, hidden) is 1 when this device can keep all clusters co-resident for the shape
+ *   (batch <= 64, hidden in {256, 512, 1024}); otherwise callers run the per-step loop over b200ad_gemm. */
 int b200ad_rnn_seq_supported(int64_t batch, int64_t hidden);
-int64_t b200ad_rnn_seq_ws_bytes(void);
-int b200ad_rnn_tanh_seq_fwd(float* hs_ext, const float* wh, int64_t T, int64_t N, int64_t H, void* ws, void* stream);
-int b200ad_rnn_tanh_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_stride_t, const float* hs_ext,
-                            const float* wh, float* dA, float* dh0, int64_t T, int64_t N, int64_t H, void* ws,
+int b200ad_rnn_tanh_seq_fwd(float* hs_ext, const float* pre, const float* wh, int64_t T, int64_t N, int64_t H,
                             void* stream);
+int b200ad_rnn_tanh_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_stride_t, const float* hs_ext,
+                            const float* wh, float* dA, float* dh0, int64_t T, int64_t N, int64_t H, void* stream);
 int b200ad_bias_act_fwd(const float* x, int64_t ldx, const float* bias, float* out, int64_t ldo,
                         int64_t rows, int64_t cols, int act, void* stream);
 /* gx = g * act'(y) (act: 1 tanh, 2 sigmoid, 3 relu on y) with row strides */

@@ -471,18 +471,16 @@ class Emulator:
     def b200ad_rnn_seq_supported(self, batch, hidden):
         return 1 if (1 <= batch <= 64 and hidden in (256, 512, 1024)) else 0
 
-    def b200ad_rnn_seq_ws_bytes(self):
-        return 256
-
-    def b200ad_rnn_tanh_seq_fwd(self, hs_ext, wh, T, N, H, ws, s):
+    def b200ad_rnn_tanh_seq_fwd(self, hs_ext, pre, wh, T, N, H, s):
         self.launches += 1
         hs = _f32(hs_ext, (T + 1) * N * H).reshape(T + 1, N, H)
+        pr = _f32(pre, T * N * H).reshape(T, N, H)
         w = _f32(wh, H * H).reshape(H, H).astype(np.float64)
         for t in range(T):
-            hs[t + 1] = np.tanh(hs[t + 1].astype(np.float64) + hs[t].astype(np.float64) @ w)
+            hs[t + 1] = np.tanh(pr[t].astype(np.float64) + hs[t].astype(np.float64) @ w)
         return 0
 
-    def b200ad_rnn_tanh_seq_bwd(self, dhs, sn, st, hs_ext, wh, dA, dh0, T, N, H, ws, s):
+    def b200ad_rnn_tanh_seq_bwd(self, dhs, sn, st, hs_ext, wh, dA, dh0, T, N, H, s):
         self.launches += 1
         hs = _f32(hs_ext, (T + 1) * N * H).reshape(T + 1, N, H)
         w = _f32(wh, H * H).reshape(H, H).astype(np.float64)

@@ -41,8 +41,8 @@ def test_rnn_seq_kernels_vs_fp64(backend, H, N, T):
     h0 = (rng.standard_normal((N, H)) * 0.5).astype(np.float32)
     pre = rng.standard_normal((T, N, H)).astype(np.float32)
     hs_ref = _fwd_ref(h0.astype(np.float64), pre.astype(np.float64), wh.astype(np.float64))
-    hs_ext = pkg.asarray(np.concatenate([h0[None], pre], axis=0))
-    D.rnn_tanh_seq_fwd_(hs_ext, pkg.asarray(wh))
+    hs_ext = pkg.asarray(np.concatenate([h0[None], np.zeros_like(pre)], axis=0))
+    D.rnn_tanh_seq_fwd_(hs_ext, pkg.asarray(pre), pkg.asarray(wh))
     assert_close(hs_ext, hs_ref, rtol=2e-5, atol=2e-6, what="rnn_seq fwd H=%d N=%d T=%d" % (H, N, T))
     # BPTT on the fp64 states (so that the backward error is measured alone), upstream gradient as a strided (N,T,H) view
     dhs_full = rng.standard_normal((N, T, H + 8)).astype(np.float32)
@@ -102,9 +102,11 @@ def test_rnn_seq_bit_reproducible_guards_and_graph_replay():
     guard = pkg.full(((T + 1) * N * H + 2 * 4096,), SENT)
     hs_ext = guard[4096:4096 + (T + 1) * N * H].reshape(T + 1, N, H)
 
+    pre_dev = pkg.asarray(init[1:])
+
     def run():
         D.copy_into_(pkg.asarray(init), hs_ext)
-        D.rnn_tanh_seq_fwd_(hs_ext, wh)
+        D.rnn_tanh_seq_fwd_(hs_ext, pre_dev, wh)
         return D.rnn_tanh_seq_bwd(dhs, hs_ext, wh)
     results = []
     for _ in range(3):
@@ -121,7 +123,7 @@ def test_rnn_seq_bit_reproducible_guards_and_graph_replay():
 
     def graphed():
         D.copy_into_(static_in, hs_ext)
-        D.rnn_tanh_seq_fwd_(hs_ext, wh)
+        D.rnn_tanh_seq_fwd_(hs_ext, pre_dev, wh)
         return D.rnn_tanh_seq_bwd(dhs, hs_ext, wh)
     gs = GraphedStep(graphed, warmup=1)
     for _ in range(2):
