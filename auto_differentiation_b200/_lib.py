@@ -89,7 +89,9 @@ SIGNATURES = {
     "b200ad_gemm_workspace_bytes": (c_int64, [POINTER(GemmDesc)]),
     "b200ad_gemm_set_recurrent_dispatch": (c_int, [c_int]),
     "b200ad_attn_supported": (c_int, [POINTER(AttnDesc)]),
-    "b200ad_attn_fwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P]),
+    "b200ad_attn_set_variant": (c_int, [c_int]),
+    "b200ad_attn_fwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),
+    "b200ad_attn_fwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P, P]),
     "b200ad_attn_bwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),
     "b200ad_attn_bwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P, P, P, P, P, P]),
     "b200ad_lstm_cell_fwd": (c_int, [P, I64, P, I64, P, I64, P, I64, P, I64, I64, I64, P]),

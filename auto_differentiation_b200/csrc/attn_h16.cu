@@ -1,0 +1,999 @@
+// Fused multi-head attention passes, generation 2: the same fp32-faithful three-product split as attn_tc.cu, but carried
+// by fp16 hi / lo pairs at the kind::f16 MMA rate instead of tf32 pairs at the kind::tf32 rate.
+//
+// Why (VERDICT r1 items 2 + 3, profiles/r2_fp16_split_probe.log): tf32 hi + lo carries 11 + 11 mantissa bits, fp16 hi + lo
+// the same 22 — but a kind::f16 tcgen05.mma covers K = 16 in the cycles a kind::tf32 one covers K = 8 (measured,
+// profiles/r1_mma_rate.log), and a 16-bit operand takes half the tensor memory: the 128-row operand tiles and the
+// probability / dS tiles shrink from 128 to 64 TMEM columns each, which frees the columns for a SECOND Y accumulator
+// (the two-score backward passes used to serialise on the single one: Y(j) -> row owners -> Z -> OUT -> Y(j+1), ~3400
+// cycles per block against 2304 of MMA time) and a second OUT accumulator in every mode.
+//
+// What fp16 lacks is exponent range.  Every operand tensor (Q, K, V, dO) is therefore multiplied by ONE power of two per
+// (batch, head) slab — 2^(14 - floor(log2 max|slab|)), from a small max-abs pre-pass — before it is split; a power of
+// two factors out of every product exactly, so the row owners undo it inside constants they apply anyway (the softmax
+// scale c2, the dS scale c, the final 1/l or output scale).  Probabilities (<= 1) are carried times 2^14 and dS times a
+// power of two derived from the bound |dP - D| <= 2 * 64 * max|dO| * max|V|; both factors ride in the exp2 argument, so
+// the per-element arithmetic is the same as before except for the split itself.  Errors are absolute, ~2^-40 of the slab
+// maximum per operand element, entering sums that are dominated by the large terms — measured against fp64 the results
+// are as close as the 3xTF32 kernels' (tests/test_fused_attention.py runs every case through both).
+//
+// Same roles as attn_tc.cu (TMA producer, MMA issuer, 4 converter warps, 8 row-owner warps; 1-CTA and CTA-pair variants),
+// same ring of six 32 KB slots, same barriers.  Differences:
+//   * slot layout [raw fp32 16 KB | fp16 hi 8 KB | fp16 lo 8 KB]; EVERY B operand is a K-major SWIZZLE_128B fp16 tile
+//     (64 rows x 128 B): the converter transposes the (kv x d) blocks that feed the OUT products while it converts them,
+//     so no MN-major descriptor is needed (their TMA boxes are unswizzled for conflict-free column reads);
+//   * A operands (and Z) sit in TMEM as packed fp16 pairs: 32 columns hi + 32 columns lo per 64 K-elements;
+//   * TMEM map: A1 [0,64) A2 [64,128) | X0 X1 | (Y0 Y1) | OUT0 OUT1; Z(j) overwrites X(j) as [g0 hi | g0 lo | g1 hi | g1 lo]
+//     (each owner group stays inside its own 32 columns), so the Y columns are free as soon as the owners have READ them:
+//     X(j+1) and Y(j+1) are both issued one block ahead and the owners never wait for a score product;
+//   * the backward modes fold every block (no two-block chains): an accumulation chain is 4 k-steps x 3 terms.
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace b200ad {
+
+constexpr int AH_DK = 64;
+constexpr int AH_BM = 128;
+constexpr int AH_BC = 64;
+constexpr int AH_NSLOT = 6;
+constexpr uint32_t AH_SLOT = 32768;          // [raw 16 KB | hi 8 KB | lo 8 KB] for a B block, or one raw A tile (32 KB)
+constexpr uint32_t AH_HI = 16384, AH_LO = 24576;
+constexpr int AH_THREADS = 512;
+constexpr uint32_t AH_SMEM = (AH_NSLOT + 1) * AH_SLOT + 1024;
+
+enum { AH_FWD = 0, AH_DV = 1, AH_DQ = 2, AH_DKM = 3 };
+
+struct AttnHParams {
+  float* out;
+  int64_t out_bs, out_hs, out_ld;
+  float* lse_w;              // FWD: (B, H, R) log2-domain log-sum-exp, written
+  const float* lse;          // other modes: read
+  const float* dvec;         // DQ / DK: D[b, h, s] = sum_d dO * O
+  const float* amax;         // (B*H, 4): max |Q|, |K|, |V|, |dO| of the (batch, head) slab
+  int32_t H, R, C;
+  int32_t row_tiles, nb, total_items;
+  float c2, c;               // scale * log2(e), scale
+  long long* prof;           // debugging aid (B200AD_ATTN_PROF=1): cycle counters of CTA 0's MMA thread and one row owner
+};
+#define AH_T(var) long long var = 0; if (p.prof) var = clock64()
+#define AH_ACC(slot, a, b) if (p.prof) prof_acc[slot] += (b) - (a)
+
+__device__ __forceinline__ void ah_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ah_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 ah_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ah_lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void ah_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void ah_tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void ah_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ah_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ah_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// kind::f16 MMAs, A operand from TMEM (packed fp16 pairs: 8 columns per 16 K-elements), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void ah_tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// ---- the split: v (already scaled into fp16 range) = hi + lo, hi = v truncated to 11 significant bits (exactly an fp16
+// value while |v| >= 2^-14; below that the conversion rounds to the subnormal grid: an absolute error <= 2^-25), lo =
+// v - hi rounded to fp16.  Returns packed pairs (element 0 in the low half).
+__device__ __forceinline__ void ah_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
+  const __half2 hh = __floats2half2_rn(h0, h1);
+  const __half2 ll = __floats2half2_rn(v0 - h0, v1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+// power of two that brings a slab with maximum magnitude `amax` into [2^14, 2^15); returns floor(log2 amax) in `e`
+__device__ __forceinline__ float ah_slab_scale(float amax, int& e) {
+  const int ex = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  if (ex == 0 || ex == 255) { e = 14; return 1.0f; }           // zero / denormal / non-finite slab: leave it alone
+  e = ex - 127;
+  // 2^(14 - e), with the exponent clamped so that products of several slab scales stay finite: slabs below 2^-46 are
+  // only brought up to 2^14 * 2^-46-ish (their hi halves may lose bits; such gradients are below fp32 noise anyway)
+  int k = 14 - e;
+  k = k > 60 ? 60 : (k < -100 ? -100 : k);
+  e = 14 - k;
+  return __uint_as_float((uint32_t)(k + 127) << 23);
+}
+__device__ __forceinline__ float ah_pow2(int e) {               // 2^e for -126 <= e <= 127
+  e = e < -126 ? -126 : (e > 127 ? 127 : e);
+  return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+
+// which slab maximum feeds which operand, per mode (0 = Q, 1 = K, 2 = V, 3 = dO)
+template <int MODE> struct AhOps;
+template <> struct AhOps<AH_FWD> { static constexpr int A1 = 0, A2 = 0, B1 = 1, B2 = 1, B3 = 2; };
+template <> struct AhOps<AH_DV>  { static constexpr int A1 = 1, A2 = 1, B1 = 0, B2 = 0, B3 = 3; };
+template <> struct AhOps<AH_DQ>  { static constexpr int A1 = 0, A2 = 3, B1 = 1, B2 = 2, B3 = 1; };
+template <> struct AhOps<AH_DKM> { static constexpr int A1 = 1, A2 = 2, B1 = 0, B2 = 3, B3 = 0; };
+
+template <int MODE, bool CP>
+__global__ void __launch_bounds__(AH_THREADS, 1)
+attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_out,
+                const AttnHParams p) {
+  constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM);
+  constexpr bool ROWSTAT = (MODE == AH_FWD || MODE == AH_DQ);   // lanes are query rows
+  constexpr uint32_t A1_COL = 0, A2_COL = 64;
+  constexpr uint32_t X_COL0 = HAS2 ? 128u : 64u;
+  constexpr uint32_t Y_COL0 = 256u;
+  constexpr uint32_t OUT_COL0 = HAS2 ? 384u : 192u;
+  constexpr uint32_t TMEM_COLS = 512;
+  using OPS = AhOps<MODE>;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_stage = smem + (size_t)AH_NSLOT * AH_SLOT;
+  __shared__ uint64_t bars[3 * AH_NSLOT + 16];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float colstat[2][128];
+  float (*rowx)[128] = colstat;
+  uint64_t* full = bars;                       // [NSLOT] TMA -> converter
+  uint64_t* conv = bars + AH_NSLOT;            // [NSLOT] converter -> MMA
+  uint64_t* empty = bars + 2 * AH_NSLOT;       // [NSLOT] MMA commit (B slots) / converter (A slots) -> TMA
+  uint64_t* a_empty = bars + 3 * AH_NSLOT;     // [2] MMA commit -> converter: last score MMA of the item retired
+  uint64_t* x_full = a_empty + 2;              // [2] MMA commit -> row owners
+  uint64_t* y_full = x_full + 2;               // [2]
+  uint64_t* z_full = y_full + 2;               // [2] row owners -> MMA
+  uint64_t* out_full = z_full + 2;             // [2] MMA commit -> row owners
+  uint64_t* out_empty = out_full + 2;          // [2] row owners -> MMA
+  uint32_t* tmem_base_slot = &tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = CP ? cluster_ctarank() : 0u;
+  const int unit_id = CP ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, units = CP ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (CP) {
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0); }
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+  auto mma_commit = [&](uint64_t* bar) { if (CP) umma2_commit_mc(bar); else umma_commit(bar); };
+  auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t desc, uint32_t idesc, uint32_t acc) {
+    if (CP) umma2_f16_ts(d, a, desc, idesc, acc); else umma_f16_ts(d, a, desc, idesc, acc);
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b1);
+    tma_prefetch_desc(&map_b3);
+    tma_prefetch_desc(&map_out);
+    if (HAS2) {
+      tma_prefetch_desc(&map_a2);
+      tma_prefetch_desc(&map_b2);
+    }
+    for (int s = 0; s < AH_NSLOT; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], CP ? 8 : 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&x_full[i], 1);
+      mbar_init(&y_full[i], 1);
+      mbar_init(&z_full[i], CP ? 16 : 256);
+      mbar_init(&out_full[i], 1);
+      mbar_init(&out_empty[i], CP ? 16 : 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { if (CP) tmem_alloc2(tmem_base_slot, TMEM_COLS); else tmem_alloc(tmem_base_slot, TMEM_COLS); }
+  tc_fence_before();
+  if (CP) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const int nb = p.nb;
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      uint32_t op = 0;
+      for (int item = unit_id; item < p.total_items; item += units) {
+        const int rt = (item % p.row_tiles) * (CP ? 2 : 1) + (int)rank, bh = item / p.row_tiles;
+        const int h = bh % p.H, b = bh / p.H;
+        const int row0 = rt * AH_BM;
+        auto acquire = [&](uint32_t bytes, uint64_t*& bar) -> uint8_t* {
+          const uint32_t s = op % AH_NSLOT;
+          mbar_wait(&empty[s], ((op / AH_NSLOT) & 1) ^ 1);
+          mbar_expect_tx(&full[s], bytes);
+          bar = &full[s];
+          ++op;
+          return smem + (size_t)s * AH_SLOT;
+        };
+        auto load_a = [&](const CUtensorMap* m) {          // 128 rows x 64: two 32-float halves, SWIZZLE_128B
+          uint64_t* bar;
+          uint8_t* dst = acquire(32768u, bar);
+          tma_load_4d(m, bar, dst, 0, row0, h, b);
+          tma_load_4d(m, bar, dst + 16384, 32, row0, h, b);
+        };
+        auto load_k = [&](const CUtensorMap* m, int col0) {   // score operand block: 64 rows x 64 (pair: this CTA's 32 rows), SWIZZLE_128B halves
+          uint64_t* bar;
+          if (CP) {
+            uint8_t* dst = acquire(8192u, bar);
+            tma_load_4d(m, bar, dst, 0, col0 + 32 * (int)rank, h, b);
+            tma_load_4d(m, bar, dst + 4096, 32, col0 + 32 * (int)rank, h, b);
+          } else {
+            uint8_t* dst = acquire(16384u, bar);
+            tma_load_4d(m, bar, dst, 0, col0, h, b);
+            tma_load_4d(m, bar, dst + 8192, 32, col0, h, b);
+          }
+        };
+        auto load_o = [&](const CUtensorMap* m, int col0) {   // OUT operand block: 64 kv rows x 64 d (pair: this CTA's 32 d), UNSWIZZLED 32-wide halves
+          uint64_t* bar;
+          if (CP) {
+            uint8_t* dst = acquire(8192u, bar);
+            tma_load_4d(m, bar, dst, 32 * (int)rank, col0, h, b);
+          } else {
+            uint8_t* dst = acquire(16384u, bar);
+            tma_load_4d(m, bar, dst, 0, col0, h, b);
+            tma_load_4d(m, bar, dst + 8192, 32, col0, h, b);
+          }
+        };
+        // ring order = consumption order of the MMA warp: A1 [A2] X(0) [Y(0)] { X(j+1) [Y(j+1)] OUT(j) }
+        load_a(&map_a1);
+        if (HAS2) load_a(&map_a2);
+        load_k(&map_b1, 0);
+        if (HAS2) load_k(&map_b2, 0);
+        for (int j = 0; j < nb; ++j) {
+          if (j + 1 < nb) {
+            load_k(&map_b1, (j + 1) * AH_BC);
+            if (HAS2) load_k(&map_b2, (j + 1) * AH_BC);
+          }
+          load_o(&map_b3, j * AH_BC);
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================================== MMA issuer (leader CTA of a pair) =====================================
+    // instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N = 64, M = 128 (256 for a pair)
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((CP ? 256 : AH_BM) >> 4) << 24);
+    uint32_t op = 0, it = 0, gb = 0;
+    long long prof_acc[4] = {0, 0, 0, 0};
+    const long long prof_t0 = p.prof ? clock64() : 0;
+    auto wait_slot = [&]() -> uint32_t {
+      const uint32_t s = op % AH_NSLOT;
+      AH_T(w0);
+      mbar_wait(&conv[s], (op / AH_NSLOT) & 1);
+      AH_T(w1);
+      AH_ACC(0, w0, w1);
+      ++op;
+      return s;
+    };
+    // score MMAs: D[128 x 64] = A(TMEM: hi at a_col, lo at a_col + 32) . B^T (K-major fp16 tiles in the slot); ELECTED thread
+    auto issue_score = [&](uint32_t s, uint32_t a_col, uint32_t d_col, uint64_t* done, uint64_t* a_done) {
+      const uint32_t sb = smem_u32(smem + (size_t)s * AH_SLOT);
+      const uint64_t dh = make_smem_desc(sb + AH_HI, 16, 1024, 2), dl = make_smem_desc(sb + AH_LO, 16, 1024, 2);
+      const uint32_t dst = tmem_base + d_col, a_hi = tmem_base + a_col, a_lo = a_hi + 32u;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_lo + kk * 8, dh + (uint64_t)(kk * 2), IDESC, kk ? 1u : 0u);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dl + (uint64_t)(kk * 2), IDESC, 1u);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dh + (uint64_t)(kk * 2), IDESC, 1u);
+      mma_commit(&empty[s]);
+      mma_commit(done);
+      if (a_done) mma_commit(a_done);
+    };
+    for (int item = unit_id; item < p.total_items; item += units, ++it) {
+      {
+        wait_slot();                                   // A1 in TMEM
+        if (HAS2) wait_slot();                         // A2 in TMEM
+        const uint32_t s_x0 = wait_slot();
+        uint32_t s_y0 = 0;
+        if (HAS2) s_y0 = wait_slot();
+        tc_fence_after();
+        if (elect_one()) {
+          issue_score(s_x0, A1_COL, X_COL0 + (gb & 1) * 64u, &x_full[gb & 1], nb == 1 ? &a_empty[0] : nullptr);
+          if (HAS2) issue_score(s_y0, A2_COL, Y_COL0 + (gb & 1) * 64u, &y_full[gb & 1], nb == 1 ? &a_empty[1] : nullptr);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < nb; ++j) {
+        // sync point of block j: the next block's score operands (issued first: their X / Y buffers were released by
+        // Z(j-1)'s OUT product, which this thread issued one iteration ago), then Z(j) and a free OUT accumulator
+        const uint32_t g = gb + j;
+        uint32_t s_x = 0, s_y = 0;
+        if (j + 1 < nb) {
+          s_x = wait_slot();
+          if (HAS2) s_y = wait_slot();
+        }
+        const uint32_t s_o = wait_slot();
+        if (j + 1 < nb) {
+          // X(j+1) overwrites the columns Z(j-1) occupied: the OUT(j-1) MMAs that read them were issued earlier by this
+          // same thread, and tcgen05.mma instructions execute in issue order
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t gx = g + 1;
+            const bool lastx = (j + 1 == nb - 1);
+            issue_score(s_x, A1_COL, X_COL0 + (gx & 1) * 64u, &x_full[gx & 1], lastx ? &a_empty[0] : nullptr);
+            if (HAS2) issue_score(s_y, A2_COL, Y_COL0 + (gx & 1) * 64u, &y_full[gx & 1], lastx ? &a_empty[1] : nullptr);
+          }
+          __syncwarp();
+        }
+        const uint32_t ob = g & 1, oph = (g >> 1) & 1;
+        AH_T(w0);
+        mbar_wait(&z_full[g & 1], (g >> 1) & 1);
+        AH_T(w1);
+        mbar_wait(&out_empty[ob], oph ^ 1);
+        AH_T(w2);
+        AH_ACC(1, w0, w1);
+        AH_ACC(2, w1, w2);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sb = smem_u32(smem + (size_t)s_o * AH_SLOT);
+          const uint64_t dh = make_smem_desc(sb + AH_HI, 16, 1024, 2), dl = make_smem_desc(sb + AH_LO, 16, 1024, 2);
+          const uint32_t dst = tmem_base + OUT_COL0 + ob * 64u, zb = tmem_base + X_COL0 + (g & 1) * 64u;
+          // Z layout inside the X buffer: [group 0: hi 16 | lo 16 | group 1: hi 16 | lo 16] packed fp16 pairs; k-step kk
+          // covers columns c in [16 kk, 16 kk + 16) = group kk >> 1, packed columns 8 (kk & 1) .. + 8
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts(dst, zb + 32u * (kk >> 1) + 16u + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, kk ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts(dst, zb + 32u * (kk >> 1) + 8u * (kk & 1), dl + (uint64_t)(kk * 2), IDESC, 1u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts(dst, zb + 32u * (kk >> 1) + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, 1u);
+          mma_commit(&empty[s_o]);
+          mma_commit(&out_full[ob]);
+        }
+        __syncwarp();
+      }
+      gb += nb;
+    }
+    if (p.prof && blockIdx.x == 0 && lane == 0) {
+      p.prof[0] = clock64() - prof_t0;   // MMA warp total
+      p.prof[1] = prof_acc[0];           // waiting for converted operand slots
+      p.prof[2] = prof_acc[1];           // waiting for Z (row owners)
+      p.prof[3] = prof_acc[2];           // waiting for a free OUT accumulator
+    }
+  }
+  } else if (warp < 8) {
+    // ===================================== converter =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    const int tid = threadIdx.x - 128;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t op = 0, it = 0;
+    float s_a1 = 1.f, s_a2 = 1.f, s_b1 = 1.f, s_b2 = 1.f, s_b3 = 1.f;
+    auto conv_a = [&](int which, float sc) {
+      const uint32_t s = op % AH_NSLOT;
+      mbar_wait(&full[s], (op / AH_NSLOT) & 1);
+      ++op;
+      mbar_wait(&a_empty[which], (it & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t slot = smem_u32(smem + (size_t)s * AH_SLOT);
+      const uint32_t col = which ? A2_COL : A1_COL;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t row = slot + hh * 16384 + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {     // SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
+          const uint4 t4 = ah_lds128(row + ((c ^ (r & 7)) << 4));
+          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[hh * 16 + 2 * c], lo[hh * 16 + 2 * c]);
+          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[hh * 16 + 2 * c + 1], lo[hh * 16 + 2 * c + 1]);
+        }
+      }
+      tmem_st_32x32b_x32(lane_base + col, hi);
+      tmem_st_32x32b_x32(lane_base + col + 32, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      arrive_leader(&conv[s]);
+      ah_bar_sync(1, 128);
+      if (tid == 0) mbar_arrive(&empty[s]);
+    };
+    // score operand block (K-major raw, two SWIZZLE_128B halves of 32 floats): row-wise conversion, same orientation
+    auto conv_k = [&](float sc) {
+      const uint32_t s = op % AH_NSLOT;
+      mbar_wait(&full[s], (op / AH_NSLOT) & 1);
+      ++op;
+      const uint32_t slot = smem_u32(smem + (size_t)s * AH_SLOT);
+      constexpr int ROWS = CP ? 32 : 64;                     // rows staged by this CTA
+      constexpr int PARTS = 128 / ROWS;                      // threads per row: 2 (32 floats each) or 4 (16 floats each)
+      constexpr int NV = 16 / PARTS;                         // float4 per thread: 8 or 4
+      const int row = tid / PARTS, part = tid % PARTS;
+      const int f0 = part * NV;                              // first float4 (of 16) of the row this thread converts
+      uint32_t hi[2 * NV], lo[2 * NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int f = f0 + i, half = f >> 3, c = f & 7;
+        const uint4 t4 = ah_lds128(slot + half * (ROWS * 128) + row * 128 + ((c ^ (row & 7)) << 4));
+        ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * i], lo[2 * i]);
+        ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * i + 1], lo[2 * i + 1]);
+      }
+      // fp16 tile: row = 128 B = 8 chunks of 8 elements; this thread's 8*NV/8... elements [8 f0 / 2 ...]: 4 floats -> 8 B,
+      // so NV float4 -> NV/2 chunks starting at chunk f0 / 2
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        const int ch = f0 / 2 + i;
+        const uint32_t dst = row * 128 + ((ch ^ (row & 7)) << 4);
+        ah_sts128(slot + AH_HI + dst, make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]));
+        ah_sts128(slot + AH_LO + dst, make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]));
+      }
+      fence_proxy_async();
+      arrive_leader(&conv[s]);
+    };
+    // OUT operand block (raw [64 kv rows][d] unswizzled, 32-float-wide halves): TRANSPOSING conversion to the K-major tile
+    // [d][kv]: thread (d, part) reads its column for 64 / PARTS consecutive kv rows (lanes = consecutive d: conflict-free)
+    auto conv_o = [&](float sc) {
+      const uint32_t s = op % AH_NSLOT;
+      mbar_wait(&full[s], (op / AH_NSLOT) & 1);
+      ++op;
+      const uint32_t slot = smem_u32(smem + (size_t)s * AH_SLOT);
+      constexpr int DS = CP ? 32 : 64;                       // d columns staged by this CTA = rows of the converted tile
+      constexpr int PARTS = 128 / DS;                        // 2 or 4 threads per d
+      constexpr int NK = 64 / PARTS;                         // kv rows per thread: 32 or 16
+      const int d = tid % DS, part = tid / DS;
+      const uint32_t src = slot + (uint32_t)(d >> 5) * 8192u + (uint32_t)(d & 31) * 4u + (uint32_t)(part * NK) * 128u;
+      uint32_t hi[NK / 2], lo[NK / 2];
+#pragma unroll
+      for (int i = 0; i < NK / 2; ++i) {
+        const float v0 = __uint_as_float(ah_lds32(src + (2 * i) * 128)) * sc;
+        const float v1 = __uint_as_float(ah_lds32(src + (2 * i + 1) * 128)) * sc;
+        ah_split2(v0, v1, hi[i], lo[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < NK / 8; ++i) {                     // 8 kv elements = one 16 B chunk
+        const int ch = part * (NK / 8) + i;
+        const uint32_t dst = d * 128 + ((ch ^ (d & 7)) << 4);
+        ah_sts128(slot + AH_HI + dst, make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]));
+        ah_sts128(slot + AH_LO + dst, make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]));
+      }
+      fence_proxy_async();
+      arrive_leader(&conv[s]);
+    };
+    for (int item = unit_id; item < p.total_items; item += units, ++it) {
+      const int bh = item / p.row_tiles;
+      {
+        int e;
+        const float* am = p.amax + (int64_t)bh * 4;
+        s_a1 = ah_slab_scale(__ldg(am + OPS::A1), e);
+        s_a2 = ah_slab_scale(__ldg(am + OPS::A2), e);
+        s_b1 = ah_slab_scale(__ldg(am + OPS::B1), e);
+        s_b2 = ah_slab_scale(__ldg(am + OPS::B2), e);
+        s_b3 = ah_slab_scale(__ldg(am + OPS::B3), e);
+      }
+      conv_a(0, s_a1);
+      if (HAS2) conv_a(1, s_a2);
+      conv_k(s_b1);
+      if (HAS2) conv_k(s_b2);
+      for (int j = 0; j < nb; ++j) {
+        if (j + 1 < nb) {
+          conv_k(s_b1);
+          if (HAS2) conv_k(s_b2);
+        }
+        conv_o(s_b3);
+      }
+    }
+  } else {
+    // ===================================== row owners =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int tid = threadIdx.x - 256;
+    const int gi = (warp - 8) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t cofs = (uint32_t)gi * 32u;
+    uint32_t gb = 0;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = p.prof ? clock64() : 0;
+    for (int item = unit_id; item < p.total_items; item += units) {
+      const int rt = (item % p.row_tiles) * (CP ? 2 : 1) + (int)rank, bh = item / p.row_tiles;
+      const int h = bh % p.H, b = bh / p.H;
+      const int grow = rt * AH_BM + r;
+      const bool row_ok = grow < p.R;
+      // ---- per-item constants: the slab scales fold into the constants the elementwise math applies anyway
+      float c2e, ce = 0.f, zexp, out_unscale;
+      {
+        const float* am = p.amax + (int64_t)bh * 4;
+        int e_a1, e_b1, e_a2, e_b2, e_b3;
+        const float sa1 = ah_slab_scale(__ldg(am + OPS::A1), e_a1), sb1 = ah_slab_scale(__ldg(am + OPS::B1), e_b1);
+        const float sb3 = ah_slab_scale(__ldg(am + OPS::B3), e_b3);
+        c2e = p.c2 / (sa1 * sb1);                                   // X_true * c2 = X' * c2e   (exact: powers of two)
+        if (HAS2) {
+          const float sa2 = ah_slab_scale(__ldg(am + OPS::A2), e_a2), sb2 = ah_slab_scale(__ldg(am + OPS::B2), e_b2);
+          ce = p.c / (sa2 * sb2);                                   // Y_true * c = Y' * ce
+          // |dP c - D c| <= 2 * 64 * c * max|dO| * max|V| < 2^(7 + (e_dO + 1) + (e_V + 1) + (e_c + 1)): Z carried times
+          // 2^(14 - that exponent) stays below 2^14
+          const int e_c = (int)((__float_as_uint(p.c) >> 23) & 0xffu) - 127;
+          const int ez = 14 - (10 + e_a2 + e_b2 + e_c);
+          zexp = (float)ez;
+          out_unscale = ah_pow2(-ez) / sb3;
+        } else {
+          zexp = 14.f;                                              // probabilities (<= 1) are carried times 2^14
+          out_unscale = ah_pow2(-14) / sb3;
+        }
+      }
+      float run[32];
+#pragma unroll
+      for (int d = 0; d < 32; ++d) run[d] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;
+      float ls_r = 0.f, d_r = 0.f;
+      if (MODE == AH_DQ && row_ok) {
+        ls_r = __ldg(p.lse + (int64_t)bh * p.R + grow) - zexp;       // the Z scale rides in the exp2 argument
+        d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow) * p.c;
+      }
+      auto fold = [&](uint32_t g, float a) {
+        const uint32_t ob = g & 1, oph = (g >> 1) & 1;
+        AH_T(f0);
+        mbar_wait(&out_full[ob], oph);
+        AH_T(f1);
+        AH_ACC(4, f0, f1);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(lane_base + OUT_COL0 + ob * 64u + cofs, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          if (MODE == AH_FWD) run[d] = fmaf(run[d], a, __uint_as_float(o[d]));
+          else run[d] += __uint_as_float(o[d]);
+        }
+        tc_fence_before();
+        arrive_leader(&out_empty[ob]);
+        AH_T(f2);
+        AH_ACC(5, f1, f2);
+      };
+      auto load_colstat = [&](int c0) -> float {
+        if (tid < 64) {
+          const int col = c0 + tid;
+          return (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) - zexp : INFINITY;
+        }
+        if (MODE == AH_DKM && tid < 128) {
+          const int col = c0 + tid - 64;
+          return (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) * p.c : 0.f;
+        }
+        return 0.f;
+      };
+      float cs_next = ROWSTAT ? 0.f : load_colstat(0);
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t g = gb + j;
+        const uint32_t bsel = g & 1;
+        const uint32_t xaddr = lane_base + X_COL0 + bsel * 64u + cofs;      // this group's 32 x columns; its Z goes to the same 32
+        const int col0 = j * AH_BC + (int)cofs;
+        float* cs = colstat[bsel];
+        AH_T(b0);
+        if (!ROWSTAT) {
+          if (tid < 128) cs[tid] = cs_next;
+          ah_bar_sync(2, 256);
+          if (j + 1 < nb) cs_next = load_colstat((j + 1) * AH_BC);
+        }
+        AH_T(b1);
+        mbar_wait(&x_full[bsel], (g >> 1) & 1);
+        if (HAS2) mbar_wait(&y_full[bsel], (g >> 1) & 1);
+        AH_T(b2);
+        AH_ACC(0, b0, b1);      // column statistics + barrier
+        AH_ACC(1, b1, b2);      // waiting for X (and Y)
+        tc_fence_after();
+        uint32_t zh[16], zl[16];
+        if (MODE == AH_FWD) {
+          uint32_t x[32];
+          tmem_ld_32x32b_x32(xaddr, x);
+          tmem_ld_wait();
+          if (col0 + 32 > p.C) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (col0 + c >= p.C) x[c] = __float_as_uint(-INFINITY);
+          }
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx[c & 3] = fmaxf(mx[c & 3], __uint_as_float(x[c]));
+          float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          ah_bar_sync(5, 256);
+          rowx[gi][r] = mb;
+          ah_bar_sync(4, 256);
+          mb = fmaxf(mb, rowx[gi ^ 1][r]);
+          const float m_new = fmaxf(m_run, mb);
+          const float alpha = ah_exp2((m_run - m_new) * c2e);
+          const float mc = m_new * c2e - zexp;                    // p * 2^14 = exp2(x c2e - m c2e + 14)
+          float sm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float p0 = ah_exp2(fmaf(__uint_as_float(x[c]), c2e, -mc));
+            const float p1 = ah_exp2(fmaf(__uint_as_float(x[c + 1]), c2e, -mc));
+            sm[c & 3] += p0;
+            sm[(c + 1) & 3] += p1;
+            ah_split2(p0, p1, zh[c >> 1], zl[c >> 1]);
+          }
+          ah_tmem_st_x16(xaddr, zh);
+          ah_tmem_st_x16(xaddr + 16, zl);
+          l_run = fmaf(l_run, alpha, (sm[0] + sm[1]) + (sm[2] + sm[3]));     // carried times 2^14 like the probabilities
+          m_run = m_new;
+          tmem_st_wait();
+          tc_fence_before();
+          arrive_leader(&z_full[bsel]);
+          { AH_T(b3); AH_ACC(2, b2, b3); }     // load + math + store + arrive
+          if (j >= 1) fold(g - 1, a_prev);
+          a_prev = alpha;
+        } else if (MODE == AH_DV) {
+          uint32_t x[32];
+          tmem_ld_32x32b_x32(xaddr, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
+            const float p0 = ah_exp2(fmaf(__uint_as_float(x[c4]), c2e, -l4.x));
+            const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
+            const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
+            const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
+            ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1]);
+            ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+          }
+          ah_tmem_st_x16(xaddr, zh);
+          ah_tmem_st_x16(xaddr + 16, zl);
+          tmem_st_wait();
+          tc_fence_before();
+          arrive_leader(&z_full[bsel]);
+          { AH_T(b3); AH_ACC(2, b2, b3); }
+          if (j >= 1) fold(g - 1, 1.f);
+        } else {
+          // DQ / DK: Z = P (Y c - D c), carried times 2^ez
+          uint32_t x[32], y[32];
+          tmem_ld_32x32b_x32(xaddr, x);
+          tmem_ld_32x32b_x32(lane_base + Y_COL0 + bsel * 64u + cofs, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+            float ls[4], dd[4], z[4];
+            if (MODE == AH_DQ) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                ls[i] = (col0 + c4 + i < p.C) ? ls_r : INFINITY;
+                dd[i] = d_r;
+              }
+            } else {
+              const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
+              const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cofs + c4);
+              ls[0] = l4.x; ls[1] = l4.y; ls[2] = l4.z; ls[3] = l4.w;
+              dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c4 + i;
+              const float pv = ah_exp2(fmaf(__uint_as_float(x[c]), c2e, -ls[i]));
+              z[i] = pv * fmaf(__uint_as_float(y[c]), ce, -dd[i]);
+            }
+            ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1]);
+            ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+          }
+          ah_tmem_st_x16(xaddr, zh);
+          ah_tmem_st_x16(xaddr + 16, zl);
+          tmem_st_wait();
+          tc_fence_before();
+          arrive_leader(&z_full[bsel]);
+          { AH_T(b3); AH_ACC(2, b2, b3); }
+          if (j >= 1) fold(g - 1, 1.f);
+        }
+      }
+      fold(gb + nb - 1, a_prev);
+      gb += nb;
+      AH_T(e0);
+      // ---- epilogue (unchanged: swizzled staging tile + TMA store)
+      if (tid == 0) ah_bulk_wait_read0();
+      float sc = out_unscale;
+      if (MODE == AH_FWD) {
+        ah_bar_sync(5, 256);
+        rowx[gi][r] = l_run;
+      }
+      ah_bar_sync(3, 256);
+      if (MODE == AH_FWD) {
+        const float l_tot = l_run + rowx[gi ^ 1][r];                 // = 2^14 * (true row sum)
+        sc = out_unscale * 16384.f / l_tot;                          // O = (OUT' / (2^14 s_V)) / (l_tot / 2^14)
+        if (gi == 0 && row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, c2e, log2f(l_tot) - 14.f);
+      }
+      {
+        const uint32_t srow = smem_u32(out_stage) + (uint32_t)gi * 16384u + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v;
+          v.x = __float_as_uint(run[4 * c] * sc); v.y = __float_as_uint(run[4 * c + 1] * sc);
+          v.z = __float_as_uint(run[4 * c + 2] * sc); v.w = __float_as_uint(run[4 * c + 3] * sc);
+          ah_sts128(srow + ((c ^ (r & 7)) << 4), v);
+        }
+      }
+      fence_proxy_async();
+      ah_bar_sync(3, 256);
+      if (tid == 0) {
+        ah_tma_store_4d(&map_out, out_stage, 0, rt * AH_BM, h, b);
+        ah_tma_store_4d(&map_out, out_stage + 16384, 32, rt * AH_BM, h, b);
+        ah_bulk_commit();
+      }
+      { AH_T(e1); AH_ACC(6, e0, e1); }        // epilogue
+    }
+    if (tid == 0) ah_bulk_wait0();
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 256) {
+      p.prof[8] = clock64() - prof_t0;
+      for (int i = 0; i < 7; ++i) p.prof[9 + i] = prof_acc[i];
+    }
+  }
+
+  tc_fence_before();
+  if (CP) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  if (warp == 1) { if (CP) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---- pre-pass: max |x| of every (batch, head) slab of one tensor -> amax[(b*H + h) * 4 + slot] (atomic max on the bits of
+// non-negative floats; the table is zeroed first).  16 lanes (one float4 each) per row of 64; a block owns AH_PRE_ROWS
+// CONSECUTIVE rows ((b, h, s) order, s fastest), so a warp keeps a running maximum in registers and issues one atomic
+// per (batch, head) it touches — a few per warp instead of one per row.
+constexpr int AH_PRE_ROWS = 512;
+
+__device__ __forceinline__ void ah_amax_flush(float m, int64_t bh, float* amax, int slot) {
+#pragma unroll
+  for (int ofs = 16; ofs > 0; ofs >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, ofs));
+  if ((threadIdx.x & 31) == 0 && bh >= 0 && m > 0.f)
+    atomicMax(reinterpret_cast<unsigned int*>(amax + bh * 4 + slot), __float_as_uint(m));
+}
+
+// DVEC: additionally D[b, h, s] = sum_d dO * O (x = dO, o = O; as attn_tc.cu's attn_dvec_kernel)
+template <bool DVEC>
+__global__ void __launch_bounds__(256) attn_amax_kernel(const float* __restrict__ x, const float* __restrict__ o,
+                                                        float* __restrict__ dvec, float* __restrict__ amax, int slot,
+                                                        int64_t rows_total, int H, int S, int64_t bs, int64_t hs, int64_t ld) {
+  const int sub = threadIdx.x & 15;
+  const int64_t first = (int64_t)blockIdx.x * AH_PRE_ROWS;
+  int64_t cur_bh = -1;          // warp-uniform: both rows of a warp are forced onto the same slab per iteration (below)
+  float m = 0.f;
+  for (int it = 0; it < AH_PRE_ROWS / 16; ++it) {
+    const int64_t row = first + it * 16 + (threadIdx.x >> 4);
+    const bool live = row < rows_total;
+    const int64_t bh = live ? row / S : -1;
+    // a warp covers two consecutive rows; if they straddle a slab boundary (or the end) flush and handle them separately
+    const int64_t bh_lo = __shfl_sync(0xffffffffu, bh, 0), bh_hi = __shfl_sync(0xffffffffu, bh, 16);
+    float v = 0.f, mm = 0.f;
+    if (live) {
+      const int64_t s_ = row % S, h = bh % H, b = bh / H;
+      const int64_t off = b * bs + h * hs + s_ * ld + sub * 4;
+      const float4 g = *reinterpret_cast<const float4*>(x + off);
+      mm = fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w)));
+      if (DVEC) {
+        const float4 a = *reinterpret_cast<const float4*>(o + off);
+        v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+      }
+    }
+    if (DVEC) {
+#pragma unroll
+      for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
+      if (sub == 0 && live) dvec[row] = v;
+    }
+    if (bh_lo == bh_hi) {
+      if (bh_lo != cur_bh) {
+        ah_amax_flush(m, cur_bh, amax, slot);
+        cur_bh = bh_lo;
+        m = 0.f;
+      }
+      m = fmaxf(m, mm);
+    } else {                       // rare: the two rows belong to different slabs -> flush the running value, then each half
+      ah_amax_flush(m, cur_bh, amax, slot);
+      cur_bh = -1;
+      m = 0.f;
+#pragma unroll
+      for (int ofs = 8; ofs > 0; ofs >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, ofs, 16));
+      if (sub == 0 && live && mm > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax + bh * 4 + slot), __float_as_uint(mm));
+    }
+  }
+  ah_amax_flush(m, cur_bh, amax, slot);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct AttnHTensor {
+  const float* ptr;
+  int64_t bs, hs, ld;
+  int64_t rows;
+};
+
+static int ah_encode(CUtensorMap* map, const AttnHTensor& t, int64_t B, int64_t H, uint32_t box_rows, bool swizzle) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(B200AD_ERR_CUDA, "attention(h16): cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[4] = {(cuuint64_t)AH_DK, (cuuint64_t)t.rows, (cuuint64_t)H, (cuuint64_t)B};
+  const int64_t fallback = t.ld * t.rows;
+  const int64_t hs = (H > 1) ? t.hs : fallback;
+  const int64_t bs = (B > 1) ? t.bs : fallback;
+  if (hs <= 0 || bs <= 0) return set_error(B200AD_ERR_UNSUPPORTED, "attention(h16): broadcast (stride 0) batch / head axes");
+  cuuint64_t strides[3] = {(cuuint64_t)t.ld * 4, (cuuint64_t)hs * 4, (cuuint64_t)bs * 4};
+  cuuint32_t box[4] = {32u, box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200AD_ERR_CUDA, "attention(h16): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B200AD_OK;
+}
+
+template <int MODE, bool CP>
+static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTensor& b1, const AttnHTensor& b2,
+                          const AttnHTensor& b3, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
+  constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM);
+  constexpr uint32_t BROWS = CP ? 32u : (uint32_t)AH_BC;
+  CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_out;
+  int rc;
+  AttnHTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
+  if ((rc = ah_encode(&m_out, to, B, H, AH_BM, true))) return rc;
+  if ((rc = ah_encode(&m_a1, a1, B, H, AH_BM, true))) return rc;
+  if ((rc = ah_encode(&m_b1, b1, B, H, BROWS, true))) return rc;
+  if ((rc = ah_encode(&m_b3, b3, B, H, AH_BC, false))) return rc;          // 64 kv rows x 32 d, unswizzled
+  if (HAS2) {
+    if ((rc = ah_encode(&m_a2, a2, B, H, AH_BM, true))) return rc;
+    if ((rc = ah_encode(&m_b2, b2, B, H, BROWS, true))) return rc;
+  } else {
+    m_a2 = m_a1;
+    m_b2 = m_b1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_h16_kernel<MODE, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AH_SMEM);
+    if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  p.row_tiles = (int32_t)ceil_div(ceil_div(p.R, AH_BM), CP ? 2 : 1);
+  p.nb = (int32_t)ceil_div(p.C, AH_BC);
+  const int64_t items = B * H * p.row_tiles;
+  p.total_items = (int32_t)items;
+  const int max_units = CP ? num_sms() / 2 : num_sms();
+  const int grid = (CP ? 2 : 1) * (int)(items < max_units ? items : max_units);
+  static const bool want_prof = getenv("B200AD_ATTN_PROF") != nullptr;
+  static long long* prof_dev = nullptr;
+  if (want_prof) {
+    if (!prof_dev) cudaMalloc(&prof_dev, 16 * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), s);
+    p.prof = prof_dev;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(AH_THREADS);
+  cfg.dynamicSmemBytes = AH_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CP ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_h16_kernel<MODE, CP>, m_a1, m_a2, m_b1, m_b2, m_b3, m_out, p);
+  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): launch: %s", cudaGetErrorString(e));
+  count_launch();
+  if (want_prof && prof_dev) {
+    long long hp[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
+    const double blocks = (double)ceil_div(p.total_items, grid / (CP ? 2 : 1)) * p.nb;
+    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f | "
+            "owner total %.0f colstat %.0f wait_XY %.0f ld+math+st %.0f wait_OUT %.0f fold %.0f epilogue %.0f\n", MODE, (int)CP, blocks,
+            hp[0] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
+            hp[11] / blocks, hp[13] / blocks, hp[14] / blocks, hp[15] / blocks);
+  }
+  if (getenv("B200AD_ATTN_SYNC")) {
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    fprintf(stderr, "[b200ad] attention h16 pass mode %d (R=%d C=%d nb=%d items=%d): %s\n", MODE, p.R, p.C, p.nb,
+            p.total_items, cudaGetErrorString(e2));
+  }
+  return check_launch("attention(h16)");
+}
+
+template <int MODE>
+static int ah_launch(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTensor& b1, const AttnHTensor& b2,
+                     const AttnHTensor& b3, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
+  static const char* e = getenv("B200AD_ATTN_PAIR");
+  const bool pair = e ? atoi(e) == 1 : (ceil_div(p.R, AH_BM) % 2 == 0);
+  if (pair) return ah_launch_impl<MODE, true>(a1, a2, b1, b2, b3, p, B, H, s);
+  return ah_launch_impl<MODE, false>(a1, a2, b1, b2, b3, p, B, H, s);
+}
+
+static int ah_amax(const float* x, const b200ad_attn_strides& st, int64_t B, int64_t H, int64_t S, float* amax, int slot,
+                   cudaStream_t s) {
+  const int64_t rows = B * H * S;
+  attn_amax_kernel<false><<<(unsigned)ceil_div(rows, AH_PRE_ROWS), 256, 0, s>>>(x, nullptr, nullptr, amax, slot, rows, (int)H,
+                                                                               (int)S, st.batch, st.head, st.row);
+  count_launch();
+  return check_launch("attention amax");
+}
+
+// entry points used by attn_tc.cu's extern "C" functions -------------------------------------------------------
+int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse, float* ws,
+                 cudaStream_t s) {
+  const int64_t B = d->batch, H = d->heads;
+  float* amax = ws;
+  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float) * 4 * B * H, s);
+  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): memset: %s", cudaGetErrorString(e));
+  int rc;
+  if ((rc = ah_amax(q, d->q, B, H, d->seq_q, amax, 0, s))) return rc;
+  if ((rc = ah_amax(k, d->k, B, H, d->seq_kv, amax, 1, s))) return rc;
+  if ((rc = ah_amax(v, d->v, B, H, d->seq_kv, amax, 2, s))) return rc;
+  AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv};
+  AttnHParams p{};
+  p.out = o; p.out_bs = d->o.batch; p.out_hs = d->o.head; p.out_ld = d->o.row;
+  p.lse_w = lse; p.amax = amax;
+  p.H = (int32_t)H; p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
+  p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
+  return ah_launch<AH_FWD>(tq, tq, tk, tk, tv, p, B, H, s);
+}
+
+int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
+                 const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, cudaStream_t s) {
+  const int64_t B = d->batch, H = d->heads;
+  float* dvec = ws;
+  float* amax = ws + B * H * d->seq_q;
+  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float) * 4 * B * H, s);
+  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): memset: %s", cudaGetErrorString(e));
+  AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q};
+  const int64_t rows = B * H * d->seq_q;
+  attn_amax_kernel<true><<<(unsigned)ceil_div(rows, AH_PRE_ROWS), 256, 0, s>>>(dout, o, dvec, amax, 3, rows, (int)H,
+                                                                              (int)d->seq_q, d->o.batch, d->o.head, d->o.row);
+  count_launch();
+  int rc = check_launch("attention dvec");
+  if (rc) return rc;
+  if ((rc = ah_amax(q, d->q, B, H, d->seq_q, amax, 0, s))) return rc;
+  if ((rc = ah_amax(k, d->k, B, H, d->seq_kv, amax, 1, s))) return rc;
+  if ((rc = ah_amax(v, d->v, B, H, d->seq_kv, amax, 2, s))) return rc;
+  AttnHParams p{};
+  p.lse = lse; p.dvec = dvec; p.amax = amax;
+  p.H = (int32_t)H;
+  p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
+  p.out = dv; p.out_bs = d->v.batch; p.out_hs = d->v.head; p.out_ld = d->v.row;
+  p.R = (int32_t)d->seq_kv; p.C = (int32_t)d->seq_q;
+  if ((rc = ah_launch<AH_DV>(tk, tk, tq, tq, tdo, p, B, H, s))) return rc;
+  p.out = dk; p.out_bs = d->k.batch; p.out_hs = d->k.head; p.out_ld = d->k.row;
+  if ((rc = ah_launch<AH_DKM>(tk, tv, tq, tdo, tq, p, B, H, s))) return rc;
+  p.out = dq; p.out_bs = d->q.batch; p.out_hs = d->q.head; p.out_ld = d->q.row;
+  p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
+  return ah_launch<AH_DQ>(tq, tdo, tk, tv, tk, p, B, H, s);
+}
+
+}  // namespace b200ad

@@ -34,6 +34,7 @@
 #include "tcgen05.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <atomic>
 
 namespace b200ad {
 
@@ -858,11 +859,25 @@ static int attn_check(const b200ad_attn_desc* d, const char** why) {
   return 1;
 }
 
+// generation 2 (attn_h16.cu): the same passes carried by fp16 hi / lo pairs at the kind::f16 rate
+int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse, float* ws,
+                 cudaStream_t s);
+int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
+                 const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, cudaStream_t s);
+
+// 0 = fp16 hi/lo split (default), 1 = 3xTF32 (generation 1)
+static std::atomic<int> g_attn_variant{getenv("B200AD_ATTN_TF32") ? 1 : 0};
+
 }  // namespace b200ad
 
 using namespace b200ad;
 
 extern "C" {
+
+int b200ad_attn_set_variant(int variant) {
+  if (variant < 0 || variant > 1) return set_error(B200AD_ERR_INVALID, "attn_set_variant: %d not in 0..1", variant);
+  return g_attn_variant.exchange(variant);
+}
 
 int b200ad_attn_supported(const b200ad_attn_desc* d) {
   const char* why = nullptr;
@@ -873,12 +888,21 @@ int b200ad_attn_supported(const b200ad_attn_desc* d) {
   return 1;
 }
 
+int64_t b200ad_attn_fwd_ws_floats(const b200ad_attn_desc* d) {
+  if (!d) return 0;
+  return 4 * d->batch * d->heads;          // slab maxima of Q, K, V (fp16-split variant)
+}
+
 int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse,
-                    void* stream) {
+                    float* ws, void* stream) {
   const char* why = "unsupported";
   if (!attn_check(d, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "attn_fwd: %s", why);
   B200AD_REQUIRE(tensor_ok(q, d->q) && tensor_ok(k, d->k) && tensor_ok(v, d->v) && tensor_ok(o, d->o) && lse,
                  "attn_fwd: null / misaligned tensor or stride not a multiple of 4 elements");
+  if (g_attn_variant.load(std::memory_order_relaxed) == 0) {
+    B200AD_REQUIRE(ws, "attn_fwd: null workspace (b200ad_attn_fwd_ws_floats)");
+    return attn_h16_fwd(d, q, k, v, o, lse, ws, (cudaStream_t)stream);
+  }
   AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
       tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv};
   AttnParams p{};
@@ -891,7 +915,7 @@ int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, c
 
 int64_t b200ad_attn_bwd_ws_floats(const b200ad_attn_desc* d) {
   if (!d) return 0;
-  return d->batch * d->heads * d->seq_q;
+  return d->batch * d->heads * (d->seq_q + 4);      // D = rowsum(dO o O), + slab maxima of Q, K, V, dO
 }
 
 int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
@@ -902,6 +926,7 @@ int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, c
                      tensor_ok(dout, d->o) && tensor_ok(dq, d->q) && tensor_ok(dk, d->k) && tensor_ok(dv, d->v) && lse && ws,
                  "attn_bwd: null / misaligned tensor or stride not a multiple of 4 elements");
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_attn_variant.load(std::memory_order_relaxed) == 0) return attn_h16_bwd(d, q, k, v, o, dout, lse, dq, dk, dv, ws, s);
   const int64_t B = d->batch, H = d->heads;
   AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
       tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q};

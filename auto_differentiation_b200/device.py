@@ -915,8 +915,9 @@ def attn_fwd(q, k, v, scale):
     lse = empty((B, H, Sq))
     d = _attn_desc(q, k, v, o, scale)
     s = stream_ptr()
+    ws = empty((max(1, int(_lib().b200ad_attn_fwd_ws_floats(ctypes.byref(d)))),))
     _timed(("attn_fwd", B, H, Sq, k.shape[2], dk), 4.0 * B * H * Sq * k.shape[2] * dk,
-           lambda: L.check(_lib().b200ad_attn_fwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, lse.ptr, s)))
+           lambda: L.check(_lib().b200ad_attn_fwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, lse.ptr, ws.ptr, s)))
     return o, lse
 
 

@@ -236,7 +236,10 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d);
 int b200ad_gemm_set_recurrent_dispatch(int mode);
 
 /* ------------------------------------------------------------------------------------------
- * Fused multi-head attention core (tcgen05, fp32-faithful 3xTF32; scores never leave the SM).
+ * Fused multi-head attention core (tcgen05, fp32-faithful three-product split; scores never leave the SM).
+ *   Two variants of the same passes: fp16 hi/lo pairs at the kind::f16 MMA rate with one power-of-two scale per
+ *   (batch, head) operand slab (default, csrc/attn_h16.cu), and tf32 hi/lo pairs (csrc/attn_tc.cu);
+ *   b200ad_attn_set_variant(0 | 1) selects one and returns the previous choice.
  *   fwd:  O = softmax(scale * Q K^T) V  per (batch, head);  lse[b,h,s] = log2-domain log-sum-exp
  *         of the scaled scores of query row s (kept for the backward instead of the S x S matrix).
  *         replaces MultiHeadAttention.forward layers.py:1351-1357 (split heads are strided views:
@@ -244,7 +247,7 @@ int b200ad_gemm_set_recurrent_dispatch(int mode);
  *   bwd:  dQ, dK, dV of the same expression given dO (the tape gradients of
  *         Test/MultiHeadAttentionTest.py:70-85: Matmul :530-533, Divide :1004-1005 without the 1e-8
  *         that only guards a zero denominator, exp :1058-1060, sum :699-704).
- *         dO shares `o`'s strides, dQ/dK/dV share q/k/v's.  ws: b200ad_attn_bwd_ws_floats floats.
+ *         dO shares `o`'s strides, dQ/dK/dV share q/k/v's.  ws: b200ad_attn_{fwd,bwd}_ws_floats floats of scratch.
  *   Built for head_dim == 64, any seq_q / seq_kv, strides multiples of 4 elements, 16 B aligned
  *   bases; b200ad_attn_supported says whether the fused path applies (otherwise the caller
  *   composes the same math from b200ad_gemm + b200ad_softmax_*).
@@ -259,8 +262,10 @@ typedef struct b200ad_attn_desc {
   b200ad_attn_strides q, k, v, o;
 } b200ad_attn_desc;
 int b200ad_attn_supported(const b200ad_attn_desc* d);
+int b200ad_attn_set_variant(int variant);
+int64_t b200ad_attn_fwd_ws_floats(const b200ad_attn_desc* d);
 int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
-                    float* o, float* lse, void* stream);
+                    float* o, float* lse, float* ws, void* stream);
 int64_t b200ad_attn_bwd_ws_floats(const b200ad_attn_desc* d);
 int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
                     const float* o, const float* dout, const float* lse, float* dq, float* dk,

@@ -378,7 +378,14 @@ class Emulator:
 
     def b200ad_attn_bwd_ws_floats(self, dref):
         d = dref._obj if hasattr(dref, "_obj") else dref
-        return d.batch * d.heads * d.seq_q
+        return d.batch * d.heads * (d.seq_q + 4)
+
+    def b200ad_attn_fwd_ws_floats(self, dref):
+        d = dref._obj if hasattr(dref, "_obj") else dref
+        return 4 * d.batch * d.heads
+
+    def b200ad_attn_set_variant(self, variant):
+        return 0
 
     def _attn_probs(self, d, q, k):
         Q = self._attn_view(_ival(q), d.q, d.batch, d.heads, d.seq_q, d.head_dim).astype(np.float64)
@@ -389,7 +396,7 @@ class Emulator:
         l = e.sum(axis=-1, keepdims=True)
         return Q, K, e / l, (m + np.log(l))[..., 0]
 
-    def b200ad_attn_fwd(self, dref, q, k, v, o, lse, s):
+    def b200ad_attn_fwd(self, dref, q, k, v, o, lse, ws, s):
         self.launches += 1
         d = dref._obj if hasattr(dref, "_obj") else dref
         if d.head_dim != 64:

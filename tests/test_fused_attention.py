@@ -135,7 +135,12 @@ def test_attn_output_guards(backend, Sq, Skv):
     lse = D.asarray(np.full(n_lse + 16, SENT, dtype=np.float32))
     d = D._attn_desc(Q, K, V, O, scale)
     s = D.stream_ptr()
-    L.check(lib.b200ad_attn_fwd(ctypes.byref(d), Q.ptr, K.ptr, V.ptr, O.ptr, lse.ptr + 32, s))
+    n_fws = int(lib.b200ad_attn_fwd_ws_floats(ctypes.byref(d)))
+    assert n_fws == 4 * B * h
+    fws = D.asarray(np.full(n_fws + 16, SENT, dtype=np.float32))
+    L.check(lib.b200ad_attn_fwd(ctypes.byref(d), Q.ptr, K.ptr, V.ptr, O.ptr, lse.ptr + 32, fws.ptr + 32, s))
+    fg = np.asarray(fws)
+    assert np.all(fg[:8] == SENT) and np.all(fg[8 + n_fws:] == SENT), "forward workspace written out of range"
     o_ref, dq_ref, dk_ref, dv_ref = _ref(q, k, v, do, scale)
     og = np.asarray(obuf)
     assert_close(og[:, 1:Sq + 1].transpose(0, 2, 1, 3), o_ref, rtol=2e-5, atol=2e-6, what="O window")
@@ -143,7 +148,9 @@ def test_attn_output_guards(backend, Sq, Skv):
     lg = np.asarray(lse)
     assert np.all(lg[:8] == SENT) and np.all(lg[8 + n_lse:] == SENT), "lse written out of range"
     (qb, dQ), (kb, dK), (vb, dV) = window(Sq), window(Skv), window(Skv)
-    ws = D.asarray(np.full(n_lse + 16, SENT, dtype=np.float32))
+    n_ws = int(lib.b200ad_attn_bwd_ws_floats(ctypes.byref(d)))
+    assert n_ws == B * h * (Sq + 4)
+    ws = D.asarray(np.full(n_ws + 16, SENT, dtype=np.float32))
     L.check(lib.b200ad_attn_bwd(ctypes.byref(d), Q.ptr, K.ptr, V.ptr, O.ptr, dO.ptr, lse.ptr + 32, dQ.ptr, dK.ptr, dV.ptr,
                                 ws.ptr + 32, s))
     for name, buf, S, ref in (("dQ", qb, Sq, dq_ref), ("dK", kb, Skv, dk_ref), ("dV", vb, Skv, dv_ref)):
@@ -151,7 +158,7 @@ def test_attn_output_guards(backend, Sq, Skv):
         assert_close(g[:, 1:S + 1].transpose(0, 2, 1, 3), ref, rtol=2e-5, atol=2e-6, what=name + " window")
         assert np.all(g[:, 0] == SENT) and np.all(g[:, S + 1] == SENT), name + " written outside its rows"
     wg = np.asarray(ws)
-    assert np.all(wg[:8] == SENT) and np.all(wg[8 + n_lse:] == SENT), "backward workspace written out of range"
+    assert np.all(wg[:8] == SENT) and np.all(wg[8 + n_ws:] == SENT), "backward workspace written out of range"
 
 
 def test_attn_large_scores_stable(backend):
@@ -229,3 +236,60 @@ def test_attn_config5_shape_properties():
     assert np.array_equal(np.asarray(O2), o) and np.array_equal(np.asarray(lse2), np.asarray(lse))
     dQ2, dK2, dV2 = D.attn_bwd(Q, K, V, O, dO, lse, scale)
     assert np.array_equal(np.asarray(dV2), np.asarray(dV)) and np.array_equal(np.asarray(dK2), np.asarray(dK))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,h,Sq,Skv", [(2, 8, 512, 512), (3, 2, 200, 136), (1, 1, 128, 64)])
+def test_attn_variants_fp16_split_and_tf32_split_agree(B, h, Sq, Skv):
+    """The two carriers of the fp32-faithful split — fp16 hi/lo at the kind::f16 rate (default) and tf32 hi/lo — against
+    fp64 and against each other, selected through b200ad_attn_set_variant."""
+    D = _D()
+    from auto_differentiation_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(B + Sq + Skv)
+    dk, scale = 64, 1.0 / 8.0
+    q, k, v = (rng.standard_normal((B, h, S, dk)).astype(np.float32) for S in (Sq, Skv, Skv))
+    do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    ref = _ref(q, k, v, do, scale)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    got = {}
+    prev = lib.b200ad_attn_set_variant(0)
+    try:
+        for variant in (0, 1):
+            lib.b200ad_attn_set_variant(variant)
+            O, lse = D.attn_fwd(Q, K, V, scale)
+            dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+            got[variant] = [np.asarray(a, dtype=np.float64) for a in (O, dQ, dK, dV)]
+            for a, r, name in zip(got[variant], ref, ("O", "dQ", "dK", "dV")):
+                assert_close(a, r, rtol=2e-5, atol=2e-6, what="variant %d %s" % (variant, name))
+    finally:
+        lib.b200ad_attn_set_variant(prev)
+    for a, b, name in zip(got[0], got[1], ("O", "dQ", "dK", "dV")):
+        assert_close(a, b, rtol=2e-5, atol=2e-6, what="fp16-split vs tf32-split " + name)
+
+
+@pytest.mark.gpu
+def test_attn_fp16_split_operand_ranges():
+    """The fp16 carrier rescales every (batch, head) operand slab by a power of two: gradients of 1e-8, values of 1e3,
+    scores up to ~40 and slabs of very different magnitude in one launch must all come out fp32-faithful."""
+    D = _D()
+    rng = np.random.default_rng(99)
+    B, h, S, dk = 2, 4, 256, 64
+    scale = 1.0 / 8.0
+    q = (rng.standard_normal((B, h, S, dk)) * 2.5).astype(np.float32)
+    k = (rng.standard_normal((B, h, S, dk)) * 2.5).astype(np.float32)
+    v = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    do = rng.standard_normal((B, h, S, dk)).astype(np.float32)
+    slab = np.array([1e3, 1.0, 1e-3, 7.0, 1e-5, 300.0, 0.02, 1.0]).reshape(B, h, 1, 1)
+    v = (v * slab).astype(np.float32)                       # per-slab magnitudes from 1e-5 to 1e3
+    do = (do * 1e-8 * slab[::-1]).astype(np.float32)        # tiny upstream gradients, differently scaled per slab
+    ref = _ref(q, k, v, do, scale)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    O, lse = D.attn_fwd(Q, K, V, scale)
+    dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    for a, r, name in zip((O, dQ, dK, dV), ref, ("O", "dQ", "dK", "dV")):
+        a = np.asarray(a, dtype=np.float64)
+        for b_ in range(B):
+            for h_ in range(h):                              # per slab: the tolerance is relative to the SLAB's scale
+                sc = max(float(np.abs(r[b_, h_]).max()), 1e-300)
+                assert_close(a[b_, h_] / sc, r[b_, h_] / sc, rtol=5e-5, atol=5e-6, what="ranges %s slab (%d,%d)" % (name, b_, h_))
