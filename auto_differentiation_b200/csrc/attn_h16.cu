@@ -38,11 +38,19 @@ namespace b200ad {
 constexpr int AH_DK = 64;
 constexpr int AH_BM = 128;
 constexpr int AH_BC = 64;
-constexpr int AH_NSLOT = 6;
-constexpr uint32_t AH_SLOT = 32768;          // [raw 16 KB | hi 8 KB | lo 8 KB] for a B block, or one raw A tile (32 KB)
-constexpr uint32_t AH_HI = 16384, AH_LO = 24576;
-constexpr int AH_THREADS = 512;
-constexpr uint32_t AH_SMEM = (AH_NSLOT + 1) * AH_SLOT + 1024;
+// shared memory: a ring for the B-operand blocks (128 KB: 4 slots of [raw 16 KB | hi 8 KB | lo 8 KB], or 8 half-size slots
+// when a CTA pair splits every block), two 32 KB staging tiles for the raw A operands, 32 KB for the output tile.
+// (The first version shared one ring of six 32 KB slots between A tiles and B blocks: the block that feeds the OUT product
+// then had a single block of lead over its consumer, and TMA latency + conversion showed up as ~700 cycles per block of
+// MMA-side waiting.)
+constexpr int AH_MAXRING = 8;
+constexpr uint32_t AH_RING_BYTES = 131072, AH_ASTAGE = 32768;
+// Converter groups of four warps each.  Two groups (640 threads; registers 48 / 72 / 136) were measured against one (512
+// threads; 80 / 112 / 152): 2.38 ms vs 2.31 ms for the config-5 backward — the second group does not pay, because the
+// conversion is not what the MMA thread waits for (profiles/r2_attn_h16_prof.log) and the owners lose registers.
+constexpr int AH_CONV_GROUPS = 1;
+constexpr int AH_THREADS = 128 + 128 * AH_CONV_GROUPS + 256;
+constexpr uint32_t AH_SMEM = AH_RING_BYTES + 2 * AH_ASTAGE + 32768 + 1024;
 
 enum { AH_FWD = 0, AH_DV = 1, AH_DQ = 2, AH_DKM = 3 };
 
@@ -159,6 +167,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                 const AttnHParams p) {
   constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM);
   constexpr bool ROWSTAT = (MODE == AH_FWD || MODE == AH_DQ);   // lanes are query rows
+  constexpr bool PAIRF = (MODE != AH_FWD);                      // backward modes: two blocks (128 K-elements) per OUT chain
   constexpr uint32_t A1_COL = 0, A2_COL = 64;
   constexpr uint32_t X_COL0 = HAS2 ? 128u : 64u;
   constexpr uint32_t Y_COL0 = 256u;
@@ -168,20 +177,28 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* out_stage = smem + (size_t)AH_NSLOT * AH_SLOT;
-  __shared__ uint64_t bars[3 * AH_NSLOT + 16];
+  constexpr int AH_NSLOT = CP ? 8 : 4;
+  constexpr uint32_t AH_SLOT = CP ? 16384u : 32768u, AH_HI = AH_SLOT / 2, AH_LO = AH_SLOT * 3 / 4;
+  uint8_t* a_stage = smem + AH_RING_BYTES;                  // [2] raw A tiles (128 rows x 64 fp32)
+  uint8_t* out_stage = smem + AH_RING_BYTES + 2 * AH_ASTAGE;
+  __shared__ uint64_t bars[3 * AH_MAXRING + 26];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float colstat[2][128];
   float (*rowx)[128] = colstat;
   uint64_t* full = bars;                       // [NSLOT] TMA -> converter
-  uint64_t* conv = bars + AH_NSLOT;            // [NSLOT] converter -> MMA
-  uint64_t* empty = bars + 2 * AH_NSLOT;       // [NSLOT] MMA commit (B slots) / converter (A slots) -> TMA
-  uint64_t* a_empty = bars + 3 * AH_NSLOT;     // [2] MMA commit -> converter: last score MMA of the item retired
+  uint64_t* conv = bars + AH_MAXRING;          // [NSLOT] converter -> MMA
+  uint64_t* empty = bars + 2 * AH_MAXRING;     // [NSLOT] MMA commit -> TMA
+  uint64_t* a_full = bars + 3 * AH_MAXRING;    // [2] TMA -> converter: raw A tile staged
+  uint64_t* a_conv = a_full + 2;               // [2] converter -> MMA: A tile (hi / lo) is in TMEM
+  uint64_t* a_free = a_conv + 2;               // [2] converter -> TMA: the staging tile has been read
+  uint64_t* a_empty = a_free + 2;              // [2] MMA commit -> converter: last score MMA of the item retired
   uint64_t* x_full = a_empty + 2;              // [2] MMA commit -> row owners
   uint64_t* y_full = x_full + 2;               // [2]
   uint64_t* z_full = y_full + 2;               // [2] row owners -> MMA
   uint64_t* out_full = z_full + 2;             // [2] MMA commit -> row owners
   uint64_t* out_empty = out_full + 2;          // [2] row owners -> MMA
+  uint64_t* cs_full = out_empty + 2;           // [2] column-statistics warp -> row owners (32 arrivals)
+  uint64_t* cs_empty = cs_full + 2;            // [2] row owners -> column-statistics warp (8 warps)
   uint32_t* tmem_base_slot = &tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -216,12 +233,17 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_conv[i], CP ? 8 : 128);
+      mbar_init(&a_free[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&x_full[i], 1);
       mbar_init(&y_full[i], 1);
       mbar_init(&z_full[i], CP ? 16 : 256);
       mbar_init(&out_full[i], 1);
       mbar_init(&out_empty[i], CP ? 16 : 256);
+      mbar_init(&cs_full[i], 32);
+      mbar_init(&cs_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -233,12 +255,13 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
   const int nb = p.nb;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (AH_CONV_GROUPS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
-      uint32_t op = 0;
-      for (int item = unit_id; item < p.total_items; item += units) {
+      uint32_t op = 0, it = 0;
+      for (int item = unit_id; item < p.total_items; item += units, ++it) {
         const int rt = (item % p.row_tiles) * (CP ? 2 : 1) + (int)rank, bh = item / p.row_tiles;
         const int h = bh % p.H, b = bh / p.H;
         const int row0 = rt * AH_BM;
@@ -250,11 +273,12 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ++op;
           return smem + (size_t)s * AH_SLOT;
         };
-        auto load_a = [&](const CUtensorMap* m) {          // 128 rows x 64: two 32-float halves, SWIZZLE_128B
-          uint64_t* bar;
-          uint8_t* dst = acquire(32768u, bar);
-          tma_load_4d(m, bar, dst, 0, row0, h, b);
-          tma_load_4d(m, bar, dst + 16384, 32, row0, h, b);
+        auto load_a = [&](const CUtensorMap* m, int which) {   // 128 rows x 64: two 32-float halves, SWIZZLE_128B
+          mbar_wait(&a_free[which], (it & 1) ^ 1);             // the converter has read the previous item's tile
+          mbar_expect_tx(&a_full[which], 32768u);
+          uint8_t* dst = a_stage + (size_t)which * AH_ASTAGE;
+          tma_load_4d(m, &a_full[which], dst, 0, row0, h, b);
+          tma_load_4d(m, &a_full[which], dst + 16384, 32, row0, h, b);
         };
         auto load_k = [&](const CUtensorMap* m, int col0) {   // score operand block: 64 rows x 64 (pair: this CTA's 32 rows), SWIZZLE_128B halves
           uint64_t* bar;
@@ -280,8 +304,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           }
         };
         // ring order = consumption order of the MMA warp: A1 [A2] X(0) [Y(0)] { X(j+1) [Y(j+1)] OUT(j) }
-        load_a(&map_a1);
-        if (HAS2) load_a(&map_a2);
+        load_a(&map_a1, 0);
+        if (HAS2) load_a(&map_a2, 1);
         load_k(&map_b1, 0);
         if (HAS2) load_k(&map_b2, 0);
         for (int j = 0; j < nb; ++j) {
@@ -297,7 +321,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     // ===================================== MMA issuer (leader CTA of a pair) =====================================
     // instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N = 64, M = 128 (256 for a pair)
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((CP ? 256 : AH_BM) >> 4) << 24);
-    uint32_t op = 0, it = 0, gb = 0;
+    uint32_t op = 0, it = 0, gb = 0, fo = 0;
     long long prof_acc[4] = {0, 0, 0, 0};
     const long long prof_t0 = p.prof ? clock64() : 0;
     auto wait_slot = [&]() -> uint32_t {
@@ -326,8 +350,11 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     };
     for (int item = unit_id; item < p.total_items; item += units, ++it) {
       {
-        wait_slot();                                   // A1 in TMEM
-        if (HAS2) wait_slot();                         // A2 in TMEM
+        AH_T(wa0);
+        mbar_wait(&a_conv[0], it & 1);                 // A1 in TMEM
+        if (HAS2) mbar_wait(&a_conv[1], it & 1);       // A2 in TMEM
+        AH_T(wa1);
+        AH_ACC(3, wa0, wa1);
         const uint32_t s_x0 = wait_slot();
         uint32_t s_y0 = 0;
         if (HAS2) s_y0 = wait_slot();
@@ -347,7 +374,6 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           s_x = wait_slot();
           if (HAS2) s_y = wait_slot();
         }
-        const uint32_t s_o = wait_slot();
         if (j + 1 < nb) {
           // X(j+1) overwrites the columns Z(j-1) occupied: the OUT(j-1) MMAs that read them were issued earlier by this
           // same thread, and tcgen05.mma instructions execute in issue order
@@ -360,12 +386,14 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           }
           __syncwarp();
         }
-        const uint32_t ob = g & 1, oph = (g >> 1) & 1;
+        const bool first = !PAIRF || (j & 1) == 0, last = !PAIRF || (j & 1) == 1 || j == nb - 1;
+        const uint32_t ob = fo & 1, oph = (fo >> 1) & 1;
         AH_T(w0);
         mbar_wait(&z_full[g & 1], (g >> 1) & 1);
         AH_T(w1);
-        mbar_wait(&out_empty[ob], oph ^ 1);
+        if (first) mbar_wait(&out_empty[ob], oph ^ 1);
         AH_T(w2);
+        const uint32_t s_o = wait_slot();             // the OUT operand block (ring order: X(j+1) [Y(j+1)] O(j))
         AH_ACC(1, w0, w1);
         AH_ACC(2, w1, w2);
         tc_fence_after();
@@ -377,7 +405,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           // covers columns c in [16 kk, 16 kk + 16) = group kk >> 1, packed columns 8 (kk & 1) .. + 8
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_ts(dst, zb + 32u * (kk >> 1) + 16u + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, kk ? 1u : 0u);
+            mma_ts(dst, zb + 32u * (kk >> 1) + 16u + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, (kk || !first) ? 1u : 0u);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             mma_ts(dst, zb + 32u * (kk >> 1) + 8u * (kk & 1), dl + (uint64_t)(kk * 2), IDESC, 1u);
@@ -385,9 +413,10 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           for (int kk = 0; kk < 4; ++kk)
             mma_ts(dst, zb + 32u * (kk >> 1) + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, 1u);
           mma_commit(&empty[s_o]);
-          mma_commit(&out_full[ob]);
+          if (last) mma_commit(&out_full[ob]);
         }
         __syncwarp();
+        if (last) ++fo;
       }
       gb += nb;
     }
@@ -396,48 +425,103 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       p.prof[1] = prof_acc[0];           // waiting for converted operand slots
       p.prof[2] = prof_acc[1];           // waiting for Z (row owners)
       p.prof[3] = prof_acc[2];           // waiting for a free OUT accumulator
+      p.prof[7] = prof_acc[3];           // waiting for the A tiles of the next item
+    }
+  } else if (warp == 2 && !ROWSTAT) {
+    // ===================================== column statistics (DV / DK) =====================================
+    // lse (and D c) of the 64 columns of block j -> colstat[g & 1], one block ahead of the row owners, handed over through
+    // an mbarrier: the owners no longer meet at a 256-thread barrier every block (measured: ~900 of 2450 cycles per block)
+    uint32_t gb = 0;
+    for (int item = unit_id; item < p.total_items; item += units) {
+      const int bh = item / p.row_tiles;
+      float zexp;
+      {
+        const float* am = p.amax + (int64_t)bh * 4;
+        int e_a2, e_b2;
+        (void)ah_slab_scale(__ldg(am + OPS::A2), e_a2);
+        (void)ah_slab_scale(__ldg(am + OPS::B2), e_b2);
+        const int e_c = (int)((__float_as_uint(p.c) >> 23) & 0xffu) - 127;
+        zexp = HAS2 ? (float)(14 - (10 + e_a2 + e_b2 + e_c)) : 14.f;
+      }
+      auto fetch = [&](int j, float (&v)[4]) {
+        const int c0 = j * AH_BC;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = c0 + lane + 32 * i;
+          v[i] = (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) - zexp : INFINITY;
+          v[2 + i] = (MODE == AH_DKM && col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) * p.c : 0.f;
+        }
+      };
+      float nxt[4];
+      fetch(0, nxt);
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t g = gb + j;
+        float cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+        if (j + 1 < nb) fetch(j + 1, nxt);
+        mbar_wait(&cs_empty[g & 1], ((g >> 1) & 1) ^ 1);
+        float* cs = colstat[g & 1];
+        cs[lane] = cur[0];
+        cs[lane + 32] = cur[1];
+        if (MODE == AH_DKM) {
+          cs[64 + lane] = cur[2];
+          cs[96 + lane] = cur[3];
+        }
+        mbar_arrive(&cs_full[g & 1]);
+      }
+      gb += nb;
     }
   }
-  } else if (warp < 8) {
-    // ===================================== converter =====================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-    const int tid = threadIdx.x - 128;
+  } else if (warp < 4 + 4 * AH_CONV_GROUPS) {
+    // ===================================== converters =====================================
+    // Two groups of four warps; group cg takes the ring operations with (op & 1) == cg and the A tile `cg`: a tile
+    // conversion is a ~450-cycle dependent instruction stream for one warp set (measured), so two tiles in flight double
+    // the conversion rate the single group could not sustain (the MMA thread waited ~700 cycles per block for it).
+    // register budget: setmaxnreg redistributes WITHIN the CTA's launch allocation (640 threads x 96 registers): 4 x 48 +
+    // 8 x 72 + 8 x 136 = 1856 <= 20 warps x 96 = 1920 per lane (an .inc beyond what the .dec's released blocks forever)
+    if (AH_CONV_GROUPS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    const int cg = (warp - 4) >> 2;
+    const int tid = (threadIdx.x - 128) & 127;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t op = 0, it = 0;
     float s_a1 = 1.f, s_a2 = 1.f, s_b1 = 1.f, s_b2 = 1.f, s_b3 = 1.f;
+    long long prof_acc[4] = {0, 0, 0, 0};
     auto conv_a = [&](int which, float sc) {
-      const uint32_t s = op % AH_NSLOT;
-      mbar_wait(&full[s], (op / AH_NSLOT) & 1);
-      ++op;
+      if (AH_CONV_GROUPS == 2 && which != cg) return;
+      mbar_wait(&a_full[which], it & 1);
       mbar_wait(&a_empty[which], (it & 1) ^ 1);
       tc_fence_after();
-      const uint32_t slot = smem_u32(smem + (size_t)s * AH_SLOT);
+      const uint32_t slot = smem_u32(a_stage + (size_t)which * AH_ASTAGE);
       const uint32_t col = which ? A2_COL : A1_COL;
-      uint32_t hi[32], lo[32];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        uint32_t hi[16], lo[16];
         const uint32_t row = slot + hh * 16384 + r * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {     // SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
           const uint4 t4 = ah_lds128(row + ((c ^ (r & 7)) << 4));
-          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[hh * 16 + 2 * c], lo[hh * 16 + 2 * c]);
-          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[hh * 16 + 2 * c + 1], lo[hh * 16 + 2 * c + 1]);
+          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * c], lo[2 * c]);
+          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * c + 1], lo[2 * c + 1]);
         }
+        ah_tmem_st_x16(lane_base + col + hh * 16, hi);
+        ah_tmem_st_x16(lane_base + col + 32 + hh * 16, lo);
       }
-      tmem_st_32x32b_x32(lane_base + col, hi);
-      tmem_st_32x32b_x32(lane_base + col + 32, lo);
       tmem_st_wait();
       tc_fence_before();
-      arrive_leader(&conv[s]);
-      ah_bar_sync(1, 128);
-      if (tid == 0) mbar_arrive(&empty[s]);
+      arrive_leader(&a_conv[which]);
+      ah_bar_sync(1 + 5 * cg, 128);
+      if (tid == 0) mbar_arrive(&a_free[which]);
     };
     // score operand block (K-major raw, two SWIZZLE_128B halves of 32 floats): row-wise conversion, same orientation
     auto conv_k = [&](float sc) {
       const uint32_t s = op % AH_NSLOT;
+      if (AH_CONV_GROUPS == 2 && (op & 1u) != (uint32_t)cg) { ++op; return; }
+      AH_T(k0);
       mbar_wait(&full[s], (op / AH_NSLOT) & 1);
+      AH_T(k1);
+      AH_ACC(0, k0, k1);
       ++op;
       const uint32_t slot = smem_u32(smem + (size_t)s * AH_SLOT);
       constexpr int ROWS = CP ? 32 : 64;                     // rows staged by this CTA
@@ -464,12 +548,17 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       }
       fence_proxy_async();
       arrive_leader(&conv[s]);
+      { AH_T(k2); AH_ACC(1, k1, k2); }
     };
     // OUT operand block (raw [64 kv rows][d] unswizzled, 32-float-wide halves): TRANSPOSING conversion to the K-major tile
     // [d][kv]: thread (d, part) reads its column for 64 / PARTS consecutive kv rows (lanes = consecutive d: conflict-free)
     auto conv_o = [&](float sc) {
       const uint32_t s = op % AH_NSLOT;
+      if (AH_CONV_GROUPS == 2 && (op & 1u) != (uint32_t)cg) { ++op; return; }
+      AH_T(k0);
       mbar_wait(&full[s], (op / AH_NSLOT) & 1);
+      AH_T(k1);
+      AH_ACC(0, k0, k1);
       ++op;
       const uint32_t slot = smem_u32(smem + (size_t)s * AH_SLOT);
       constexpr int DS = CP ? 32 : 64;                       // d columns staged by this CTA = rows of the converted tile
@@ -493,6 +582,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       }
       fence_proxy_async();
       arrive_leader(&conv[s]);
+      { AH_T(k2); AH_ACC(2, k1, k2); }
     };
     for (int item = unit_id; item < p.total_items; item += units, ++it) {
       const int bh = item / p.row_tiles;
@@ -517,16 +607,22 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         conv_o(s_b3);
       }
     }
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 128) {
+      p.prof[4] = prof_acc[0];           // converter: waiting for TMA
+      p.prof[5] = prof_acc[1];           // converter: score operand blocks
+      p.prof[6] = prof_acc[2];           // converter: OUT operand blocks
+    }
   } else {
     // ===================================== row owners =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-    const int tid = threadIdx.x - 256;
-    const int gi = (warp - 8) >> 2;
+    if (AH_CONV_GROUPS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int tid = threadIdx.x - (128 + 128 * AH_CONV_GROUPS);
+    const int gi = (warp - 4 - 4 * AH_CONV_GROUPS) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t cofs = (uint32_t)gi * 32u;
-    uint32_t gb = 0;
+    uint32_t gb = 0, fo = 0;
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = p.prof ? clock64() : 0;
     for (int item = unit_id; item < p.total_items; item += units) {
@@ -565,8 +661,9 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         ls_r = __ldg(p.lse + (int64_t)bh * p.R + grow) - zexp;       // the Z scale rides in the exp2 argument
         d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow) * p.c;
       }
-      auto fold = [&](uint32_t g, float a) {
-        const uint32_t ob = g & 1, oph = (g >> 1) & 1;
+      auto fold = [&](float a) {
+        const uint32_t ob = fo & 1, oph = (fo >> 1) & 1;
+        ++fo;
         AH_T(f0);
         mbar_wait(&out_full[ob], oph);
         AH_T(f1);
@@ -585,18 +682,6 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         AH_T(f2);
         AH_ACC(5, f1, f2);
       };
-      auto load_colstat = [&](int c0) -> float {
-        if (tid < 64) {
-          const int col = c0 + tid;
-          return (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) - zexp : INFINITY;
-        }
-        if (MODE == AH_DKM && tid < 128) {
-          const int col = c0 + tid - 64;
-          return (col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) * p.c : 0.f;
-        }
-        return 0.f;
-      };
-      float cs_next = ROWSTAT ? 0.f : load_colstat(0);
       for (int j = 0; j < nb; ++j) {
         const uint32_t g = gb + j;
         const uint32_t bsel = g & 1;
@@ -604,11 +689,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const int col0 = j * AH_BC + (int)cofs;
         float* cs = colstat[bsel];
         AH_T(b0);
-        if (!ROWSTAT) {
-          if (tid < 128) cs[tid] = cs_next;
-          ah_bar_sync(2, 256);
-          if (j + 1 < nb) cs_next = load_colstat((j + 1) * AH_BC);
-        }
+        if (!ROWSTAT) mbar_wait(&cs_full[bsel], (g >> 1) & 1);      // this block's lse / D columns are in shared memory
         AH_T(b1);
         mbar_wait(&x_full[bsel], (g >> 1) & 1);
         if (HAS2) mbar_wait(&y_full[bsel], (g >> 1) & 1);
@@ -654,7 +735,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           tc_fence_before();
           arrive_leader(&z_full[bsel]);
           { AH_T(b3); AH_ACC(2, b2, b3); }     // load + math + store + arrive
-          if (j >= 1) fold(g - 1, a_prev);
+          if (j >= 1) fold(a_prev);
           a_prev = alpha;
         } else if (MODE == AH_DV) {
           uint32_t x[32];
@@ -670,15 +751,18 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1]);
             ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs_empty[bsel]);            // this warp has read the block's column statistics
           ah_tmem_st_x16(xaddr, zh);
           ah_tmem_st_x16(xaddr + 16, zl);
           tmem_st_wait();
           tc_fence_before();
           arrive_leader(&z_full[bsel]);
           { AH_T(b3); AH_ACC(2, b2, b3); }
-          if (j >= 1) fold(g - 1, 1.f);
+          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         } else {
           // DQ / DK: Z = P (Y c - D c), carried times 2^ez
+          const bool full_block = col0 + 32 <= p.C;
           uint32_t x[32], y[32];
           tmem_ld_32x32b_x32(xaddr, x);
           tmem_ld_32x32b_x32(lane_base + Y_COL0 + bsel * 64u + cofs, y);
@@ -689,8 +773,13 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             if (MODE == AH_DQ) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                ls[i] = (col0 + c4 + i < p.C) ? ls_r : INFINITY;
+                ls[i] = ls_r;
                 dd[i] = d_r;
+              }
+              if (!full_block) {                       // only the last block of a row can be ragged
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col0 + c4 + i >= p.C) ls[i] = INFINITY;
               }
             } else {
               const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
@@ -707,16 +796,20 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1]);
             ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
           }
+          if (MODE == AH_DKM) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs_empty[bsel]);
+          }
           ah_tmem_st_x16(xaddr, zh);
           ah_tmem_st_x16(xaddr + 16, zl);
           tmem_st_wait();
           tc_fence_before();
           arrive_leader(&z_full[bsel]);
           { AH_T(b3); AH_ACC(2, b2, b3); }
-          if (j >= 1) fold(g - 1, 1.f);
+          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         }
       }
-      fold(gb + nb - 1, a_prev);
+      fold(a_prev);
       gb += nb;
       AH_T(e0);
       // ---- epilogue (unchanged: swizzled staging tile + TMA store)
@@ -752,7 +845,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       { AH_T(e1); AH_ACC(6, e0, e1); }        // epilogue
     }
     if (tid == 0) ah_bulk_wait0();
-    if (p.prof && blockIdx.x == 0 && threadIdx.x == 256) {
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 128 + 128 * AH_CONV_GROUPS) {
       p.prof[8] = clock64() - prof_t0;
       for (int i = 0; i < 7; ++i) p.prof[9 + i] = prof_acc[i];
     }
@@ -777,13 +870,27 @@ __device__ __forceinline__ void ah_amax_flush(float m, int64_t bh, float* amax, 
     atomicMax(reinterpret_cast<unsigned int*>(amax + bh * 4 + slot), __float_as_uint(m));
 }
 
-// DVEC: additionally D[b, h, s] = sum_d dO * O (x = dO, o = O; as attn_tc.cu's attn_dvec_kernel)
-template <bool DVEC>
-__global__ void __launch_bounds__(256) attn_amax_kernel(const float* __restrict__ x, const float* __restrict__ o,
-                                                        float* __restrict__ dvec, float* __restrict__ amax, int slot,
-                                                        int64_t rows_total, int H, int S, int64_t bs, int64_t hs, int64_t ld) {
+// One launch covers up to four tensors (blockIdx.y = job = amax slot).  A job may additionally produce
+// D[b, h, s] = sum_d x * o (x = dO, o = O; as attn_tc.cu's attn_dvec_kernel).
+struct AhAmaxJob {
+  const float* x;
+  const float* o;        // non-null: also write dvec
+  float* dvec;
+  int64_t rows_total, bs, hs, ld;
+  int32_t S, slot;
+};
+struct AhAmaxJobs { AhAmaxJob job[4]; };
+
+__global__ void __launch_bounds__(256) attn_amax_kernel(const AhAmaxJobs jobs, float* __restrict__ amax, int H) {
+  const AhAmaxJob& jb = jobs.job[blockIdx.y];
+  const float* __restrict__ x = jb.x;
+  const float* __restrict__ o = jb.o;
+  const int64_t rows_total = jb.rows_total, bs = jb.bs, hs = jb.hs, ld = jb.ld;
+  const int S = jb.S, slot = jb.slot;
+  const bool DVEC = o != nullptr;
   const int sub = threadIdx.x & 15;
   const int64_t first = (int64_t)blockIdx.x * AH_PRE_ROWS;
+  if (first >= rows_total) return;
   int64_t cur_bh = -1;          // warp-uniform: both rows of a warp are forced onto the same slab per iteration (below)
   float m = 0.f;
   for (int it = 0; it < AH_PRE_ROWS / 16; ++it) {
@@ -806,7 +913,7 @@ __global__ void __launch_bounds__(256) attn_amax_kernel(const float* __restrict_
     if (DVEC) {
 #pragma unroll
       for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
-      if (sub == 0 && live) dvec[row] = v;
+      if (sub == 0 && live) jb.dvec[row] = v;
     }
     if (bh_lo == bh_hi) {
       if (bh_lo != cur_bh) {
@@ -912,9 +1019,9 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
     cudaStreamSynchronize(s);
     cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
     const double blocks = (double)ceil_div(p.total_items, grid / (CP ? 2 : 1)) * p.nb;
-    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f | "
-            "owner total %.0f colstat %.0f wait_XY %.0f ld+math+st %.0f wait_OUT %.0f fold %.0f epilogue %.0f\n", MODE, (int)CP, blocks,
-            hp[0] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
+    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_A %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f | "
+            "converter wait_tma %.0f conv_k %.0f conv_o %.0f | owner total %.0f colstat %.0f wait_XY %.0f ld+math+st %.0f wait_OUT %.0f fold %.0f epilogue %.0f\n", MODE, (int)CP, blocks,
+            hp[0] / blocks, hp[7] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[4] / blocks, hp[5] / blocks, hp[6] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
             hp[11] / blocks, hp[13] / blocks, hp[14] / blocks, hp[15] / blocks);
   }
   if (getenv("B200AD_ATTN_SYNC")) {
@@ -934,11 +1041,23 @@ static int ah_launch(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTe
   return ah_launch_impl<MODE, false>(a1, a2, b1, b2, b3, p, B, H, s);
 }
 
-static int ah_amax(const float* x, const b200ad_attn_strides& st, int64_t B, int64_t H, int64_t S, float* amax, int slot,
-                   cudaStream_t s) {
-  const int64_t rows = B * H * S;
-  attn_amax_kernel<false><<<(unsigned)ceil_div(rows, AH_PRE_ROWS), 256, 0, s>>>(x, nullptr, nullptr, amax, slot, rows, (int)H,
-                                                                               (int)S, st.batch, st.head, st.row);
+static AhAmaxJob ah_job(const float* x, const b200ad_attn_strides& st, int64_t B, int64_t H, int64_t S, int slot,
+                        const float* o = nullptr, float* dvec = nullptr) {
+  AhAmaxJob j;
+  j.x = x; j.o = o; j.dvec = dvec;
+  j.rows_total = B * H * S; j.bs = st.batch; j.hs = st.head; j.ld = st.row;
+  j.S = (int32_t)S; j.slot = slot;
+  return j;
+}
+
+// zero the table, then ONE launch for all tensors
+static int ah_prepass(const AhAmaxJobs& jobs, int n_jobs, float* amax, int64_t B, int64_t H, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float) * 4 * B * H, s);
+  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): memset: %s", cudaGetErrorString(e));
+  int64_t max_rows = 0;
+  for (int i = 0; i < n_jobs; ++i) max_rows = jobs.job[i].rows_total > max_rows ? jobs.job[i].rows_total : max_rows;
+  dim3 grid((unsigned)ceil_div(max_rows, AH_PRE_ROWS), (unsigned)n_jobs);
+  attn_amax_kernel<<<grid, 256, 0, s>>>(jobs, amax, (int)H);
   count_launch();
   return check_launch("attention amax");
 }
@@ -948,12 +1067,13 @@ int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
                  cudaStream_t s) {
   const int64_t B = d->batch, H = d->heads;
   float* amax = ws;
-  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float) * 4 * B * H, s);
-  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): memset: %s", cudaGetErrorString(e));
+  AhAmaxJobs jobs;
+  jobs.job[0] = ah_job(q, d->q, B, H, d->seq_q, 0);
+  jobs.job[1] = ah_job(k, d->k, B, H, d->seq_kv, 1);
+  jobs.job[2] = ah_job(v, d->v, B, H, d->seq_kv, 2);
+  jobs.job[3] = jobs.job[2];
   int rc;
-  if ((rc = ah_amax(q, d->q, B, H, d->seq_q, amax, 0, s))) return rc;
-  if ((rc = ah_amax(k, d->k, B, H, d->seq_kv, amax, 1, s))) return rc;
-  if ((rc = ah_amax(v, d->v, B, H, d->seq_kv, amax, 2, s))) return rc;
+  if ((rc = ah_prepass(jobs, 3, amax, B, H, s))) return rc;
   AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
       tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv};
   AttnHParams p{};
@@ -969,19 +1089,15 @@ int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   const int64_t B = d->batch, H = d->heads;
   float* dvec = ws;
   float* amax = ws + B * H * d->seq_q;
-  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float) * 4 * B * H, s);
-  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): memset: %s", cudaGetErrorString(e));
   AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
       tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q};
-  const int64_t rows = B * H * d->seq_q;
-  attn_amax_kernel<true><<<(unsigned)ceil_div(rows, AH_PRE_ROWS), 256, 0, s>>>(dout, o, dvec, amax, 3, rows, (int)H,
-                                                                              (int)d->seq_q, d->o.batch, d->o.head, d->o.row);
-  count_launch();
-  int rc = check_launch("attention dvec");
-  if (rc) return rc;
-  if ((rc = ah_amax(q, d->q, B, H, d->seq_q, amax, 0, s))) return rc;
-  if ((rc = ah_amax(k, d->k, B, H, d->seq_kv, amax, 1, s))) return rc;
-  if ((rc = ah_amax(v, d->v, B, H, d->seq_kv, amax, 2, s))) return rc;
+  AhAmaxJobs jobs;
+  jobs.job[0] = ah_job(q, d->q, B, H, d->seq_q, 0);
+  jobs.job[1] = ah_job(k, d->k, B, H, d->seq_kv, 1);
+  jobs.job[2] = ah_job(v, d->v, B, H, d->seq_kv, 2);
+  jobs.job[3] = ah_job(dout, d->o, B, H, d->seq_q, 3, o, dvec);      // + D = rowsum(dO o O)
+  int rc;
+  if ((rc = ah_prepass(jobs, 4, amax, B, H, s))) return rc;
   AttnHParams p{};
   p.lse = lse; p.dvec = dvec; p.amax = amax;
   p.H = (int32_t)H;

@@ -296,22 +296,35 @@ __global__ void __launch_bounds__(256) xent_bwd_kernel(const float* probs, const
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (vec_ok) {  // cols % 4 == 0
+    // four float4 per thread and iteration, all loads before the first store: an in-place pass (dx == probs) otherwise
+    // alternates single reads and writes to the same DRAM pages (ncu: 4.1 TB/s against 5.7+ for the out-of-place kernels)
     const int64_t n4 = (rows * cols) >> 2, c4 = cols >> 2;
-    for (int64_t i = tid; i < n4; i += stride) {
-      const int64_t r = i / c4, c = (i - r * c4) << 2;
-      const int64_t t_raw = labels[r];
-      const int64_t t = wrap_label(t_raw, cols);
-      float4 p = ld_stream_coherent(reinterpret_cast<const float4*>(probs) + i);
-      if (t_raw == ignore_label) {
-        p = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        if (t == c) p.x -= 1.f;
-        if (t == c + 1) p.y -= 1.f;
-        if (t == c + 2) p.z -= 1.f;
-        if (t == c + 3) p.w -= 1.f;
-        p.x *= k; p.y *= k; p.z *= k; p.w *= k;
+    for (int64_t i0 = tid; i0 < n4; i0 += 4 * stride) {
+      float4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n4) p[u] = ld_stream_coherent(reinterpret_cast<const float4*>(probs) + i);
       }
-      stg_stream(reinterpret_cast<float4*>(dx) + i, p);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i >= n4) break;
+        const int64_t r = i / c4, c = (i - r * c4) << 2;
+        const int64_t t_raw = labels[r];
+        const int64_t t = wrap_label(t_raw, cols);
+        float4 q = p[u];
+        if (t_raw == ignore_label) {
+          q = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          if (t == c) q.x -= 1.f;
+          if (t == c + 1) q.y -= 1.f;
+          if (t == c + 2) q.z -= 1.f;
+          if (t == c + 3) q.w -= 1.f;
+          q.x *= k; q.y *= k; q.z *= k; q.w *= k;
+        }
+        stg_stream(reinterpret_cast<float4*>(dx) + i, q);
+      }
     }
   } else {
     const int64_t n = rows * cols;

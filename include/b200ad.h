@@ -237,9 +237,10 @@ int b200ad_gemm_set_recurrent_dispatch(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention core (tcgen05, fp32-faithful three-product split; scores never leave the SM).
- *   Two variants of the same passes: fp16 hi/lo pairs at the kind::f16 MMA rate with one power-of-two scale per
- *   (batch, head) operand slab (default, csrc/attn_h16.cu), and tf32 hi/lo pairs (csrc/attn_tc.cu);
- *   b200ad_attn_set_variant(0 | 1) selects one and returns the previous choice.
+ *   Two carriers of the same split: tf32 hi/lo pairs (csrc/attn_tc.cu, variant 1) and fp16 hi/lo pairs at the
+ *   kind::f16 MMA rate with one power-of-two scale per (batch, head) operand slab (csrc/attn_h16.cu, variant 0).
+ *   b200ad_attn_set_variant(-1 | 0 | 1) selects one and returns the previous choice; -1 (default) = the measured
+ *   best mix: forward on variant 1, backward on variant 0.
  *   fwd:  O = softmax(scale * Q K^T) V  per (batch, head);  lse[b,h,s] = log2-domain log-sum-exp
  *         of the scaled scores of query row s (kept for the backward instead of the S x S matrix).
  *         replaces MultiHeadAttention.forward layers.py:1351-1357 (split heads are strided views:

@@ -255,7 +255,7 @@ def test_attn_variants_fp16_split_and_tf32_split_agree(B, h, Sq, Skv):
     got = {}
     prev = lib.b200ad_attn_set_variant(0)
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, -1):
             lib.b200ad_attn_set_variant(variant)
             O, lse = D.attn_fwd(Q, K, V, scale)
             dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
@@ -273,6 +273,15 @@ def test_attn_fp16_split_operand_ranges():
     """The fp16 carrier rescales every (batch, head) operand slab by a power of two: gradients of 1e-8, values of 1e3,
     scores up to ~40 and slabs of very different magnitude in one launch must all come out fp32-faithful."""
     D = _D()
+    from auto_differentiation_b200 import _lib as L
+    prev = L.load().b200ad_attn_set_variant(0)
+    try:
+        _ranges_body(D)
+    finally:
+        L.load().b200ad_attn_set_variant(prev)
+
+
+def _ranges_body(D):
     rng = np.random.default_rng(99)
     B, h, S, dk = 2, 4, 256, 64
     scale = 1.0 / 8.0
