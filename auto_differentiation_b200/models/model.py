@@ -47,8 +47,10 @@ def chunk_plan(n_rows, max_rows, first=32, growth=1.3, taper=2):
 
 class _InputStreamer:
     """Host -> device streaming of row chunks of a host array, owned by the model and reused by every `forward`
-    (nothing is allocated per step).  Each chunk is copied as sub-copies of <= `piece` rows spread over `n_streams`
-    copy streams into a ring of `depth` staging buffers; compute waits on the chunk's events, the copy streams wait
+    (nothing is allocated per step).  Each chunk is copied as sub-copies of <= `piece` rows on `n_streams` copy streams
+    (default 1: with 8 ranks sharing the host fabric a second stream per rank measured 8 % slower, 54.7 vs 50.6 ms per
+    step, and alone one stream already runs at the PCIe line rate, profiles/r2_h2d_probe_n8.json) into a ring of `depth`
+    staging buffers; compute waits on the chunk's events, the copy streams wait
     on the event that says the kernels of the chunk that last used the buffer are done.  On a CPU-only test backend
     it degenerates to synchronous per-chunk uploads."""
 
@@ -58,7 +60,7 @@ class _InputStreamer:
         self.torch = torch
         self.max_rows, self.row_shape, self.depth = int(max_rows), tuple(row_shape), depth
         self.piece = max(1, int(os.environ.get("B200AD_H2D_PIECE_ROWS", "32")))
-        n_streams = max(1, int(os.environ.get("B200AD_H2D_STREAMS", "2")))
+        n_streams = max(1, int(os.environ.get("B200AD_H2D_STREAMS", "1")))
         self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
         self.bufs = [torch.empty((self.max_rows,) + self.row_shape, dtype=torch.float32, device="cuda")
                      for _ in range(depth)]

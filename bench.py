@@ -358,7 +358,7 @@ def run_c5(args):
                "h2d_bytes_per_step": int(b_local * SEQ * DMODEL * 4 + b_local * 8), "d2h_bytes_per_step": 4,
                "steps": e2e_steps, "api": "AttentionClassifier.forward(x_host, t) / backward() / Adam.update",
                "host_binding": numa_binding, "input_chunks": len(chunk_plan(b_local, args.micro_batch)),
-               "h2d_streams": int(os.environ.get("B200AD_H2D_STREAMS", "2"))}
+               "h2d_streams": int(os.environ.get("B200AD_H2D_STREAMS", "1"))}
 
     # ---- data-parallel parity: reduced gradients of `world` ranks == one rank on the same global batch ----
     dp_par = None
