@@ -322,7 +322,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     // instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N = 64, M = 128 (256 for a pair)
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((CP ? 256 : AH_BM) >> 4) << 24);
     uint32_t op = 0, it = 0, gb = 0, fo = 0;
-    long long prof_acc[4] = {0, 0, 0, 0};
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     const long long prof_t0 = p.prof ? clock64() : 0;
     auto wait_slot = [&]() -> uint32_t {
       const uint32_t s = op % AH_NSLOT;
@@ -377,6 +377,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         if (j + 1 < nb) {
           // X(j+1) overwrites the columns Z(j-1) occupied: the OUT(j-1) MMAs that read them were issued earlier by this
           // same thread, and tcgen05.mma instructions execute in issue order
+          AH_T(i0);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t gx = g + 1;
@@ -385,6 +386,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             if (HAS2) issue_score(s_y, A2_COL, Y_COL0 + (gx & 1) * 64u, &y_full[gx & 1], lastx ? &a_empty[1] : nullptr);
           }
           __syncwarp();
+          AH_T(i1);
+          AH_ACC(4, i0, i1);
         }
         const bool first = !PAIRF || (j & 1) == 0, last = !PAIRF || (j & 1) == 1 || j == nb - 1;
         const uint32_t ob = fo & 1, oph = (fo >> 1) & 1;
@@ -396,6 +399,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const uint32_t s_o = wait_slot();             // the OUT operand block (ring order: X(j+1) [Y(j+1)] O(j))
         AH_ACC(1, w0, w1);
         AH_ACC(2, w1, w2);
+        AH_T(o0);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sb = smem_u32(smem + (size_t)s_o * AH_SLOT);
@@ -416,6 +420,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           if (last) mma_commit(&out_full[ob]);
         }
         __syncwarp();
+        { AH_T(o1); AH_ACC(5, o0, o1); }
         if (last) ++fo;
       }
       gb += nb;
@@ -426,6 +431,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       p.prof[2] = prof_acc[1];           // waiting for Z (row owners)
       p.prof[3] = prof_acc[2];           // waiting for a free OUT accumulator
       p.prof[7] = prof_acc[3];           // waiting for the A tiles of the next item
+      p.prof[16] = prof_acc[4];          // issuing the score products of the next block
+      p.prof[17] = prof_acc[5];          // issuing the OUT product
     }
   } else if (warp == 2 && !ROWSTAT) {
     // ===================================== column statistics (DV / DK) =====================================
@@ -995,8 +1002,8 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   static const bool want_prof = getenv("B200AD_ATTN_PROF") != nullptr;
   static long long* prof_dev = nullptr;
   if (want_prof) {
-    if (!prof_dev) cudaMalloc(&prof_dev, 16 * sizeof(long long));
-    cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), s);
+    if (!prof_dev) cudaMalloc(&prof_dev, 24 * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, 24 * sizeof(long long), s);
     p.prof = prof_dev;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1015,13 +1022,13 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): launch: %s", cudaGetErrorString(e));
   count_launch();
   if (want_prof && prof_dev) {
-    long long hp[16];
+    long long hp[24];
     cudaStreamSynchronize(s);
     cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
     const double blocks = (double)ceil_div(p.total_items, grid / (CP ? 2 : 1)) * p.nb;
-    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_A %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f | "
+    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_A %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f issue_scores %.0f issue_out %.0f | "
             "converter wait_tma %.0f conv_k %.0f conv_o %.0f | owner total %.0f colstat %.0f wait_XY %.0f ld+math+st %.0f wait_OUT %.0f fold %.0f epilogue %.0f\n", MODE, (int)CP, blocks,
-            hp[0] / blocks, hp[7] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[4] / blocks, hp[5] / blocks, hp[6] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
+            hp[0] / blocks, hp[7] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[16] / blocks, hp[17] / blocks, hp[4] / blocks, hp[5] / blocks, hp[6] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
             hp[11] / blocks, hp[13] / blocks, hp[14] / blocks, hp[15] / blocks);
   }
   if (getenv("B200AD_ATTN_SYNC")) {
