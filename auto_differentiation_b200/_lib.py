@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200ad_fill": (c_int, [P, I64, c_float, P]),
     "b200ad_axpby": (c_int, [P, P, I64, c_float, c_float, P]),
     "b200ad_dropout_fwd": (c_int, [P, P, P, P, I64, c_float, c_float, P]),
+    "b200ad_uniform": (c_int, [P, I64, ctypes.c_uint64, ctypes.c_uint64, P]),
     "b200ad_gemm": (c_int, [POINTER(GemmDesc), P, P, P, P, P, I64, P]),
     "b200ad_gemm_supported": (c_int, [POINTER(GemmDesc), P, P, P]),
     "b200ad_gemm_workspace_bytes": (c_int64, [POINTER(GemmDesc)]),

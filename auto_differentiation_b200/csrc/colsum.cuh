@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) colsum_wide_kernel(P prod, float* __restr
 // Slab count for stage 1: fill ~148 x 8 CTAs but keep >= 64 rows per slab.
 inline int64_t colsum_slabs(int64_t outer, int64_t red, int64_t inner, int vec) {
   const int64_t colblocks = ceil_div(inner, 32 * vec);
-  int64_t target = (int64_t)B200AD_NUM_SMS * 8 / (colblocks * outer > 0 ? colblocks * outer : 1);
+  int64_t target = (int64_t)sm_count() * 8 / (colblocks * outer > 0 ? colblocks * outer : 1);
   if (target < 1) target = 1;
   int64_t max_slabs = red / 64;
   if (max_slabs < 1) max_slabs = 1;

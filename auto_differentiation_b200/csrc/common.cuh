@@ -6,12 +6,14 @@
 #include <stdarg.h>
 #include "../../include/b200ad.h"
 
-#define B200AD_NUM_SMS 148
+#define B200AD_NUM_SMS 148   /* B200; only the fallback when the device query fails: launch sizing uses sm_count() */
 
 namespace b200ad {
 
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
+// multiprocessor count of the current device (queried once per process; 148 on B200)
+int sm_count();
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -32,7 +34,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // waves (148 SMs x 8 resident 256-thread CTAs = full occupancy).
 inline int stream_grid(int64_t work_items, int per_block, int ctas_per_sm = 8) {
   int64_t need = ceil_div(work_items, per_block);
-  int64_t cap = (int64_t)B200AD_NUM_SMS * ctas_per_sm;
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }

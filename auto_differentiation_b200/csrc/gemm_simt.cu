@@ -150,7 +150,7 @@ int gemm_simt_launch(const GemmArgs& p, cudaStream_t s) {
                      (long long)batches);
   // 128x128 tiles when they give at least ~one wave of CTAs, else 64x64.
   const int64_t big_tiles = ceil_div(p.m, 128) * ceil_div(p.n, 128) * batches;
-  if (p.m >= 96 && p.n >= 96 && big_tiles >= B200AD_NUM_SMS) launch_cfg<128, 128, 8, 8>(p, s);
+  if (p.m >= 96 && p.n >= 96 && big_tiles >= sm_count()) launch_cfg<128, 128, 8, 8>(p, s);
   else launch_cfg<64, 64, 4, 4>(p, s);
   count_launch();
   return check_launch("gemm(simt)");

@@ -153,6 +153,36 @@ __global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restric
   }
 }
 
+// U[0,1) draws for TimeDropout (the reference draws np.random.rand, layers.py:687): counter-based Philox4x32-10, four
+// floats per counter, so the stream depends only on (seed, offset) — not on the grid — and consecutive calls continue
+// it by advancing `offset` by ceil(n / 4) counters.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__global__ void __launch_bounds__(256) uniform_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = (n + 3) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint64_t c = offset + (uint64_t)i;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    // 24 random bits -> [0, 1) exactly representable in fp32
+    const float f[4] = {(r.x >> 8) * 5.9604644775390625e-8f, (r.y >> 8) * 5.9604644775390625e-8f,
+                        (r.z >> 8) * 5.9604644775390625e-8f, (r.w >> 8) * 5.9604644775390625e-8f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * i + j < n) out[4 * i + j] = f[j];
+  }
+}
+
 struct StridedDesc {
   int rank;
   int out_strided;
@@ -232,7 +262,7 @@ using namespace b200ad;
 
 static int64_t narrow_slabs(int64_t outer, int64_t red, int64_t inner) {
   const int64_t k = 256 / inner;
-  int64_t target = (int64_t)B200AD_NUM_SMS * 8 / (outer > 0 ? outer : 1);
+  int64_t target = (int64_t)sm_count() * 8 / (outer > 0 ? outer : 1);
   if (target < 1) target = 1;
   int64_t max_slabs = red / (8 * k);
   if (max_slabs < 1) max_slabs = 1;
@@ -243,7 +273,7 @@ static int64_t narrow_slabs(int64_t outer, int64_t red, int64_t inner) {
 
 static void rowsum_plan(int64_t rows, int64_t len, int64_t* chunk, int64_t* nchunks) {
   // want ~148*8*8 warps busy; only split rows that are long.
-  const int64_t want = (int64_t)B200AD_NUM_SMS * 64;
+  const int64_t want = (int64_t)sm_count() * 64;
   int64_t nc = 1;
   if (rows < want && len >= 8192) {
     nc = want / (rows > 0 ? rows : 1);
@@ -386,6 +416,15 @@ int b200ad_dropout_fwd(const float* x, const float* u, float* mask, float* y, in
                                                                                                   scale, vec_ok);
   count_launch();
   return check_launch("dropout_fwd");
+}
+
+int b200ad_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  B200AD_REQUIRE(n >= 0, "uniform: negative size");
+  if (n == 0) return B200AD_OK;
+  B200AD_REQUIRE(out, "uniform: null pointer");
+  uniform_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+  count_launch();
+  return check_launch("uniform");
 }
 
 int b200ad_strided_copy(const float* in, float* out, int rank, const int64_t* shape,

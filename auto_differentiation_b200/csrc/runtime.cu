@@ -18,6 +18,19 @@ int set_error(int code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        v <= 0) {
+      cudaGetLastError();
+      return B200AD_NUM_SMS;
+    }
+    return v;
+  }();
+  return n;
+}
+
 }  // namespace b200ad
 
 extern "C" {

@@ -394,10 +394,21 @@ def dropout_fwd(x, u, ratio, scale):
     return y, mask
 
 
+_rng_state = {"seed": 0x1234ABCD5678EF01, "offset": 0}
+
+
+def seed_uniform(seed):
+    """Re-seed the device dropout stream (Philox counter restarts at 0)."""
+    _rng_state["seed"], _rng_state["offset"] = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+
+
 def uniform(shape):
-    """U[0,1) draws on the device (torch's CUDA generator: plumbing, like the allocator)."""
-    require_cuda()
-    return DeviceArray(torch.rand(tuple(int(s) for s in shape), dtype=_F32, device=_DEVICE))
+    """U[0,1) draws on the device from the library's own counter-based generator (b200ad_uniform, Philox4x32-10)."""
+    out = empty(tuple(int(s) for s in shape))
+    n = out.size
+    L.check(_lib().b200ad_uniform(out.ptr, n, _rng_state["seed"], _rng_state["offset"], stream_ptr()))
+    _rng_state["offset"] += (n + 3) // 4
+    return out
 
 
 def broadcast_to(a, shape):

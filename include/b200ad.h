@@ -190,6 +190,9 @@ int b200ad_axpby(const float* x, float* y, int64_t n, float a, float b, void* st
  * Backward (:696-697) is binary_fwd(MUL, dout, mask). */
 int b200ad_dropout_fwd(const float* x, const float* u, float* mask, float* y, int64_t n, float ratio,
                        float scale, void* stream);
+/* U[0,1) draws on the device for the dropout masks (reference: np.random.rand, layers/layers.py:687): Philox4x32-10,
+ * element i comes from counter offset + i/4; callers advance `offset` by ceil(n/4) per call.  24-bit resolution. */
+int b200ad_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contractions.   C[b0,b1] = alpha * op(A[b0,b1]) @ op(B[b0,b1]) + beta * C[b0,b1]

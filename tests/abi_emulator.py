@@ -326,6 +326,12 @@ class Emulator:
     def b200ad_gemm_workspace_bytes(self, d):
         return 0
 
+    def b200ad_uniform(self, out, n, seed, offset, s):
+        self.launches += 1
+        rng = np.random.default_rng([int(seed) & 0xFFFFFFFF, int(seed) >> 32, int(offset)])
+        _f32(out, n)[...] = np.floor(rng.random(n) * (1 << 24)) / (1 << 24)
+        return 0
+
     def b200ad_gemm_supported(self, d, a, b, c):
         return 1
 

@@ -484,3 +484,25 @@ def test_cluster_kernels_bitwise_repeatable():
         noise.fill_(rep)                                     # unrelated traffic between repetitions
         for a, b in zip(first, run()):
             assert np.array_equal(a, b), "repetition %d differs" % rep
+
+
+def test_uniform_stream(backend):
+    """The dropout draws come from the library's own Philox stream (b200ad_uniform): values in [0, 1) on a 2^-24 grid,
+    uniform moments, reproducible from the seed, and consecutive calls continue the stream instead of repeating it."""
+    from auto_differentiation_b200 import device as D
+    D.seed_uniform(42)
+    a = np.asarray(D.uniform((1000, 333)))
+    b = np.asarray(D.uniform((1000, 333)))
+    D.seed_uniform(42)
+    a2 = np.asarray(D.uniform((1000, 333)))
+    c = np.asarray(D.uniform((7,)))                       # odd tail (n % 4 != 0)
+    np.testing.assert_array_equal(a, a2)
+    assert a.min() >= 0.0 and a.max() < 1.0 and c.shape == (7,)
+    assert np.all(a * (1 << 24) == np.floor(a * (1 << 24)))
+    assert abs(a.mean() - 0.5) < 2e-3 and abs(a.var() - 1.0 / 12.0) < 2e-3
+    assert not np.array_equal(a, b) and abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 5e-3
+    if backend == "cuda":                                 # known-answer: Philox4x32-10, counter 0, key (seed lo, seed hi)
+        D.seed_uniform(0)
+        first = np.asarray(D.uniform((4,)))
+        ref = np.array([0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8], dtype=np.uint64)      # Random123 KAT, zero key / counter
+        np.testing.assert_array_equal(first, ((ref >> 8).astype(np.float64) / (1 << 24)).astype(np.float32))
