@@ -8,25 +8,41 @@ namespace b200ad {
 // NumPy index semantics: -vocab <= i < 0 wraps around.
 __device__ __forceinline__ int64_t wrap_index(int64_t i, int64_t vocab) { return i < 0 ? i + vocab : i; }
 
-// one warp per gathered row
+// one warp per gathered row, four rows in flight per warp: the four index loads go out together and so do the row
+// loads, so a warp exposes one round trip per four rows instead of one per row (ncu before: 55 % of the copy bandwidth)
 __global__ void __launch_bounds__(256) embedding_gather_kernel(const float* __restrict__ w, const int64_t* __restrict__ idx,
                                                                float* __restrict__ out, int64_t n_idx, int64_t vocab,
                                                                int64_t dim, int vec_ok) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_idx; r += warps) {
-    const int64_t v = wrap_index(idx[r], vocab);
-    const bool ok = (v >= 0 && v < vocab);
-    const float* src = w + (ok ? v : 0) * dim;
-    float* dst = out + r * dim;
+  constexpr int U = 4;
+  for (int64_t r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * U; r0 < n_idx; r0 += warps * U) {
+    int64_t v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u;
+      v[u] = r < n_idx ? wrap_index(__ldg(idx + r), vocab) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) ok[u] = (v[u] >= 0 && v[u] < vocab);
     if (vec_ok) {
       const int64_t d4 = dim >> 2;
       for (int64_t c = lane; c < d4; c += 32) {
-        float4 t = ok ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(NAN, NAN, NAN, NAN);
-        stg_stream(reinterpret_cast<float4*>(dst) + c, t);
+        float4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          t[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(w + v[u] * dim) + c) : make_float4(NAN, NAN, NAN, NAN);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (r0 + u < n_idx) stg_stream(reinterpret_cast<float4*>(out + (r0 + u) * dim) + c, t[u]);
       }
     } else {
-      for (int64_t c = lane; c < dim; c += 32) dst[c] = ok ? __ldg(src + c) : NAN;
+      for (int64_t c = lane; c < dim; c += 32) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (r0 + u < n_idx) out[(r0 + u) * dim + c] = ok[u] ? __ldg(w + v[u] * dim + c) : NAN;
+      }
     }
   }
 }

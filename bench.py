@@ -105,15 +105,17 @@ def c5_params_np(seed=1239, dtype=np.float64):
     return [w.astype(dtype) for w in ws + [W1, np.zeros(HIDDEN), W2, np.zeros(CLASSES)]]
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r1_summary.md §3), keyed by the GEMM shape bench.py reports as the dominant kernel.
-# (labelled: a table captured under ncu on a separate run, profiles/r1_summary.md — not measured inside this run)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from committed `ncu --set full` captures, keyed by the GEMM shape
+# / attention pass bench.py reports as the dominant kernel.  A LABELLED TABLE, not measured inside this run: the attention
+# entries come from profiles/r2_ncu_tensor_kernels.csv (captured at 64 sequences per launch, scaled to 256 here; the
+# backward = dV + dK + dQ passes + the slab-maximum / D pre-pass, which reads O, dO, Q, K, V once), the GEMM entries from
+# profiles/r1_summary.md section 3.
 NCU_TRAFFIC_BYTES = {
     (512, 64, 512, 2048): 2416e6 + 262e6,        # batched d_k=64 attention products (algorithmic: 2684 MB)
     (131072, 512, 512, 1): 269.6e6 + 224.9e6,    # projection, gemm_tc3_kernel (algorithmic: 537 MB)
     (512, 512, 131072, 1): 536.9e6 + 6.9e6,      # split-K weight gradient, gemm_tc3_kernel (algorithmic: 537 MB + partials in L2)
-    "attn_fwd": 805.5e6 + 251.7e6,               # fused attention forward (CTA-pair pass): Q + K + V read, O written (algorithmic: 1074 MB)
-    "attn_bwd": 544.1e6 + 1056.9e6 + 1334.8e6 + 1336.9e6,   # dvec + dV + dK + dQ pair passes (algorithmic: 537 + 1074 + 1342 + 1342 MB)
+    "attn_fwd": 4 * (201.4e6 + 46.7e6),          # fused attention forward (tf32 split, CTA-pair pass): algorithmic 1074 MB
+    "attn_bwd": 4 * (249.8e6 + 321.4e6 + 322.1e6 + 335.5e6),   # fp16-split passes + pre-pass: algorithmic 2147 MB
 }
 
 
