@@ -1,1 +1,3 @@
-timeout 120 python profiles/ncu_targets.py > gpurun_out/r2_ncu_plain.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc3|attn_tc_kernel|attn_h16_kernel|rnn_seq_kernel' -o gpurun_out/r2_tensor_kernels -f python profiles/ncu_targets.py > gpurun_out/r2_ncu_full.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/r2_ncu_full.log; ls -la gpurun_out/r2_tensor_kernels.ncu-rep
+timeout 150 python -m pytest tests/test_rnn_seq.py -m gpu -q -x 2>&1 | tail -4
+timeout 120 python profiles/rnn_seq_probe.py 2>&1 | tail -2
+B200AD_RNN_SEQ_PROF=1 timeout 120 python profiles/rnn_seq_probe.py 2>&1 | grep -A10 "rnn_seq prof" | head -11 | tee gpurun_out/r2h_prof.log
