@@ -51,6 +51,9 @@ def main():
 
     def timed(name, nbytes, fn):
         best = None
+        if not os.environ.get("MEMBOUND_NO_WARM"):
+            fn()                      # first use of a kernel pays its lazy load: not part of the measurement
+            torch.cuda.synchronize()
         for _ in range(reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
