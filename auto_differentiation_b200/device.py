@@ -777,13 +777,38 @@ def _batch_plan(bshape, strides_list):
     return merged
 
 
+_matmul_plans = {}
+
+
 def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, precision=None, trans_a=False,
            trans_b=False):
     """np.matmul on device views: (..., M, K) @ (..., K, N) with broadcast batch axes.
     `trans_a/trans_b` apply a logical transpose of the last two axes first (free: folded into the
     kernel's operand layout).  `out` may be any view whose last axis is contiguous (written in place,
     `beta` accumulates)."""
+    # ---- fast path: the same operand geometry was planned before (layers call the same products every step; the
+    # planning below costs ~10 us of Python per call, which bounds the launch-latency-bound configs)
     ta, tb = a.t, b.t
+    key = (ta.shape, ta.stride(), tb.shape, tb.stride(), None if out is None else (out.t.shape, out.t.stride()),
+           trans_a, trans_b, act, precision, alpha, beta, bias is None, _default_precision[0])
+    hit = _matmul_plans.get(key)
+    if hit is not None:
+        d, ws_bytes, out_shape, tkey, flops = hit
+        if out is None:
+            out = empty(out_shape)
+        ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
+        timer = _gemm_timer[0]
+        if timer is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.check(_lib().b200ad_gemm(ctypes.byref(d), ta.data_ptr(), tb.data_ptr(), out.t.data_ptr(),
+                                   bias.ptr if bias is not None else None, ws.data_ptr() if ws is not None else None,
+                                   ws_bytes, stream_ptr()))
+        if timer is not None:
+            e1.record()
+            timer.records.append((tkey, flops, e0, e1))
+        return out
+    cacheable = True
     if ta.dim() == 1:
         ta = ta.unsqueeze(0)
     if tb.dim() == 1:
@@ -801,10 +826,12 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
     if la is None:
         ta = DeviceArray(ta).contiguous().t
         la = (0, max(K, 1))
+        cacheable = False                  # an operand had to be compacted first: not a pure view plan
     lb = _mat_layout(tb, K, N)
     if lb is None:
         tb = DeviceArray(tb).contiguous().t
         lb = (0, max(N, 1))
+        cacheable = False
     bshape = tuple(np.broadcast_shapes(tuple(ta.shape[:-2]), tuple(tb.shape[:-2])))
     nb = len(bshape)
 
@@ -843,6 +870,11 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
     ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
     wptr = ws.data_ptr() if ws is not None else None
     pa, pb, pc = ta.data_ptr(), tb.data_ptr(), tc.data_ptr()
+    if cacheable and not outer and a.t.dim() >= 2 and b.t.dim() >= 2:
+        if len(_matmul_plans) > 4096:
+            _matmul_plans.clear()
+        _matmul_plans[key] = (d, ws_bytes, tuple(tc.shape), (M, N, K, d.batch0 * d.batch1, la[0], lb[0], prec),
+                              2.0 * M * N * K * d.batch0 * d.batch1)
     timer = _gemm_timer[0]
     if timer is not None and not outer:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
