@@ -425,8 +425,20 @@ static int rs_launch(const RnnSeqParams& prm_in, const RsPlan& pl, cudaStream_t 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = RS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  // The CTAs of one launch wait on one another, so every launch needs all of its CTAs resident.  Two such launches on
+  // different streams could each hold a part of the SMs and starve each other (the bounded waits would turn that into a
+  // launch failure, not a hang): launches of this process are therefore chained through an event — each waits for the
+  // previous one to finish.  (Not under stream capture: a captured graph orders its own nodes.)
+  static cudaEvent_t last_done = nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+  if (!capturing) {
+    if (!last_done) cudaEventCreateWithFlags(&last_done, cudaEventDisableTiming);
+    else cudaStreamWaitEvent(s, last_done, 0);
+  }
   e = cudaLaunchKernelEx(&cfg, rnn_seq_kernel, prm);
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "rnn_seq: launch: %s", cudaGetErrorString(e));
+  if (!capturing && last_done) cudaEventRecord(last_done, s);
   count_launch();
   if (want_prof && prof_dev) {      // debugging aid: synchronous read-back of the per-segment cycle counters (per half pipeline)
     const int pipes = RS_CL * pl.clusters * (prm.N > RS_HB ? 2 : 1);

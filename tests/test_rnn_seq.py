@@ -132,3 +132,34 @@ def test_rnn_seq_bit_reproducible_guards_and_graph_replay():
     np.testing.assert_array_equal(np.asarray(hs_ext), results[0][0])
     np.testing.assert_array_equal(np.asarray(dA_g), results[0][1])
     np.testing.assert_array_equal(np.asarray(dh0_g), results[0][2])
+
+
+@pytest.mark.gpu
+def test_rnn_seq_two_streams():
+    """Two persistent launches issued on different streams (each needs every one of its CTAs resident): the library chains
+    them, and both produce exactly what a lone launch produces."""
+    import torch
+    import auto_differentiation_b200 as pkg
+    from auto_differentiation_b200 import device as D
+    H, N, T = 1024, 64, 24
+    if not D.rnn_seq_supported(N, H):
+        pytest.skip("persistent recurrence not available on this device")
+    rng = np.random.default_rng(8)
+    wh = pkg.asarray(rng.standard_normal((H, H)) / np.sqrt(H))
+    pres = [pkg.asarray(rng.standard_normal((T, N, H))) for _ in range(2)]
+    lone = []
+    for p in pres:
+        hs = D.zeros((T + 1, N, H))
+        D.rnn_tanh_seq_fwd_(hs, p, wh)
+        torch.cuda.synchronize()
+        lone.append(np.asarray(hs).copy())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [D.zeros((T + 1, N, H)) for _ in range(2)]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for st, hs, p in zip(streams, outs, pres):
+            with torch.cuda.stream(st):
+                D.rnn_tanh_seq_fwd_(hs, p, wh)
+    torch.cuda.synchronize()
+    for got, ref in zip(outs, lone):
+        np.testing.assert_array_equal(np.asarray(got), ref)
