@@ -18,7 +18,7 @@
 // are as close as the 3xTF32 kernels' (tests/test_fused_attention.py runs every case through both).
 //
 // Same roles as attn_tc.cu (TMA producer, MMA issuer, 4 converter warps, 8 row-owner warps; 1-CTA and CTA-pair variants),
-// same ring of six 32 KB slots, same barriers.  Differences:
+// same barriers.  Differences:
 //   * slot layout [raw fp32 16 KB | fp16 hi 8 KB | fp16 lo 8 KB]; EVERY B operand is a K-major SWIZZLE_128B fp16 tile
 //     (64 rows x 128 B): the converter transposes the (kv x d) blocks that feed the OUT products while it converts them,
 //     so no MN-major descriptor is needed (their TMA boxes are unswizzled for conflict-free column reads);
@@ -39,12 +39,17 @@ constexpr int AH_DK = 64;
 constexpr int AH_BM = 128;
 constexpr int AH_BC = 64;
 // shared memory: a ring for the B-operand blocks (128 KB: 4 slots of [raw 16 KB | hi 8 KB | lo 8 KB], or 8 half-size slots
-// when a CTA pair splits every block), two 32 KB staging tiles for the raw A operands, 32 KB for the output tile.
+// when a CTA pair splits every block), two 32 KB staging tiles for the raw A operands, 32 KB for the output tile (written
+// straight from the owners' registers, 128 B per thread and row, the outputs measured 2.5x slower per item: the scattered
+// 16 B stores also slowed the converters' shared-memory traffic down).
 // (The first version shared one ring of six 32 KB slots between A tiles and B blocks: the block that feeds the OUT product
 // then had a single block of lead over its consumer, and TMA latency + conversion showed up as ~700 cycles per block of
 // MMA-side waiting.)
-constexpr int AH_MAXRING = 8;
-constexpr uint32_t AH_RING_BYTES = 131072, AH_ASTAGE = 32768;
+#ifndef AH_RING_KB
+#define AH_RING_KB 128
+#endif
+constexpr uint32_t AH_RING_BYTES = AH_RING_KB * 1024u, AH_ASTAGE = 32768;
+constexpr int AH_MAXRING = AH_RING_BYTES / 16384;
 // Converter groups of four warps each.  Two groups (640 threads; registers 48 / 72 / 136) were measured against one (512
 // threads; 80 / 112 / 152): 2.38 ms vs 2.31 ms for the config-5 backward — the second group does not pay, because the
 // conversion is not what the MMA thread waits for (profiles/r2_attn_h16_prof.log) and the owners lose registers.
@@ -52,11 +57,13 @@ constexpr int AH_CONV_GROUPS = 1;
 constexpr int AH_THREADS = 128 + 128 * AH_CONV_GROUPS + 256;
 constexpr uint32_t AH_SMEM = AH_RING_BYTES + 2 * AH_ASTAGE + 32768 + 1024;
 
-enum { AH_FWD = 0, AH_DV = 1, AH_DQ = 2, AH_DKM = 3 };
+enum { AH_FWD = 0, AH_DV = 1, AH_DQ = 2, AH_DKM = 3, AH_DKV = 4 };   // AH_DKV: dK and dV in ONE pass (S and P computed once)
 
 struct AttnHParams {
   float* out;
   int64_t out_bs, out_hs, out_ld;
+  float* out2;               // AH_DKV: the second output (dV; `out` is dK)
+  int64_t out2_bs, out2_hs, out2_ld;
   float* lse_w;              // FWD: (B, H, R) log2-domain log-sum-exp, written
   const float* lse;          // other modes: read
   const float* dvec;         // DQ / DK: D[b, h, s] = sum_d dO * O
@@ -68,6 +75,11 @@ struct AttnHParams {
 };
 #define AH_T(var) long long var = 0; if (p.prof) var = clock64()
 #define AH_ACC(slot, a, b) if (p.prof) prof_acc[slot] += (b) - (a)
+// event trace of ONE item of CTA 0 (its third): prof[24 + ((role * 16 + block) * 16 + event)] = clock64(); roles: 0 MMA thread,
+// 1 converter thread 0, 2 row owner thread 0, 3 TMA producer
+constexpr int AH_TRACE_ITEM = 2, AH_PROF_WORDS = 24 + 4 * 16 * 16;
+#define AH_TR(role, itv, blk, ev, cond) \
+  if (p.prof && blockIdx.x == 0 && (itv) == AH_TRACE_ITEM && (blk) < 16 && (cond)) p.prof[24 + (((role) * 16 + (blk)) * 16 + (ev))] = clock64()
 
 __device__ __forceinline__ void ah_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -116,6 +128,12 @@ __device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void ah_tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 __device__ __forceinline__ void ah_tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -154,18 +172,27 @@ __device__ __forceinline__ float ah_pow2(int e) {               // 2^e for -126 
 
 // which slab maximum feeds which operand, per mode (0 = Q, 1 = K, 2 = V, 3 = dO)
 template <int MODE> struct AhOps;
-template <> struct AhOps<AH_FWD> { static constexpr int A1 = 0, A2 = 0, B1 = 1, B2 = 1, B3 = 2; };
-template <> struct AhOps<AH_DV>  { static constexpr int A1 = 1, A2 = 1, B1 = 0, B2 = 0, B3 = 3; };
-template <> struct AhOps<AH_DQ>  { static constexpr int A1 = 0, A2 = 3, B1 = 1, B2 = 2, B3 = 1; };
-template <> struct AhOps<AH_DKM> { static constexpr int A1 = 1, A2 = 2, B1 = 0, B2 = 3, B3 = 0; };
+template <> struct AhOps<AH_FWD> { static constexpr int A1 = 0, A2 = 0, B1 = 1, B2 = 1, B3 = 2, B4 = 2; };
+template <> struct AhOps<AH_DV>  { static constexpr int A1 = 1, A2 = 1, B1 = 0, B2 = 0, B3 = 3, B4 = 3; };
+template <> struct AhOps<AH_DQ>  { static constexpr int A1 = 0, A2 = 3, B1 = 1, B2 = 2, B3 = 1, B4 = 1; };
+template <> struct AhOps<AH_DKM> { static constexpr int A1 = 1, A2 = 2, B1 = 0, B2 = 3, B3 = 0, B4 = 0; };
+template <> struct AhOps<AH_DKV> { static constexpr int A1 = 1, A2 = 2, B1 = 0, B2 = 3, B3 = 0, B4 = 3; };
 
 template <int MODE, bool CP>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
-                const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_out,
+                const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_b4,
+                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
                 const AttnHParams p) {
-  constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM);
+  constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM || MODE == AH_DKV);
+  // AH_DKV: per block two OUT products, dK += dS^T . Q (Z1 = dS^T over the X columns) and dV += P^T . dO (Z2 = P^T over the
+  // Y columns, free once the owners have read dP^T); the two accumulators are single-buffered ([384,448) dK, [448,512) dV)
+  constexpr bool FUSED = (MODE == AH_DKV);
+  // one converter group converts the two score operand blocks of a block (and AH_DKV's two OUT operand blocks) together and
+  // arrives on the first slot's barrier before the second's: the MMA thread waits on the second only, one wait per pair (a wait on its side is
+  // not free even when the barrier has long completed: profiles/r1_mma_rate.log, ~150 cycles of idle tensor pipe each)
+  constexpr bool MERGE = HAS2 && AH_CONV_GROUPS == 1;
   constexpr bool ROWSTAT = (MODE == AH_FWD || MODE == AH_DQ);   // lanes are query rows
   constexpr bool PAIRF = (MODE != AH_FWD);                      // backward modes: two blocks (128 K-elements) per OUT chain
   constexpr uint32_t A1_COL = 0, A2_COL = 64;
@@ -177,7 +204,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int AH_NSLOT = CP ? 8 : 4;
+  constexpr int AH_NSLOT = CP ? AH_MAXRING : AH_MAXRING / 2;
   constexpr uint32_t AH_SLOT = CP ? 16384u : 32768u, AH_HI = AH_SLOT / 2, AH_LO = AH_SLOT * 3 / 4;
   uint8_t* a_stage = smem + AH_RING_BYTES;                  // [2] raw A tiles (128 rows x 64 fp32)
   uint8_t* out_stage = smem + AH_RING_BYTES + 2 * AH_ASTAGE;
@@ -223,6 +250,10 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     tma_prefetch_desc(&map_b1);
     tma_prefetch_desc(&map_b3);
     tma_prefetch_desc(&map_out);
+    if (FUSED) {
+      tma_prefetch_desc(&map_b4);
+      tma_prefetch_desc(&map_out2);
+    }
     if (HAS2) {
       tma_prefetch_desc(&map_a2);
       tma_prefetch_desc(&map_b2);
@@ -303,7 +334,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             tma_load_4d(m, bar, dst + 8192, 32, col0, h, b);
           }
         };
-        // ring order = consumption order of the MMA warp: A1 [A2] X(0) [Y(0)] { X(j+1) [Y(j+1)] OUT(j) }
+        // ring order = consumption order of the MMA warp: A1 [A2] X(0) [Y(0)] { X(j+1) [Y(j+1)] OUT(j) [OUT2(j)] }
         load_a(&map_a1, 0);
         if (HAS2) load_a(&map_a2, 1);
         load_k(&map_b1, 0);
@@ -311,9 +342,14 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         for (int j = 0; j < nb; ++j) {
           if (j + 1 < nb) {
             load_k(&map_b1, (j + 1) * AH_BC);
+            AH_TR(3, it, j, 0, true);
             if (HAS2) load_k(&map_b2, (j + 1) * AH_BC);
+            AH_TR(3, it, j, 1, true);
           }
           load_o(&map_b3, j * AH_BC);
+          AH_TR(3, it, j, 2, true);
+          if (FUSED) load_o(&map_b4, j * AH_BC);
+          AH_TR(3, it, j, 3, true);
         }
       }
     }
@@ -332,6 +368,12 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       AH_ACC(0, w0, w1);
       ++op;
       return s;
+    };
+    // a pair of slots converted together: one wait (on the second slot's barrier) covers both
+    auto wait_pair = [&](uint32_t& s_first) -> uint32_t {
+      s_first = op % AH_NSLOT;
+      ++op;
+      return wait_slot();
     };
     // score MMAs: D[128 x 64] = A(TMEM: hi at a_col, lo at a_col + 32) . B^T (K-major fp16 tiles in the slot); ELECTED thread
     auto issue_score = [&](uint32_t s, uint32_t a_col, uint32_t d_col, uint64_t* done, uint64_t* a_done) {
@@ -355,10 +397,13 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         if (HAS2) mbar_wait(&a_conv[1], it & 1);       // A2 in TMEM
         AH_T(wa1);
         AH_ACC(3, wa0, wa1);
-        const uint32_t s_x0 = wait_slot();
-        uint32_t s_y0 = 0;
-        if (HAS2) s_y0 = wait_slot();
-        tc_fence_after();
+        uint32_t s_x0 = 0, s_y0 = 0;
+        if (MERGE) s_y0 = wait_pair(s_x0);
+        else {
+          s_x0 = wait_slot();
+          if (HAS2) s_y0 = wait_slot();
+        }
+        tc_fence_after();                              // the converters' tcgen05.st of the A tiles
         if (elect_one()) {
           issue_score(s_x0, A1_COL, X_COL0 + (gb & 1) * 64u, &x_full[gb & 1], nb == 1 ? &a_empty[0] : nullptr);
           if (HAS2) issue_score(s_y0, A2_COL, Y_COL0 + (gb & 1) * 64u, &y_full[gb & 1], nb == 1 ? &a_empty[1] : nullptr);
@@ -370,15 +415,20 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         // Z(j-1)'s OUT product, which this thread issued one iteration ago), then Z(j) and a free OUT accumulator
         const uint32_t g = gb + j;
         uint32_t s_x = 0, s_y = 0;
+        AH_TR(0, it, j, 0, lane == 0);
         if (j + 1 < nb) {
-          s_x = wait_slot();
-          if (HAS2) s_y = wait_slot();
+          if (MERGE) s_y = wait_pair(s_x);
+          else {
+            s_x = wait_slot();
+            if (HAS2) s_y = wait_slot();
+          }
         }
+        AH_TR(0, it, j, 1, lane == 0);
         if (j + 1 < nb) {
           // X(j+1) overwrites the columns Z(j-1) occupied: the OUT(j-1) MMAs that read them were issued earlier by this
-          // same thread, and tcgen05.mma instructions execute in issue order
+          // same thread, and tcgen05.mma instructions execute in issue order.  (No tcgen05 fence here: the owners' TMEM
+          // accesses to these buffers were ordered by the fence after z_full(j-1); the operand tiles are shared memory.)
           AH_T(i0);
-          tc_fence_after();
           if (elect_one()) {
             const uint32_t gx = g + 1;
             const bool lastx = (j + 1 == nb - 1);
@@ -389,38 +439,52 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           AH_T(i1);
           AH_ACC(4, i0, i1);
         }
+        AH_TR(0, it, j, 2, lane == 0);
         const bool first = !PAIRF || (j & 1) == 0, last = !PAIRF || (j & 1) == 1 || j == nb - 1;
-        const uint32_t ob = fo & 1, oph = (fo >> 1) & 1;
+        const uint32_t ob = FUSED ? 0u : (fo & 1), oph = FUSED ? (fo & 1) : ((fo >> 1) & 1);
         AH_T(w0);
         mbar_wait(&z_full[g & 1], (g >> 1) & 1);
         AH_T(w1);
+        AH_TR(0, it, j, 3, lane == 0);
         if (first) mbar_wait(&out_empty[ob], oph ^ 1);
         AH_T(w2);
-        const uint32_t s_o = wait_slot();             // the OUT operand block (ring order: X(j+1) [Y(j+1)] O(j))
+        uint32_t s_o = 0, s_o2 = 0;                // the OUT operand block(s) (ring order: X(j+1) [Y(j+1)] O(j) [O2(j)])
+        if (FUSED && MERGE) s_o2 = wait_pair(s_o);
+        else {
+          s_o = wait_slot();
+          if (FUSED) s_o2 = wait_slot();
+        }
+        AH_TR(0, it, j, 4, lane == 0);
         AH_ACC(1, w0, w1);
         AH_ACC(2, w1, w2);
         AH_T(o0);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sb = smem_u32(smem + (size_t)s_o * AH_SLOT);
+        // OUT MMAs: D[128 x 64] (+)= Z (TMEM, packed fp16 pairs) . B (K-major fp16 tile of the slot).  Z layout inside a
+        // 64-column score buffer, per owner group of 32 columns: [hi 16 | lo 16] (k-step kk = group kk >> 1, packed columns
+        // 8 (kk & 1) .. + 8), or for AH_DKV, whose owners work in halves of 16 elements, [hi 8 | lo 8 | hi 8 | lo 8]
+        auto issue_out = [&](uint32_t slot, uint32_t zb, uint32_t dst) {
+          const uint32_t sb = smem_u32(smem + (size_t)slot * AH_SLOT);
           const uint64_t dh = make_smem_desc(sb + AH_HI, 16, 1024, 2), dl = make_smem_desc(sb + AH_LO, 16, 1024, 2);
-          const uint32_t dst = tmem_base + OUT_COL0 + ob * 64u, zb = tmem_base + X_COL0 + (g & 1) * 64u;
-          // Z layout inside the X buffer: [group 0: hi 16 | lo 16 | group 1: hi 16 | lo 16] packed fp16 pairs; k-step kk
-          // covers columns c in [16 kk, 16 kk + 16) = group kk >> 1, packed columns 8 (kk & 1) .. + 8
+          auto zhi = [&](int kk) -> uint32_t {
+            return FUSED ? zb + 32u * (kk >> 1) + 16u * (kk & 1) : zb + 32u * (kk >> 1) + 8u * (kk & 1);
+          };
+          auto zlo = [&](int kk) -> uint32_t { return zhi(kk) + (FUSED ? 8u : 16u); };
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_ts(dst, zb + 32u * (kk >> 1) + 16u + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, (kk || !first) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zlo(kk), dh + (uint64_t)(kk * 2), IDESC, (kk || !first) ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_ts(dst, zb + 32u * (kk >> 1) + 8u * (kk & 1), dl + (uint64_t)(kk * 2), IDESC, 1u);
+          for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zhi(kk), dl + (uint64_t)(kk * 2), IDESC, 1u);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_ts(dst, zb + 32u * (kk >> 1) + 8u * (kk & 1), dh + (uint64_t)(kk * 2), IDESC, 1u);
-          mma_commit(&empty[s_o]);
+          for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zhi(kk), dh + (uint64_t)(kk * 2), IDESC, 1u);
+          mma_commit(&empty[slot]);
+        };
+        if (elect_one()) {
+          issue_out(s_o, tmem_base + X_COL0 + (g & 1) * 64u, tmem_base + OUT_COL0 + ob * 64u);
+          if (FUSED) issue_out(s_o2, tmem_base + Y_COL0 + (g & 1) * 64u, tmem_base + OUT_COL0 + 64u);
           if (last) mma_commit(&out_full[ob]);
         }
         __syncwarp();
         { AH_T(o1); AH_ACC(5, o0, o1); }
+        AH_TR(0, it, j, 7, lane == 0);
         if (last) ++fo;
       }
       gb += nb;
@@ -441,14 +505,18 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     uint32_t gb = 0;
     for (int item = unit_id; item < p.total_items; item += units) {
       const int bh = item / p.row_tiles;
-      float zexp;
+      float zexp, dmul = p.c;
       {
         const float* am = p.amax + (int64_t)bh * 4;
         int e_a2, e_b2;
         (void)ah_slab_scale(__ldg(am + OPS::A2), e_a2);
         (void)ah_slab_scale(__ldg(am + OPS::B2), e_b2);
         const int e_c = (int)((__float_as_uint(p.c) >> 23) & 0xffu) - 127;
-        zexp = HAS2 ? (float)(14 - (10 + e_a2 + e_b2 + e_c)) : 14.f;
+        const int ez = 14 - (10 + e_a2 + e_b2 + e_c);
+        zexp = (HAS2 && !FUSED) ? (float)ez : 14.f;
+        // AH_DKV: the probabilities are carried times 2^14 (they are an operand themselves), so the remaining factor of the
+        // dS scale, 2^(ez - 14), rides on (dP c - D c) instead of in the exp2 argument
+        if (FUSED) dmul = p.c * ah_pow2(ez - 14);
       }
       auto fetch = [&](int j, float (&v)[4]) {
         const int c0 = j * AH_BC;
@@ -456,7 +524,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         for (int i = 0; i < 2; ++i) {
           const int col = c0 + lane + 32 * i;
           v[i] = (col < p.C) ? __ldg(p.lse + (int64_t)bh * p.C + col) - zexp : INFINITY;
-          v[2 + i] = (MODE == AH_DKM && col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) * p.c : 0.f;
+          v[2 + i] = ((MODE == AH_DKM || FUSED) && col < p.C) ? __ldg(p.dvec + (int64_t)bh * p.C + col) * dmul : 0.f;
         }
       };
       float nxt[4];
@@ -469,7 +537,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         float* cs = colstat[g & 1];
         cs[lane] = cur[0];
         cs[lane + 32] = cur[1];
-        if (MODE == AH_DKM) {
+        if (MODE == AH_DKM || FUSED) {
           cs[64 + lane] = cur[2];
           cs[96 + lane] = cur[3];
         }
@@ -493,7 +561,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t op = 0, it = 0;
-    float s_a1 = 1.f, s_a2 = 1.f, s_b1 = 1.f, s_b2 = 1.f, s_b3 = 1.f;
+    float s_a1 = 1.f, s_a2 = 1.f, s_b1 = 1.f, s_b2 = 1.f, s_b3 = 1.f, s_b4 = 1.f;
+    int tr_j = 0;                     // block index for the event trace
     long long prof_acc[4] = {0, 0, 0, 0};
     auto conv_a = [&](int which, float sc) {
       if (AH_CONV_GROUPS == 2 && which != cg) return;
@@ -591,6 +660,98 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       arrive_leader(&conv[s]);
       { AH_T(k2); AH_ACC(2, k1, k2); }
     };
+    // Two ring operations in one go (the two score operand blocks of a block, or AH_DKV's two OUT operand blocks): the loads
+    // of both tiles are in flight together and one proxy fence covers both — a single tile is a latency-bound stream for
+    // four warps (~450 cycles for 16 elements per thread, measured).
+    auto conv_k2 = [&](float sc_a, float sc_b) {
+      const uint32_t sa = op % AH_NSLOT, pa = (op / AH_NSLOT) & 1;
+      ++op;
+      const uint32_t sb_ = op % AH_NSLOT, pb = (op / AH_NSLOT) & 1;
+      ++op;
+      AH_T(k0);
+      mbar_wait(&full[sa], pa);
+      mbar_wait(&full[sb_], pb);
+      AH_T(k1);
+      AH_ACC(0, k0, k1);
+      AH_TR(1, it, tr_j, 1, tid == 0);
+      constexpr int ROWS = CP ? 32 : 64;
+      constexpr int PARTS = 128 / ROWS;
+      constexpr int NV = 16 / PARTS;
+      const int row = tid / PARTS, part = tid % PARTS;
+      const int f0 = part * NV;
+      const uint32_t slot_a = smem_u32(smem + (size_t)sa * AH_SLOT), slot_b = smem_u32(smem + (size_t)sb_ * AH_SLOT);
+      uint4 ta[NV], tb[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int f = f0 + i, half = f >> 3, c = f & 7;
+        const uint32_t off = half * (ROWS * 128) + row * 128 + ((c ^ (row & 7)) << 4);
+        ta[i] = ah_lds128(slot_a + off);
+        tb[i] = ah_lds128(slot_b + off);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t slot = t ? slot_b : slot_a;
+        const float sc = t ? sc_b : sc_a;
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint4 t4 = t ? tb[2 * i + u] : ta[2 * i + u];
+            ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * u], lo[2 * u]);
+            ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * u + 1], lo[2 * u + 1]);
+          }
+          const int ch = f0 / 2 + i;
+          const uint32_t dst = row * 128 + ((ch ^ (row & 7)) << 4);
+          ah_sts128(slot + AH_HI + dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          ah_sts128(slot + AH_LO + dst, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        }
+      }
+      fence_proxy_async();
+      arrive_leader(&conv[sa]);             // (keeps the slot's phase in step with the ring; nobody waits on it:
+      arrive_leader(&conv[sb_]);            //  the MMA thread waits for the pair on the second slot's barrier only)
+      { AH_T(k2); AH_ACC(1, k1, k2); }
+    };
+    auto conv_o2 = [&](float sc_a, float sc_b) {
+      const uint32_t sa = op % AH_NSLOT, pa = (op / AH_NSLOT) & 1;
+      ++op;
+      const uint32_t sb_ = op % AH_NSLOT, pb = (op / AH_NSLOT) & 1;
+      ++op;
+      AH_T(k0);
+      mbar_wait(&full[sa], pa);
+      mbar_wait(&full[sb_], pb);
+      AH_T(k1);
+      AH_ACC(0, k0, k1);
+      AH_TR(1, it, tr_j, 3, tid == 0);
+      constexpr int DS = CP ? 32 : 64;
+      constexpr int PARTS = 128 / DS;
+      constexpr int NK = 64 / PARTS;
+      const int d = tid % DS, part = tid / DS;
+      const uint32_t rel = (uint32_t)(d >> 5) * 8192u + (uint32_t)(d & 31) * 4u + (uint32_t)(part * NK) * 128u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t slot = smem_u32(smem + (size_t)(t ? sb_ : sa) * AH_SLOT);
+        const float sc = t ? sc_b : sc_a;
+        uint32_t hi[NK / 2], lo[NK / 2];
+#pragma unroll
+        for (int i = 0; i < NK / 2; ++i) {
+          const float v0 = __uint_as_float(ah_lds32(slot + rel + (2 * i) * 128)) * sc;
+          const float v1 = __uint_as_float(ah_lds32(slot + rel + (2 * i + 1) * 128)) * sc;
+          ah_split2(v0, v1, hi[i], lo[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NK / 8; ++i) {
+          const int ch = part * (NK / 8) + i;
+          const uint32_t dst = d * 128 + ((ch ^ (d & 7)) << 4);
+          ah_sts128(slot + AH_HI + dst, make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]));
+          ah_sts128(slot + AH_LO + dst, make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]));
+        }
+      }
+      fence_proxy_async();
+      arrive_leader(&conv[sa]);
+      arrive_leader(&conv[sb_]);
+      { AH_T(k2); AH_ACC(2, k1, k2); }
+    };
     for (int item = unit_id; item < p.total_items; item += units, ++it) {
       const int bh = item / p.row_tiles;
       {
@@ -601,17 +762,32 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         s_b1 = ah_slab_scale(__ldg(am + OPS::B1), e);
         s_b2 = ah_slab_scale(__ldg(am + OPS::B2), e);
         s_b3 = ah_slab_scale(__ldg(am + OPS::B3), e);
+        s_b4 = ah_slab_scale(__ldg(am + OPS::B4), e);
       }
       conv_a(0, s_a1);
       if (HAS2) conv_a(1, s_a2);
-      conv_k(s_b1);
-      if (HAS2) conv_k(s_b2);
+      if (MERGE) conv_k2(s_b1, s_b2);
+      else {
+        conv_k(s_b1);
+        if (HAS2) conv_k(s_b2);
+      }
       for (int j = 0; j < nb; ++j) {
+        AH_TR(1, it, j, 0, tid == 0);
+        tr_j = j;
         if (j + 1 < nb) {
-          conv_k(s_b1);
-          if (HAS2) conv_k(s_b2);
+          if (MERGE) conv_k2(s_b1, s_b2);
+          else {
+            conv_k(s_b1);
+            if (HAS2) conv_k(s_b2);
+          }
         }
-        conv_o(s_b3);
+        AH_TR(1, it, j, 2, tid == 0);
+        if (FUSED && MERGE) conv_o2(s_b3, s_b4);
+        else {
+          conv_o(s_b3);
+          if (FUSED) conv_o(s_b4);
+        }
+        AH_TR(1, it, j, 4, tid == 0);
       }
     }
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 128) {
@@ -629,7 +805,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t cofs = (uint32_t)gi * 32u;
-    uint32_t gb = 0, fo = 0;
+    uint32_t gb = 0, fo = 0, itn = 0;
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = p.prof ? clock64() : 0;
     for (int item = unit_id; item < p.total_items; item += units) {
@@ -638,10 +814,10 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       const int grow = rt * AH_BM + r;
       const bool row_ok = grow < p.R;
       // ---- per-item constants: the slab scales fold into the constants the elementwise math applies anyway
-      float c2e, ce = 0.f, zexp, out_unscale;
+      float c2e, ce = 0.f, zexp, out_unscale, out2_unscale = 0.f;
       {
         const float* am = p.amax + (int64_t)bh * 4;
-        int e_a1, e_b1, e_a2, e_b2, e_b3;
+        int e_a1, e_b1, e_a2, e_b2, e_b3, e_b4;
         const float sa1 = ah_slab_scale(__ldg(am + OPS::A1), e_a1), sb1 = ah_slab_scale(__ldg(am + OPS::B1), e_b1);
         const float sb3 = ah_slab_scale(__ldg(am + OPS::B3), e_b3);
         c2e = p.c2 / (sa1 * sb1);                                   // X_true * c2 = X' * c2e   (exact: powers of two)
@@ -654,14 +830,20 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           const int ez = 14 - (10 + e_a2 + e_b2 + e_c);
           zexp = (float)ez;
           out_unscale = ah_pow2(-ez) / sb3;
+          if (FUSED) {
+            ce *= ah_pow2(ez - 14);                                 // see the column-statistics warp
+            out2_unscale = ah_pow2(-14) / ah_slab_scale(__ldg(am + OPS::B4), e_b4);
+          }
         } else {
           zexp = 14.f;                                              // probabilities (<= 1) are carried times 2^14
           out_unscale = ah_pow2(-14) / sb3;
         }
       }
-      float run[32];
+      float run[32], run2[32];      // run2: AH_DKV's dV accumulator (dead otherwise)
 #pragma unroll
       for (int d = 0; d < 32; ++d) run[d] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) run2[d] = 0.f;
       float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;
       float ls_r = 0.f, d_r = 0.f;
       if (MODE == AH_DQ && row_ok) {
@@ -669,7 +851,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         d_r = __ldg(p.dvec + (int64_t)bh * p.R + grow) * p.c;
       }
       auto fold = [&](float a) {
-        const uint32_t ob = fo & 1, oph = (fo >> 1) & 1;
+        const uint32_t ob = FUSED ? 0u : (fo & 1), oph = FUSED ? (fo & 1) : ((fo >> 1) & 1);
         ++fo;
         AH_T(f0);
         mbar_wait(&out_full[ob], oph);
@@ -684,6 +866,12 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           if (MODE == AH_FWD) run[d] = fmaf(run[d], a, __uint_as_float(o[d]));
           else run[d] += __uint_as_float(o[d]);
         }
+        if (FUSED) {
+          tmem_ld_32x32b_x32(lane_base + OUT_COL0 + 64u + cofs, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 32; ++d) run2[d] += __uint_as_float(o[d]);
+        }
         tc_fence_before();
         arrive_leader(&out_empty[ob]);
         AH_T(f2);
@@ -696,11 +884,15 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const int col0 = j * AH_BC + (int)cofs;
         float* cs = colstat[bsel];
         AH_T(b0);
+        AH_TR(2, itn, j, 0, tid == 0);
         if (!ROWSTAT) mbar_wait(&cs_full[bsel], (g >> 1) & 1);      // this block's lse / D columns are in shared memory
         AH_T(b1);
-        mbar_wait(&x_full[bsel], (g >> 1) & 1);
+        // (two-score modes: Y's commit is issued after X's MMAs by the same thread, so it covers both products)
+        if (!HAS2) mbar_wait(&x_full[bsel], (g >> 1) & 1);
+        AH_TR(2, itn, j, 1, tid == 0);
         if (HAS2) mbar_wait(&y_full[bsel], (g >> 1) & 1);
         AH_T(b2);
+        AH_TR(2, itn, j, 2, tid == 0);
         AH_ACC(0, b0, b1);      // column statistics + barrier
         AH_ACC(1, b1, b2);      // waiting for X (and Y)
         tc_fence_after();
@@ -767,6 +959,48 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           arrive_leader(&z_full[bsel]);
           { AH_T(b3); AH_ACC(2, b2, b3); }
           if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
+        } else if (FUSED) {
+          // dK + dV: Z2 = P 2^14 (over the Y columns), Z1 = Z2 (Y c - D c) 2^(ez - 14) (over the X columns); in two halves of
+          // 16 columns (register budget: two running tiles), each half's hi / lo pairs land on the 16 columns it has read
+          const uint32_t yaddr = lane_base + Y_COL0 + bsel * 64u + cofs;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t x[16], y[16];
+            tmem_ld_32x32b_x16(xaddr + 16u * hf, x);
+            tmem_ld_32x32b_x16(yaddr + 16u * hf, y);
+            tmem_ld_wait();
+            uint32_t z1h[8], z1l[8], z2h[8], z2l[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + 16 * hf + c4);
+              const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cofs + 16 * hf + c4);
+              const float p0 = ah_exp2(fmaf(__uint_as_float(x[c4]), c2e, -l4.x));
+              const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
+              const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
+              const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
+              ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1]);
+              ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1]);
+              ah_split2(p0 * fmaf(__uint_as_float(y[c4]), ce, -d4.x), p1 * fmaf(__uint_as_float(y[c4 + 1]), ce, -d4.y),
+                        z1h[c4 >> 1], z1l[c4 >> 1]);
+              ah_split2(p2 * fmaf(__uint_as_float(y[c4 + 2]), ce, -d4.z), p3 * fmaf(__uint_as_float(y[c4 + 3]), ce, -d4.w),
+                        z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1]);
+            }
+            if (hf == 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&cs_empty[bsel]);
+            }
+            ah_tmem_st_x8(xaddr + 16u * hf, z1h);
+            ah_tmem_st_x8(xaddr + 16u * hf + 8u, z1l);
+            ah_tmem_st_x8(yaddr + 16u * hf, z2h);
+            ah_tmem_st_x8(yaddr + 16u * hf + 8u, z2l);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          arrive_leader(&z_full[bsel]);
+          { AH_T(b3); AH_ACC(2, b2, b3); }
+          AH_TR(2, itn, j, 3, tid == 0);
+          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
+          AH_TR(2, itn, j, 4, tid == 0);
         } else {
           // DQ / DK: Z = P (Y c - D c), carried times 2^ez
           const bool full_block = col0 + 32 <= p.C;
@@ -819,37 +1053,41 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       fold(a_prev);
       gb += nb;
       AH_T(e0);
-      // ---- epilogue (unchanged: swizzled staging tile + TMA store)
-      if (tid == 0) ah_bulk_wait_read0();
+      // ---- epilogue: swizzled staging tile + TMA store (AH_DKV: dK, then dV through the same staging tile)
       float sc = out_unscale;
       if (MODE == AH_FWD) {
         ah_bar_sync(5, 256);
         rowx[gi][r] = l_run;
       }
-      ah_bar_sync(3, 256);
-      if (MODE == AH_FWD) {
-        const float l_tot = l_run + rowx[gi ^ 1][r];                 // = 2^14 * (true row sum)
-        sc = out_unscale * 16384.f / l_tot;                          // O = (OUT' / (2^14 s_V)) / (l_tot / 2^14)
-        if (gi == 0 && row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, c2e, log2f(l_tot) - 14.f);
-      }
-      {
+      auto store_tile = [&](const float (&acc)[32], float mul, const CUtensorMap* m) {
+        if (tid == 0) ah_bulk_wait_read0();
+        ah_bar_sync(3, 256);
+        if (MODE == AH_FWD) {
+          const float l_tot = l_run + rowx[gi ^ 1][r];                 // = 2^14 * (true row sum)
+          mul = out_unscale * 16384.f / l_tot;                         // O = (OUT' / (2^14 s_V)) / (l_tot / 2^14)
+          if (gi == 0 && row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, c2e, log2f(l_tot) - 14.f);
+        }
         const uint32_t srow = smem_u32(out_stage) + (uint32_t)gi * 16384u + r * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4 v;
-          v.x = __float_as_uint(run[4 * c] * sc); v.y = __float_as_uint(run[4 * c + 1] * sc);
-          v.z = __float_as_uint(run[4 * c + 2] * sc); v.w = __float_as_uint(run[4 * c + 3] * sc);
+          v.x = __float_as_uint(acc[4 * c] * mul); v.y = __float_as_uint(acc[4 * c + 1] * mul);
+          v.z = __float_as_uint(acc[4 * c + 2] * mul); v.w = __float_as_uint(acc[4 * c + 3] * mul);
           ah_sts128(srow + ((c ^ (r & 7)) << 4), v);
         }
-      }
-      fence_proxy_async();
-      ah_bar_sync(3, 256);
-      if (tid == 0) {
-        ah_tma_store_4d(&map_out, out_stage, 0, rt * AH_BM, h, b);
-        ah_tma_store_4d(&map_out, out_stage + 16384, 32, rt * AH_BM, h, b);
-        ah_bulk_commit();
-      }
+        fence_proxy_async();
+        ah_bar_sync(3, 256);
+        if (tid == 0) {
+          ah_tma_store_4d(m, out_stage, 0, rt * AH_BM, h, b);
+          ah_tma_store_4d(m, out_stage + 16384, 32, rt * AH_BM, h, b);
+          ah_bulk_commit();
+        }
+      };
+      store_tile(run, sc, &map_out);
+      if (FUSED) store_tile(run2, out2_unscale, &map_out2);
       { AH_T(e1); AH_ACC(6, e0, e1); }        // epilogue
+      AH_TR(2, itn, 15, 0, tid == 0);
+      ++itn;
     }
     if (tid == 0) ah_bulk_wait0();
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 128 + 128 * AH_CONV_GROUPS) {
@@ -898,44 +1136,64 @@ __global__ void __launch_bounds__(256) attn_amax_kernel(const AhAmaxJobs jobs, f
   const int sub = threadIdx.x & 15;
   const int64_t first = (int64_t)blockIdx.x * AH_PRE_ROWS;
   if (first >= rows_total) return;
+  // (b, h, s) of this block's first row by 64-bit division ONCE; per row only 32-bit arithmetic relative to it
+  const int64_t bh_first = first / S;
+  const uint32_t s_first = (uint32_t)(first - bh_first * S), uS = (uint32_t)S, uH = (uint32_t)H;
+  const uint32_t rows_here = (uint32_t)((rows_total - first) < AH_PRE_ROWS ? (rows_total - first) : AH_PRE_ROWS);
   int64_t cur_bh = -1;          // warp-uniform: both rows of a warp are forced onto the same slab per iteration (below)
   float m = 0.f;
-  for (int it = 0; it < AH_PRE_ROWS / 16; ++it) {
-    const int64_t row = first + it * 16 + (threadIdx.x >> 4);
-    const bool live = row < rows_total;
-    const int64_t bh = live ? row / S : -1;
-    // a warp covers two consecutive rows; if they straddle a slab boundary (or the end) flush and handle them separately
-    const int64_t bh_lo = __shfl_sync(0xffffffffu, bh, 0), bh_hi = __shfl_sync(0xffffffffu, bh, 16);
-    float v = 0.f, mm = 0.f;
-    if (live) {
-      const int64_t s_ = row % S, h = bh % H, b = bh / H;
-      const int64_t off = b * bs + h * hs + s_ * ld + sub * 4;
-      const float4 g = *reinterpret_cast<const float4*>(x + off);
-      mm = fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w)));
+  // four row groups per trip: their loads are issued together (one 16 B load per thread and trip left the kernel
+  // latency-bound at 3.1 TB/s: profiles/r2_attn_ncu_passes.csv)
+  constexpr int UN = 4;
+  for (int it0 = 0; it0 < AH_PRE_ROWS / 16; it0 += UN) {
+    int64_t rowv[UN], bhv[UN];
+    float4 gv[UN], av[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint32_t rl = (uint32_t)((it0 + u) * 16 + (threadIdx.x >> 4));
+      const bool live = rl < rows_here;
+      const uint32_t s_lin = s_first + rl, dq = s_lin / uS;
+      rowv[u] = first + rl;
+      bhv[u] = live ? bh_first + dq : -1;
+      gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      av[u] = gv[u];
+      if (live) {
+        const uint32_t s_ = s_lin - dq * uS, ubh = (uint32_t)bhv[u], b = ubh / uH, h = ubh - b * uH;
+        const int64_t off = (int64_t)b * bs + (int64_t)h * hs + (int64_t)s_ * ld + sub * 4;
+        gv[u] = __ldg(reinterpret_cast<const float4*>(x + off));
+        if (DVEC) av[u] = __ldg(reinterpret_cast<const float4*>(o + off));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t row = rowv[u], bh = bhv[u];
+      const bool live = bh >= 0;
+      // a warp covers two consecutive rows; if they straddle a slab boundary (or the end) flush and handle them separately
+      const int64_t bh_lo = __shfl_sync(0xffffffffu, bh, 0), bh_hi = __shfl_sync(0xffffffffu, bh, 16);
+      const float4 g = gv[u];
+      float mm = fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w)));
       if (DVEC) {
-        const float4 a = *reinterpret_cast<const float4*>(o + off);
-        v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
-      }
-    }
-    if (DVEC) {
+        const float4 a = av[u];
+        float v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
 #pragma unroll
-      for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
-      if (sub == 0 && live) jb.dvec[row] = v;
-    }
-    if (bh_lo == bh_hi) {
-      if (bh_lo != cur_bh) {
+        for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
+        if (sub == 0 && live) jb.dvec[row] = v;
+      }
+      if (bh_lo == bh_hi) {
+        if (bh_lo != cur_bh) {
+          ah_amax_flush(m, cur_bh, amax, slot);
+          cur_bh = bh_lo;
+          m = 0.f;
+        }
+        m = fmaxf(m, mm);
+      } else {                       // rare: the two rows belong to different slabs -> flush the running value, then each half
         ah_amax_flush(m, cur_bh, amax, slot);
-        cur_bh = bh_lo;
+        cur_bh = -1;
         m = 0.f;
-      }
-      m = fmaxf(m, mm);
-    } else {                       // rare: the two rows belong to different slabs -> flush the running value, then each half
-      ah_amax_flush(m, cur_bh, amax, slot);
-      cur_bh = -1;
-      m = 0.f;
 #pragma unroll
-      for (int ofs = 8; ofs > 0; ofs >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, ofs, 16));
-      if (sub == 0 && live && mm > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax + bh * 4 + slot), __float_as_uint(mm));
+        for (int ofs = 8; ofs > 0; ofs >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, ofs, 16));
+        if (sub == 0 && live && mm > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax + bh * 4 + slot), __float_as_uint(mm));
+      }
     }
   }
   ah_amax_flush(m, cur_bh, amax, slot);
@@ -970,10 +1228,10 @@ static int ah_encode(CUtensorMap* map, const AttnHTensor& t, int64_t B, int64_t 
 
 template <int MODE, bool CP>
 static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTensor& b1, const AttnHTensor& b2,
-                          const AttnHTensor& b3, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
-  constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM);
+                          const AttnHTensor& b3, const AttnHTensor& b4, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
+  constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM || MODE == AH_DKV);
   constexpr uint32_t BROWS = CP ? 32u : (uint32_t)AH_BC;
-  CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_out;
+  CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_b4, m_out, m_out2;
   int rc;
   AttnHTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
   if ((rc = ah_encode(&m_out, to, B, H, AH_BM, true))) return rc;
@@ -986,6 +1244,14 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   } else {
     m_a2 = m_a1;
     m_b2 = m_b1;
+  }
+  if (MODE == AH_DKV) {
+    AttnHTensor to2{p.out2, p.out2_bs, p.out2_hs, p.out2_ld, p.R};
+    if ((rc = ah_encode(&m_out2, to2, B, H, AH_BM, true))) return rc;
+    if ((rc = ah_encode(&m_b4, b4, B, H, AH_BC, false))) return rc;
+  } else {
+    m_out2 = m_out;
+    m_b4 = m_b3;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -1002,8 +1268,8 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   static const bool want_prof = getenv("B200AD_ATTN_PROF") != nullptr;
   static long long* prof_dev = nullptr;
   if (want_prof) {
-    if (!prof_dev) cudaMalloc(&prof_dev, 24 * sizeof(long long));
-    cudaMemsetAsync(prof_dev, 0, 24 * sizeof(long long), s);
+    if (!prof_dev) cudaMalloc(&prof_dev, AH_PROF_WORDS * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, AH_PROF_WORDS * sizeof(long long), s);
     p.prof = prof_dev;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1018,11 +1284,11 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_h16_kernel<MODE, CP>, m_a1, m_a2, m_b1, m_b2, m_b3, m_out, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_h16_kernel<MODE, CP>, m_a1, m_a2, m_b1, m_b2, m_b3, m_b4, m_out, m_out2, p);
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): launch: %s", cudaGetErrorString(e));
   count_launch();
   if (want_prof && prof_dev) {
-    long long hp[24];
+    static long long hp[AH_PROF_WORDS];
     cudaStreamSynchronize(s);
     cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
     const double blocks = (double)ceil_div(p.total_items, grid / (CP ? 2 : 1)) * p.nb;
@@ -1030,6 +1296,22 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
             "converter wait_tma %.0f conv_k %.0f conv_o %.0f | owner total %.0f colstat %.0f wait_XY %.0f ld+math+st %.0f wait_OUT %.0f fold %.0f epilogue %.0f\n", MODE, (int)CP, blocks,
             hp[0] / blocks, hp[7] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[16] / blocks, hp[17] / blocks, hp[4] / blocks, hp[5] / blocks, hp[6] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
             hp[11] / blocks, hp[13] / blocks, hp[14] / blocks, hp[15] / blocks);
+    if (atoi(getenv("B200AD_ATTN_PROF")) >= 2) {      // event trace of one item (cycles since its first recorded event)
+      long long t0 = 0;
+      for (int i = 24; i < AH_PROF_WORDS; ++i)
+        if (hp[i] && (!t0 || hp[i] < t0)) t0 = hp[i];
+      static const char* role[4] = {"mma", "conv", "owner", "tma"};
+      for (int r = 0; r < 4; ++r)
+        for (int j = 0; j < 16; ++j) {
+          const long long* e = hp + 24 + (r * 16 + j) * 16;
+          bool any = false;
+          for (int k = 0; k < 16; ++k) any |= e[k] != 0;
+          if (!any) continue;
+          fprintf(stderr, "[ah_trace] mode %d %-5s blk %2d:", MODE, role[r], j);
+          for (int k = 0; k < 8; ++k) fprintf(stderr, " %6lld", e[k] ? e[k] - t0 : -1LL);
+          fprintf(stderr, "\n");
+        }
+    }
   }
   if (getenv("B200AD_ATTN_SYNC")) {
     cudaError_t e2 = cudaStreamSynchronize(s);
@@ -1041,11 +1323,11 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
 
 template <int MODE>
 static int ah_launch(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTensor& b1, const AttnHTensor& b2,
-                     const AttnHTensor& b3, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
+                     const AttnHTensor& b3, const AttnHTensor& b4, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
   static const char* e = getenv("B200AD_ATTN_PAIR");
   const bool pair = e ? atoi(e) == 1 : (ceil_div(p.R, AH_BM) % 2 == 0);
-  if (pair) return ah_launch_impl<MODE, true>(a1, a2, b1, b2, b3, p, B, H, s);
-  return ah_launch_impl<MODE, false>(a1, a2, b1, b2, b3, p, B, H, s);
+  if (pair) return ah_launch_impl<MODE, true>(a1, a2, b1, b2, b3, b4, p, B, H, s);
+  return ah_launch_impl<MODE, false>(a1, a2, b1, b2, b3, b4, p, B, H, s);
 }
 
 static AhAmaxJob ah_job(const float* x, const b200ad_attn_strides& st, int64_t B, int64_t H, int64_t S, int slot,
@@ -1059,6 +1341,7 @@ static AhAmaxJob ah_job(const float* x, const b200ad_attn_strides& st, int64_t B
 
 // zero the table, then ONE launch for all tensors
 static int ah_prepass(const AhAmaxJobs& jobs, int n_jobs, float* amax, int64_t B, int64_t H, cudaStream_t s) {
+  if (B * H > 0x7fffffffll) return set_error(B200AD_ERR_UNSUPPORTED, "attention(h16): batch * heads exceeds 2^31");
   cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float) * 4 * B * H, s);
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): memset: %s", cudaGetErrorString(e));
   int64_t max_rows = 0;
@@ -1088,11 +1371,11 @@ int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   p.lse_w = lse; p.amax = amax;
   p.H = (int32_t)H; p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
   p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
-  return ah_launch<AH_FWD>(tq, tq, tk, tk, tv, p, B, H, s);
+  return ah_launch<AH_FWD>(tq, tq, tk, tk, tv, tv, p, B, H, s);
 }
 
 int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
-                 const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, cudaStream_t s) {
+                 const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, bool split_dkv, cudaStream_t s) {
   const int64_t B = d->batch, H = d->heads;
   float* dvec = ws;
   float* amax = ws + B * H * d->seq_q;
@@ -1109,14 +1392,24 @@ int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   p.lse = lse; p.dvec = dvec; p.amax = amax;
   p.H = (int32_t)H;
   p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
-  p.out = dv; p.out_bs = d->v.batch; p.out_hs = d->v.head; p.out_ld = d->v.row;
   p.R = (int32_t)d->seq_kv; p.C = (int32_t)d->seq_q;
-  if ((rc = ah_launch<AH_DV>(tk, tk, tq, tq, tdo, p, B, H, s))) return rc;
-  p.out = dk; p.out_bs = d->k.batch; p.out_hs = d->k.head; p.out_ld = d->k.row;
-  if ((rc = ah_launch<AH_DKM>(tk, tv, tq, tdo, tq, p, B, H, s))) return rc;
+  // dK and dV come out of ONE pass over the (kv tile, q block) grid: S^T and P^T are computed once for both (seven GEMM units
+  // for the backward instead of eight, one exp per score instead of two).  b200ad_attn_set_variant(2) (or
+  // B200AD_ATTN_SPLIT_DKV=1) runs the two separate passes: kept for A/B measurements and as a second witness in the tests.
+  static const bool env_split = getenv("B200AD_ATTN_SPLIT_DKV") && atoi(getenv("B200AD_ATTN_SPLIT_DKV")) == 1;
+  if (split_dkv || env_split) {
+    p.out = dv; p.out_bs = d->v.batch; p.out_hs = d->v.head; p.out_ld = d->v.row;
+    if ((rc = ah_launch<AH_DV>(tk, tk, tq, tq, tdo, tdo, p, B, H, s))) return rc;
+    p.out = dk; p.out_bs = d->k.batch; p.out_hs = d->k.head; p.out_ld = d->k.row;
+    if ((rc = ah_launch<AH_DKM>(tk, tv, tq, tdo, tq, tq, p, B, H, s))) return rc;
+  } else {
+    p.out = dk; p.out_bs = d->k.batch; p.out_hs = d->k.head; p.out_ld = d->k.row;
+    p.out2 = dv; p.out2_bs = d->v.batch; p.out2_hs = d->v.head; p.out2_ld = d->v.row;
+    if ((rc = ah_launch<AH_DKV>(tk, tv, tq, tdo, tq, tdo, p, B, H, s))) return rc;
+  }
   p.out = dq; p.out_bs = d->q.batch; p.out_hs = d->q.head; p.out_ld = d->q.row;
   p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
-  return ah_launch<AH_DQ>(tq, tdo, tk, tv, tk, p, B, H, s);
+  return ah_launch<AH_DQ>(tq, tdo, tk, tv, tk, tk, p, B, H, s);
 }
 
 }  // namespace b200ad

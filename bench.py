@@ -393,7 +393,10 @@ def run_c5(args):
         achieved = flops / (avg_ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"]
         if isinstance(key[0], str):     # fused attention pass: ("attn_fwd" | "attn_bwd", B, H, Sq, Skv, dk)
-            kname = "b200ad_%s batch=%d heads=%d seq_q=%d seq_kv=%d head_dim=%d (3xTF32)" % key
+            # default attention variant: forward 3xTF32 (csrc/attn_tc.cu), backward fp16 hi/lo split (csrc/attn_h16.cu)
+            h16 = (key[0] == "attn_bwd" and os.environ.get("B200AD_ATTN_TF32", "0") != "1") or os.environ.get("B200AD_ATTN_H16", "0") == "1"
+            kname = "b200ad_%s batch=%d heads=%d seq_q=%d seq_kv=%d head_dim=%d (%s)" % (
+                key + ("fp16 hi/lo split, kind::f16" if h16 else "3xTF32, kind::tf32",))
             traffic = NCU_TRAFFIC_BYTES.get(key[0])
             if traffic is not None:
                 traffic = traffic * key[1] / 256.0      # the ncu capture was taken at 256 sequences per launch; traffic is linear in it
@@ -408,7 +411,8 @@ def run_c5(args):
             issued = 3.0 if key[0] == "attn_fwd" else attn_bwd_units * 3.0 / 4.0
         else:
             issued = 3.0 if int(key[6]) in (1, 3) else 1.0       # b200ad_gemm_precision: TF32X3 / AUTO
-        tf32_peak = peak / 2.0
+        h16_kernel = isinstance(key[0], str) and h16
+        pipe_peak = peak if h16_kernel else peak / 2.0      # kind::f16 issues at the bf16 rate, kind::tf32 at half of it
         # every timed tensor-core kernel family with its share of the step (the dominant one is `kernel`)
         fam = sorted(((("%s" % (k[0],)) if isinstance(k[0], str) else "gemm %dx%dx%d b%d %s%s" % (k[:4] + ("NT"[k[4]], "NT"[k[5]])), v[1])
                       for k, v in gemm.items()), key=lambda kv: -kv[1])
@@ -422,9 +426,11 @@ def run_c5(args):
                 "share_of_step": ms_tot / (ms_step * args.steps), "all_gemm_share_of_step": total_gemm_ms / (ms_step * args.steps),
                 "step_tflops": C5_FLOP_PER_SEQ * GLOBAL_BATCH / world / (ms_step * 1e-3) / 1e12,
                 "tensor_pipe": {"issued_tflops": achieved * issued, "issued_per_algorithmic_flop": issued,
-                                "tf32_peak": tf32_peak, "frac": achieved * issued / tf32_peak,
-                                "note": "kind::tf32 MMA flops issued (3xTF32 split; backward attention also recomputes "
-                                        "S / dP per pass) against the TF32 dense peak = half of the measured bf16 peak"}}
+                                "pipe_peak": pipe_peak, "mma_kind": "f16" if h16_kernel else "tf32",
+                                "frac": achieved * issued / pipe_peak,
+                                "note": "MMA flops issued (three products per product: the fp32-faithful hi/lo split; backward "
+                                        "attention also recomputes S / dP per pass) against the dense peak of the MMA kind: "
+                                        "kind::f16 = the measured bf16 peak, kind::tf32 = half of it"}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, sec, n = cpu_reference_steps(2, 1, 64, budget_s=25.0)

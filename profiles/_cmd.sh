@@ -1,8 +1,13 @@
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|FAILED" | tail -3
-for w in c3 c1 c4; do timeout 300 python bench.py --workload $w > gpurun_out/r2j_$w.json 2>/dev/null; done
+timeout 600 python -m pytest tests/test_fused_attention.py -m gpu -q -x 2>&1 | tail -2
+timeout 200 python profiles/attn_probe.py timing 2>&1 | grep -E "micro-batch" 
+ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max,dram__bytes_read.sum --clock-control none -k regex:attn -c 16 --csv --log-file gpurun_out/attn_ncu.csv python profiles/attn_probe.py timing > gpurun_out/attn_ncu.log 2>&1
 python - <<'PY'
-import json
-for w in ("c3","c1","c4"):
-    d=json.loads(open('gpurun_out/r2j_%s.json'%w).read().strip().splitlines()[-1])
-    print(w, json.dumps(d.get("through_api"))[:700])
+import csv
+rows=[r for r in csv.reader(l for l in open('gpurun_out/attn_ncu.csv') if l.startswith('"'))]
+hdr=rows[0]; ki=hdr.index("Kernel Name"); mi=hdr.index("Metric Name"); vi=hdr.index("Metric Value"); ii=hdr.index("ID")
+out={}
+for r in rows[1:]:
+    out.setdefault((int(r[ii]), r[ki][:40]), {})[r[mi]]=r[vi]
+for k in sorted(out)[-4:]:
+    print(k, out[k])
 PY

@@ -255,7 +255,7 @@ def test_attn_variants_fp16_split_and_tf32_split_agree(B, h, Sq, Skv):
     got = {}
     prev = lib.b200ad_attn_set_variant(0)
     try:
-        for variant in (0, 1, -1):
+        for variant in (0, 1, 2, -1):
             lib.b200ad_attn_set_variant(variant)
             O, lse = D.attn_fwd(Q, K, V, scale)
             dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
@@ -266,6 +266,9 @@ def test_attn_variants_fp16_split_and_tf32_split_agree(B, h, Sq, Skv):
         lib.b200ad_attn_set_variant(prev)
     for a, b, name in zip(got[0], got[1], ("O", "dQ", "dK", "dV")):
         assert_close(a, b, rtol=2e-5, atol=2e-6, what="fp16-split vs tf32-split " + name)
+    # variant 0 computes dK and dV in one fused pass, variant 2 in two separate ones: same operands, same split
+    for a, b, name in zip(got[0], got[2], ("O", "dQ", "dK", "dV")):
+        assert_close(a, b, rtol=2e-6, atol=2e-7, what="fused dK+dV pass vs separate passes " + name)
 
 
 @pytest.mark.gpu
