@@ -54,6 +54,9 @@ constexpr int AH_MAXRING = AH_RING_BYTES / 16384;
 // threads; 80 / 112 / 152): 2.38 ms vs 2.31 ms for the config-5 backward — the second group does not pay, because the
 // conversion is not what the MMA thread waits for (profiles/r2_attn_h16_prof.log) and the owners lose registers.
 constexpr int AH_CONV_GROUPS = 1;
+#ifndef AH_SPLIT_ISSUE
+#define AH_SPLIT_ISSUE 1
+#endif
 constexpr int AH_THREADS = 128 + 128 * AH_CONV_GROUPS + 256;
 constexpr uint32_t AH_SMEM = AH_RING_BYTES + 2 * AH_ASTAGE + 32768 + 1024;
 
@@ -208,7 +211,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
   constexpr uint32_t AH_SLOT = CP ? 16384u : 32768u, AH_HI = AH_SLOT / 2, AH_LO = AH_SLOT * 3 / 4;
   uint8_t* a_stage = smem + AH_RING_BYTES;                  // [2] raw A tiles (128 rows x 64 fp32)
   uint8_t* out_stage = smem + AH_RING_BYTES + 2 * AH_ASTAGE;
-  __shared__ uint64_t bars[3 * AH_MAXRING + 26];
+  __shared__ uint64_t bars[3 * AH_MAXRING + 28];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float colstat[2][128];
   float (*rowx)[128] = colstat;
@@ -226,6 +229,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
   uint64_t* out_empty = out_full + 2;          // [2] row owners -> MMA
   uint64_t* cs_full = out_empty + 2;           // [2] column-statistics warp -> row owners (32 arrivals)
   uint64_t* cs_empty = cs_full + 2;            // [2] row owners -> column-statistics warp (8 warps)
+  uint64_t* o_issued = cs_empty + 2;           // [2] OUT-issuing warp -> score-issuing warp: OUT(g) has been issued
   uint32_t* tmem_base_slot = &tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -275,6 +279,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       mbar_init(&out_empty[i], CP ? 16 : 256);
       mbar_init(&cs_full[i], 32);
       mbar_init(&cs_empty[i], 8);
+      mbar_init(&o_issued[i], 1);
     }
     fence_barrier_init();
   }
@@ -353,10 +358,18 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && rank == 0) {
-    // ===================================== MMA issuer (leader CTA of a pair) =====================================
+  } else if ((warp == 1 || (AH_SPLIT_ISSUE && warp == 3)) && rank == 0) {
+    // ===================================== MMA issuers (leader CTA of a pair) =====================================
+    // Two issuing warps: warp 1 issues the score products (X = A1 . B1^T, Y = A2 . B2^T), warp 3 the OUT products.  A wait
+    // or a tcgen05 fence on an issuing thread leaves the tensor pipe idle for 150-250 cycles even when the barrier has long
+    // completed (profiles/r1_mma_rate.log: 33 -> 47 cycles per MMA with three waits per 24 MMAs; the per-item event trace of
+    // this kernel showed one thread spending ~3700 cycles per block on 1536 cycles of MMA work) — with two issuers one
+    // warp's synchronisation overlaps the other's MMAs.  Ordering between them: X(g) / Y(g) overwrite the columns that
+    // Z(g-2) occupied, so the score warp waits until the OUT warp has ISSUED OUT(g-2) (o_issued; tcgen05.mma instructions
+    // of one CTA execute in issue order), not until they have completed.
     // instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N = 64, M = 128 (256 for a pair)
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((CP ? 256 : AH_BM) >> 4) << 24);
+    const bool do_s = warp == 1, do_o = !AH_SPLIT_ISSUE || warp == 3;
     uint32_t op = 0, it = 0, gb = 0, fo = 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     const long long prof_t0 = p.prof ? clock64() : 0;
@@ -390,56 +403,58 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       mma_commit(done);
       if (a_done) mma_commit(a_done);
     };
+    // the score products of global block gx (item-local index jx): operand slots, the OUT warp's progress, then the MMAs
+    auto scores = [&](uint32_t gx, int jx) {
+      uint32_t s_x = 0, s_y = 0;
+      if (MERGE) s_y = wait_pair(s_x);
+      else {
+        s_x = wait_slot();
+        if (HAS2) s_y = wait_slot();
+      }
+      if (AH_SPLIT_ISSUE && gx >= 2) {
+        AH_T(q0);
+        mbar_wait(&o_issued[gx & 1], ((gx >> 1) & 1) ^ 1);
+        AH_T(q1);
+        AH_ACC(2, q0, q1);
+      }
+      AH_T(i0);
+      // (single issuer: no tcgen05 fence needed here — the owners' TMEM accesses to these buffers were ordered by the fence
+      // after z_full(g-2), and the operand tiles are shared memory; the A tiles are fenced in the item prologue)
+      if (AH_SPLIT_ISSUE || jx == 0) tc_fence_after();
+      if (elect_one()) {
+        const bool lastx = (jx == nb - 1);
+        issue_score(s_x, A1_COL, X_COL0 + (gx & 1) * 64u, &x_full[gx & 1], lastx ? &a_empty[0] : nullptr);
+        if (HAS2) issue_score(s_y, A2_COL, Y_COL0 + (gx & 1) * 64u, &y_full[gx & 1], lastx ? &a_empty[1] : nullptr);
+      }
+      __syncwarp();
+      AH_T(i1);
+      AH_ACC(4, i0, i1);
+    };
     for (int item = unit_id; item < p.total_items; item += units, ++it) {
-      {
+      if (do_s) {
         AH_T(wa0);
         mbar_wait(&a_conv[0], it & 1);                 // A1 in TMEM
         if (HAS2) mbar_wait(&a_conv[1], it & 1);       // A2 in TMEM
         AH_T(wa1);
         AH_ACC(3, wa0, wa1);
-        uint32_t s_x0 = 0, s_y0 = 0;
-        if (MERGE) s_y0 = wait_pair(s_x0);
-        else {
-          s_x0 = wait_slot();
-          if (HAS2) s_y0 = wait_slot();
-        }
-        tc_fence_after();                              // the converters' tcgen05.st of the A tiles
-        if (elect_one()) {
-          issue_score(s_x0, A1_COL, X_COL0 + (gb & 1) * 64u, &x_full[gb & 1], nb == 1 ? &a_empty[0] : nullptr);
-          if (HAS2) issue_score(s_y0, A2_COL, Y_COL0 + (gb & 1) * 64u, &y_full[gb & 1], nb == 1 ? &a_empty[1] : nullptr);
-        }
-        __syncwarp();
+        scores(gb, 0);
+      } else {
+        op += HAS2 ? 2 : 1;
       }
       for (int j = 0; j < nb; ++j) {
-        // sync point of block j: the next block's score operands (issued first: their X / Y buffers were released by
-        // Z(j-1)'s OUT product, which this thread issued one iteration ago), then Z(j) and a free OUT accumulator
+        // block j: the next block's score products first (their X / Y buffers were released by OUT(j-1)), then Z(j) and a
+        // free OUT accumulator for the OUT product(s)
         const uint32_t g = gb + j;
-        uint32_t s_x = 0, s_y = 0;
-        AH_TR(0, it, j, 0, lane == 0);
+        AH_TR(0, it, j, 0, lane == 0 && do_s);
         if (j + 1 < nb) {
-          if (MERGE) s_y = wait_pair(s_x);
-          else {
-            s_x = wait_slot();
-            if (HAS2) s_y = wait_slot();
-          }
+          if (do_s) scores(g + 1, j + 1);
+          else op += HAS2 ? 2 : 1;
         }
-        AH_TR(0, it, j, 1, lane == 0);
-        if (j + 1 < nb) {
-          // X(j+1) overwrites the columns Z(j-1) occupied: the OUT(j-1) MMAs that read them were issued earlier by this
-          // same thread, and tcgen05.mma instructions execute in issue order.  (No tcgen05 fence here: the owners' TMEM
-          // accesses to these buffers were ordered by the fence after z_full(j-1); the operand tiles are shared memory.)
-          AH_T(i0);
-          if (elect_one()) {
-            const uint32_t gx = g + 1;
-            const bool lastx = (j + 1 == nb - 1);
-            issue_score(s_x, A1_COL, X_COL0 + (gx & 1) * 64u, &x_full[gx & 1], lastx ? &a_empty[0] : nullptr);
-            if (HAS2) issue_score(s_y, A2_COL, Y_COL0 + (gx & 1) * 64u, &y_full[gx & 1], lastx ? &a_empty[1] : nullptr);
-          }
-          __syncwarp();
-          AH_T(i1);
-          AH_ACC(4, i0, i1);
+        AH_TR(0, it, j, 2, lane == 0 && do_s);
+        if (!do_o) {
+          op += FUSED ? 2 : 1;
+          continue;
         }
-        AH_TR(0, it, j, 2, lane == 0);
         const bool first = !PAIRF || (j & 1) == 0, last = !PAIRF || (j & 1) == 1 || j == nb - 1;
         const uint32_t ob = FUSED ? 0u : (fo & 1), oph = FUSED ? (fo & 1) : ((fo >> 1) & 1);
         AH_T(w0);
@@ -456,7 +471,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         }
         AH_TR(0, it, j, 4, lane == 0);
         AH_ACC(1, w0, w1);
-        AH_ACC(2, w1, w2);
+        if (!AH_SPLIT_ISSUE) AH_ACC(2, w1, w2);
         AH_T(o0);
         tc_fence_after();
         // OUT MMAs: D[128 x 64] (+)= Z (TMEM, packed fp16 pairs) . B (K-major fp16 tile of the slot).  Z layout inside a
@@ -481,6 +496,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           issue_out(s_o, tmem_base + X_COL0 + (g & 1) * 64u, tmem_base + OUT_COL0 + ob * 64u);
           if (FUSED) issue_out(s_o2, tmem_base + Y_COL0 + (g & 1) * 64u, tmem_base + OUT_COL0 + 64u);
           if (last) mma_commit(&out_full[ob]);
+          if (AH_SPLIT_ISSUE) mbar_arrive(&o_issued[g & 1]);      // the score warp may now overwrite these X / Y buffers
         }
         __syncwarp();
         { AH_T(o1); AH_ACC(5, o0, o1); }
@@ -490,13 +506,19 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       gb += nb;
     }
     if (p.prof && blockIdx.x == 0 && lane == 0) {
-      p.prof[0] = clock64() - prof_t0;   // MMA warp total
-      p.prof[1] = prof_acc[0];           // waiting for converted operand slots
-      p.prof[2] = prof_acc[1];           // waiting for Z (row owners)
-      p.prof[3] = prof_acc[2];           // waiting for a free OUT accumulator
-      p.prof[7] = prof_acc[3];           // waiting for the A tiles of the next item
-      p.prof[16] = prof_acc[4];          // issuing the score products of the next block
-      p.prof[17] = prof_acc[5];          // issuing the OUT product
+      if (do_s) {
+        p.prof[0] = clock64() - prof_t0;   // score-issuing warp total
+        p.prof[1] = prof_acc[0];           // waiting for converted score operand slots
+        p.prof[7] = prof_acc[3];           // waiting for the A tiles of the next item
+        p.prof[16] = prof_acc[4];          // issuing the score products
+        if (AH_SPLIT_ISSUE) p.prof[3] = prof_acc[2];   // waiting for the OUT warp (buffer reuse)
+      }
+      if (do_o) {
+        p.prof[2] = prof_acc[1];           // waiting for Z (row owners)
+        if (!AH_SPLIT_ISSUE) p.prof[3] = prof_acc[2];  // waiting for a free OUT accumulator
+        p.prof[17] = prof_acc[5];          // issuing the OUT product(s)
+        if (AH_SPLIT_ISSUE) p.prof[18] = prof_acc[0];  // OUT warp: waiting for converted OUT operand slots
+      }
     }
   } else if (warp == 2 && !ROWSTAT) {
     // ===================================== column statistics (DV / DK) =====================================
@@ -1292,7 +1314,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
     cudaStreamSynchronize(s);
     cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
     const double blocks = (double)ceil_div(p.total_items, grid / (CP ? 2 : 1)) * p.nb;
-    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_A %.0f wait_conv %.0f wait_Z %.0f wait_out_empty %.0f issue_scores %.0f issue_out %.0f | "
+    fprintf(stderr, "[ah_prof] mode %d pair %d blocks/CTA %.0f | per block: MMA thread total %.0f wait_A %.0f wait_conv %.0f wait_Z %.0f wait_out_empty|o_issued %.0f issue_scores %.0f issue_out %.0f | "
             "converter wait_tma %.0f conv_k %.0f conv_o %.0f | owner total %.0f colstat %.0f wait_XY %.0f ld+math+st %.0f wait_OUT %.0f fold %.0f epilogue %.0f\n", MODE, (int)CP, blocks,
             hp[0] / blocks, hp[7] / blocks, hp[1] / blocks, hp[2] / blocks, hp[3] / blocks, hp[16] / blocks, hp[17] / blocks, hp[4] / blocks, hp[5] / blocks, hp[6] / blocks, hp[8] / blocks, hp[9] / blocks, hp[10] / blocks,
             hp[11] / blocks, hp[13] / blocks, hp[14] / blocks, hp[15] / blocks);

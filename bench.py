@@ -383,7 +383,10 @@ def run_c5(args):
         return
 
     pk = peaks()
-    attn_bwd_units = float(os.environ.get("B200AD_ATTN_BWD_UNITS", "8"))    # GEMM units the backward passes issue (dV 2 + dK 3 + dQ 3)
+    # GEMM units the backward passes issue: fused dK+dV pass 4 (S, dP, dK, dV) + dQ pass 3 (S, dP, dQ); 8 with the tf32 carrier
+    # or B200AD_ATTN_SPLIT_DKV=1 (dV 2 + dK 3 + dQ 3)
+    split_bwd = os.environ.get("B200AD_ATTN_TF32", "0") == "1" or os.environ.get("B200AD_ATTN_SPLIT_DKV", "0") == "1"
+    attn_bwd_units = float(os.environ.get("B200AD_ATTN_BWD_UNITS", "8" if split_bwd else "7"))
     # dominant kernel = the GEMM shape with the largest accumulated device time in the timed region
     roof = None
     if gemm:
@@ -405,8 +408,8 @@ def run_c5(args):
             traffic = NCU_TRAFFIC_BYTES.get(tuple(int(v) for v in key[:4]))
         # tcgen05 kind::tf32 flops the kernel actually issues per algorithmic flop: three products per product
         # (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, the fp32-faithful split), and for the backward attention passes the
-        # flash-style recomputation of S (dV pass) and of S and dP (dK and dQ passes): (2 + 3 + 3) x 3 GEMM units issued
-        # per 4 algorithmic ones (backward = 2 x (QK^T + PV) = 8 S^2 d_k flops per (batch, head))
+        # flash-style recomputation of S and dP (once for the fused dK+dV pass, once for the dQ pass): (4 + 3) x 3 GEMM units
+        # issued per 4 algorithmic ones (backward = 2 x (QK^T + PV) = 8 S^2 d_k flops per (batch, head))
         if isinstance(key[0], str):
             issued = 3.0 if key[0] == "attn_fwd" else attn_bwd_units * 3.0 / 4.0
         else:

@@ -1,13 +1,6 @@
-timeout 600 python -m pytest tests/test_fused_attention.py -m gpu -q -x 2>&1 | tail -2
-timeout 200 python profiles/attn_probe.py timing 2>&1 | grep -E "micro-batch" 
-ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max,dram__bytes_read.sum --clock-control none -k regex:attn -c 16 --csv --log-file gpurun_out/attn_ncu.csv python profiles/attn_probe.py timing > gpurun_out/attn_ncu.log 2>&1
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(l for l in open('gpurun_out/attn_ncu.csv') if l.startswith('"'))]
-hdr=rows[0]; ki=hdr.index("Kernel Name"); mi=hdr.index("Metric Name"); vi=hdr.index("Metric Value"); ii=hdr.index("ID")
-out={}
-for r in rows[1:]:
-    out.setdefault((int(r[ii]), r[ki][:40]), {})[r[mi]]=r[vi]
-for k in sorted(out)[-4:]:
-    print(k, out[k])
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|FAILED|Error" | tail -5
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/r2l_bench.json 2>gpurun_out/r2l_bench.err; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2l_bench.json').read().splitlines() if l.startswith('{')][-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['roofline']['shares'], d['roofline']['tensor_pipe'])
 PY
