@@ -1081,10 +1081,13 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         ah_bar_sync(5, 256);
         rowx[gi][r] = l_run;
       }
+      // every owner warp stages its own 32 rows x 32 columns (4 KB, a 1024 B-aligned SWIZZLE_128B region) and stores it with
+      // its own TMA instruction: no 256-thread barriers in the epilogue (time-neutral against one store per CTA, measured)
       auto store_tile = [&](const float (&acc)[32], float mul, const CUtensorMap* m) {
-        if (tid == 0) ah_bulk_wait_read0();
-        ah_bar_sync(3, 256);
+        if (lane == 0) ah_bulk_wait_read0();                           // this warp's previous store has read its region
+        __syncwarp();
         if (MODE == AH_FWD) {
+          ah_bar_sync(3, 256);
           const float l_tot = l_run + rowx[gi ^ 1][r];                 // = 2^14 * (true row sum)
           mul = out_unscale * 16384.f / l_tot;                         // O = (OUT' / (2^14 s_V)) / (l_tot / 2^14)
           if (gi == 0 && row_ok) p.lse_w[(int64_t)bh * p.R + grow] = fmaf(m_run, c2e, log2f(l_tot) - 14.f);
@@ -1098,10 +1101,9 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ah_sts128(srow + ((c ^ (r & 7)) << 4), v);
         }
         fence_proxy_async();
-        ah_bar_sync(3, 256);
-        if (tid == 0) {
-          ah_tma_store_4d(m, out_stage, 0, rt * AH_BM, h, b);
-          ah_tma_store_4d(m, out_stage + 16384, 32, rt * AH_BM, h, b);
+        __syncwarp();
+        if (lane == 0) {
+          ah_tma_store_4d(m, out_stage + (uint32_t)gi * 16384u + (uint32_t)q * 4096u, gi * 32, rt * AH_BM + q * 32, h, b);
           ah_bulk_commit();
         }
       };
@@ -1111,7 +1113,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       AH_TR(2, itn, 15, 0, tid == 0);
       ++itn;
     }
-    if (tid == 0) ah_bulk_wait0();
+    if (lane == 0) ah_bulk_wait0();
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 128 + 128 * AH_CONV_GROUPS) {
       p.prof[8] = clock64() - prof_t0;
       for (int i = 0; i < 7; ++i) p.prof[9 + i] = prof_acc[i];
@@ -1256,7 +1258,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_b4, m_out, m_out2;
   int rc;
   AttnHTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
-  if ((rc = ah_encode(&m_out, to, B, H, AH_BM, true))) return rc;
+  if ((rc = ah_encode(&m_out, to, B, H, 32, true))) return rc;        // one box per owner warp: 32 rows x 32 columns
   if ((rc = ah_encode(&m_a1, a1, B, H, AH_BM, true))) return rc;
   if ((rc = ah_encode(&m_b1, b1, B, H, BROWS, true))) return rc;
   if ((rc = ah_encode(&m_b3, b3, B, H, AH_BC, false))) return rc;          // 64 kv rows x 32 d, unswizzled
@@ -1269,7 +1271,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   }
   if (MODE == AH_DKV) {
     AttnHTensor to2{p.out2, p.out2_bs, p.out2_hs, p.out2_ld, p.R};
-    if ((rc = ah_encode(&m_out2, to2, B, H, AH_BM, true))) return rc;
+    if ((rc = ah_encode(&m_out2, to2, B, H, 32, true))) return rc;
     if ((rc = ah_encode(&m_b4, b4, B, H, AH_BC, false))) return rc;
   } else {
     m_out2 = m_out;
