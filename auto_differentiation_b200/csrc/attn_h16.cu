@@ -57,6 +57,9 @@ constexpr int AH_CONV_GROUPS = 1;
 #ifndef AH_SPLIT_ISSUE
 #define AH_SPLIT_ISSUE 1
 #endif
+#ifndef AH_PINGPONG
+#define AH_PINGPONG 0
+#endif
 constexpr int AH_THREADS = 128 + 128 * AH_CONV_GROUPS + 256;
 constexpr uint32_t AH_SMEM = AH_RING_BYTES + 2 * AH_ASTAGE + 32768 + 1024;
 
@@ -196,6 +199,12 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
   // arrives on the first slot's barrier before the second's: the MMA thread waits on the second only, one wait per pair (a wait on its side is
   // not free even when the barrier has long completed: profiles/r1_mma_rate.log, ~150 cycles of idle tensor pipe each)
   constexpr bool MERGE = HAS2 && AH_CONV_GROUPS == 1;
+  // Row owners, backward modes, -DAH_PINGPONG=1: the two groups of four warps take ALTERNATE blocks (all 64 columns each)
+  // instead of half of every block, so that one group's waits overlap the other's math.  Measured at the config-5
+  // micro-batch: 2.01 ms against 1.96 ms in lockstep — block g and block g+2 share their X / Y buffers, so a group's next
+  // block waits for Z(g) -> OUT(g) -> X/Y(g+2) (~2100 cycles) after every block it converts, which lockstep hides behind
+  // the block in between.  Off by default; it would need a third score buffer (TMEM is full) to pay.
+  constexpr bool PINGPONG = AH_PINGPONG && MODE != AH_FWD;
   constexpr bool ROWSTAT = (MODE == AH_FWD || MODE == AH_DQ);   // lanes are query rows
   constexpr bool PAIRF = (MODE != AH_FWD);                      // backward modes: two blocks (128 K-elements) per OUT chain
   constexpr uint32_t A1_COL = 0, A2_COL = 64;
@@ -274,11 +283,11 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       mbar_init(&a_empty[i], 1);
       mbar_init(&x_full[i], 1);
       mbar_init(&y_full[i], 1);
-      mbar_init(&z_full[i], CP ? 16 : 256);
+      mbar_init(&z_full[i], PINGPONG ? (CP ? 8 : 128) : (CP ? 16 : 256));
       mbar_init(&out_full[i], 1);
       mbar_init(&out_empty[i], CP ? 16 : 256);
       mbar_init(&cs_full[i], 32);
-      mbar_init(&cs_empty[i], 8);
+      mbar_init(&cs_empty[i], PINGPONG ? 4 : 8);
       mbar_init(&o_issued[i], 1);
     }
     fence_barrier_init();
@@ -905,6 +914,10 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const uint32_t xaddr = lane_base + X_COL0 + bsel * 64u + cofs;      // this group's 32 x columns; its Z goes to the same 32
         const int col0 = j * AH_BC + (int)cofs;
         float* cs = colstat[bsel];
+        if (PINGPONG && (int)(g & 1) != gi) {          // the other group's block; fold the chain that just closed, if any
+          if (j >= 1 && ((j - 1) & 1)) fold(1.f);
+          continue;
+        }
         AH_T(b0);
         AH_TR(2, itn, j, 0, tid == 0);
         if (!ROWSTAT) mbar_wait(&cs_full[bsel], (g >> 1) & 1);      // this block's lse / D columns are in shared memory
@@ -958,63 +971,103 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           { AH_T(b3); AH_ACC(2, b2, b3); }     // load + math + store + arrive
           if (j >= 1) fold(a_prev);
           a_prev = alpha;
-        } else if (MODE == AH_DV) {
-          uint32_t x[32];
-          tmem_ld_32x32b_x32(xaddr, x);
-          tmem_ld_wait();
+        } else {
+          // ---- backward modes.  Lockstep: this thread's group converts its own 32 columns of every block.  Ping-pong: the
+          // thread converts all 64 columns (two column groups, one after the other) of every other block.
+          const int cq_lo = PINGPONG ? 0 : gi, cq_hi = PINGPONG ? 2 : gi + 1;
+          for (int cq = cq_lo; cq < cq_hi; ++cq) {
+            const uint32_t cm = (uint32_t)cq * 32u;
+            const uint32_t xa = lane_base + X_COL0 + bsel * 64u + cm, ya = lane_base + Y_COL0 + bsel * 64u + cm;
+            const int colm = j * AH_BC + (int)cm;
+            if (MODE == AH_DV) {
+              uint32_t x[32];
+              tmem_ld_32x32b_x32(xa, x);
+              tmem_ld_wait();
 #pragma unroll
-          for (int c4 = 0; c4 < 32; c4 += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
-            const float p0 = ah_exp2(fmaf(__uint_as_float(x[c4]), c2e, -l4.x));
-            const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
-            const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
-            const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
-            ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1]);
-            ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+              for (int c4 = 0; c4 < 32; c4 += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(cs + cm + c4);
+                const float p0 = ah_exp2(fmaf(__uint_as_float(x[c4]), c2e, -l4.x));
+                const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
+                const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
+                const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
+                ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1]);
+                ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+              }
+              ah_tmem_st_x16(xa, zh);
+              ah_tmem_st_x16(xa + 16, zl);
+            } else if (FUSED) {
+              // dK + dV: Z2 = P 2^14 (over the Y columns), Z1 = Z2 (Y c - D c) 2^(ez - 14) (over the X columns); in halves of
+              // 16 columns (register budget: two running tiles), each half's hi / lo pairs land on the 16 columns it has read
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                uint32_t x[16], y[16];
+                tmem_ld_32x32b_x16(xa + 16u * hf, x);
+                tmem_ld_32x32b_x16(ya + 16u * hf, y);
+                tmem_ld_wait();
+                uint32_t z1h[8], z1l[8], z2h[8], z2l[8];
+#pragma unroll
+                for (int c4 = 0; c4 < 16; c4 += 4) {
+                  const float4 l4 = *reinterpret_cast<const float4*>(cs + cm + 16 * hf + c4);
+                  const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cm + 16 * hf + c4);
+                  const float p0 = ah_exp2(fmaf(__uint_as_float(x[c4]), c2e, -l4.x));
+                  const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
+                  const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
+                  const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
+                  ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1]);
+                  ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1]);
+                  ah_split2(p0 * fmaf(__uint_as_float(y[c4]), ce, -d4.x), p1 * fmaf(__uint_as_float(y[c4 + 1]), ce, -d4.y),
+                            z1h[c4 >> 1], z1l[c4 >> 1]);
+                  ah_split2(p2 * fmaf(__uint_as_float(y[c4 + 2]), ce, -d4.z), p3 * fmaf(__uint_as_float(y[c4 + 3]), ce, -d4.w),
+                            z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1]);
+                }
+                ah_tmem_st_x8(xa + 16u * hf, z1h);
+                ah_tmem_st_x8(xa + 16u * hf + 8u, z1l);
+                ah_tmem_st_x8(ya + 16u * hf, z2h);
+                ah_tmem_st_x8(ya + 16u * hf + 8u, z2l);
+              }
+            } else {
+              // DQ / DK: Z = P (Y c - D c), carried times 2^ez
+              const bool full_block = colm + 32 <= p.C;
+              uint32_t x[32], y[32];
+              tmem_ld_32x32b_x32(xa, x);
+              tmem_ld_32x32b_x32(ya, y);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c4 = 0; c4 < 32; c4 += 4) {
+                float ls[4], dd[4], z[4];
+                if (MODE == AH_DQ) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    ls[i] = ls_r;
+                    dd[i] = d_r;
+                  }
+                  if (!full_block) {                       // only the last block of a row can be ragged
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      if (colm + c4 + i >= p.C) ls[i] = INFINITY;
+                  }
+                } else {
+                  const float4 l4 = *reinterpret_cast<const float4*>(cs + cm + c4);
+                  const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cm + c4);
+                  ls[0] = l4.x; ls[1] = l4.y; ls[2] = l4.z; ls[3] = l4.w;
+                  dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int c = c4 + i;
+                  const float pv = ah_exp2(fmaf(__uint_as_float(x[c]), c2e, -ls[i]));
+                  z[i] = pv * fmaf(__uint_as_float(y[c]), ce, -dd[i]);
+                }
+                ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1]);
+                ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+              }
+              ah_tmem_st_x16(xa, zh);
+              ah_tmem_st_x16(xa + 16, zl);
+            }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&cs_empty[bsel]);            // this warp has read the block's column statistics
-          ah_tmem_st_x16(xaddr, zh);
-          ah_tmem_st_x16(xaddr + 16, zl);
-          tmem_st_wait();
-          tc_fence_before();
-          arrive_leader(&z_full[bsel]);
-          { AH_T(b3); AH_ACC(2, b2, b3); }
-          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
-        } else if (FUSED) {
-          // dK + dV: Z2 = P 2^14 (over the Y columns), Z1 = Z2 (Y c - D c) 2^(ez - 14) (over the X columns); in two halves of
-          // 16 columns (register budget: two running tiles), each half's hi / lo pairs land on the 16 columns it has read
-          const uint32_t yaddr = lane_base + Y_COL0 + bsel * 64u + cofs;
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t x[16], y[16];
-            tmem_ld_32x32b_x16(xaddr + 16u * hf, x);
-            tmem_ld_32x32b_x16(yaddr + 16u * hf, y);
-            tmem_ld_wait();
-            uint32_t z1h[8], z1l[8], z2h[8], z2l[8];
-#pragma unroll
-            for (int c4 = 0; c4 < 16; c4 += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + 16 * hf + c4);
-              const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cofs + 16 * hf + c4);
-              const float p0 = ah_exp2(fmaf(__uint_as_float(x[c4]), c2e, -l4.x));
-              const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
-              const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
-              const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
-              ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1]);
-              ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1]);
-              ah_split2(p0 * fmaf(__uint_as_float(y[c4]), ce, -d4.x), p1 * fmaf(__uint_as_float(y[c4 + 1]), ce, -d4.y),
-                        z1h[c4 >> 1], z1l[c4 >> 1]);
-              ah_split2(p2 * fmaf(__uint_as_float(y[c4 + 2]), ce, -d4.z), p3 * fmaf(__uint_as_float(y[c4 + 3]), ce, -d4.w),
-                        z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1]);
-            }
-            if (hf == 1) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&cs_empty[bsel]);
-            }
-            ah_tmem_st_x8(xaddr + 16u * hf, z1h);
-            ah_tmem_st_x8(xaddr + 16u * hf + 8u, z1l);
-            ah_tmem_st_x8(yaddr + 16u * hf, z2h);
-            ah_tmem_st_x8(yaddr + 16u * hf + 8u, z2l);
+          if (!ROWSTAT) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs_empty[bsel]);            // this warp has read the block's column statistics
           }
           tmem_st_wait();
           tc_fence_before();
@@ -1023,53 +1076,6 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           AH_TR(2, itn, j, 3, tid == 0);
           if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
           AH_TR(2, itn, j, 4, tid == 0);
-        } else {
-          // DQ / DK: Z = P (Y c - D c), carried times 2^ez
-          const bool full_block = col0 + 32 <= p.C;
-          uint32_t x[32], y[32];
-          tmem_ld_32x32b_x32(xaddr, x);
-          tmem_ld_32x32b_x32(lane_base + Y_COL0 + bsel * 64u + cofs, y);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c4 = 0; c4 < 32; c4 += 4) {
-            float ls[4], dd[4], z[4];
-            if (MODE == AH_DQ) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                ls[i] = ls_r;
-                dd[i] = d_r;
-              }
-              if (!full_block) {                       // only the last block of a row can be ragged
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (col0 + c4 + i >= p.C) ls[i] = INFINITY;
-              }
-            } else {
-              const float4 l4 = *reinterpret_cast<const float4*>(cs + cofs + c4);
-              const float4 d4 = *reinterpret_cast<const float4*>(cs + 64 + cofs + c4);
-              ls[0] = l4.x; ls[1] = l4.y; ls[2] = l4.z; ls[3] = l4.w;
-              dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = c4 + i;
-              const float pv = ah_exp2(fmaf(__uint_as_float(x[c]), c2e, -ls[i]));
-              z[i] = pv * fmaf(__uint_as_float(y[c]), ce, -dd[i]);
-            }
-            ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1]);
-            ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
-          }
-          if (MODE == AH_DKM) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cs_empty[bsel]);
-          }
-          ah_tmem_st_x16(xaddr, zh);
-          ah_tmem_st_x16(xaddr + 16, zl);
-          tmem_st_wait();
-          tc_fence_before();
-          arrive_leader(&z_full[bsel]);
-          { AH_T(b3); AH_ACC(2, b2, b3); }
-          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
         }
       }
       fold(a_prev);
