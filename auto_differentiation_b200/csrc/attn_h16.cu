@@ -60,6 +60,9 @@ constexpr int AH_CONV_GROUPS = 1;
 #ifndef AH_PINGPONG
 #define AH_PINGPONG 0
 #endif
+#ifndef AH_CHAIN
+#define AH_CHAIN 2
+#endif
 constexpr int AH_THREADS = 128 + 128 * AH_CONV_GROUPS + 256;
 constexpr uint32_t AH_SMEM = AH_RING_BYTES + 2 * AH_ASTAGE + 32768 + 1024;
 
@@ -206,7 +209,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
   // the block in between.  Off by default; it would need a third score buffer (TMEM is full) to pay.
   constexpr bool PINGPONG = AH_PINGPONG && MODE != AH_FWD;
   constexpr bool ROWSTAT = (MODE == AH_FWD || MODE == AH_DQ);   // lanes are query rows
-  constexpr bool PAIRF = (MODE != AH_FWD);                      // backward modes: two blocks (128 K-elements) per OUT chain
+  constexpr bool PAIRF = (MODE != AH_FWD);                      // backward modes: AH_CHAIN blocks (64 K-elements each) per OUT chain
+  constexpr int CH = AH_CHAIN;
   constexpr uint32_t A1_COL = 0, A2_COL = 64;
   constexpr uint32_t X_COL0 = HAS2 ? 128u : 64u;
   constexpr uint32_t Y_COL0 = 256u;
@@ -464,7 +468,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           op += FUSED ? 2 : 1;
           continue;
         }
-        const bool first = !PAIRF || (j & 1) == 0, last = !PAIRF || (j & 1) == 1 || j == nb - 1;
+        const bool first = !PAIRF || (j % CH) == 0, last = !PAIRF || (j % CH) == CH - 1 || j == nb - 1;
         const uint32_t ob = FUSED ? 0u : (fo & 1), oph = FUSED ? (fo & 1) : ((fo >> 1) & 1);
         AH_T(w0);
         mbar_wait(&z_full[g & 1], (g >> 1) & 1);
@@ -915,7 +919,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const int col0 = j * AH_BC + (int)cofs;
         float* cs = colstat[bsel];
         if (PINGPONG && (int)(g & 1) != gi) {          // the other group's block; fold the chain that just closed, if any
-          if (j >= 1 && ((j - 1) & 1)) fold(1.f);
+          if (j >= 1 && ((j - 1) % CH) == CH - 1) fold(1.f);
           continue;
         }
         AH_T(b0);
@@ -1074,7 +1078,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           arrive_leader(&z_full[bsel]);
           { AH_T(b3); AH_ACC(2, b2, b3); }
           AH_TR(2, itn, j, 3, tid == 0);
-          if (j >= 1 && ((j - 1) & 1)) fold(1.f);      // block j-1 closed a two-block chain
+          if (j >= 1 && ((j - 1) % CH) == CH - 1) fold(1.f);      // block j-1 closed a chain
           AH_TR(2, itn, j, 4, tid == 0);
         }
       }
