@@ -1170,67 +1170,53 @@ __global__ void __launch_bounds__(256) attn_amax_kernel(const AhAmaxJobs jobs, f
   const int sub = threadIdx.x & 15;
   const int64_t first = (int64_t)blockIdx.x * AH_PRE_ROWS;
   if (first >= rows_total) return;
-  // (b, h, s) of this block's first row by 64-bit division ONCE; per row only 32-bit arithmetic relative to it
+  // The block's rows are walked slab segment by slab segment (a segment = the rows of one (batch, head) slab inside the
+  // block): the (b, h, s) arithmetic happens once per segment, the row loop is a strided 16 B load + max per thread with
+  // four loads in flight, and every warp issues one atomic per segment.  (Per-row slab bookkeeping made the first version
+  // instruction-bound: 71 % issue-active at 4.9 TB/s, profiles/r2_attn_passes_ncu.csv.)
   const int64_t bh_first = first / S;
-  const uint32_t s_first = (uint32_t)(first - bh_first * S), uS = (uint32_t)S, uH = (uint32_t)H;
+  const uint32_t uS = (uint32_t)S, uH = (uint32_t)H;
   const uint32_t rows_here = (uint32_t)((rows_total - first) < AH_PRE_ROWS ? (rows_total - first) : AH_PRE_ROWS);
-  int64_t cur_bh = -1;          // warp-uniform: both rows of a warp are forced onto the same slab per iteration (below)
-  float m = 0.f;
-  // four row groups per trip: their loads are issued together (one 16 B load per thread and trip left the kernel
-  // latency-bound at 3.1 TB/s: profiles/r2_attn_ncu_passes.csv)
-  constexpr int UN = 4;
-  for (int it0 = 0; it0 < AH_PRE_ROWS / 16; it0 += UN) {
-    int64_t rowv[UN], bhv[UN];
-    float4 gv[UN], av[UN];
+  uint32_t rl = 0, s0 = (uint32_t)(first - bh_first * S), bh = (uint32_t)bh_first;
+  const uint32_t rsub = threadIdx.x >> 4;
+  while (rl < rows_here) {
+    const uint32_t seg = (uS - s0) < (rows_here - rl) ? (uS - s0) : (rows_here - rl);
+    const uint32_t b = bh / uH, h = bh - b * uH;
+    const int64_t base = (int64_t)b * bs + (int64_t)h * hs + (int64_t)s0 * ld + sub * 4;
+    float* dv = DVEC ? jb.dvec + (first + rl) : nullptr;
+    float m = 0.f;
+    for (uint32_t rb = 0; rb < seg; rb += 64) {        // block-uniform trip count (the shuffles below need whole warps)
+      const uint32_t r0 = rb + rsub;
+      float4 gv[4], av[4];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint32_t rl = (uint32_t)((it0 + u) * 16 + (threadIdx.x >> 4));
-      const bool live = rl < rows_here;
-      const uint32_t s_lin = s_first + rl, dq = s_lin / uS;
-      rowv[u] = first + rl;
-      bhv[u] = live ? bh_first + dq : -1;
-      gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      av[u] = gv[u];
-      if (live) {
-        const uint32_t s_ = s_lin - dq * uS, ubh = (uint32_t)bhv[u], b = ubh / uH, h = ubh - b * uH;
-        const int64_t off = (int64_t)b * bs + (int64_t)h * hs + (int64_t)s_ * ld + sub * 4;
-        gv[u] = __ldg(reinterpret_cast<const float4*>(x + off));
-        if (DVEC) av[u] = __ldg(reinterpret_cast<const float4*>(o + off));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int64_t row = rowv[u], bh = bhv[u];
-      const bool live = bh >= 0;
-      // a warp covers two consecutive rows; if they straddle a slab boundary (or the end) flush and handle them separately
-      const int64_t bh_lo = __shfl_sync(0xffffffffu, bh, 0), bh_hi = __shfl_sync(0xffffffffu, bh, 16);
-      const float4 g = gv[u];
-      float mm = fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w)));
-      if (DVEC) {
-        const float4 a = av[u];
-        float v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
-#pragma unroll
-        for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
-        if (sub == 0 && live) jb.dvec[row] = v;
-      }
-      if (bh_lo == bh_hi) {
-        if (bh_lo != cur_bh) {
-          ah_amax_flush(m, cur_bh, amax, slot);
-          cur_bh = bh_lo;
-          m = 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t r = r0 + 16u * u;
+        gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        av[u] = gv[u];
+        if (r < seg) {
+          gv[u] = __ldg(reinterpret_cast<const float4*>(x + base + (int64_t)r * ld));
+          if (DVEC) av[u] = __ldg(reinterpret_cast<const float4*>(o + base + (int64_t)r * ld));
         }
-        m = fmaxf(m, mm);
-      } else {                       // rare: the two rows belong to different slabs -> flush the running value, then each half
-        ah_amax_flush(m, cur_bh, amax, slot);
-        cur_bh = -1;
-        m = 0.f;
+      }
 #pragma unroll
-        for (int ofs = 8; ofs > 0; ofs >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, ofs, 16));
-        if (sub == 0 && live && mm > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax + bh * 4 + slot), __float_as_uint(mm));
+      for (int u = 0; u < 4; ++u) {
+        const float4 g = gv[u];
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
+        if (DVEC) {
+          const float4 a = av[u];
+          float v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+#pragma unroll
+          for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
+          const uint32_t r = r0 + 16u * u;
+          if (sub == 0 && r < seg) dv[r] = v;
+        }
       }
     }
+    ah_amax_flush(m, (int64_t)bh, amax, slot);
+    rl += seg;
+    s0 = 0;
+    ++bh;
   }
-  ah_amax_flush(m, cur_bh, amax, slot);
 }
 
 // ---------------------------------------------------------------------------------------------------------

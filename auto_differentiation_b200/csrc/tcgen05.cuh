@@ -20,8 +20,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait is the potentially-blocking form: with a suspend-time hint (ns) the hardware parks the thread until the phase
+// completes or the hint runs out; without one the limit is short and a waiting warp spins through the loop below (36 % of
+// the instructions the fused attention backward executes, ncu source counters).  Parking was measured SLOWER, though:
+// -DB200AD_MBAR_HINT_NS=20000 takes the config-5 attention backward from 1.90 to 2.02-2.13 ms and the forward from 0.58 to
+// 0.61 ms (GEMMs unchanged) — the wake-up costs more than the issue slots the spinning takes.  Default: no hint.
+#ifndef B200AD_MBAR_HINT_NS
+#define B200AD_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if B200AD_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)B200AD_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -29,6 +46,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a launch failure (trap) after ~2 s instead of a hung GPU.
