@@ -868,7 +868,7 @@ int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
 
 // 0 = fp16 hi/lo split (generation 2), 1 = tf32 hi/lo split (generation 1).  Default: generation 1 for the forward pass
 // and generation 2 for the backward passes — measured at the config-5 micro-batch (256 sequences): forward 0.59 ms (tf32)
-// vs 0.84 ms (fp16, three slab-maximum pre-passes included), backward 2.45 ms (tf32) vs 2.31 ms (fp16).  -1 = that mix.
+// vs 0.77 ms (fp16, slab-maximum pre-pass included), backward 2.45 ms (tf32) vs 1.89 ms (fp16).  -1 = that mix.
 // 2 = generation 2 with dV and dK as two separate passes (the default fuses them into one).
 static std::atomic<int> g_attn_variant{getenv("B200AD_ATTN_TF32") ? 1 : (getenv("B200AD_ATTN_H16") ? 0 : -1)};
 
