@@ -1156,7 +1156,7 @@ struct AhAmaxJob {
   const float* o;        // non-null: also write dvec
   float* dvec;
   int64_t rows_total, bs, hs, ld;
-  int32_t S, slot;
+  int32_t S, slot, dk;
 };
 struct AhAmaxJobs { AhAmaxJob job[4]; };
 
@@ -1166,6 +1166,7 @@ __global__ void __launch_bounds__(256) attn_amax_kernel(const AhAmaxJobs jobs, f
   const float* __restrict__ o = jb.o;
   const int64_t rows_total = jb.rows_total, bs = jb.bs, hs = jb.hs, ld = jb.ld;
   const int S = jb.S, slot = jb.slot;
+  const bool col_ok = (int)(threadIdx.x & 15) * 4 < jb.dk;       // head sizes below 64: the row's tail lanes hold nothing
   const bool DVEC = o != nullptr;
   const int sub = threadIdx.x & 15;
   const int64_t first = (int64_t)blockIdx.x * AH_PRE_ROWS;
@@ -1193,7 +1194,7 @@ __global__ void __launch_bounds__(256) attn_amax_kernel(const AhAmaxJobs jobs, f
         const uint32_t r = r0 + 16u * u;
         gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         av[u] = gv[u];
-        if (r < seg) {
+        if (r < seg && col_ok) {
           gv[u] = __ldg(reinterpret_cast<const float4*>(x + base + (int64_t)r * ld));
           if (DVEC) av[u] = __ldg(reinterpret_cast<const float4*>(o + base + (int64_t)r * ld));
         }
@@ -1226,12 +1227,14 @@ struct AttnHTensor {
   const float* ptr;
   int64_t bs, hs, ld;
   int64_t rows;
+  int64_t dk = AH_DK;    // head dimension (<= 64, multiple of 4) = the tensor map's inner extent: columns dk .. 63 of every
+                         // 64-wide tile are TMA zero fill on the way in and clipped on the way out
 };
 
 static int ah_encode(CUtensorMap* map, const AttnHTensor& t, int64_t B, int64_t H, uint32_t box_rows, bool swizzle) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(B200AD_ERR_CUDA, "attention(h16): cuTensorMapEncodeTiled is not available");
-  cuuint64_t dims[4] = {(cuuint64_t)AH_DK, (cuuint64_t)t.rows, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t dims[4] = {(cuuint64_t)t.dk, (cuuint64_t)t.rows, (cuuint64_t)H, (cuuint64_t)B};
   const int64_t fallback = t.ld * t.rows;
   const int64_t hs = (H > 1) ? t.hs : fallback;
   const int64_t bs = (B > 1) ? t.bs : fallback;
@@ -1253,7 +1256,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   constexpr uint32_t BROWS = CP ? 32u : (uint32_t)AH_BC;
   CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_b4, m_out, m_out2;
   int rc;
-  AttnHTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
+  AttnHTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R, a1.dk};
   if ((rc = ah_encode(&m_out, to, B, H, 32, true))) return rc;        // one box per owner warp: 32 rows x 32 columns
   if ((rc = ah_encode(&m_a1, a1, B, H, AH_BM, true))) return rc;
   if ((rc = ah_encode(&m_b1, b1, B, H, BROWS, true))) return rc;
@@ -1266,7 +1269,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
     m_b2 = m_b1;
   }
   if (MODE == AH_DKV) {
-    AttnHTensor to2{p.out2, p.out2_bs, p.out2_hs, p.out2_ld, p.R};
+    AttnHTensor to2{p.out2, p.out2_bs, p.out2_hs, p.out2_ld, p.R, a1.dk};
     if ((rc = ah_encode(&m_out2, to2, B, H, 32, true))) return rc;
     if ((rc = ah_encode(&m_b4, b4, B, H, AH_BC, false))) return rc;
   } else {
@@ -1355,7 +1358,7 @@ static AhAmaxJob ah_job(const float* x, const b200ad_attn_strides& st, int64_t B
   AhAmaxJob j;
   j.x = x; j.o = o; j.dvec = dvec;
   j.rows_total = B * H * S; j.bs = st.batch; j.hs = st.head; j.ld = st.row;
-  j.S = (int32_t)S; j.slot = slot;
+  j.S = (int32_t)S; j.slot = slot; j.dk = AH_DK;
   return j;
 }
 
@@ -1382,10 +1385,12 @@ int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   jobs.job[1] = ah_job(k, d->k, B, H, d->seq_kv, 1);
   jobs.job[2] = ah_job(v, d->v, B, H, d->seq_kv, 2);
   jobs.job[3] = jobs.job[2];
+  for (int i = 0; i < 4; ++i) jobs.job[i].dk = (int32_t)d->head_dim;
   int rc;
   if ((rc = ah_prepass(jobs, 3, amax, B, H, s))) return rc;
-  AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
-      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv};
+  const int64_t hd = d->head_dim;
+  AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv, hd};
   AttnHParams p{};
   p.out = o; p.out_bs = d->o.batch; p.out_hs = d->o.head; p.out_ld = d->o.row;
   p.lse_w = lse; p.amax = amax;
@@ -1399,13 +1404,15 @@ int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   const int64_t B = d->batch, H = d->heads;
   float* dvec = ws;
   float* amax = ws + B * H * d->seq_q;
-  AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
-      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q};
+  const int64_t hd = d->head_dim;
+  AttnHTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv, hd}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q, hd};
   AhAmaxJobs jobs;
   jobs.job[0] = ah_job(q, d->q, B, H, d->seq_q, 0);
   jobs.job[1] = ah_job(k, d->k, B, H, d->seq_kv, 1);
   jobs.job[2] = ah_job(v, d->v, B, H, d->seq_kv, 2);
   jobs.job[3] = ah_job(dout, d->o, B, H, d->seq_q, 3, o, dvec);      // + D = rowsum(dO o O)
+  for (int i = 0; i < 4; ++i) jobs.job[i].dk = (int32_t)d->head_dim;
   int rc;
   if ((rc = ah_prepass(jobs, 4, amax, B, H, s))) return rc;
   AttnHParams p{};

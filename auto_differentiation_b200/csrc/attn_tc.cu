@@ -708,7 +708,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
 // D[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d]: 16 lanes (one float4 each) per (b, h, s) row of 64
 __global__ void __launch_bounds__(256) attn_dvec_kernel(const float* __restrict__ o, const float* __restrict__ dout,
                                                         float* __restrict__ dvec, int64_t rows_total, int H, int S,
-                                                        int64_t bs, int64_t hs, int64_t ld) {
+                                                        int64_t bs, int64_t hs, int64_t ld, int dk) {
   const int sub = threadIdx.x & 15;
   const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 4);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); row < rows_total; row += stride) {
@@ -716,9 +716,12 @@ __global__ void __launch_bounds__(256) attn_dvec_kernel(const float* __restrict_
     const int64_t s = row % S, bh = row / S;
     const int64_t h = bh % H, b = bh / H;
     const int64_t off = b * bs + h * hs + s * ld + sub * 4;
-    const float4 a = *reinterpret_cast<const float4*>(o + off);
-    const float4 g = *reinterpret_cast<const float4*>(dout + off);
-    float v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+    float v = 0.f;
+    if (sub * 4 < dk) {
+      const float4 a = *reinterpret_cast<const float4*>(o + off);
+      const float4 g = *reinterpret_cast<const float4*>(dout + off);
+      v = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+    }
 #pragma unroll
     for (int ofs = 8; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs, 16);
     if (sub == 0) dvec[row] = v;
@@ -732,12 +735,14 @@ struct AttnTensor {
   const float* ptr;
   int64_t bs, hs, ld;   // element strides: batch, head, row
   int64_t rows;         // sequence length of this tensor
+  int64_t dk = AT_DK;   // head dimension (<= 64, multiple of 4): the tensor map's inner extent; columns dk .. 63 of every
+                        // 64-wide tile are TMA zero fill on the way in and clipped on the way out
 };
 
 static int encode_attn(CUtensorMap* map, const AttnTensor& t, int64_t B, int64_t H, uint32_t box_rows, bool mn_major) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(B200AD_ERR_CUDA, "attention(tcgen05): cuTensorMapEncodeTiled is not available");
-  cuuint64_t dims[4] = {(cuuint64_t)AT_DK, (cuuint64_t)t.rows, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t dims[4] = {(cuuint64_t)t.dk, (cuuint64_t)t.rows, (cuuint64_t)H, (cuuint64_t)B};
   // a size-1 axis may carry any stride: give it a legal dummy (multiple of 16 B)
   const int64_t fallback = t.ld * t.rows;
   const int64_t hs = (H > 1) ? t.hs : fallback;
@@ -766,7 +771,7 @@ static int launch_pass_impl(const AttnTensor& a1, const AttnTensor& a2, const At
   constexpr uint32_t BROWS = CP ? 32u : (uint32_t)AT_BC;      // rows of a K-major B block staged per CTA
   CUtensorMap m_a1, m_a2, m_b1, m_b2, m_b3, m_out;
   int rc;
-  AttnTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R};
+  AttnTensor to{p.out, p.out_bs, p.out_hs, p.out_ld, p.R, a1.dk};
   if ((rc = encode_attn(&m_out, to, B, H, AT_BM, false))) return rc;
   if ((rc = encode_attn(&m_a1, a1, B, H, AT_BM, false))) return rc;
   if ((rc = encode_attn(&m_b1, b1, B, H, BROWS, false))) return rc;
@@ -851,7 +856,7 @@ static int launch_pass(const AttnTensor& a1, const AttnTensor& a2, const AttnTen
 static int attn_check(const b200ad_attn_desc* d, const char** why) {
   auto no = [&](const char* w) { if (why) *why = w; return 0; };
   if (!d) return no("null descriptor");
-  if (d->head_dim != AT_DK) return no("head_dim must be 64");
+  if (d->head_dim < 4 || d->head_dim > AT_DK || (d->head_dim & 3)) return no("head_dim must be a multiple of 4 in 4..64");
   if (d->batch < 1 || d->heads < 1 || d->seq_q < 1 || d->seq_kv < 1) return no("empty problem");
   if (d->batch * d->heads * ceil_div(d->seq_q > d->seq_kv ? d->seq_q : d->seq_kv, AT_BM) >= (1ll << 31)) return no("too many tiles");
   if (d->seq_q >= (1ll << 31) || d->seq_kv >= (1ll << 31)) return no("sequence too long");
@@ -907,8 +912,9 @@ int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, c
     B200AD_REQUIRE(ws, "attn_fwd: null workspace (b200ad_attn_fwd_ws_floats)");
     return attn_h16_fwd(d, q, k, v, o, lse, ws, (cudaStream_t)stream);
   }
-  AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
-      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv};
+  const int64_t hd = d->head_dim;
+  AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv, hd};
   AttnParams p{};
   p.out = o; p.out_bs = d->o.batch; p.out_hs = d->o.head; p.out_ld = d->o.row;
   p.lse_w = lse; p.lse = nullptr; p.dvec = nullptr;
@@ -933,12 +939,13 @@ int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, c
   if (const int var = g_attn_variant.load(std::memory_order_relaxed); var != 1)
     return attn_h16_bwd(d, q, k, v, o, dout, lse, dq, dk, dv, ws, var == 2, s);
   const int64_t B = d->batch, H = d->heads;
-  AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv},
-      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q};
+  const int64_t hd = d->head_dim;
+  AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},
+      tv{v, d->v.batch, d->v.head, d->v.row, d->seq_kv, hd}, tdo{dout, d->o.batch, d->o.head, d->o.row, d->seq_q, hd};
   // D = rowsum(dO o O)
   const int64_t rows = B * H * d->seq_q;
   attn_dvec_kernel<<<stream_grid(rows, 16), 256, 0, s>>>(o, dout, ws, rows, (int)H, (int)d->seq_q, d->o.batch, d->o.head,
-                                                         d->o.row);
+                                                         d->o.row, (int)d->head_dim);
   count_launch();
   int rc = check_launch("attention dvec");
   if (rc) return rc;

@@ -253,9 +253,10 @@ int b200ad_gemm_set_recurrent_dispatch(int mode);
  *         Test/MultiHeadAttentionTest.py:70-85: Matmul :530-533, Divide :1004-1005 without the 1e-8
  *         that only guards a zero denominator, exp :1058-1060, sum :699-704).
  *         dO shares `o`'s strides, dQ/dK/dV share q/k/v's.  ws: b200ad_attn_{fwd,bwd}_ws_floats floats of scratch.
- *   Built for head_dim == 64, any seq_q / seq_kv, strides multiples of 4 elements, 16 B aligned
- *   bases; b200ad_attn_supported says whether the fused path applies (otherwise the caller
- *   composes the same math from b200ad_gemm + b200ad_softmax_*).
+ *   Built for head_dim <= 64 and a multiple of 4 (tiles are 64 wide: smaller heads are zero-filled on the way in by the
+ *   tensor maps and clipped on the way out), any seq_q / seq_kv, strides multiples of 4 elements, 16 B aligned
+ *   bases; b200ad_attn_supported says whether the fused path applies (otherwise — e.g. the reference test's
+ *   d_k = 5, whose rows are not 16 B aligned — the caller composes the same math from b200ad_gemm + b200ad_softmax_*).
  * ------------------------------------------------------------------------------------------ */
 typedef struct b200ad_attn_strides {
   int64_t batch, head, row; /* element strides */

@@ -380,7 +380,7 @@ class Emulator:
 
     def b200ad_attn_supported(self, dref):
         d = dref._obj if hasattr(dref, "_obj") else dref
-        return 1 if d.head_dim == 64 else 0
+        return 1 if 4 <= d.head_dim <= 64 and d.head_dim % 4 == 0 else 0
 
     def b200ad_attn_bwd_ws_floats(self, dref):
         d = dref._obj if hasattr(dref, "_obj") else dref
@@ -405,8 +405,8 @@ class Emulator:
     def b200ad_attn_fwd(self, dref, q, k, v, o, lse, ws, s):
         self.launches += 1
         d = dref._obj if hasattr(dref, "_obj") else dref
-        if d.head_dim != 64:
-            return self._fail("attn_fwd: head_dim must be 64", -3)
+        if not (4 <= d.head_dim <= 64 and d.head_dim % 4 == 0):
+            return self._fail("attn_fwd: head_dim must be a multiple of 4 in 4..64", -3)
         _, _, P, ln_lse = self._attn_probs(d, q, k)
         V = self._attn_view(_ival(v), d.v, d.batch, d.heads, d.seq_kv, d.head_dim).astype(np.float64)
         self._attn_view(_ival(o), d.o, d.batch, d.heads, d.seq_q, d.head_dim)[...] = P @ V

@@ -79,6 +79,45 @@ def test_attn_fwd_bwd_vs_fp64(backend, B, h, Sq, Skv):
     assert_close(np.asarray(dK), dk_ref, rtol=2e-5, atol=2e-6, what="dK")
 
 
+@pytest.mark.parametrize("dk", [32, 16, 48, 8, 4])
+def test_attn_head_sizes_below_64(backend, dk):
+    """Head sizes that are multiples of 4 up to 64 run on the fused passes (64-wide tiles, zero fill beyond d_k): both
+    carriers, ragged lengths, against fp64.  (d_k = 5, the reference test's shape, is not 16 B aligned: composition path,
+    tests/test_layers_parity.py.)"""
+    D = _D()
+    B, h, Sq, Skv = 3, 2, 200, 136
+    rng = np.random.default_rng(dk)
+    q = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    k = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+    v = rng.standard_normal((B, h, Skv, dk)).astype(np.float32)
+    do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    scale = 1.0 / math.sqrt(dk)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    assert D.attn_supported(Q, K, V)
+    ref = _ref(q, k, v, do, scale)
+    variants = (-1,) if backend == "emu" else (-1, 0, 1)
+    lib = None
+    if backend != "emu":
+        from auto_differentiation_b200 import _lib as L
+        lib = L.load()
+    prev = lib.b200ad_attn_set_variant(-1) if lib else None
+    try:
+        for variant in variants:
+            if lib:
+                lib.b200ad_attn_set_variant(variant)
+            O, lse = D.attn_fwd(Q, K, V, scale)
+            dQ, dK, dV = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+            for a, r, name in zip((O, dQ, dK, dV), ref, ("O", "dQ", "dK", "dV")):
+                assert np.asarray(a).shape == r.shape
+                assert_close(np.asarray(a), r, rtol=2e-5, atol=2e-6, what="d_k=%d variant %d %s" % (dk, variant, name))
+    finally:
+        if lib:
+            lib.b200ad_attn_set_variant(prev)
+    # head sizes the fused passes do not take
+    bad = _heads(D, rng.standard_normal((1, 1, 16, 6)).astype(np.float32))
+    assert not D.attn_supported(bad, bad, bad)
+
+
 def test_attn_ragged_fuzz(backend):
     """Seeded random (batch, heads, seq_q, seq_kv) incl. lengths that are not multiples of the 128-row tile or the
     64-column block, odd tile counts, one-block and many-block rows."""
