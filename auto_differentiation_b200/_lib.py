@@ -89,6 +89,7 @@ SIGNATURES = {
     "b200ad_gemm_supported": (c_int, [POINTER(GemmDesc), P, P, P]),
     "b200ad_gemm_workspace_bytes": (c_int64, [POINTER(GemmDesc)]),
     "b200ad_gemm_set_recurrent_dispatch": (c_int, [c_int]),
+    "b200ad_gemm_reload_env": (c_int, []),
     "b200ad_attn_supported": (c_int, [POINTER(AttnDesc)]),
     "b200ad_attn_set_variant": (c_int, [c_int]),
     "b200ad_attn_fwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),
@@ -102,6 +103,10 @@ SIGNATURES = {
     "b200ad_rnn_seq_supported": (c_int, [I64, I64]),
     "b200ad_rnn_tanh_seq_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
     "b200ad_rnn_tanh_seq_bwd": (c_int, [P, I64, I64, P, P, P, P, I64, I64, I64, P]),
+    "b200ad_lstm_seq_supported": (c_int, [I64, I64]),
+    "b200ad_lstm_seq_workspace_bytes": (I64, [I64, I64]),
+    "b200ad_lstm_seq_fwd": (c_int, [P, P, P, P, P, I64, I64, I64, P, I64, P]),
+    "b200ad_lstm_seq_bwd": (c_int, [P, I64, I64, P, P, P, P, P, P, P, I64, I64, I64, P, I64, P]),
     "b200ad_bias_act_fwd": (c_int, [P, I64, P, P, I64, I64, I64, c_int, P]),
     "b200ad_act_bwd": (c_int, [P, I64, P, I64, P, I64, I64, I64, c_int, P]),
     "b200ad_adam_multi": (c_int, [P, c_int, I64, P, P, c_float, c_float, c_float, c_float, c_float, P, P]),

@@ -3,8 +3,21 @@
 // Reference bodies replaced: LSTM.forward layers.py:624-646, LSTM.backward :648-676 (gate part),
 // RNN.forward :166-173 / backward :175-177, FeedForward/ReLU :1242-1290, TimeAffine bias add :280.
 #include "common.cuh"
+#include "gemm_internal.cuh"
 
 namespace b200ad {
+
+// V consecutive floats of a split-K partial matrix (16 B load when V = 4: the partial rows are 16 B aligned then)
+template <int V>
+__device__ __forceinline__ void add_partial(float (&acc)[V], const float* __restrict__ p) {
+  if constexpr (V == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  } else {
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc[u] += __ldg(p + u);
+  }
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -26,6 +39,7 @@ __device__ __forceinline__ float act_bwd(float g, float y) {
 // One thread per (row, 4 hidden units) when VEC, else per (row, unit).
 template <bool VEC>
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const float* __restrict__ a, int64_t lda,
+                                                            const float* __restrict__ part, int splits, int64_t pstride,
                                                             const float* __restrict__ c_prev, int64_t ldcp,
                                                             float* __restrict__ gates, int64_t ldg,
                                                             float* __restrict__ c_next, int64_t ldcn,
@@ -46,6 +60,15 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const float* __restr
     } else {
       af[0] = a[r * lda + j]; ag[0] = a[r * lda + h + j]; ai[0] = a[r * lda + 2 * h + j];
       ao[0] = a[r * lda + 3 * h + j]; cp[0] = c_prev[r * ldcp + j];
+    }
+    if (part) {     // A += h_{t-1} Wh, still in split-K partial form ([split][n][4h]): summed here instead of in a pass of its own
+      const float* pr = part + r * 4 * h + j;
+      for (int sp = 0; sp < splits; ++sp, pr += pstride) {
+        add_partial<V>(af, pr);
+        add_partial<V>(ag, pr + h);
+        add_partial<V>(ai, pr + 2 * h);
+        add_partial<V>(ao, pr + 3 * h);
+      }
     }
 #pragma unroll
     for (int u = 0; u < V; ++u) {
@@ -73,6 +96,7 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const float* __restr
 template <bool VEC>
 __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
     const float* __restrict__ dh_a, int64_t ld_dha, const float* __restrict__ dh_b, int64_t ld_dhb,
+    const float* __restrict__ part, int splits, int64_t pstride,
     const float* __restrict__ dc_next, const float* __restrict__ gates, int64_t ldg,
     const float* __restrict__ c_prev, int64_t ldcp, const float* __restrict__ c_next, int64_t ldcn,
     float* __restrict__ da, int64_t ldda, float* __restrict__ dc_prev, int64_t n, int64_t h) {
@@ -101,6 +125,10 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
       if (dc_next) dcn[0] = dc_next[r * h + j];
       f[0] = gates[r * ldg + j]; g[0] = gates[r * ldg + h + j]; ii[0] = gates[r * ldg + 2 * h + j];
       o[0] = gates[r * ldg + 3 * h + j]; cp[0] = c_prev[r * ldcp + j]; cn[0] = c_next[r * ldcn + j];
+    }
+    if (part) {     // the recurrent gradient dA_{t+1} Wh^T in split-K partial form ([split][n][h])
+      const float* pr = part + r * h + j;
+      for (int sp = 0; sp < splits; ++sp, pr += pstride) add_partial<V>(dhb, pr);
     }
 #pragma unroll
     for (int u = 0; u < V; ++u) {
@@ -187,6 +215,41 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const float* __restri
 
 static inline bool ld_ok(int64_t ld) { return (ld & 3) == 0; }
 
+int lstm_cell_fwd_launch(const float* a, int64_t lda, const float* part, int splits, int64_t part_stride, const float* c_prev,
+                         int64_t ldc_prev, float* gates, int64_t ldg, float* c_next, int64_t ldc_next, float* h_next, int64_t ldh,
+                         int64_t n, int64_t h, cudaStream_t s) {
+  B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_fwd: negative shape");
+  if (n == 0 || h == 0) return B200AD_OK;
+  B200AD_REQUIRE(a && c_prev && gates && c_next && h_next, "lstm_cell_fwd: null pointer");
+  B200AD_REQUIRE(lda >= 4 * h && ldg >= 4 * h && ldc_prev >= h && ldc_next >= h && ldh >= h, "lstm_cell_fwd: bad ld");
+  const bool vec = (h % 4 == 0) && ld_ok(lda) && ld_ok(ldc_prev) && ld_ok(ldg) && ld_ok(ldc_next) && ld_ok(ldh) &&
+                   aligned16(a) && aligned16(c_prev) && aligned16(gates) && aligned16(c_next) && aligned16(h_next) &&
+                   (!part || (aligned16(part) && (part_stride & 3) == 0));
+  const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
+  if (vec) lstm_cell_fwd_kernel<true><<<grid, 256, 0, s>>>(a, lda, part, splits, part_stride, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h);
+  else lstm_cell_fwd_kernel<false><<<grid, 256, 0, s>>>(a, lda, part, splits, part_stride, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h);
+  count_launch();
+  return check_launch("lstm_cell_fwd");
+}
+
+int lstm_cell_bwd_launch(const float* dh_a, int64_t ld_dha, const float* dh_b, int64_t ld_dhb, const float* part, int splits,
+                         int64_t part_stride, const float* dc_next, const float* gates, int64_t ldg, const float* c_prev,
+                         int64_t ldc_prev, const float* c_next, int64_t ldc_next, float* da, int64_t ldda, float* dc_prev,
+                         int64_t n, int64_t h, cudaStream_t s) {
+  B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_bwd: negative shape");
+  if (n == 0 || h == 0) return B200AD_OK;
+  B200AD_REQUIRE(dh_a && gates && c_prev && c_next && da && dc_prev, "lstm_cell_bwd: null pointer");
+  const bool vec = (h % 4 == 0) && ld_ok(ld_dha) && (!dh_b || ld_ok(ld_dhb)) && ld_ok(ldg) && ld_ok(ldc_prev) &&
+                   ld_ok(ldc_next) && ld_ok(ldda) && aligned16(dh_a) && (!dh_b || aligned16(dh_b)) &&
+                   (!dc_next || aligned16(dc_next)) && aligned16(gates) && aligned16(c_prev) && aligned16(c_next) &&
+                   aligned16(da) && aligned16(dc_prev) && (!part || (aligned16(part) && (part_stride & 3) == 0));
+  const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
+  if (vec) lstm_cell_bwd_kernel<true><<<grid, 256, 0, s>>>(dh_a, ld_dha, dh_b, ld_dhb, part, splits, part_stride, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h);
+  else lstm_cell_bwd_kernel<false><<<grid, 256, 0, s>>>(dh_a, ld_dha, dh_b, ld_dhb, part, splits, part_stride, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h);
+  count_launch();
+  return check_launch("lstm_cell_bwd");
+}
+
 }  // namespace b200ad
 
 using namespace b200ad;
@@ -196,18 +259,8 @@ extern "C" {
 int b200ad_lstm_cell_fwd(const float* a, int64_t lda, const float* c_prev, int64_t ldc_prev, float* gates,
                          int64_t ldg, float* c_next, int64_t ldc_next, float* h_next, int64_t ldh, int64_t n,
                          int64_t h, void* stream) {
-  B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_fwd: negative shape");
-  if (n == 0 || h == 0) return B200AD_OK;
-  B200AD_REQUIRE(a && c_prev && gates && c_next && h_next, "lstm_cell_fwd: null pointer");
-  B200AD_REQUIRE(lda >= 4 * h && ldg >= 4 * h && ldc_prev >= h && ldc_next >= h && ldh >= h, "lstm_cell_fwd: bad ld");
-  const bool vec = (h % 4 == 0) && ld_ok(lda) && ld_ok(ldc_prev) && ld_ok(ldg) && ld_ok(ldc_next) && ld_ok(ldh) &&
-                   aligned16(a) && aligned16(c_prev) && aligned16(gates) && aligned16(c_next) && aligned16(h_next);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
-  if (vec) lstm_cell_fwd_kernel<true><<<grid, 256, 0, s>>>(a, lda, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h);
-  else lstm_cell_fwd_kernel<false><<<grid, 256, 0, s>>>(a, lda, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h);
-  count_launch();
-  return check_launch("lstm_cell_fwd");
+  return lstm_cell_fwd_launch(a, lda, nullptr, 0, 0, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h,
+                              (cudaStream_t)stream);
 }
 
 int b200ad_lstm_cell_bwd(const float* dh_a, int64_t ld_dha, const float* dh_b, int64_t ld_dhb, const float* dc_next,
@@ -215,19 +268,8 @@ int b200ad_lstm_cell_bwd(const float* dh_a, int64_t ld_dha, const float* dh_b, i
                          int64_t ldc_next, const float* h_next, int64_t ldh, float* da, int64_t ldda, float* dc_prev,
                          int64_t n, int64_t h, void* stream) {
   (void)h_next; (void)ldh;  // h' = o*tanh(c') is recomputed from the cached gates
-  B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_bwd: negative shape");
-  if (n == 0 || h == 0) return B200AD_OK;
-  B200AD_REQUIRE(dh_a && gates && c_prev && c_next && da && dc_prev, "lstm_cell_bwd: null pointer");
-  const bool vec = (h % 4 == 0) && ld_ok(ld_dha) && (!dh_b || ld_ok(ld_dhb)) && ld_ok(ldg) && ld_ok(ldc_prev) &&
-                   ld_ok(ldc_next) && ld_ok(ldda) && aligned16(dh_a) && (!dh_b || aligned16(dh_b)) &&
-                   (!dc_next || aligned16(dc_next)) && aligned16(gates) && aligned16(c_prev) && aligned16(c_next) &&
-                   aligned16(da) && aligned16(dc_prev);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
-  if (vec) lstm_cell_bwd_kernel<true><<<grid, 256, 0, s>>>(dh_a, ld_dha, dh_b, ld_dhb, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h);
-  else lstm_cell_bwd_kernel<false><<<grid, 256, 0, s>>>(dh_a, ld_dha, dh_b, ld_dhb, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h);
-  count_launch();
-  return check_launch("lstm_cell_bwd");
+  return lstm_cell_bwd_launch(dh_a, ld_dha, dh_b, ld_dhb, nullptr, 0, 0, dc_next, gates, ldg, c_prev, ldc_prev, c_next,
+                              ldc_next, da, ldda, dc_prev, n, h, (cudaStream_t)stream);
 }
 
 static int launch_act_bwd(const float* ga, int64_t ldga, const float* gb, int64_t ldgb, const float* y, int64_t ldy,

@@ -36,6 +36,11 @@ static std::atomic<int> g_recurrent_dispatch{0};
 
 extern "C" {
 
+int b200ad_gemm_reload_env(void) {
+  gemm_tc_reload_env();
+  return B200AD_OK;
+}
+
 int b200ad_gemm_set_recurrent_dispatch(int mode) {
   if (mode < 0 || mode > 2) return set_error(B200AD_ERR_INVALID, "gemm_set_recurrent_dispatch: mode %d not in 0..2", mode);
   return g_recurrent_dispatch.exchange(mode);

@@ -19,6 +19,8 @@
 // Both operand majors are fed natively: a row-major (rows x K) operand is K-major, a (K x cols) row-major
 // operand is MN-major (UMMA descriptor major bit), so NN / NT / TN / TT need no transposes.
 // Skinny problems (weight gradients: M,N ~ 512, K ~ 1e5) use split-K with a deterministic two-pass reduce.
+#include <atomic>
+#include <mutex>
 #include "common.cuh"
 #include "gemm_internal.cuh"
 #include "tcgen05.cuh"
@@ -1292,10 +1294,44 @@ static int encode_operand(CUtensorMap* map, const float* base, const OperandPlan
   return B200AD_OK;
 }
 
+// The tuning / debugging knobs of this file, read from the environment ONCE (ten getenv calls per launch were 2-5 us of
+// host time on paths that are host-bound: the recurrent steps, the B = 16 attention layer).  b200ad_gemm_reload_env()
+// re-reads them (profiles/gemm_tc_probe.py flips them between launches).
+struct TcEnv {      // parsed values (not the getenv pointers: the host language may replace the strings later)
+  bool has_bn, has_pair, has_chunk_kb, no_tma_store;
+  int bn, pair, stages, splits, mask_hi, atmem, probe, chunk_kb;
+};
+static std::atomic<int> g_tc_env_gen{1};
+static const TcEnv& tc_env() {
+  static TcEnv env;
+  static int seen = 0;
+  static std::mutex mu;
+  const int gen = g_tc_env_gen.load(std::memory_order_acquire);
+  if (seen != gen) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto num = [](const char* name, int dflt, bool* has = nullptr) {
+      const char* v = getenv(name);
+      if (has) *has = v != nullptr;
+      return v ? atoi(v) : dflt;
+    };
+    env.bn = num("B200AD_TC_BN", 0, &env.has_bn);
+    env.pair = num("B200AD_TC_PAIR", 3, &env.has_pair);
+    env.stages = num("B200AD_TC_STAGES", 0);
+    env.splits = num("B200AD_TC_SPLITS", 0);
+    env.mask_hi = num("B200AD_TC_MASK_HI", 0);
+    env.atmem = num("B200AD_TC_ATMEM", 1);
+    env.probe = num("B200AD_TC_PROBE", 0);
+    env.chunk_kb = num("B200AD_TC_CHUNK_KB", 0, &env.has_chunk_kb);
+    env.no_tma_store = getenv("B200AD_TC_NO_TMA_STORE") != nullptr;
+    seen = gen;
+  }
+  return env;
+}
+void gemm_tc_reload_env() { g_tc_env_gen.fetch_add(1, std::memory_order_acq_rel); }
+
 static int pick_bn(int64_t n) {
-  const char* env = getenv("B200AD_TC_BN");
-  if (env) {
-    int v = atoi(env);
+  if (tc_env().has_bn) {
+    const int v = tc_env().bn;
     if (v == 64 || v == 128 || v == 256) return v;
   }
   if (n <= 64) return 64;
@@ -1329,12 +1365,11 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   // the SMs by a deeper split-K.  Measured on the 64 x 1024 x 1024 step inside a CUDA graph: BN = 256 / 4 splits 19.3 us,
   // BN = 64 / 8 splits 9.7 us, 16 splits 11.6 us (profiles/r1_summary.md, config 4).  A fused "last CTA sums the
   // partials" epilogue was measured too: 38.8 us (one CTA's 128 threads are far slower than the grid-wide second pass).
-  const bool single_row_tile = pl.x3 && g.m <= TC_BM && g.n >= 256 && g.batch0 * g.batch1 == 1 && !getenv("B200AD_TC_BN");
+  const bool single_row_tile = pl.x3 && g.m <= TC_BM && g.n >= 256 && g.batch0 * g.batch1 == 1 && !tc_env().has_bn;
   if (single_row_tile) pl.bn = 64;
   // CTA-pair kernel: opt-in.  Measured on B200 (profiles/r1_gemm_tc_probe.md): +3..7 % on 4096^3 / 8192^3, but
   // -5 % on the (131072 x 512 x 512) projection shapes of config 5 (the chunk fold waits for two epilogues).
-  const char* ep = getenv("B200AD_TC_PAIR");
-  const int pair_mode = ep ? atoi(ep) : 3;
+  const int pair_mode = tc_env().pair;
   // Measured on B200 (profiles/r1_summary.md §4): the generation-3 pair kernel (A in TMEM, running totals in registers,
   // interleaved half-tile chains, compact TMA-store epilogue) beats the 1-CTA kernel on every 256-wide shape:
   // 131072 x 512 x 512 projections 150 -> 236, 8192^3 192 -> 260, split-K dW 179 -> 234, K = 256 gates 139 -> 225 TFLOP/s.
@@ -1349,8 +1384,7 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
                                  : (TC_BM * TC_BK * 4 + pl.bn * TC_BK * 4) * (pl.x3 ? 2 : 1);
   int st = (int)((TC_SMEM_LIMIT - 1024 - 256) / stage);
   if (st > 8) st = 8;
-  const char* env = getenv("B200AD_TC_STAGES");
-  if (env && atoi(env) >= 1 && atoi(env) <= st) st = atoi(env);
+  if (tc_env().stages >= 1 && tc_env().stages <= st) st = tc_env().stages;
   pl.stages = st;
   pl.smem_bytes = (uint32_t)st * stage + 1024 + 256;
   if (pl.pair) {   // 4 raw stages + 2 lo stages of 32 KB
@@ -1374,8 +1408,7 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
   }
-  const char* es = getenv("B200AD_TC_SPLITS");
-  if (es && atoi(es) >= 1) splits = atoi(es);
+  if (tc_env().splits >= 1) splits = tc_env().splits;
   pl.kblocks_per_split = (int)ceil_div(pl.kblocks_total, splits);
   pl.splits = (int)ceil_div(pl.kblocks_total, pl.kblocks_per_split);   // no empty splits
   return pl;
@@ -1405,8 +1438,9 @@ int64_t gemm_tc_workspace_bytes(const GemmArgs& g, int precision) {
   return (int64_t)pl.splits * pl.batches * g.m * g.n * 4;
 }
 
-int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes, cudaStream_t s) {
+int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes, cudaStream_t s, TcSplitInfo* split_out) {
   TcPlan pl = make_plan(g, precision);
+  if (split_out) *split_out = TcSplitInfo{nullptr, 1, 0};
   const int64_t need = pl.splits > 1 ? (int64_t)pl.splits * pl.batches * g.m * g.n * 4 : 0;
   if (need > 0 && (!ws || ws_bytes < need)) {
     // not enough workspace for split-K: run un-split
@@ -1443,20 +1477,16 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   // tcgen05 reads fp32 smem operands as tf32 by IGNORING the 13 low mantissa bits (measured: identical error with
   // and without rewriting the hi tile, profiles/gemm_tc_probe.py "x3 without hi masking"), so the raw tile already
   // is Ah = trunc(A); only the lo tile is materialised.  B200AD_TC_MASK_HI=1 restores the explicit rewrite.
-  const char* mh = getenv("B200AD_TC_MASK_HI");
-  p.mask_hi = mh ? atoi(mh) : 0;
+  p.mask_hi = tc_env().mask_hi;
   p.act = g.act; p.alpha = g.alpha; p.beta = g.beta;
-  const char* at = getenv("B200AD_TC_ATMEM");
-  p.a_tmem = at ? atoi(at) : 1;
+  p.a_tmem = tc_env().atmem;
   p.tma_store = 0;
-  const char* pb = getenv("B200AD_TC_PROBE");
-  p.probe = pb ? atoi(pb) : 0;
+  p.probe = tc_env().probe;
   // TMEM accumulation chain length: 128 K-elements (see the epilogue's fold).  Measured on B200
   // (profiles/gemm_tc_probe.py): max err/sqrt(K) 6.5e-6 at K=4096 (fp32 SIMT: 1.6e-5) for a 3 % slowdown; 8
   // k-blocks give 1.2e-5, no chunking grows linearly with K.  Single-pass TF32 is a 10-bit-mantissa probe
   // anyway, so it accumulates the whole K range in place.
-  const char* ck = getenv("B200AD_TC_CHUNK_KB");
-  int chunk_kb = ck ? atoi(ck) : 128 / TC_BK;
+  int chunk_kb = tc_env().has_chunk_kb ? tc_env().chunk_kb : 128 / TC_BK;
   if (chunk_kb < 1 || !pl.x3) chunk_kb = 1 << 30;
   p.chunked = (pl.kblocks_per_split > chunk_kb) ? 1 : 0;
   p.chunk_kb = p.chunked ? chunk_kb : (1 << 30);
@@ -1483,7 +1513,7 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
       const int64_t s1 = p.partial ? g.m * g.n : g.c_stride1, s0 = p.partial ? (int64_t)pl.batches * g.m * g.n : g.c_stride0;
       const int64_t d2 = p.partial ? pl.batches : g.batch1, d3 = p.partial ? pl.splits : g.batch0;
       const bool ok = (p.partial || g.beta == 0.f) && aligned16(cbase) && (ld & 3) == 0 && (d2 <= 1 || (s1 > 0 && (s1 & 3) == 0)) &&
-                      (d3 <= 1 || (s0 > 0 && (s0 & 3) == 0)) && !getenv("B200AD_TC_NO_TMA_STORE");
+                      (d3 <= 1 || (s0 > 0 && (s0 & 3) == 0)) && !tc_env().no_tma_store;
       if (ok) {
         EncodeTiledFn enc = get_encode_fn();
         const int64_t fb = ld * g.m;
@@ -1501,7 +1531,9 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
     count_launch();
     rc = check_launch("gemm(tcgen05 pair/TS)");
     if (rc) return rc;
-    if (pl.splits > 1) {
+    if (pl.splits > 1 && split_out) {
+      *split_out = TcSplitInfo{reinterpret_cast<const float*>(ws), pl.splits, g.m * g.n * pl.batches};
+    } else if (pl.splits > 1) {
       const int64_t total = g.m * g.n * pl.batches;
       splitk_reduce_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(ws), pl.splits, p);
       count_launch();
@@ -1522,7 +1554,9 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
     count_launch();
     rc = check_launch("gemm(tcgen05 pair)");
     if (rc) return rc;
-    if (pl.splits > 1) {
+    if (pl.splits > 1 && split_out) {
+      *split_out = TcSplitInfo{reinterpret_cast<const float*>(ws), pl.splits, g.m * g.n * pl.batches};
+    } else if (pl.splits > 1) {
       const int64_t total = g.m * g.n * pl.batches;
       splitk_reduce_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(ws), pl.splits, p);
       count_launch();
@@ -1547,7 +1581,9 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   count_launch();
   rc = check_launch("gemm(tcgen05)");
   if (rc) return rc;
-  if (pl.splits > 1) {
+  if (pl.splits > 1 && split_out) {
+    *split_out = TcSplitInfo{reinterpret_cast<const float*>(ws), pl.splits, g.m * g.n * pl.batches};
+  } else if (pl.splits > 1) {
     const int64_t total = g.m * g.n * pl.batches;
     splitk_reduce_kernel<<<stream_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(ws), pl.splits, p);
     count_launch();

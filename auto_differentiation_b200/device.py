@@ -1053,6 +1053,51 @@ def rnn_seq_supported(batch, hidden):
     return _rnn_seq_ok[key]
 
 
+_lstm_seq_ok = {}
+
+
+def lstm_seq_supported(batch, hidden):
+    """Whether the LSTM time loops run from one C call (csrc/lstm_seq.cu) for this (batch, hidden)."""
+    if not _persistent_recurrence[0]:
+        return False
+    key = (int(batch), int(hidden))
+    if key not in _lstm_seq_ok:
+        _lstm_seq_ok[key] = bool(_lib().b200ad_lstm_seq_supported(key[0], key[1]))
+    return _lstm_seq_ok[key]
+
+
+def _lstm_seq_ws(N, H):
+    nbytes = int(_lib().b200ad_lstm_seq_workspace_bytes(N, H))
+    return (empty(((nbytes + 3) // 4,)) if nbytes else None), nbytes
+
+
+def lstm_seq_fwd_(hs_ext, cs_ext, gates, pre, wh):
+    """hs_ext / cs_ext (T+1, N, H) with [0] = h_0 / c_0; pre (T, N, 4H) = x Wx + b (scratch afterwards); gates (T, N, 4H):
+    all T steps of the LSTM recurrence from one C call (two launches per step)."""
+    T1, N, H = hs_ext.shape
+    wh = wh.contiguous()
+    ws, nbytes = _lstm_seq_ws(N, H)
+    L.check(_lib().b200ad_lstm_seq_fwd(hs_ext.ptr, cs_ext.ptr, gates.ptr, pre.ptr, wh.ptr, T1 - 1, N, H,
+                                       ws.ptr if ws is not None else None, nbytes, stream_ptr()))
+    return hs_ext
+
+
+def lstm_seq_bwd(dhs, hs_ext, cs_ext, gates, wh):
+    """BPTT of the LSTM recurrence from one C call.  dhs: (N, T, H) view with a contiguous last axis.  Returns
+    (dA (T, N, 4H), dh0 (N, H))."""
+    T1, N, H = hs_ext.shape
+    T = T1 - 1
+    wh = wh.contiguous()
+    if dhs.t.stride(2) != 1 or (dhs.t.stride(0) & 3) or (dhs.t.stride(1) & 3) or (dhs.ptr & 15):
+        dhs = dhs.copy()
+    dA, dh0, dc = empty((T, N, 4 * H)), empty((N, H)), empty((2, N, H))
+    ws, nbytes = _lstm_seq_ws(N, H)
+    L.check(_lib().b200ad_lstm_seq_bwd(dhs.ptr, dhs.t.stride(0), dhs.t.stride(1), hs_ext.ptr, cs_ext.ptr, gates.ptr, wh.ptr,
+                                       dA.ptr, dh0.ptr, dc.ptr, T, N, H, ws.ptr if ws is not None else None, nbytes,
+                                       stream_ptr()))
+    return dA, dh0
+
+
 def rnn_tanh_seq_fwd_(hs_ext, pre, wh):
     """hs_ext (T+1, N, H) contiguous with hs_ext[0] = h_0; pre (T, N, H): hs_ext[t+1] = tanh(pre[t] + hs_ext[t] @ wh)
     for all t, in ONE launch."""

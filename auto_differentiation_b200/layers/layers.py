@@ -395,11 +395,15 @@ class TimeLSTM(_TimeRecurrent):
         gates = D.empty((T, N, 4 * H))
         D.copy_into_(self.h, hs_ext[0])
         D.copy_into_(self.c, cs_ext[0])
-        lib = L.load()
-        for t in range(T):
-            D.matmul(hs_ext[t], wh, out=pre[t], beta=1.0)   # A_t = x_t@wx + b + h_{t-1}@wh     :632
-            _cell_call(lib.b200ad_lstm_cell_fwd, pre[t].ptr, 4 * H, cs_ext[t].ptr, H, gates[t].ptr, 4 * H,
-                       cs_ext[t + 1].ptr, H, hs_ext[t + 1].ptr, H, N, H)
+        if D.lstm_seq_supported(N, H):
+            # all T dependent steps from one C call (csrc/lstm_seq.cu): two launches per step, no host-language loop
+            D.lstm_seq_fwd_(hs_ext, cs_ext, gates, pre, wh)
+        else:
+            lib = L.load()
+            for t in range(T):
+                D.matmul(hs_ext[t], wh, out=pre[t], beta=1.0)   # A_t = x_t@wx + b + h_{t-1}@wh     :632
+                _cell_call(lib.b200ad_lstm_cell_fwd, pre[t].ptr, 4 * H, cs_ext[t].ptr, H, gates[t].ptr, 4 * H,
+                           cs_ext[t + 1].ptr, H, hs_ext[t + 1].ptr, H, N, H)
         self.h, self.c = hs_ext[T], cs_ext[T]
         self._cache = (xs_tm, hs_ext, cs_ext, gates)
         out = hs_ext[1:].transpose(1, 0, 2)
@@ -412,6 +416,9 @@ class TimeLSTM(_TimeRecurrent):
         T, N, Dm = xs_tm.shape
         H = wh.shape[0]
         dhs = _last_contig(_dev(dhs))
+        if D.lstm_seq_supported(N, H):
+            dA, self.dh = D.lstm_seq_bwd(dhs, hs_ext, cs_ext, gates, wh)
+            return self._weight_grads(xs_tm, hs_ext[:T], dA)
         dA = D.empty((T, N, 4 * H))
         dc_bufs = (D.empty((N, H)), D.empty((N, H)))
         dh, dc = None, None

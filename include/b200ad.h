@@ -237,6 +237,8 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d);
  * single-launch exact-fp32 cluster kernel.  mode 0 (default) picks by whether `stream` is being captured into a
  * CUDA graph (device time vs host launch cost), 1 pins the first, 2 the second.  Returns the previous mode. */
 int b200ad_gemm_set_recurrent_dispatch(int mode);
+/* The B200AD_TC_* tuning / debugging environment knobs of the tcgen05 GEMM are read once; this re-reads them. */
+int b200ad_gemm_reload_env(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention core (tcgen05, fp32-faithful three-product split; scores never leave the SM).
@@ -313,6 +315,24 @@ int b200ad_rnn_tanh_seq_fwd(float* hs_ext, const float* pre, const float* wh, in
                             void* stream);
 int b200ad_rnn_tanh_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_stride_t, const float* hs_ext,
                             const float* wh, float* dA, float* dh0, int64_t T, int64_t N, int64_t H, void* stream);
+/* LSTM time loops from ONE call (csrc/lstm_seq.cu): the T dependent steps of TimeLSTM.forward (layers/layers.py:573-576,
+ * cell :624-646) and of its BPTT (:588-596, cell :648-676), two launches per step (tcgen05 split-K recurrent product +
+ * a cell kernel that sums the split-K partials) issued by a C loop instead of three per step from the host language.
+ *   fwd: hs_ext / cs_ext are (T+1, N, H) time-major with [0] = h_0 / c_0 on entry, [t+1] written; pre is (T, N, 4H) =
+ *        x_t Wx + b (gate order f | g | i | o, layers.py:636-639) and is scratch afterwards; gates (T, N, 4H) receives the
+ *        activated gates the backward needs; wh is (H, 4H) row-major.
+ *   bwd: dhs is element (n, t, :) at dhs + n*stride_n + t*stride_t (the (N, T, H) upstream gradient); dA (T, N, 4H) and
+ *        dh0 (N, H) = dL/dh_0 are written; dc_scratch: 2*N*H floats.
+ *   workspace: b200ad_lstm_seq_workspace_bytes(N, H) bytes.  b200ad_lstm_seq_supported says whether the shape runs on
+ *   this path (otherwise the caller loops over b200ad_gemm + b200ad_lstm_cell_*). */
+int b200ad_lstm_seq_supported(int64_t batch, int64_t hidden);
+int64_t b200ad_lstm_seq_workspace_bytes(int64_t batch, int64_t hidden);
+int b200ad_lstm_seq_fwd(float* hs_ext, float* cs_ext, float* gates, const float* pre, const float* wh, int64_t T,
+                        int64_t N, int64_t H, void* workspace, int64_t workspace_bytes, void* stream);
+int b200ad_lstm_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_stride_t, const float* hs_ext,
+                        const float* cs_ext, const float* gates, const float* wh, float* dA, float* dh0,
+                        float* dc_scratch, int64_t T, int64_t N, int64_t H, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 int b200ad_bias_act_fwd(const float* x, int64_t ldx, const float* bias, float* out, int64_t ldo,
                         int64_t rows, int64_t cols, int act, void* stream);
 /* gx = g * act'(y) (act: 1 tanh, 2 sigmoid, 3 relu on y) with row strides */

@@ -17,11 +17,11 @@ def run_group(group):
     import numpy as np
     import torch
     from auto_differentiation_b200 import _lib as L, device as D
-
     rng = np.random.default_rng(0)
 
     def case(name, M, N, K, ta=False, tb=False, prec="tf32", batch=None, alpha=1.0, beta=0.0, bias=False, act=0,
              time_it=False):
+        L.load().b200ad_gemm_reload_env()      # the library caches its B200AD_TC_* knobs; the groups below flip them
         try:
             bs = batch or ()
             A = rng.standard_normal(bs + ((K, M) if ta else (M, K)))

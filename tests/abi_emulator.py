@@ -335,6 +335,9 @@ class Emulator:
     def b200ad_gemm_supported(self, d, a, b, c):
         return 1
 
+    def b200ad_gemm_reload_env(self):
+        return 0
+
     def b200ad_gemm_set_recurrent_dispatch(self, mode):
         return 0
 
@@ -479,6 +482,38 @@ class Emulator:
         if dh_b:
             d = d + _rows(dh_b, ld_dhb, n, h)
         _rows(dt, lddt, n, h)[...] = self._actb(d, _rows(h_next, ldh, n, h).astype(np.float64), 1)
+        return 0
+
+    def b200ad_lstm_seq_supported(self, batch, hidden):
+        return 1 if (batch >= 1 and hidden >= 4 and hidden % 4 == 0 and batch * 4 * hidden * hidden >= (1 << 18)) else 0
+
+    def b200ad_lstm_seq_workspace_bytes(self, batch, hidden):
+        return 0
+
+    def b200ad_lstm_seq_fwd(self, hs_ext, cs_ext, gates, pre, wh, T, N, H, ws, ws_bytes, s):
+        w = _f32(wh, H * 4 * H).reshape(H, 4 * H).astype(np.float64)
+        for t in range(T):
+            a_t = _ival(pre) + 4 * t * N * 4 * H
+            A = _f32(a_t, N * 4 * H).reshape(N, 4 * H)
+            A[...] = A.astype(np.float64) + _f32(_ival(hs_ext) + 4 * t * N * H, N * H).reshape(N, H).astype(np.float64) @ w
+            self.launches += 1
+            self.b200ad_lstm_cell_fwd(a_t, 4 * H, _ival(cs_ext) + 4 * t * N * H, H, _ival(gates) + 4 * t * N * 4 * H, 4 * H,
+                                      _ival(cs_ext) + 4 * (t + 1) * N * H, H, _ival(hs_ext) + 4 * (t + 1) * N * H, H, N, H, s)
+        return 0
+
+    def b200ad_lstm_seq_bwd(self, dhs, sn, st, hs_ext, cs_ext, gates, wh, dA, dh0, dc_scratch, T, N, H, ws, ws_bytes, s):
+        w = _f32(wh, H * 4 * H).reshape(H, 4 * H).astype(np.float64)
+        have = False
+        for t in reversed(range(T)):
+            dc_out = _ival(dc_scratch) + 4 * (t & 1) * N * H
+            dc_in = None if t == T - 1 else _ival(dc_scratch) + 4 * ((t + 1) & 1) * N * H
+            da_t = _ival(dA) + 4 * t * N * 4 * H
+            self.b200ad_lstm_cell_bwd(_ival(dhs) + 4 * t * st, sn, _ival(dh0) if have else None, H, dc_in,
+                                      _ival(gates) + 4 * t * N * 4 * H, 4 * H, _ival(cs_ext) + 4 * t * N * H, H,
+                                      _ival(cs_ext) + 4 * (t + 1) * N * H, H, None, H, da_t, 4 * H, dc_out, N, H, s)
+            _f32(dh0, N * H).reshape(N, H)[...] = _f32(da_t, N * 4 * H).reshape(N, 4 * H).astype(np.float64) @ w.T
+            self.launches += 1
+            have = True
         return 0
 
     def b200ad_rnn_seq_supported(self, batch, hidden):

@@ -163,3 +163,36 @@ def test_rnn_seq_two_streams():
     torch.cuda.synchronize()
     for got, ref in zip(outs, lone):
         np.testing.assert_array_equal(np.asarray(got), ref)
+
+
+@pytest.mark.parametrize("N,T,Dm,H", [(16, 6, 24, 64), (64, 5, 32, 256), (33, 3, 16, 128)])
+def test_time_lstm_sequence_call_equals_loop_and_oracle(backend, N, T, Dm, H):
+    """TimeLSTM with the time loops issued from one C call (csrc/lstm_seq.cu: tcgen05 split-K recurrent product + a cell
+    kernel that sums the partials itself) against the oracle (TimeLSTM.forward / backward, layers/layers.py:561-597) and
+    against the per-step loop over b200ad_gemm + b200ad_lstm_cell_* it replaces (`set_persistent_recurrence(False)`)."""
+    from auto_differentiation_b200 import device as D
+    from auto_differentiation_b200.layers import layers as Ls
+    if not D.lstm_seq_supported(N, H):
+        pytest.skip("LSTM sequence call not available for N=%d H=%d" % (N, H))
+    rng = np.random.default_rng(N + T + H)
+    xs = rng.standard_normal((N, T, Dm))
+    Wx = rng.standard_normal((Dm, 4 * H)) / np.sqrt(Dm)
+    Wh = rng.standard_normal((H, 4 * H)) / np.sqrt(H)
+    b = rng.standard_normal(4 * H) * 0.1
+    dhs = rng.standard_normal((N, T, H))
+    hs_o, caches, _, _ = O.time_lstm_forward(xs, Wx, Wh, b)
+    dxs_o, (gWx, gWh, gb), dh_o = O.time_lstm_backward(caches, Wx, Wh, dhs)
+    outs = {}
+    for seq in (True, False):
+        D.set_persistent_recurrence(seq)
+        try:
+            layer = Ls.TimeLSTM(Wx, Wh, b)
+            hs = layer.forward(xs)
+            dxs = layer.backward(dhs)
+            outs[seq] = [np.asarray(a, dtype=np.float64) for a in (hs, dxs, *layer.grads, layer.dh)]
+        finally:
+            D.set_persistent_recurrence(True)
+        for got, ref, name in zip(outs[seq], (hs_o, dxs_o, gWx, gWh, gb, dh_o), ("hs", "dxs", "dWx", "dWh", "db", "dh0")):
+            assert_close(got, ref, rtol=2e-5, atol=2e-6, what="TimeLSTM %s (%s)" % (name, "one call" if seq else "per-step loop"))
+    for a, c, name in zip(outs[True], outs[False], ("hs", "dxs", "dWx", "dWh", "db", "dh0")):
+        assert_close(a, c, rtol=2e-5, atol=2e-6, what="TimeLSTM one call vs per-step loop: " + name)
