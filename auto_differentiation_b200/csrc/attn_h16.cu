@@ -17,16 +17,24 @@
 // maximum per operand element, entering sums that are dominated by the large terms — measured against fp64 the results
 // are as close as the 3xTF32 kernels' (tests/test_fused_attention.py runs every case through both).
 //
-// Same roles as attn_tc.cu (TMA producer, MMA issuer, 4 converter warps, 8 row-owner warps; 1-CTA and CTA-pair variants),
-// same barriers.  Differences:
+// Roles per CTA (512 threads; 1-CTA and CTA-pair variants): TMA producer (warp 0), two MMA-issuing warps (warp 1: score
+// products, warp 3: OUT products — one warp's waits and fences overlap the other's MMAs), column statistics (warp 2, the
+// kv-row-owner modes), 4 converter warps, 8 row-owner warps.  Against attn_tc.cu:
 //   * slot layout [raw fp32 16 KB | fp16 hi 8 KB | fp16 lo 8 KB]; EVERY B operand is a K-major SWIZZLE_128B fp16 tile
 //     (64 rows x 128 B): the converter transposes the (kv x d) blocks that feed the OUT products while it converts them,
-//     so no MN-major descriptor is needed (their TMA boxes are unswizzled for conflict-free column reads);
+//     so no MN-major descriptor is needed (their TMA boxes are unswizzled for conflict-free column reads); the two score
+//     operand blocks of a block (and AH_DKV's two OUT operand blocks) are converted in one trip;
 //   * A operands (and Z) sit in TMEM as packed fp16 pairs: 32 columns hi + 32 columns lo per 64 K-elements;
-//   * TMEM map: A1 [0,64) A2 [64,128) | X0 X1 | (Y0 Y1) | OUT0 OUT1; Z(j) overwrites X(j) as [g0 hi | g0 lo | g1 hi | g1 lo]
-//     (each owner group stays inside its own 32 columns), so the Y columns are free as soon as the owners have READ them:
-//     X(j+1) and Y(j+1) are both issued one block ahead and the owners never wait for a score product;
-//   * the backward modes fold every block (no two-block chains): an accumulation chain is 4 k-steps x 3 terms.
+//   * TMEM map: A1 [0,64) A2 [64,128) | X0 X1 | (Y0 Y1) | OUT0 OUT1; Z(j) overwrites X(j) (each owner group stays inside
+//     its own 32 columns), so the Y columns are free as soon as the owners have READ them: X(j+1) and Y(j+1) are both
+//     issued one block ahead;
+//   * modes: AH_FWD, AH_DQ (lanes = query rows), AH_DV, AH_DKM (lanes = kv rows; kept as the "separate passes" witness) and
+//     AH_DKV — dK and dV in ONE pass: S^T and P^T are computed once, Z1 = dS^T lands on the X columns and Z2 = P^T on the Y
+//     columns, the two OUT accumulators are single-buffered ([384,448) dK, [448,512) dV).  The default backward is
+//     pre-pass (slab maxima + D) -> AH_DKV -> AH_DQ;
+//   * the backward modes fold their OUT accumulators into registers every AH_CHAIN = 2 blocks (24 truncating accumulation
+//     steps per chain), with round-to-nearest adds.
+// DESIGN 3.4 has the measured account of what bounds these passes and of the variants that were tried.
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <cuda.h>
@@ -39,9 +47,9 @@ constexpr int AH_DK = 64;
 constexpr int AH_BM = 128;
 constexpr int AH_BC = 64;
 // shared memory: a ring for the B-operand blocks (128 KB: 4 slots of [raw 16 KB | hi 8 KB | lo 8 KB], or 8 half-size slots
-// when a CTA pair splits every block), two 32 KB staging tiles for the raw A operands, 32 KB for the output tile (written
-// straight from the owners' registers, 128 B per thread and row, the outputs measured 2.5x slower per item: the scattered
-// 16 B stores also slowed the converters' shared-memory traffic down).
+// when a CTA pair splits every block), two 32 KB staging tiles for the raw A operands, 32 KB for the output tile (TMA
+// stores; writing the outputs straight from the owners' registers, 128 B per thread and row, measured 2.5x slower per
+// item: the scattered 16 B stores also slowed the converters' shared-memory traffic down).
 // (The first version shared one ring of six 32 KB slots between A tiles and B blocks: the block that feeds the OUT product
 // then had a single block of lead over its consumer, and TMA latency + conversion showed up as ~700 cycles per block of
 // MMA-side waiting.)
@@ -51,8 +59,9 @@ constexpr int AH_BC = 64;
 constexpr uint32_t AH_RING_BYTES = AH_RING_KB * 1024u, AH_ASTAGE = 32768;
 constexpr int AH_MAXRING = AH_RING_BYTES / 16384;
 // Converter groups of four warps each.  Two groups (640 threads; registers 48 / 72 / 136) were measured against one (512
-// threads; 80 / 112 / 152): 2.38 ms vs 2.31 ms for the config-5 backward — the second group does not pay, because the
-// conversion is not what the MMA thread waits for (profiles/r2_attn_h16_prof.log) and the owners lose registers.
+// threads; 80 / 112 / 152) on the first three-pass version: 2.38 ms vs 2.31 ms for the config-5 backward — the second
+// group does not pay, because the conversion is not what the MMA thread waits for (profiles/r2_attn_h16_prof.log) and the
+// owners lose registers.  (The paired conversions and the one-wait-per-pair protocol below assume one group.)
 constexpr int AH_CONV_GROUPS = 1;
 #ifndef AH_SPLIT_ISSUE
 #define AH_SPLIT_ISSUE 1
