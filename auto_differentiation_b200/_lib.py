@@ -96,6 +96,7 @@ SIGNATURES = {
     "b200ad_attn_fwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P, P]),
     "b200ad_attn_bwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),
     "b200ad_attn_bwd": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P, P, P, P, P, P]),
+    "b200ad_attn_bwd_maxima": (c_int, [POINTER(AttnDesc), P, P, P, P, P, P, P, P, P, P, P, P]),
     "b200ad_lstm_cell_fwd": (c_int, [P, I64, P, I64, P, I64, P, I64, P, I64, I64, I64, P]),
     "b200ad_lstm_cell_bwd": (c_int, [P, I64, P, I64, P, P, I64, P, I64, P, I64, P, I64, P, I64, P,
                                      I64, I64, P]),

@@ -57,6 +57,9 @@ struct AttnParams {
   int32_t H, R, C;           // heads; extent of the lane dimension; extent of the column dimension
   int32_t row_tiles, nb, total_items;
   float c2, c;               // scale * log2(e), scale
+  float* amax_w;             // FWD, optional: (B*H, 4) table, slots 0..2 receive max |Q|, |K|, |V| of the (batch, head) slab
+                             // (atomic max on the bit patterns; zeroed by the launcher) — handed to the fp16-split backward,
+                             // which otherwise re-reads the three tensors for them
   long long* prof;           // -DAT_PROFILE: per-role cycle counters of block 0 (debug builds only)
   int32_t probe;             // diagnostic bits (results are garbage, only the rate matters): 1 = converter skips the B lo
                              // tiles, 2 = row owners skip the elementwise math and the Z stores, 4 = no TMA loads
@@ -390,6 +393,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t op = 0, it = 0;
+    const bool track = (MODE == AT_FWD) && p.amax_w != nullptr;
+    uint32_t mx_a = 0, mx_k = 0, mx_v = 0;        // running max |x| bit patterns of this thread's Q, K, V elements
     auto conv_a = [&](int which) {
       const uint32_t s = op % AT_NSLOT;
       mbar_wait(&full[s], (op / AT_NSLOT) & 1);
@@ -409,6 +414,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
+          if (MODE == AT_FWD) mx_a = max(mx_a, v[j] & 0x7fffffffu);
           const uint32_t hi = tf32_hi(v[j]);
           l[j] = tf32_lo(v[j], hi);
           v[j] = hi;
@@ -422,7 +428,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       named_bar_sync(1, 128);             // every converter thread has read its row: the slot can be refilled
       if (tid == 0) mbar_arrive(&empty[s]);
     };
-    auto conv_b = [&]() {
+    auto conv_b = [&](uint32_t& mx) {
       const uint32_t s = op % AT_NSLOT;
       mbar_wait(&full[s], (op / AT_NSLOT) & 1);
       ++op;
@@ -432,6 +438,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
       for (int i = 0; i < 8; ++i) {                           // pair: 8 KB raw -> 8 KB lo per CTA
         if (i >= n_vec) break;
         const uint4 v = lds128(raw + i * 2048);
+        if (MODE == AT_FWD) mx = max(max(mx, max(v.x & 0x7fffffffu, v.y & 0x7fffffffu)), max(v.z & 0x7fffffffu, v.w & 0x7fffffffu));
         uint4 l;
         l.x = tf32_lo(v.x, tf32_hi(v.x));
         l.y = tf32_lo(v.y, tf32_hi(v.y));
@@ -446,7 +453,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant
     for (int item = unit_id; item < p.total_items; item += units, ++it) {
       conv_a(0);
       if (HAS2) conv_a(1);
-      for (int i = 0; i < n_b; ++i) conv_b();
+      // FWD ring order of the B blocks: K(0), then { K(j), V(j-1) } for j = 1 .. nb-1, then V(nb-1)
+      for (int i = 0; i < n_b; ++i) conv_b((MODE != AT_FWD || i == 0 || (i < n_b - 1 && (i & 1))) ? mx_k : mx_v);
+      if (track) {      // one atomic per warp, slot and item ((batch, head) changes between items)
+        const int bh = item / p.row_tiles;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+          mx_a = max(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, ofs));
+          mx_k = max(mx_k, __shfl_xor_sync(0xffffffffu, mx_k, ofs));
+          mx_v = max(mx_v, __shfl_xor_sync(0xffffffffu, mx_v, ofs));
+        }
+        if (lane == 0) {
+          unsigned int* t = reinterpret_cast<unsigned int*>(p.amax_w + (int64_t)bh * 4);
+          if (mx_a) atomicMax(t + 0, mx_a);
+          if (mx_k) atomicMax(t + 1, mx_k);
+          if (mx_v) atomicMax(t + 2, mx_v);
+        }
+      }
+      mx_a = mx_k = mx_v = 0;
     }
   } else {
     // ===================================== row owners =====================================
@@ -868,12 +892,12 @@ static int attn_check(const b200ad_attn_desc* d, const char** why) {
 int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse, float* ws,
                  cudaStream_t s);
 int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
-                 const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, bool split_dkv,
-                 cudaStream_t s);
+                 const float* dout, const float* lse, const float* fwd_maxima, float* dq, float* dk, float* dv, float* ws,
+                 bool split_dkv, cudaStream_t s);
 
 // 0 = fp16 hi/lo split (generation 2), 1 = tf32 hi/lo split (generation 1).  Default: generation 1 for the forward pass
 // and generation 2 for the backward passes — measured at the config-5 micro-batch (256 sequences): forward 0.59 ms (tf32)
-// vs 0.77 ms (fp16, slab-maximum pre-pass included), backward 2.45 ms (tf32) vs 1.89 ms (fp16).  -1 = that mix.
+// vs 0.77 ms (fp16, slab-maximum pre-pass included), backward 2.45 ms (tf32) vs 1.80 ms (fp16).  -1 = that mix.
 // 2 = generation 2 with dV and dK as two separate passes (the default fuses them into one).
 static std::atomic<int> g_attn_variant{getenv("B200AD_ATTN_TF32") ? 1 : (getenv("B200AD_ATTN_H16") ? 0 : -1)};
 
@@ -920,6 +944,11 @@ int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, c
   p.lse_w = lse; p.lse = nullptr; p.dvec = nullptr;
   p.H = (int32_t)d->heads; p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
   p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
+  p.amax_w = ws;               // optional: slab maxima of Q / K / V for the backward (b200ad_attn_bwd_maxima)
+  if (ws) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 4 * d->batch * d->heads, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attn_fwd: memset: %s", cudaGetErrorString(e));
+  }
   return launch_pass<AT_FWD>(tq, tq, tk, tk, tv, p, d->batch, d->heads, (cudaStream_t)stream);
 }
 
@@ -930,6 +959,12 @@ int64_t b200ad_attn_bwd_ws_floats(const b200ad_attn_desc* d) {
 
 int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
                     const float* dout, const float* lse, float* dq, float* dk, float* dv, float* ws, void* stream) {
+  return b200ad_attn_bwd_maxima(d, q, k, v, o, dout, lse, nullptr, dq, dk, dv, ws, stream);
+}
+
+int b200ad_attn_bwd_maxima(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
+                           const float* dout, const float* lse, const float* fwd_ws, float* dq, float* dk, float* dv,
+                           float* ws, void* stream) {
   const char* why = "unsupported";
   if (!attn_check(d, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "attn_bwd: %s", why);
   B200AD_REQUIRE(tensor_ok(q, d->q) && tensor_ok(k, d->k) && tensor_ok(v, d->v) && tensor_ok(o, d->o) &&
@@ -937,7 +972,7 @@ int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, c
                  "attn_bwd: null / misaligned tensor or stride not a multiple of 4 elements");
   cudaStream_t s = (cudaStream_t)stream;
   if (const int var = g_attn_variant.load(std::memory_order_relaxed); var != 1)
-    return attn_h16_bwd(d, q, k, v, o, dout, lse, dq, dk, dv, ws, var == 2, s);
+    return attn_h16_bwd(d, q, k, v, o, dout, lse, fwd_ws, dq, dk, dv, ws, var == 2, s);
   const int64_t B = d->batch, H = d->heads;
   const int64_t hd = d->head_dim;
   AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},

@@ -950,17 +950,25 @@ def _timed(key, flops, call):
     timer.records.append((key, flops, e0, e1))
 
 
+class _Lse(DeviceArray):
+    """The log-sum-exp array a forward attention pass returns, carrying that pass's workspace: the kernel leaves the slab
+    maxima of Q / K / V in it, which saves the backward of the SAME q / k / v three tensor reads.  Views and copies are plain
+    DeviceArrays (the backward then computes the maxima itself)."""
+    __slots__ = ("fwd_ws",)
+
+
 def attn_fwd(q, k, v, scale):
     """O = softmax(scale * q k^T) v per (batch, head).  Returns (O as a (B, h, S, d) view of a (B, S, h, d)
     buffer — i.e. already in merged-head layout —, lse (B, h, S) in the log2 domain)."""
     B, H, Sq, dk = q.shape
     o = empty((B, Sq, H, dk)).transpose(0, 2, 1, 3)
-    lse = empty((B, H, Sq))
+    lse = _Lse(empty((B, H, Sq)).t)
     d = _attn_desc(q, k, v, o, scale)
     s = stream_ptr()
     ws = empty((max(1, int(_lib().b200ad_attn_fwd_ws_floats(ctypes.byref(d)))),))
     _timed(("attn_fwd", B, H, Sq, k.shape[2], dk), 4.0 * B * H * Sq * k.shape[2] * dk,
            lambda: L.check(_lib().b200ad_attn_fwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, lse.ptr, ws.ptr, s)))
+    lse.fwd_ws = ws
     return o, lse
 
 
@@ -990,12 +998,14 @@ def attn_bwd(q, k, v, o, dout, lse, scale):
         d = _attn_desc(q, k, v, o, scale)
         dq, dk_, dv = empty(q.shape), empty(k.shape), empty(v.shape)
     ws = empty((int(_lib().b200ad_attn_bwd_ws_floats(ctypes.byref(d))),))
+    fwd_ws = getattr(lse, "fwd_ws", None)          # the forward's slab maxima, if `lse` is the object attn_fwd returned
     s = stream_ptr()
     # algorithmic flops: backward = 2 x forward = 8 Sq Skv dk per (batch, head); the S / dP recomputation
     # the passes do is issued work, not algorithmic work
     _timed(("attn_bwd", B, H, Sq, Skv, dk), 8.0 * B * H * Sq * Skv * dk,
-           lambda: L.check(_lib().b200ad_attn_bwd(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr,
-                                                  dq.ptr, dk_.ptr, dv.ptr, ws.ptr, s)))
+           lambda: L.check(_lib().b200ad_attn_bwd_maxima(ctypes.byref(d), q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr,
+                                                         fwd_ws.ptr if fwd_ws is not None else None,
+                                                         dq.ptr, dk_.ptr, dv.ptr, ws.ptr, s)))
     return dq, dk_, dv
 
 

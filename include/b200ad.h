@@ -254,7 +254,8 @@ int b200ad_gemm_reload_env(void);
  *   bwd:  dQ, dK, dV of the same expression given dO (the tape gradients of
  *         Test/MultiHeadAttentionTest.py:70-85: Matmul :530-533, Divide :1004-1005 without the 1e-8
  *         that only guards a zero denominator, exp :1058-1060, sum :699-704).
- *         dO shares `o`'s strides, dQ/dK/dV share q/k/v's.  ws: b200ad_attn_{fwd,bwd}_ws_floats floats of scratch.
+ *         dO shares `o`'s strides, dQ/dK/dV share q/k/v's.  ws: b200ad_attn_{fwd,bwd}_ws_floats floats of scratch
+ *         (the forward's may be NULL on the default variant; when given, it receives the slab maxima of Q / K / V).
  *   Built for head_dim <= 64 and a multiple of 4 (tiles are 64 wide: smaller heads are zero-filled on the way in by the
  *   tensor maps and clipped on the way out), any seq_q / seq_kv, strides multiples of 4 elements, 16 B aligned
  *   bases; b200ad_attn_supported says whether the fused path applies (otherwise — e.g. the reference test's
@@ -271,6 +272,9 @@ typedef struct b200ad_attn_desc {
 } b200ad_attn_desc;
 int b200ad_attn_supported(const b200ad_attn_desc* d);
 int b200ad_attn_set_variant(int variant);
+/* b200ad_attn_bwd_maxima: b200ad_attn_bwd with the workspace of the b200ad_attn_fwd call on the SAME q / k / v (fwd_ws; may
+ * be NULL): the forward leaves max |Q|, |K|, |V| per (batch, head) in it, which saves the fp16-split backward three of the
+ * five tensor reads of its pre-pass. */
 int64_t b200ad_attn_fwd_ws_floats(const b200ad_attn_desc* d);
 int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
                     float* o, float* lse, float* ws, void* stream);
@@ -278,6 +282,9 @@ int64_t b200ad_attn_bwd_ws_floats(const b200ad_attn_desc* d);
 int b200ad_attn_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
                     const float* o, const float* dout, const float* lse, float* dq, float* dk,
                     float* dv, float* ws, void* stream);
+int b200ad_attn_bwd_maxima(const b200ad_attn_desc* d, const float* q, const float* k, const float* v,
+                           const float* o, const float* dout, const float* lse, const float* fwd_ws,
+                           float* dq, float* dk, float* dv, float* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Recurrent cells (elementwise halves; the gate GEMMs go through b200ad_gemm).

@@ -1,11 +1,8 @@
-L=auto_differentiation_b200/libb200ad.so
-cp $L /tmp/orig.so
-for rep in 1 2; do
-for v in head regs160 defer; do
-  cp profiles/_lib_$v.so $L
-  echo -n "$v: "; timeout 200 python profiles/attn_probe.py timing 2>&1 | grep -E "micro-batch bwd"
-done
-done
-cp profiles/_lib_defer.so $L
-timeout 300 python -m pytest tests/test_fused_attention.py -m gpu -q 2>&1 | tail -1
-cp /tmp/orig.so $L
+B200AD_PARITY_REPORT=gpurun_out/r2_parity_ledger_gpu.json timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|FAILED|Error" | tail -5
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c5_n1.json 2>gpurun_out/r2_bench_c5_n1.err; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_bench_c5_n1.json').read().splitlines() if l.startswith('{')][-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['roofline']['shares'])
+for k,v in d.get('workloads',{}).items(): print(k, v.get('value'), v.get('unit'), v.get('ms_per_step'))
+PY

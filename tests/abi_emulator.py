@@ -416,6 +416,9 @@ class Emulator:
         _f32(_ival(lse), d.batch * d.heads * d.seq_q)[:] = (ln_lse / np.log(2.0)).reshape(-1)
         return 0
 
+    def b200ad_attn_bwd_maxima(self, dref, q, k, v, o, dout, lse, fwd_ws, dq, dk, dv, ws, s):
+        return self.b200ad_attn_bwd(dref, q, k, v, o, dout, lse, dq, dk, dv, ws, s)
+
     def b200ad_attn_bwd(self, dref, q, k, v, o, dout, lse, dq, dk, dv, ws, s):
         self.launches += 4
         d = dref._obj if hasattr(dref, "_obj") else dref

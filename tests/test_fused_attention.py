@@ -344,3 +344,33 @@ def _ranges_body(D):
             for h_ in range(h):                              # per slab: the tolerance is relative to the SLAB's scale
                 sc = max(float(np.abs(r[b_, h_]).max()), 1e-300)
                 assert_close(a[b_, h_] / sc, r[b_, h_] / sc, rtol=5e-5, atol=5e-6, what="ranges %s slab (%d,%d)" % (name, b_, h_))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,h,Sq,Skv,dk", [(3, 2, 200, 136, 64), (2, 8, 512, 512, 64), (2, 3, 100, 300, 32)])
+def test_attn_forward_hands_slab_maxima_to_backward(B, h, Sq, Skv, dk):
+    """The forward leaves max |Q|, |K|, |V| per (batch, head) slab in its workspace; the backward of the same operands takes
+    them from there instead of re-reading the three tensors.  The table must equal the slab maxima exactly, and the
+    gradients must be bit-identical to a backward that computes the maxima itself."""
+    D = _D()
+    rng = np.random.default_rng(B + Sq + dk)
+    mag = np.exp(rng.uniform(np.log(1e-3), np.log(1e2), (3, B, h, 1, 1)))          # slabs of very different magnitude
+    q = (rng.standard_normal((B, h, Sq, dk)) * mag[0]).astype(np.float32)
+    k = (rng.standard_normal((B, h, Skv, dk)) * mag[1]).astype(np.float32)
+    v = (rng.standard_normal((B, h, Skv, dk)) * mag[2]).astype(np.float32)
+    do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    scale = 1.0 / (math.sqrt(dk) * float(np.abs(q).max() * np.abs(k).max()) ** 0.5)   # keeps the scores moderate
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    O, lse = D.attn_fwd(Q, K, V, scale)
+    table = getattr(lse, "fwd_ws", None)
+    assert table is not None
+    t = np.asarray(table).reshape(B * h, 4)
+    for slot, a in enumerate((q, k, v)):
+        assert np.array_equal(t[:, slot], np.abs(a).reshape(B * h, -1).max(axis=1)), "slab maxima, slot %d" % slot
+    with_hint = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    without = D.attn_bwd(Q, K, V, O, dO, D.DeviceArray(lse.t), scale)
+    for a, b_, name in zip(with_hint, without, ("dQ", "dK", "dV")):
+        assert np.array_equal(np.asarray(a), np.asarray(b_)), name
+    ref = _ref(q, k, v, do, scale)
+    for a, r, name in zip(with_hint, ref[1:], ("dQ", "dK", "dV")):
+        assert_close(np.asarray(a), r, rtol=2e-5, atol=2e-6, what="maxima from the forward: " + name)
