@@ -1366,7 +1366,10 @@ static TcPlan make_plan(const GemmArgs& g, int precision) {
   // BN = 64 / 8 splits 9.7 us, 16 splits 11.6 us (profiles/r1_summary.md, config 4).  A fused "last CTA sums the
   // partials" epilogue was measured too: 38.8 us (one CTA's 128 threads are far slower than the grid-wide second pass).
   const bool single_row_tile = pl.x3 && g.m <= TC_BM && g.n >= 256 && g.batch0 * g.batch1 == 1 && !tc_env().has_bn;
-  if (single_row_tile) pl.bn = 64;
+  // ... and 128-column tiles when they still fill the machine with >= 128 K-elements per split: half the re-reads of the
+  // activation rows, which every column tile loads (the LSTM's 4H-wide products: 64 x 4096 x 1024 15.2 vs 18.3 us,
+  // 64 x 1024 x 4096 14.7 vs 17.0 us per product + reduce, profiles/lstm_step_gemm_probe.py; BN = 256: 20 us)
+  if (single_row_tile) pl.bn = (ceil_div(g.n, 128) * (g.k / 128) >= num_sms()) ? 128 : 64;
   // CTA-pair kernel: opt-in.  Measured on B200 (profiles/r1_gemm_tc_probe.md): +3..7 % on 4096^3 / 8192^3, but
   // -5 % on the (131072 x 512 x 512) projection shapes of config 5 (the chunk fold waits for two epilogues).
   const int pair_mode = tc_env().pair;
