@@ -44,7 +44,11 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const float* __restr
                                                             float* __restrict__ gates, int64_t ldg,
                                                             float* __restrict__ c_next, int64_t ldcn,
                                                             float* __restrict__ h_next, int64_t ldh,
-                                                            int64_t n, int64_t h) {
+                                                            int64_t n, int64_t h, int pdl) {
+  if (pdl) {      // programmatic dependent launch (lstm_seq.cu): release the successor's set-up, wait for the predecessor's data
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   constexpr int V = VEC ? 4 : 1;
   const int64_t hv = h / V, total = n * hv;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -99,7 +103,11 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
     const float* __restrict__ part, int splits, int64_t pstride,
     const float* __restrict__ dc_next, const float* __restrict__ gates, int64_t ldg,
     const float* __restrict__ c_prev, int64_t ldcp, const float* __restrict__ c_next, int64_t ldcn,
-    float* __restrict__ da, int64_t ldda, float* __restrict__ dc_prev, int64_t n, int64_t h) {
+    float* __restrict__ da, int64_t ldda, float* __restrict__ dc_prev, int64_t n, int64_t h, int pdl) {
+  if (pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   constexpr int V = VEC ? 4 : 1;
   const int64_t hv = h / V, total = n * hv;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -215,9 +223,24 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const float* __restri
 
 static inline bool ld_ok(int64_t ld) { return (ld & 3) == 0; }
 
+static cudaLaunchConfig_t pdl_config(int grid, int block, cudaStream_t s, bool pdl) {
+  static thread_local cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.stream = s;
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cfg;
+}
+
 int lstm_cell_fwd_launch(const float* a, int64_t lda, const float* part, int splits, int64_t part_stride, const float* c_prev,
                          int64_t ldc_prev, float* gates, int64_t ldg, float* c_next, int64_t ldc_next, float* h_next, int64_t ldh,
-                         int64_t n, int64_t h, cudaStream_t s) {
+                         int64_t n, int64_t h, cudaStream_t s, bool pdl) {
   B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_fwd: negative shape");
   if (n == 0 || h == 0) return B200AD_OK;
   B200AD_REQUIRE(a && c_prev && gates && c_next && h_next, "lstm_cell_fwd: null pointer");
@@ -226,8 +249,11 @@ int lstm_cell_fwd_launch(const float* a, int64_t lda, const float* part, int spl
                    aligned16(a) && aligned16(c_prev) && aligned16(gates) && aligned16(c_next) && aligned16(h_next) &&
                    (!part || (aligned16(part) && (part_stride & 3) == 0));
   const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
-  if (vec) lstm_cell_fwd_kernel<true><<<grid, 256, 0, s>>>(a, lda, part, splits, part_stride, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h);
-  else lstm_cell_fwd_kernel<false><<<grid, 256, 0, s>>>(a, lda, part, splits, part_stride, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h);
+  cudaLaunchConfig_t cfg = pdl_config(grid, 256, s, pdl);
+  const int ipdl = pdl ? 1 : 0;
+  cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, lstm_cell_fwd_kernel<true>, a, lda, part, splits, part_stride, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h, ipdl)
+                      : cudaLaunchKernelEx(&cfg, lstm_cell_fwd_kernel<false>, a, lda, part, splits, part_stride, c_prev, ldc_prev, gates, ldg, c_next, ldc_next, h_next, ldh, n, h, ipdl);
+  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "lstm_cell_fwd: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("lstm_cell_fwd");
 }
@@ -235,7 +261,7 @@ int lstm_cell_fwd_launch(const float* a, int64_t lda, const float* part, int spl
 int lstm_cell_bwd_launch(const float* dh_a, int64_t ld_dha, const float* dh_b, int64_t ld_dhb, const float* part, int splits,
                          int64_t part_stride, const float* dc_next, const float* gates, int64_t ldg, const float* c_prev,
                          int64_t ldc_prev, const float* c_next, int64_t ldc_next, float* da, int64_t ldda, float* dc_prev,
-                         int64_t n, int64_t h, cudaStream_t s) {
+                         int64_t n, int64_t h, cudaStream_t s, bool pdl) {
   B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_bwd: negative shape");
   if (n == 0 || h == 0) return B200AD_OK;
   B200AD_REQUIRE(dh_a && gates && c_prev && c_next && da && dc_prev, "lstm_cell_bwd: null pointer");
@@ -244,8 +270,11 @@ int lstm_cell_bwd_launch(const float* dh_a, int64_t ld_dha, const float* dh_b, i
                    (!dc_next || aligned16(dc_next)) && aligned16(gates) && aligned16(c_prev) && aligned16(c_next) &&
                    aligned16(da) && aligned16(dc_prev) && (!part || (aligned16(part) && (part_stride & 3) == 0));
   const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
-  if (vec) lstm_cell_bwd_kernel<true><<<grid, 256, 0, s>>>(dh_a, ld_dha, dh_b, ld_dhb, part, splits, part_stride, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h);
-  else lstm_cell_bwd_kernel<false><<<grid, 256, 0, s>>>(dh_a, ld_dha, dh_b, ld_dhb, part, splits, part_stride, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h);
+  cudaLaunchConfig_t cfg = pdl_config(grid, 256, s, pdl);
+  const int ipdl = pdl ? 1 : 0;
+  cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel<true>, dh_a, ld_dha, dh_b, ld_dhb, part, splits, part_stride, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h, ipdl)
+                      : cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel<false>, dh_a, ld_dha, dh_b, ld_dhb, part, splits, part_stride, dc_next, gates, ldg, c_prev, ldc_prev, c_next, ldc_next, da, ldda, dc_prev, n, h, ipdl);
+  if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "lstm_cell_bwd: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("lstm_cell_bwd");
 }

@@ -10,6 +10,12 @@
 
 namespace b200ad {
 
+// Programmatic dependent launch: let the next kernel of the stream start its prologue / wait until the previous kernel of
+// the stream has completed and its writes are visible.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 // multiprocessor count of the current device (queried once per process; 148 on B200)

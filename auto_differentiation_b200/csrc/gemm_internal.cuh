@@ -15,6 +15,10 @@ struct GemmArgs {
   int64_t a_stride0, a_stride1, b_stride0, b_stride1, c_stride0, c_stride1;
   float alpha, beta;
   int trans_a, trans_b, act;
+  // programmatic dependent launch (the LSTM time loop, lstm_seq.cu): the kernel is launched with
+  // cudaLaunchAttributeProgrammaticStreamSerialization, sets itself up while its predecessor drains and waits
+  // (griddepcontrol.wait) before it touches global memory.  Only the 1-CTA tcgen05 kernels honour it.
+  int pdl = 0;
 };
 
 int gemm_simt_launch(const GemmArgs& p, cudaStream_t s);
@@ -37,11 +41,11 @@ int gemm_tc_launch(const GemmArgs& p, int precision, void* ws, int64_t ws_bytes,
 // takes sum_s part[s] as the recurrent gradient dh_b.
 int lstm_cell_fwd_launch(const float* a, int64_t lda, const float* part, int splits, int64_t part_stride, const float* c_prev,
                          int64_t ldc_prev, float* gates, int64_t ldg, float* c_next, int64_t ldc_next, float* h_next, int64_t ldh,
-                         int64_t n, int64_t h, cudaStream_t s);
+                         int64_t n, int64_t h, cudaStream_t s, bool pdl = false);
 int lstm_cell_bwd_launch(const float* dh_a, int64_t ld_dha, const float* dh_b, int64_t ld_dhb, const float* part, int splits,
                          int64_t part_stride, const float* dc_next, const float* gates, int64_t ldg, const float* c_prev,
                          int64_t ldc_prev, const float* c_next, int64_t ldc_next, float* da, int64_t ldda, float* dc_prev,
-                         int64_t n, int64_t h, cudaStream_t s);
+                         int64_t n, int64_t h, cudaStream_t s, bool pdl = false);
 
 // skinny fp32 kernel for the recurrent time steps, M <= 64 (gemm_skinny.cu)
 bool gemm_skinny_supported(const GemmArgs& p, bool host_bound);

@@ -56,6 +56,7 @@ struct TcParams {
   int32_t tma_store;           // gemm_tc3_kernel: the output tile leaves through shared memory + cp.async.bulk.tensor stores
   int32_t chunk_kb, chunked;   // TMEM accumulation chunk (k-blocks); chunked: buffer 0 = chunk sum X, buffer 1 = running total Y
   float alpha, beta;
+  int32_t pdl;                 // launched as a programmatic dependent: set up first, then wait for the predecessor's data
 };
 
 template <int ACT>
@@ -86,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.pdl) pdl_launch_dependents();       // the successor may begin ITS set-up; it waits for this grid's completion itself
   // TMEM: two accumulator buffers; when the chunk accumulators can ping-pong (BN <= 128) a third region holds the
   // running total Y, so the fold of chunk c overlaps the MMAs of chunk c+1.  BN = 256 has room for X and Y only.
   constexpr bool PINGPONG = (BN <= 128);
@@ -116,6 +118,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // barriers, tensor memory and descriptors are in place: from here on the kernel reads its operands and writes its output
+  if (p.pdl) pdl_wait();
 
   const int total_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;
 
@@ -1482,6 +1486,7 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
   // is Ah = trunc(A); only the lo tile is materialised.  B200AD_TC_MASK_HI=1 restores the explicit rewrite.
   p.mask_hi = tc_env().mask_hi;
   p.act = g.act; p.alpha = g.alpha; p.beta = g.beta;
+  p.pdl = 0;
   p.a_tmem = tc_env().atmem;
   p.tma_store = 0;
   p.probe = tc_env().probe;
@@ -1575,7 +1580,23 @@ int gemm_tc_launch(const GemmArgs& g, int precision, void* ws, int64_t ws_bytes,
       if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05): smem attribute: %s", cudaGetErrorString(e)); \
       attr_set = true;                                                                                          \
     }                                                                                                           \
-    gemm_tc_kernel<BNV><<<grid, TC_THREADS, pl.smem_bytes, s>>>(map_a, map_b, p, pl.stages);                    \
+    if (g.pdl) {                                                                                                \
+      p.pdl = 1;                                                                                                \
+      cudaLaunchConfig_t cfg = {};                                                                              \
+      cfg.gridDim = dim3((unsigned)grid);                                                                       \
+      cfg.blockDim = dim3(TC_THREADS);                                                                          \
+      cfg.dynamicSmemBytes = pl.smem_bytes;                                                                     \
+      cfg.stream = s;                                                                                           \
+      cudaLaunchAttribute attr[1];                                                                              \
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+      attr[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+      cfg.attrs = attr;                                                                                         \
+      cfg.numAttrs = 1;                                                                                         \
+      e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BNV>, map_a, map_b, (const TcParams)p, (const int)pl.stages); \
+      if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "gemm(tcgen05): launch: %s", cudaGetErrorString(e)); \
+    } else {                                                                                                    \
+      gemm_tc_kernel<BNV><<<grid, TC_THREADS, pl.smem_bytes, s>>>(map_a, map_b, p, pl.stages);                  \
+    }                                                                                                           \
   } while (0)
   if (pl.bn == 64) LAUNCH_BN(64);
   else if (pl.bn == 128) LAUNCH_BN(128);

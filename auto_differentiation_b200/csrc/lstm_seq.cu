@@ -7,9 +7,18 @@
 // (K = 4H) does not tile onto 148 SMs at all with tf32 pairs.  What this loop removes is the host side (the
 // reference-API time loop cost 19 ms per step eagerly against 12.9 ms of device time) and one third of the launches.
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm_internal.cuh"
 
 namespace b200ad {
+
+// Every launch of the loops is a programmatic dependent of the one before: its set-up (barriers, tensor memory, descriptor
+// prefetch, block scheduling) overlaps the predecessor's tail, and it waits for the predecessor's data itself.
+// B200AD_LSTM_NO_PDL=1 turns that off (A/B measurements).
+static bool lstm_pdl() {
+  static const bool v = getenv("B200AD_LSTM_NO_PDL") == nullptr;
+  return v;
+}
 
 static GemmArgs lstm_step_gemm(const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int64_t m,
                                int64_t n, int64_t k, int trans_b, float beta) {
@@ -20,6 +29,7 @@ static GemmArgs lstm_step_gemm(const float* a, int64_t lda, const float* b, int6
   g.batch0 = g.batch1 = 1;
   g.alpha = 1.f; g.beta = beta;
   g.trans_a = 0; g.trans_b = trans_b; g.act = 0;
+  g.pdl = lstm_pdl() ? 1 : 0;
   return g;
 }
 
@@ -72,7 +82,7 @@ int b200ad_lstm_seq_fwd(float* hs_ext, float* cs_ext, float* gates, const float*
     if (rc) return rc;
     // splits > 1: `pre` is left untouched and the cell sums x_t Wx + b + partials; otherwise the product already sits in a_t
     rc = lstm_cell_fwd_launch(a_t, 4 * H, sp.splits > 1 ? sp.partial : nullptr, sp.splits, sp.stride, cs_ext + t * nh, H,
-                              gates + t * 4 * nh, 4 * H, cs_ext + (t + 1) * nh, H, hs_ext + (t + 1) * nh, H, N, H, s);
+                              gates + t * 4 * nh, 4 * H, cs_ext + (t + 1) * nh, H, hs_ext + (t + 1) * nh, H, N, H, s, lstm_pdl());
     if (rc) return rc;
   }
   return B200AD_OK;
@@ -96,7 +106,7 @@ int b200ad_lstm_seq_bwd(const float* dhs, int64_t dhs_stride_n, int64_t dhs_stri
     const bool partial = have_dh && sp.splits > 1;
     int rc = lstm_cell_bwd_launch(dhs + t * dhs_stride_t, dhs_stride_n, (have_dh && !partial) ? dh0 : nullptr, H,
                                   partial ? sp.partial : nullptr, sp.splits, sp.stride, dc_in, gates + t * 4 * nh, 4 * H,
-                                  cs_ext + t * nh, H, cs_ext + (t + 1) * nh, H, da + t * 4 * nh, 4 * H, dc_out, N, H, s);
+                                  cs_ext + t * nh, H, cs_ext + (t + 1) * nh, H, da + t * 4 * nh, 4 * H, dc_out, N, H, s, lstm_pdl());
     if (rc) return rc;
     GemmArgs g = lstm_bwd_gemm(da + t * 4 * nh, wh, dh0, N, H);
     const char* why = "unsupported";
