@@ -245,7 +245,9 @@ int lstm_cell_fwd_launch(const float* a, int64_t lda, const float* part, int spl
   if (n == 0 || h == 0) return B200AD_OK;
   B200AD_REQUIRE(a && c_prev && gates && c_next && h_next, "lstm_cell_fwd: null pointer");
   B200AD_REQUIRE(lda >= 4 * h && ldg >= 4 * h && ldc_prev >= h && ldc_next >= h && ldh >= h, "lstm_cell_fwd: bad ld");
-  const bool vec = (h % 4 == 0) && ld_ok(lda) && ld_ok(ldc_prev) && ld_ok(ldg) && ld_ok(ldc_next) && ld_ok(ldh) &&
+  // (16 B accesses only when that still leaves every SM several warps: a recurrent step of 64 x 1024 units is latency-bound,
+  // 64 blocks of float4 threads measured slower than 256 blocks of scalar ones)
+  const bool vec = (h % 4 == 0) && n * h >= (int64_t)sm_count() * 2048 && ld_ok(lda) && ld_ok(ldc_prev) && ld_ok(ldg) && ld_ok(ldc_next) && ld_ok(ldh) &&
                    aligned16(a) && aligned16(c_prev) && aligned16(gates) && aligned16(c_next) && aligned16(h_next) &&
                    (!part || (aligned16(part) && (part_stride & 3) == 0));
   const int grid = stream_grid(n * h / (vec ? 4 : 1), 256);
@@ -265,7 +267,7 @@ int lstm_cell_bwd_launch(const float* dh_a, int64_t ld_dha, const float* dh_b, i
   B200AD_REQUIRE(n >= 0 && h >= 0, "lstm_cell_bwd: negative shape");
   if (n == 0 || h == 0) return B200AD_OK;
   B200AD_REQUIRE(dh_a && gates && c_prev && c_next && da && dc_prev, "lstm_cell_bwd: null pointer");
-  const bool vec = (h % 4 == 0) && ld_ok(ld_dha) && (!dh_b || ld_ok(ld_dhb)) && ld_ok(ldg) && ld_ok(ldc_prev) &&
+  const bool vec = (h % 4 == 0) && n * h >= (int64_t)sm_count() * 2048 && ld_ok(ld_dha) && (!dh_b || ld_ok(ld_dhb)) && ld_ok(ldg) && ld_ok(ldc_prev) &&
                    ld_ok(ldc_next) && ld_ok(ldda) && aligned16(dh_a) && (!dh_b || aligned16(dh_b)) &&
                    (!dc_next || aligned16(dc_next)) && aligned16(gates) && aligned16(c_prev) && aligned16(c_next) &&
                    aligned16(da) && aligned16(dc_prev) && (!part || (aligned16(part) && (part_stride & 3) == 0));
