@@ -48,6 +48,9 @@ CASES = [
     (3, 8, 512, 512),      # config 3/5 shape per sequence
     (40, 8, 128, 128),     # 320 work items > 148 SMs: persistent loop, odd/even block counts across items
     (25, 8, 192, 64),      # nb = 1: A tile released by the first score MMA
+    (2, 2, 1, 1),          # a single query against a single key
+    (1, 3, 5, 3),          # fewer rows than one warp, odd everything
+    (1, 1, 129, 65),       # one row / one column past a tile / block boundary
 ]
 
 

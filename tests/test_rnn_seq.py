@@ -165,7 +165,7 @@ def test_rnn_seq_two_streams():
         np.testing.assert_array_equal(np.asarray(got), ref)
 
 
-@pytest.mark.parametrize("N,T,Dm,H", [(16, 6, 24, 64), (64, 5, 32, 256), (33, 3, 16, 128)])
+@pytest.mark.parametrize("N,T,Dm,H", [(16, 6, 24, 64), (64, 5, 32, 256), (33, 3, 16, 128), (1, 1, 8, 256), (2, 7, 12, 512)])
 def test_time_lstm_sequence_call_equals_loop_and_oracle(backend, N, T, Dm, H):
     """TimeLSTM with the time loops issued from one C call (csrc/lstm_seq.cu: tcgen05 split-K recurrent product + a cell
     kernel that sums the partials itself) against the oracle (TimeLSTM.forward / backward, layers/layers.py:561-597) and
