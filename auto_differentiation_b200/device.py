@@ -40,10 +40,15 @@ def require_cuda():
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
 
 
 def stream_ptr():
-    """cudaStream_t of torch's current stream on the current device (the launch stream of every kernel)."""
+    """cudaStream_t of torch's current stream on the current device (the launch stream of every kernel).  Called once per
+    launch: goes through torch's C entry points directly (the Python wrappers cost ~1.5 us each, which shows on the
+    launch-latency-bound paths)."""
+    if _raw_stream is not None and _raw_device is not None and _cuda_ok[0]:
+        return _raw_stream(_raw_device())
     if _raw_stream is not None:
         return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
@@ -910,9 +915,22 @@ def _attn_strides(s, t):
     s.batch, s.head, s.row = (int(t.stride(0)), int(t.stride(1)), int(t.stride(2)))
 
 
+_attn_descs = {}       # (shapes, strides, dtypes, scale) -> AttnDesc | None: layers call the same geometry every step
+
+
 def _attn_desc(q, k, v, o, scale):
     """q/k/v/o: DeviceArray views (B, h, S, d) with a contiguous last axis, or None if that does not hold."""
     ts = [x.t for x in (q, k, v, o)]
+    key = (tuple((t.shape, t.stride(), t.dtype) for t in ts), float(scale))
+    if key in _attn_descs:
+        return _attn_descs[key]
+    if len(_attn_descs) > 512:
+        _attn_descs.clear()
+    d = _attn_descs[key] = _attn_desc_build(ts, scale)
+    return d
+
+
+def _attn_desc_build(ts, scale):
     if any(t.dim() != 4 or t.dtype != _F32 or (t.shape[3] > 1 and t.stride(3) != 1) for t in ts):
         return None
     B, H, Sq, dk = ts[0].shape
