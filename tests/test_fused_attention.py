@@ -377,3 +377,29 @@ def test_attn_forward_hands_slab_maxima_to_backward(B, h, Sq, Skv, dk):
     ref = _ref(q, k, v, do, scale)
     for a, r, name in zip(with_hint, ref[1:], ("dQ", "dK", "dV")):
         assert_close(np.asarray(a), r, rtol=2e-5, atol=2e-6, what="maxima from the forward: " + name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,h,Sq,Skv,dk", [(12, 8, 512, 512, 64), (9, 4, 333, 200, 64)])
+def test_attn_passes_bit_reproducible_under_load(B, h, Sq, Skv, dk):
+    """Two MMA-issuing warps, aliased score buffers and spin-wait hand-offs must not make a result depend on the schedule:
+    the same inputs give bit-identical O / lse / dQ / dK / dV on every repetition, with unrelated work in between
+    (profiles/attn_stress.py is the long version: 510 repetitions, profiles/r2_attn_stress.log)."""
+    import torch
+    D = _D()
+    g = torch.Generator(device="cuda").manual_seed(B + Sq)
+    bufs = [torch.randn((B, S, h * dk), device="cuda", generator=g) for S in (Sq, Skv, Skv, Sq)]
+    Q, K, V, dO = (D.DeviceArray(b).reshape(B, b.shape[1], h, dk).transpose(0, 2, 1, 3) for b in bufs)
+    scale = 1.0 / math.sqrt(dk)
+    noise = torch.randn((2048, 2048), device="cuda", generator=g)
+    ref = None
+    for i in range(12):
+        if i % 3 == 1:
+            noise = noise @ noise.T * 1e-4
+        O, lse = D.attn_fwd(Q, K, V, scale)
+        cur = [t.t.clone() for t in (O, lse) + tuple(D.attn_bwd(Q, K, V, O, dO, lse, scale))]
+        if ref is None:
+            ref = cur
+        else:
+            for name, a, b_ in zip(("O", "lse", "dQ", "dK", "dV"), ref, cur):
+                assert torch.equal(a, b_), "%s differs on repetition %d" % (name, i)
