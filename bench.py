@@ -114,12 +114,11 @@ NCU_TRAFFIC_BYTES = {
     (512, 64, 512, 2048): 2416e6 + 262e6,        # batched d_k=64 attention products (algorithmic: 2684 MB)
     (131072, 512, 512, 1): 269.6e6 + 224.9e6,    # projection, gemm_tc3_kernel (algorithmic: 537 MB)
     (512, 512, 131072, 1): 536.9e6 + 6.9e6,      # split-K weight gradient, gemm_tc3_kernel (algorithmic: 537 MB + partials in L2)
-    # fused attention, ncu at 256 sequences per launch (profiles/r2_attn_passes_ncu.csv): forward (tf32 split, CTA-pair pass),
-    # algorithmic 1074 MB; backward = dO-maximum / D pre-pass + fused dK+dV pass + dQ pass (fp16 split), algorithmic 2147 MB.
-    # (The pre-pass figure is its two tensor reads, dO and O: the maxima of Q / K / V come from the forward's workspace since
-    # the capture was taken, when the pre-pass still read all five tensors = 1342.3 MB.)
-    "attn_fwd": 805.4e6 + 247.1e6,
-    "attn_bwd": (536.9e6 + 3.6e6) + (1122.1e6 + 504.4e6) + (1082.3e6 + 251.0e6),
+    # fused attention, ncu at 256 sequences per launch (profiles/r2_attn_passes_ncu_final.csv): forward (tf32 split, CTA-pair
+    # pass), algorithmic 1074 MB; backward = dO-maximum / D pre-pass + fused dK+dV pass + dQ pass (fp16 split), algorithmic
+    # 2147 MB
+    "attn_fwd": 805.4e6 + 248.6e6,
+    "attn_bwd": (536.9e6 + 3.4e6) + (1162.0e6 + 504.9e6) + (1082.6e6 + 248.3e6),
 }
 
 
