@@ -89,6 +89,8 @@ struct AttnHParams {
   int32_t H, R, C;
   int32_t row_tiles, nb, total_items;
   float c2, c;               // scale * log2(e), scale
+  int32_t single;            // looser-tolerance variant: only the hi . hi product of every contraction is issued (11-bit
+                             // operands, the kind::f16 counterpart of a bf16 GEMM): a third of the MMA work
   long long* prof;           // debugging aid (B200AD_ATTN_PROF=1): cycle counters of CTA 0's MMA thread and one row owner
 };
 #define AH_T(var) long long var = 0; if (p.prof) var = clock64()
@@ -164,7 +166,14 @@ __device__ __forceinline__ void ah_tmem_st_x16(uint32_t taddr, const uint32_t (&
 // ---- the split: v (already scaled into fp16 range) = hi + lo, hi = v truncated to 11 significant bits (exactly an fp16
 // value while |v| >= 2^-14; below that the conversion rounds to the subnormal grid: an absolute error <= 2^-25), lo =
 // v - hi rounded to fp16.  Returns packed pairs (element 0 in the low half).
-__device__ __forceinline__ void ah_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+// `single` (the looser-tolerance variant, only hi . hi products are issued): hi = v rounded to nearest instead, lo unused.
+__device__ __forceinline__ void ah_split2(float v0, float v1, uint32_t& hi, uint32_t& lo, bool single = false) {
+  if (single) {
+    const __half2 hh = __floats2half2_rn(v0, v1);
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = 0u;
+    return;
+  }
   const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
   const __half2 hh = __floats2half2_rn(h0, h1);
   const __half2 ll = __floats2half2_rn(v0 - h0, v1 - h1);
@@ -415,12 +424,14 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       const uint32_t sb = smem_u32(smem + (size_t)s * AH_SLOT);
       const uint64_t dh = make_smem_desc(sb + AH_HI, 16, 1024, 2), dl = make_smem_desc(sb + AH_LO, 16, 1024, 2);
       const uint32_t dst = tmem_base + d_col, a_hi = tmem_base + a_col, a_lo = a_hi + 32u;
+      if (!p.single) {     // the two cross terms first (small), the dominant hi . hi term last
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_lo + kk * 8, dh + (uint64_t)(kk * 2), IDESC, kk ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_lo + kk * 8, dh + (uint64_t)(kk * 2), IDESC, kk ? 1u : 0u);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dl + (uint64_t)(kk * 2), IDESC, 1u);
+        for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dl + (uint64_t)(kk * 2), IDESC, 1u);
+      }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dh + (uint64_t)(kk * 2), IDESC, 1u);
+      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dh + (uint64_t)(kk * 2), IDESC, (kk || !p.single) ? 1u : 0u);
       mma_commit(&empty[s]);
       mma_commit(done);
       if (a_done) mma_commit(a_done);
@@ -506,12 +517,15 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             return FUSED ? zb + 32u * (kk >> 1) + 16u * (kk & 1) : zb + 32u * (kk >> 1) + 8u * (kk & 1);
           };
           auto zlo = [&](int kk) -> uint32_t { return zhi(kk) + (FUSED ? 8u : 16u); };
+          if (!p.single) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zlo(kk), dh + (uint64_t)(kk * 2), IDESC, (kk || !first) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zlo(kk), dh + (uint64_t)(kk * 2), IDESC, (kk || !first) ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zhi(kk), dl + (uint64_t)(kk * 2), IDESC, 1u);
+            for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zhi(kk), dl + (uint64_t)(kk * 2), IDESC, 1u);
+          }
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zhi(kk), dh + (uint64_t)(kk * 2), IDESC, 1u);
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts(dst, zhi(kk), dh + (uint64_t)(kk * 2), IDESC, (p.single && kk == 0 && first) ? 0u : 1u);
           mma_commit(&empty[slot]);
         };
         if (elect_one()) {
@@ -622,8 +636,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 #pragma unroll
         for (int c = 0; c < 8; ++c) {     // SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
           const uint4 t4 = ah_lds128(row + ((c ^ (r & 7)) << 4));
-          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * c], lo[2 * c]);
-          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * c + 1], lo[2 * c + 1]);
+          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * c], lo[2 * c], p.single);
+          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * c + 1], lo[2 * c + 1], p.single);
         }
         ah_tmem_st_x16(lane_base + col + hh * 16, hi);
         ah_tmem_st_x16(lane_base + col + 32 + hh * 16, lo);
@@ -654,8 +668,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       for (int i = 0; i < NV; ++i) {
         const int f = f0 + i, half = f >> 3, c = f & 7;
         const uint4 t4 = ah_lds128(slot + half * (ROWS * 128) + row * 128 + ((c ^ (row & 7)) << 4));
-        ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * i], lo[2 * i]);
-        ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * i + 1], lo[2 * i + 1]);
+        ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * i], lo[2 * i], p.single);
+        ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * i + 1], lo[2 * i + 1], p.single);
       }
       // fp16 tile: row = 128 B = 8 chunks of 8 elements; this thread's 8*NV/8... elements [8 f0 / 2 ...]: 4 floats -> 8 B,
       // so NV float4 -> NV/2 chunks starting at chunk f0 / 2
@@ -691,7 +705,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       for (int i = 0; i < NK / 2; ++i) {
         const float v0 = __uint_as_float(ah_lds32(src + (2 * i) * 128)) * sc;
         const float v1 = __uint_as_float(ah_lds32(src + (2 * i + 1) * 128)) * sc;
-        ah_split2(v0, v1, hi[i], lo[i]);
+        ah_split2(v0, v1, hi[i], lo[i], p.single);
       }
 #pragma unroll
       for (int i = 0; i < NK / 8; ++i) {                     // 8 kv elements = one 16 B chunk
@@ -742,8 +756,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const uint4 t4 = t ? tb[2 * i + u] : ta[2 * i + u];
-            ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * u], lo[2 * u]);
-            ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * u + 1], lo[2 * u + 1]);
+            ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * u], lo[2 * u], p.single);
+            ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * u + 1], lo[2 * u + 1], p.single);
           }
           const int ch = f0 / 2 + i;
           const uint32_t dst = row * 128 + ((ch ^ (row & 7)) << 4);
@@ -781,7 +795,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         for (int i = 0; i < NK / 2; ++i) {
           const float v0 = __uint_as_float(ah_lds32(slot + rel + (2 * i) * 128)) * sc;
           const float v1 = __uint_as_float(ah_lds32(slot + rel + (2 * i + 1) * 128)) * sc;
-          ah_split2(v0, v1, hi[i], lo[i]);
+          ah_split2(v0, v1, hi[i], lo[i], p.single);
         }
 #pragma unroll
         for (int i = 0; i < NK / 8; ++i) {
@@ -972,7 +986,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             const float p1 = ah_exp2(fmaf(__uint_as_float(x[c + 1]), c2e, -mc));
             sm[c & 3] += p0;
             sm[(c + 1) & 3] += p1;
-            ah_split2(p0, p1, zh[c >> 1], zl[c >> 1]);
+            ah_split2(p0, p1, zh[c >> 1], zl[c >> 1], p.single);
           }
           ah_tmem_st_x16(xaddr, zh);
           ah_tmem_st_x16(xaddr + 16, zl);
@@ -1003,8 +1017,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                 const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
                 const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
                 const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
-                ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1]);
-                ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+                ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1], p.single);
+                ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1], p.single);
               }
               ah_tmem_st_x16(xa, zh);
               ah_tmem_st_x16(xa + 16, zl);
@@ -1026,12 +1040,12 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                   const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
                   const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
                   const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
-                  ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1]);
-                  ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1]);
+                  ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1], p.single);
+                  ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1], p.single);
                   ah_split2(p0 * fmaf(__uint_as_float(y[c4]), ce, -d4.x), p1 * fmaf(__uint_as_float(y[c4 + 1]), ce, -d4.y),
-                            z1h[c4 >> 1], z1l[c4 >> 1]);
+                            z1h[c4 >> 1], z1l[c4 >> 1], p.single);
                   ah_split2(p2 * fmaf(__uint_as_float(y[c4 + 2]), ce, -d4.z), p3 * fmaf(__uint_as_float(y[c4 + 3]), ce, -d4.w),
-                            z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1]);
+                            z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1], p.single);
                 }
                 ah_tmem_st_x8(xa + 16u * hf, z1h);
                 ah_tmem_st_x8(xa + 16u * hf + 8u, z1l);
@@ -1071,8 +1085,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                   const float pv = ah_exp2(fmaf(__uint_as_float(x[c]), c2e, -ls[i]));
                   z[i] = pv * fmaf(__uint_as_float(y[c]), ce, -dd[i]);
                 }
-                ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1]);
-                ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1]);
+                ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1], p.single);
+                ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1], p.single);
               }
               ah_tmem_st_x16(xa, zh);
               ah_tmem_st_x16(xa + 16, zl);
@@ -1386,7 +1400,7 @@ static int ah_prepass(const AhAmaxJobs& jobs, int n_jobs, float* amax, int64_t B
 
 // entry points used by attn_tc.cu's extern "C" functions -------------------------------------------------------
 int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse, float* ws,
-                 cudaStream_t s) {
+                 bool single, cudaStream_t s) {
   const int64_t B = d->batch, H = d->heads;
   float* amax = ws;
   AhAmaxJobs jobs;
@@ -1403,6 +1417,7 @@ int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   AttnHParams p{};
   p.out = o; p.out_bs = d->o.batch; p.out_hs = d->o.head; p.out_ld = d->o.row;
   p.lse_w = lse; p.amax = amax;
+  p.single = single ? 1 : 0;
   p.H = (int32_t)H; p.R = (int32_t)d->seq_q; p.C = (int32_t)d->seq_kv;
   p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
   return ah_launch<AH_FWD>(tq, tq, tk, tk, tv, tv, p, B, H, s);
@@ -1410,7 +1425,7 @@ int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
 
 int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
                  const float* dout, const float* lse, const float* fwd_maxima, float* dq, float* dk, float* dv, float* ws,
-                 bool split_dkv, cudaStream_t s) {
+                 bool split_dkv, bool single, cudaStream_t s) {
   const int64_t B = d->batch, H = d->heads;
   float* dvec = ws;
   float* amax = ws + B * H * d->seq_q;
@@ -1437,6 +1452,7 @@ int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, cons
   }
   AttnHParams p{};
   p.lse = lse; p.dvec = dvec; p.amax = amax;
+  p.single = single ? 1 : 0;
   p.H = (int32_t)H;
   p.c = d->scale; p.c2 = d->scale * 1.4426950408889634f;
   p.R = (int32_t)d->seq_kv; p.C = (int32_t)d->seq_q;

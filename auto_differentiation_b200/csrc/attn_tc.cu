@@ -890,15 +890,17 @@ static int attn_check(const b200ad_attn_desc* d, const char** why) {
 
 // generation 2 (attn_h16.cu): the same passes carried by fp16 hi / lo pairs at the kind::f16 rate
 int attn_h16_fwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, float* o, float* lse, float* ws,
-                 cudaStream_t s);
+                 bool single, cudaStream_t s);
 int attn_h16_bwd(const b200ad_attn_desc* d, const float* q, const float* k, const float* v, const float* o,
                  const float* dout, const float* lse, const float* fwd_maxima, float* dq, float* dk, float* dv, float* ws,
-                 bool split_dkv, cudaStream_t s);
+                 bool split_dkv, bool single, cudaStream_t s);
 
 // 0 = fp16 hi/lo split (generation 2), 1 = tf32 hi/lo split (generation 1).  Default: generation 1 for the forward pass
 // and generation 2 for the backward passes — measured at the config-5 micro-batch (256 sequences): forward 0.59 ms (tf32)
 // vs 0.77 ms (fp16, slab-maximum pre-pass included), backward 2.45 ms (tf32) vs 1.80 ms (fp16).  -1 = that mix.
 // 2 = generation 2 with dV and dK as two separate passes (the default fuses them into one).
+// 3 = generation 2 issuing only the hi . hi product of every contraction: the looser-tolerance variant (11-bit operands,
+//     relative error ~1e-3 like a bf16 GEMM; north_star's "bf16 tensor-core variants to a stated looser tolerance").
 static std::atomic<int> g_attn_variant{getenv("B200AD_ATTN_TF32") ? 1 : (getenv("B200AD_ATTN_H16") ? 0 : -1)};
 
 }  // namespace b200ad
@@ -908,7 +910,7 @@ using namespace b200ad;
 extern "C" {
 
 int b200ad_attn_set_variant(int variant) {
-  if (variant < -1 || variant > 2) return set_error(B200AD_ERR_INVALID, "attn_set_variant: %d not in -1..2", variant);
+  if (variant < -1 || variant > 3) return set_error(B200AD_ERR_INVALID, "attn_set_variant: %d not in -1..3", variant);
   return g_attn_variant.exchange(variant);
 }
 
@@ -932,9 +934,9 @@ int b200ad_attn_fwd(const b200ad_attn_desc* d, const float* q, const float* k, c
   if (!attn_check(d, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "attn_fwd: %s", why);
   B200AD_REQUIRE(tensor_ok(q, d->q) && tensor_ok(k, d->k) && tensor_ok(v, d->v) && tensor_ok(o, d->o) && lse,
                  "attn_fwd: null / misaligned tensor or stride not a multiple of 4 elements");
-  if (const int var = g_attn_variant.load(std::memory_order_relaxed); var == 0 || var == 2) {      // (the default mix runs the forward on generation 1)
+  if (const int var = g_attn_variant.load(std::memory_order_relaxed); var == 0 || var == 2 || var == 3) {      // (the default mix runs the forward on generation 1)
     B200AD_REQUIRE(ws, "attn_fwd: null workspace (b200ad_attn_fwd_ws_floats)");
-    return attn_h16_fwd(d, q, k, v, o, lse, ws, (cudaStream_t)stream);
+    return attn_h16_fwd(d, q, k, v, o, lse, ws, var == 3, (cudaStream_t)stream);
   }
   const int64_t hd = d->head_dim;
   AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},
@@ -972,7 +974,7 @@ int b200ad_attn_bwd_maxima(const b200ad_attn_desc* d, const float* q, const floa
                  "attn_bwd: null / misaligned tensor or stride not a multiple of 4 elements");
   cudaStream_t s = (cudaStream_t)stream;
   if (const int var = g_attn_variant.load(std::memory_order_relaxed); var != 1)
-    return attn_h16_bwd(d, q, k, v, o, dout, lse, fwd_ws, dq, dk, dv, ws, var == 2, s);
+    return attn_h16_bwd(d, q, k, v, o, dout, lse, fwd_ws, dq, dk, dv, ws, var == 2, var == 3, s);
   const int64_t B = d->batch, H = d->heads;
   const int64_t hd = d->head_dim;
   AttnTensor tq{q, d->q.batch, d->q.head, d->q.row, d->seq_q, hd}, tk{k, d->k.batch, d->k.head, d->k.row, d->seq_kv, hd},

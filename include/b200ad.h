@@ -244,9 +244,12 @@ int b200ad_gemm_reload_env(void);
  * Fused multi-head attention core (tcgen05, fp32-faithful three-product split; scores never leave the SM).
  *   Two carriers of the same split: tf32 hi/lo pairs (csrc/attn_tc.cu, variant 1) and fp16 hi/lo pairs at the
  *   kind::f16 MMA rate with one power-of-two scale per (batch, head) operand slab (csrc/attn_h16.cu, variant 0).
- *   b200ad_attn_set_variant(-1 | 0 | 1 | 2) selects one and returns the previous choice; -1 (default) = the measured
+ *   b200ad_attn_set_variant(-1 | 0 | 1 | 2 | 3) selects one and returns the previous choice; -1 (default) = the measured
  *   best mix: forward on variant 1, backward on variant 0.  The fp16 backward computes dK and dV in ONE pass (S and P
- *   once for both); variant 2 = variant 0 with dV and dK as two separate passes (A/B measurements, second witness).
+ *   once for both); variant 2 = variant 0 with dV and dK as two separate passes (A/B measurements, second witness);
+ *   variant 3 = the LOOSER-TOLERANCE variant: variant 0 issuing only the hi . hi product of every contraction (fp16 operands
+ *   with 11 significant bits, fp32 accumulation): relative error ~1e-3 of the tensor scale, a third of the MMA work — the
+ *   attention counterpart of B200AD_GEMM_BF16.
  *   fwd:  O = softmax(scale * Q K^T) V  per (batch, head);  lse[b,h,s] = log2-domain log-sum-exp
  *         of the scaled scores of query row s (kept for the backward instead of the S x S matrix).
  *         replaces MultiHeadAttention.forward layers.py:1351-1357 (split heads are strided views:

@@ -1,12 +1,10 @@
-timeout 300 python -m pytest tests/test_fused_attention.py -m gpu -q -k "reproducible" 2>&1 | tail -1
-timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active \
-    --clock-control none -k regex:'attn' -s 4 -c 8 --csv --log-file gpurun_out/r2_attn_passes_ncu_final.csv python profiles/attn_probe.py timing > gpurun_out/attn_ncu.log 2>&1
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(l for l in open('gpurun_out/r2_attn_passes_ncu_final.csv') if l.startswith('"'))]
-hdr=rows[0]; ki=hdr.index("Kernel Name"); mi=hdr.index("Metric Name"); vi=hdr.index("Metric Value"); ii=hdr.index("ID")
-out={}
-for r in rows[1:]:
-    out.setdefault((int(r[ii]), r[ki][:36]), {})[r[mi].split('.')[0][-24:]]=r[vi]
-for k in sorted(out): print(k, out[k])
+timeout 600 python -m pytest tests/test_fused_attention.py -m gpu -q 2>&1 | grep -E "passed|failed|FAILED|Error|single-product" | sort -r | head -8
+B200AD_ATTN_H16=1 python - <<'PY'
+import os
 PY
+timeout 300 python bench.py --steps 5 --warmup 3 --precision bf16 --no-workloads --no-cpu-baseline > gpurun_out/r2_bench_c5_n1_bf16.json 2>gpurun_out/bf16.err; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_bench_c5_n1_bf16.json').read().splitlines() if l.startswith('{')][-1])
+print({k:d[k] for k in ('value','ms_per_step','dtype','loss')}, d['e2e']['value'], d['roofline']['kernel'], d['roofline']['avg_launch_ms'], d['roofline']['shares'])
+PY
+tail -3 gpurun_out/bf16.err

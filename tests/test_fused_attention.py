@@ -403,3 +403,32 @@ def test_attn_passes_bit_reproducible_under_load(B, h, Sq, Skv, dk):
         else:
             for name, a, b_ in zip(("O", "lse", "dQ", "dK", "dV"), ref, cur):
                 assert torch.equal(a, b_), "%s differs on repetition %d" % (name, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,h,Sq,Skv", [(2, 8, 512, 512), (3, 2, 200, 136)])
+def test_attn_looser_tolerance_variant(B, h, Sq, Skv):
+    """b200ad_attn_set_variant(3): only the hi . hi fp16 product of every contraction (operands rounded to 11 significant
+    bits, fp32 accumulation) — the attention counterpart of the bf16 GEMM variant (north_star: "to a stated looser
+    tolerance").  Stated tolerance: 4e-3 of the tensor scale (rtol = atol-of-scale = 4e-3); it must also be a DIFFERENT
+    result from the fp32-faithful one (else the variant is not being exercised)."""
+    D = _D()
+    from auto_differentiation_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(B * 7 + Sq)
+    dk, scale = 64, 1.0 / 8.0
+    q, k, v = (rng.standard_normal((B, h, S, dk)).astype(np.float32) for S in (Sq, Skv, Skv))
+    do = rng.standard_normal((B, h, Sq, dk)).astype(np.float32)
+    ref = _ref(q, k, v, do, scale)
+    Q, K, V, dO = (_heads(D, a) for a in (q, k, v, do))
+    prev = lib.b200ad_attn_set_variant(3)
+    try:
+        O, lse = D.attn_fwd(Q, K, V, scale)
+        grads = D.attn_bwd(Q, K, V, O, dO, lse, scale)
+    finally:
+        lib.b200ad_attn_set_variant(prev)
+    got = [np.asarray(a, dtype=np.float64) for a in (O,) + tuple(grads)]
+    for a, r, name in zip(got, ref, ("O", "dQ", "dK", "dV")):
+        assert_close(a, r, rtol=4e-3, atol=4e-3, what="single-product variant " + name)
+    worst = max(float(np.abs(a - r).max() / np.abs(r).max()) for a, r in zip(got, ref))
+    assert worst > 2e-5, "variant 3 produced fp32-faithful results: the single-product path was not taken"
