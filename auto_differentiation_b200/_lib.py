@@ -22,7 +22,7 @@ U_COT, U_CSC, U_ARCCOS = range(26, 29)
 B_ADD, B_SUB, B_MUL, B_DIV = range(4)
 FULL, ROW, COL, SCALAR = range(4)
 # enum b200ad_gemm_precision
-GEMM_FP32, GEMM_TF32X3, GEMM_BF16, GEMM_AUTO, GEMM_TF32 = range(5)
+GEMM_FP32, GEMM_TF32X3, GEMM_BF16, GEMM_AUTO, GEMM_TF32, GEMM_F16X3 = range(6)
 ACT_NONE, ACT_TANH, ACT_SIGMOID, ACT_RELU = range(4)
 OPT_CHUNK = 4096
 ARG_WS_BYTES = 1184 * 8 + 1184 * 4
@@ -90,6 +90,9 @@ SIGNATURES = {
     "b200ad_gemm_workspace_bytes": (c_int64, [POINTER(GemmDesc)]),
     "b200ad_gemm_set_recurrent_dispatch": (c_int, [c_int]),
     "b200ad_gemm_reload_env": (c_int, []),
+    "b200ad_gemm_set_f16x3_auto": (c_int, [c_int]),
+    "b200ad_gemm_shared_a": (c_int, [POINTER(GemmDesc), P, c_int32, POINTER(c_void_p), POINTER(c_void_p),
+                                     POINTER(c_void_p), P, I64, P]),
     "b200ad_attn_supported": (c_int, [POINTER(AttnDesc)]),
     "b200ad_attn_set_variant": (c_int, [c_int]),
     "b200ad_attn_fwd_ws_floats": (c_int64, [POINTER(AttnDesc)]),

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_internal.cuh"
 #include <atomic>
+#include <stdlib.h>
 
 using namespace b200ad;
 
@@ -14,7 +15,7 @@ static int fill_args(const b200ad_gemm_desc* d, const float* a, const float* b, 
   B200AD_REQUIRE(d->m >= 0 && d->n >= 0 && d->k >= 0, "gemm: negative dimension");
   B200AD_REQUIRE(d->batch0 >= 1 && d->batch1 >= 1, "gemm: batch extents must be >= 1");
   B200AD_REQUIRE(d->act >= 0 && d->act <= 3, "gemm: bad activation %d", d->act);
-  B200AD_REQUIRE(d->precision >= 0 && d->precision <= 4, "gemm: bad precision %d", d->precision);
+  B200AD_REQUIRE(d->precision >= 0 && d->precision <= 5, "gemm: bad precision %d", d->precision);
   const int64_t a_inner = d->trans_a ? d->m : d->k, b_inner = d->trans_b ? d->k : d->n;
   B200AD_REQUIRE(d->lda >= a_inner && d->ldb >= b_inner && d->ldc >= d->n,
                  "gemm: leading dimension smaller than the row (lda=%lld ldb=%lld ldc=%lld)", (long long)d->lda,
@@ -34,6 +35,43 @@ static int fill_args(const b200ad_gemm_desc* d, const float* a, const float* b, 
 // 0 = by capture state (default), 1 = device time decides (the captured behaviour), 2 = single launch (the eager behaviour)
 static std::atomic<int> g_recurrent_dispatch{0};
 
+// AUTO -> F16X3 (gemm_h16.cu) where it measures faster than the in-kernel 3xTF32 split: the operand pre-pass must be the
+// fused one-pass row split (row-major op(A), K <= 1024: the activations of a projection) and small against the product.
+static std::atomic<int> g_f16x3_auto{-1};
+static bool f16x3_auto_enabled() {
+  int v = g_f16x3_auto.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("B200AD_GEMM_F16X3_AUTO");
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_f16x3_auto.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+static int64_t f16x3_min_m() {
+  static std::atomic<int64_t> v{-1};
+  int64_t m = v.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("B200AD_GEMM_F16X3_MIN_M");
+    m = e ? atoll(e) : 16384;              // below that the launch-bound configs (config 3: M = 8192) measure no gain
+    if (m < 256) m = 256;
+    v.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
+static bool f16x3_auto_pick(const GemmArgs& g) {
+  if (!f16x3_auto_enabled()) return false;
+  if (g.trans_a || g.m < f16x3_min_m() || g.n < 256 || g.k < 128 || g.k > 1024) return false;
+  if (g.n * g.batch0 * g.batch1 > g.m) return false;           // B (its split is the slow transposing pass) stays small against A
+  const char* why = nullptr;
+  return gemm_h16_supported(g, &why);
+}
+// what AUTO resolves to for the tensor-core shapes (the skinny recurrent kernels are decided at launch time)
+static int auto_precision(const GemmArgs& g) {
+  if (f16x3_auto_pick(g)) return B200AD_GEMM_F16X3;
+  const char* why = nullptr;
+  return gemm_tc_supported(g, B200AD_GEMM_TF32X3, &why) ? B200AD_GEMM_TF32X3 : B200AD_GEMM_FP32;
+}
+
 extern "C" {
 
 int b200ad_gemm_reload_env(void) {
@@ -46,12 +84,19 @@ int b200ad_gemm_set_recurrent_dispatch(int mode) {
   return g_recurrent_dispatch.exchange(mode);
 }
 
+int b200ad_gemm_set_f16x3_auto(int enabled) {
+  const int prev = f16x3_auto_enabled() ? 1 : 0;
+  g_f16x3_auto.store(enabled ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
 int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float* b, const float* c) {
   GemmArgs g;
   if (fill_args(d, a, b, const_cast<float*>(c), nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32 || d->precision == B200AD_GEMM_AUTO) return 1;
   const char* why = nullptr;
   if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_supported(g, &why) ? 1 : 0;
+  if (d->precision == B200AD_GEMM_F16X3) return gemm_h16_supported(g, &why) ? 1 : 0;
   return gemm_tc_supported(g, d->precision, &why) ? 1 : 0;
 }
 
@@ -60,6 +105,8 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d) {
   if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
   if (d->precision == B200AD_GEMM_FP32) return 0;
   if (d->precision == B200AD_GEMM_BF16) return gemm_bf16_workspace_bytes(g);
+  if (d->precision == B200AD_GEMM_F16X3) return gemm_h16_workspace_bytes(g);
+  if (d->precision == B200AD_GEMM_AUTO && g.k > 0 && f16x3_auto_pick(g)) return gemm_h16_workspace_bytes(g);
   if (d->precision == B200AD_GEMM_AUTO && gemm_skinny_supported(g, false)) {
     // skinny recurrent-step kernels need no workspace.  (Pointer alignment is part of the check; with the null pointers
     // of this query it passes, and a misaligned operand at launch time falls back to an un-split tensor-core launch.)
@@ -91,16 +138,43 @@ int b200ad_gemm(const b200ad_gemm_desc* d, const float* a, const float* b, float
     if (gemm_skinny_supported(g, !device_time)) return gemm_skinny_launch(g, s);
   }
   if (prec == B200AD_GEMM_AUTO) {
-    const char* why = nullptr;
-    prec = gemm_tc_supported(g, B200AD_GEMM_TF32X3, &why) ? B200AD_GEMM_TF32X3 : B200AD_GEMM_FP32;
+    prec = g.k > 0 ? auto_precision(g) : B200AD_GEMM_FP32;
+    // a caller that sized its workspace before the F16X3 switch was flipped still gets a correct product
+    if (prec == B200AD_GEMM_F16X3 && (!workspace || workspace_bytes < gemm_h16_workspace_bytes(g))) {
+      const char* w2 = nullptr;
+      prec = gemm_tc_supported(g, B200AD_GEMM_TF32X3, &w2) ? B200AD_GEMM_TF32X3 : B200AD_GEMM_FP32;
+    }
   }
   if (prec == B200AD_GEMM_FP32 || g.k == 0) return gemm_simt_launch(g, s);
   const char* why = "unsupported";
+  if (prec == B200AD_GEMM_F16X3) {
+    if (!gemm_h16_supported(g, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(f16x3): %s", why);
+    return gemm_h16_launch(g, workspace, workspace_bytes, s);
+  }
   if (prec == B200AD_GEMM_BF16) {
     if (!gemm_bf16_supported(g, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(bf16): %s", why);
     return gemm_bf16_launch(g, workspace, workspace_bytes, s);
   }
   if (!gemm_tc_supported(g, prec, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm(tcgen05): %s", why);
   return gemm_tc_launch(g, prec, workspace, workspace_bytes, s);
+}
+
+int b200ad_gemm_shared_a(const b200ad_gemm_desc* d, const float* a, int32_t count, const float* const* bs, float* const* cs,
+                         const float* const* biases, void* workspace, int64_t workspace_bytes, void* stream) {
+  B200AD_REQUIRE(count >= 0 && (count == 0 || (bs && cs)), "gemm_shared_a: null operand list");
+  GemmArgs g;
+  int rc = fill_args(d, a, count ? bs[0] : nullptr, count ? cs[0] : nullptr, nullptr, &g);
+  if (rc) return rc;
+  int prec = d->precision;
+  if (prec == B200AD_GEMM_AUTO && g.m > 0 && g.n > 0 && g.k > 0 && f16x3_auto_pick(g)) prec = B200AD_GEMM_F16X3;
+  if (prec == B200AD_GEMM_F16X3 && g.m > 0 && g.n > 0 && g.k > 0 && workspace && workspace_bytes >= gemm_h16_workspace_bytes(g)) {
+    const char* why = "unsupported";
+    if (!gemm_h16_supported(g, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm_shared_a(f16x3): %s", why);
+    for (int i = 0; i < count; ++i) B200AD_REQUIRE(bs[i] && cs[i] && a, "gemm_shared_a: null pointer");
+    return gemm_h16_shared_a_launch(g, count, bs, cs, biases, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  for (int i = 0; i < count; ++i)
+    if ((rc = b200ad_gemm(d, a, bs[i], cs[i], biases ? biases[i] : nullptr, workspace, workspace_bytes, stream))) return rc;
+  return B200AD_OK;
 }
 }

@@ -56,4 +56,11 @@ bool gemm_bf16_supported(const GemmArgs& p, const char** why);
 int64_t gemm_bf16_workspace_bytes(const GemmArgs& p);
 int gemm_bf16_launch(const GemmArgs& p, void* ws, int64_t ws_bytes, cudaStream_t s);
 
+// fp16 hi/lo three-product variant (gemm_h16.cu): operand split pre-pass + pure TMA / MMA cta_group::2 kernel
+bool gemm_h16_supported(const GemmArgs& p, const char** why);
+int64_t gemm_h16_workspace_bytes(const GemmArgs& p);
+int gemm_h16_launch(const GemmArgs& p, void* ws, int64_t ws_bytes, cudaStream_t s);
+int gemm_h16_shared_a_launch(const GemmArgs& p, int count, const float* const* bs, float* const* cs, const float* const* biases,
+                             void* ws, int64_t ws_bytes, cudaStream_t s);
+
 }  // namespace b200ad

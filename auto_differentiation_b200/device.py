@@ -718,14 +718,23 @@ def embedding_scatter_add_(dout, idx, dw):
 # GEMM on (possibly strided) views
 # --------------------------------------------------------------------------------------------------
 _GEMM_PRECISION = {"auto": L.GEMM_AUTO, "fp32": L.GEMM_FP32, "tf32x3": L.GEMM_TF32X3, "bf16": L.GEMM_BF16,
-                   "tf32": L.GEMM_TF32}
+                   "tf32": L.GEMM_TF32, "f16x3": L.GEMM_F16X3}
 _default_precision = [L.GEMM_AUTO]
 
 
 def set_gemm_precision(name):
     """'auto' (fp32-faithful: tcgen05 3xTF32 where the shape allows, else fp32 SIMT), 'fp32',
-    'tf32x3', 'bf16' (tensor-core bf16 inputs / fp32 accumulate — looser tolerance)."""
+    'tf32x3', 'f16x3' (fp32-faithful like tf32x3: fp16 hi/lo pairs with row scales at the kind::f16 MMA rate),
+    'bf16' (tensor-core bf16 inputs / fp32 accumulate — looser tolerance)."""
     _default_precision[0] = _GEMM_PRECISION[name]
+
+
+def set_f16x3_auto(flag):
+    """Whether 'auto' may resolve to 'f16x3' for the large row-major-A products (b200ad_gemm_set_f16x3_auto).
+    Returns the previous setting."""
+    _matmul_plans.clear()                  # cached plans carry the workspace size of the path they were planned for
+    _shared_a_plans.clear()
+    return bool(_lib().b200ad_gemm_set_f16x3_auto(1 if flag else 0))
 
 
 def get_gemm_precision():
@@ -898,6 +907,57 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
             oc = sum(i * st[2] for i, (_, st) in zip(idx, outer)) * 4
             L.check(lib.b200ad_gemm(ctypes.byref(d), pa + oa, pb + ob, pc + oc, bias_ptr, wptr, ws_bytes, s))
     return out
+
+
+_shared_a_plans = {}
+
+
+def matmul_shared_a(a, bs, precision=None):
+    """[a @ b for b in bs] for 2-D operands that share their geometry, through ONE b200ad_gemm_shared_a call: on the
+    fp16-split path the shared operand is split once for all products (the Q / K / V projections of self-attention,
+    reference layers/layers.py:1347-1349).  Anything else is a loop of `matmul`."""
+    ta, tbs = a.t, [b.t for b in bs]
+    same = (len(tbs) > 1 and ta.dim() == 2 and all(t.dim() == 2 and t.shape == tbs[0].shape and t.stride() == tbs[0].stride()
+                                                   for t in tbs) and ta.shape[1] == tbs[0].shape[0])
+    if not same:
+        return [matmul(a, b, precision=precision) for b in bs]
+    key = (ta.shape, ta.stride(), tbs[0].shape, tbs[0].stride(), len(tbs), precision, _default_precision[0])
+    hit = _shared_a_plans.get(key)
+    if hit is None:
+        M, K = ta.shape
+        N = tbs[0].shape[1]
+        la, lb = _mat_layout(ta, M, K), _mat_layout(tbs[0], K, N)
+        if la is None or lb is None or M == 0 or N == 0 or K == 0:
+            return [matmul(a, b, precision=precision) for b in bs]
+        d = L.GemmDesc()
+        d.precision = _default_precision[0] if precision is None else _GEMM_PRECISION.get(precision, precision)
+        d.trans_a, d.trans_b, d.act = la[0], lb[0], L.ACT_NONE
+        d.m, d.n, d.k = M, N, K
+        d.lda, d.ldb, d.ldc = la[1], lb[1], N
+        d.batch0 = d.batch1 = 1
+        d.alpha, d.beta = 1.0, 0.0
+        ws_bytes = int(_lib().b200ad_gemm_workspace_bytes(ctypes.byref(d)))
+        if len(_shared_a_plans) > 256:
+            _shared_a_plans.clear()
+        hit = _shared_a_plans[key] = (d, ws_bytes, (M, N), (M, N, K, 1, la[0], lb[0], d.precision), 2.0 * M * N * K)
+    d, ws_bytes, out_shape, tkey, flops = hit
+    outs = [empty(out_shape) for _ in tbs]
+    n = len(tbs)
+    arr = ctypes.c_void_p * n
+    ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
+    timer = _gemm_timer[0]
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(_lib().b200ad_gemm_shared_a(ctypes.byref(d), ta.data_ptr(), n, arr(*[t.data_ptr() for t in tbs]),
+                                        arr(*[o.t.data_ptr() for o in outs]), None,
+                                        ws.data_ptr() if ws is not None else None, ws_bytes, stream_ptr()))
+    if timer is not None:
+        e1.record()
+        # one record per product so that launch counts and per-launch flops stay comparable with `matmul` records
+        timer.records.append((tkey, flops * n, e0, e1))
+        timer.shared_a_products = getattr(timer, "shared_a_products", 0) + n
+    return outs
 
 
 # --------------------------------------------------------------------------------------------------

@@ -679,14 +679,19 @@ class MultiHeadAttention:
         self.accumulate = False
 
     def forward(self, query, key, value):
-        query, key, value = _dev(query), _dev(key), _dev(value)
+        shared = query is key and key is value      # self-attention: one upload, one operand split for Q / K / V
+        query = _dev(query)
+        key, value = (query, query) if shared else (_dev(key), _dev(value))
         B, S, Dm = query.shape
         h = self.num_heads
         wq, wk, wv, wo = self.weights
         Hd = wq.shape[1]
         dk = Hd // h
         q2, k2, v2 = (a.reshape(B * S, Dm) for a in (query, key, value))
-        Q, K, V = D.matmul(q2, wq), D.matmul(k2, wk), D.matmul(v2, wv)          # :1347-1349
+        if shared:
+            Q, K, V = D.matmul_shared_a(q2, [wq, wk, wv])                        # :1347-1349
+        else:
+            Q, K, V = D.matmul(q2, wq), D.matmul(k2, wk), D.matmul(v2, wv)      # :1347-1349
         Qh, Kh, Vh = (a.reshape(B, S, h, dk).transpose(0, 2, 1, 3) for a in (Q, K, V))
         scale = 1.0 / math.sqrt(dk)
         if D.attn_supported(Qh, Kh, Vh):

@@ -210,7 +210,12 @@ int b200ad_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, void* 
  *                                 (fp32-faithful: |err| ~ 2^-21 relative; meets rtol 1e-5)
  *              B200AD_GEMM_BF16   tcgen05 kind::f16 bf16 inputs, fp32 accumulate in TMEM
  *                                 (looser tolerance: rtol 2e-2 of |A||B| row-norm bound)
- *              B200AD_GEMM_AUTO   TF32X3 when the shape/alignment allows the TMA path, else FP32
+ *              B200AD_GEMM_F16X3  tcgen05 kind::f16 on fp16 hi/lo pairs with one power-of-two scale per operand
+ *                                 row, 3-term split (fp32-faithful like TF32X3 at twice its MMA rate; the operands
+ *                                 are split by a pre-pass into the workspace, csrc/gemm_h16.cu)
+ *              B200AD_GEMM_AUTO   fp32-faithful: F16X3 for the large row-major-A products where it measures faster
+ *                                 (b200ad_gemm_set_f16x3_auto), TF32X3 when the shape/alignment allows the TMA
+ *                                 path, else FP32
  *   b200ad_gemm_supported tells whether `precision` can run this problem (1) or not (0).
  * ------------------------------------------------------------------------------------------ */
 enum b200ad_gemm_precision {
@@ -218,7 +223,8 @@ enum b200ad_gemm_precision {
   B200AD_GEMM_TF32X3 = 1,
   B200AD_GEMM_BF16 = 2,
   B200AD_GEMM_AUTO = 3,
-  B200AD_GEMM_TF32 = 4 /* single-pass tf32 (diagnostic / roofline probe) */
+  B200AD_GEMM_TF32 = 4, /* single-pass tf32 (diagnostic / roofline probe) */
+  B200AD_GEMM_F16X3 = 5
 };
 typedef struct b200ad_gemm_desc {
   int32_t precision, trans_a, trans_b, act;
@@ -239,6 +245,17 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d);
 int b200ad_gemm_set_recurrent_dispatch(int mode);
 /* The B200AD_TC_* tuning / debugging environment knobs of the tcgen05 GEMM are read once; this re-reads them. */
 int b200ad_gemm_reload_env(void);
+/* Whether B200AD_GEMM_AUTO may pick F16X3 (1, default; environment B200AD_GEMM_F16X3_AUTO=0 starts with 0) for the
+ * shapes where it measures faster than TF32X3: op(A) row-major with K <= 1024 (one fused split pass), M >= 16384
+ * (environment B200AD_GEMM_F16X3_MIN_M), N >= 256, K >= 128, B no larger than A.  Returns the previous setting. */
+int b200ad_gemm_set_f16x3_auto(int enabled);
+/* C_i = alpha * op(A) @ op(B_i) + beta * C_i (+ bias_i, activation) for i < count with ONE shared A operand: the
+ * Q / K / V projections of self-attention multiply the same input (layers/layers.py:1347-1349).  With precision
+ * F16X3 (or AUTO resolving to it) A is split once for all products; any other precision loops b200ad_gemm.
+ * All B_i / C_i share the descriptor's geometry; `biases` may be NULL.  Workspace: b200ad_gemm_workspace_bytes(d). */
+int b200ad_gemm_shared_a(const b200ad_gemm_desc* d, const float* a, int32_t count, const float* const* bs,
+                         float* const* cs, const float* const* biases, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention core (tcgen05, fp32-faithful three-product split; scores never leave the SM).

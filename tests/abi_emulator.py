@@ -341,6 +341,16 @@ class Emulator:
     def b200ad_gemm_set_recurrent_dispatch(self, mode):
         return 0
 
+    def b200ad_gemm_set_f16x3_auto(self, enabled):
+        return 1
+
+    def b200ad_gemm_shared_a(self, dref, a, count, bs, cs, biases, ws, ws_bytes, s):
+        for i in range(count):
+            rc = self.b200ad_gemm(dref, a, bs[i], cs[i], biases[i] if biases else None, ws, ws_bytes, s)
+            if rc:
+                return rc
+        return 0
+
     def b200ad_gemm(self, dref, a, b, c, bias, ws, ws_bytes, s):
         self.launches += 1
         d = dref._obj if hasattr(dref, "_obj") else dref

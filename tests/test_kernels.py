@@ -292,6 +292,99 @@ def test_gemm_bf16_variant_stated_tolerance(backend, M, N, K, ta, tb):
         assert_close(got, ref, rtol=2e-5, atol=2e-5 * np.sqrt(K), what="bf16 GEMM vs fp64 on bf16-rounded inputs")
 
 
+F16X3_CASES = [(1, 1, 1), (7, 9, 5), (256, 512, 256), (257, 259, 96), (300, 300, 33 * 32 + 8), (130, 1000, 72), (2048, 264, 64),
+               (512, 512, 8192), (640, 384, 1031)]
+
+
+@pytest.mark.parametrize("M,N,K", F16X3_CASES)
+def test_gemm_f16x3_all_layouts_and_epilogues(backend, M, N, K):
+    """fp16 hi/lo three-product variant (B200AD_GEMM_F16X3, csrc/gemm_h16.cu) held to the SAME tolerance as the default
+    fp32-faithful path: all four operand layouts (row split / column-maximum + transposing split pre-passes), tile and K
+    tails, split-K (K = 8192), K % 8 != 0 (padded planes), fused epilogues."""
+    D, L = _D(), _Lc()
+    rng = np.random.default_rng(M * 5 + N * 3 + K)
+    A, B = rng.standard_normal((M, K)).astype(np.float32), rng.standard_normal((K, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    tol = dict(rtol=2e-5, atol=2e-6 * np.sqrt(K))
+    a, b = D.asarray(A), D.asarray(B)
+    at, bt = D.asarray(A.T.copy()), D.asarray(B.T.copy())
+    assert_close(D.matmul(a, b, precision="f16x3"), ref, what="NN", **tol)
+    assert_close(D.matmul(at, b, trans_a=True, precision="f16x3"), ref, what="TN", **tol)
+    assert_close(D.matmul(a, bt, trans_b=True, precision="f16x3"), ref, what="NT", **tol)
+    assert_close(D.matmul(at, bt, trans_a=True, trans_b=True, precision="f16x3"), ref, what="TT", **tol)
+    bias = rng.standard_normal(N).astype(np.float32)
+    assert_close(D.matmul(a, b, bias=D.asarray(bias), act=L.ACT_TANH, precision="f16x3"), np.tanh(ref + bias), what="bias+tanh", **tol)
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    c = D.asarray(c0.copy())
+    D.matmul(a, b, out=c, alpha=0.5, beta=2.0, precision="f16x3")
+    assert_close(c, 0.5 * ref + 2.0 * c0, what="alpha/beta", **tol)
+
+
+def test_gemm_f16x3_row_scales_and_dynamic_range(backend):
+    """The power-of-two row scales keep the split fp32-faithful when operand rows span ten decades (1e-6 .. 1e4) and for
+    gradient-sized rows (1e-8): every output element is held to an ELEMENTWISE bound relative to sum_k |a||b| (a max-norm
+    tolerance would hide a lost small row).  Also an all-zero row and a batched head-split view."""
+    D = _D()
+    rng = np.random.default_rng(77)
+    M, N, K = 384, 320, 520
+    A = rng.standard_normal((M, K)) * 10.0 ** rng.uniform(-6, 4, size=(M, 1))
+    B = rng.standard_normal((K, N)) * 10.0 ** rng.uniform(-6, 4, size=(1, N))
+    A[5] = 0.0
+    A[7] *= 1e-8 / np.abs(A[7]).max()
+    A, B = A.astype(np.float32), B.astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    bound = (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64))
+    for ta, tb in ((False, False), (True, True)):
+        a = D.asarray(A.T.copy() if ta else A)
+        b = D.asarray(B.T.copy() if tb else B)
+        got = np.asarray(D.matmul(a, b, trans_a=ta, trans_b=tb, precision="f16x3"), dtype=np.float64)
+        ratio = np.abs(got - ref) / (4e-6 * bound + 1e-38)
+        from conftest import record_parity
+        i = np.unravel_index(np.argmax(ratio), ratio.shape)
+        record_parity("f16x3 elementwise ta=%d tb=%d" % (ta, tb), abs(got[i] - ref[i]), 4e-6 * bound[i] + 1e-38, ratio.max(), 4e-6, 0.0, ratio.size)
+        assert ratio.max() <= 1.0, "f16x3 elementwise error %.3g of the 4e-6 |A||B| bound (ta=%d tb=%d)" % (ratio.max(), ta, tb)
+        assert np.all(got[5] == 0.0)
+    Bt, h, S, dk = 3, 4, 160, 72
+    x = rng.standard_normal((Bt, S, h * dk)).astype(np.float32)
+    y = rng.standard_normal((Bt, S, h * dk)).astype(np.float32)
+    xh = D.asarray(x).reshape(Bt, S, h, dk).transpose(0, 2, 1, 3)
+    yh = D.asarray(y).reshape(Bt, S, h, dk).transpose(0, 2, 1, 3)
+    got = D.matmul(xh, yh, trans_b=True, precision="f16x3")
+    xr = x.reshape(Bt, S, h, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    yr = y.reshape(Bt, S, h, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    assert_close(got, xr @ yr.transpose(0, 1, 3, 2), rtol=2e-5, atol=2e-6 * np.sqrt(dk), what="f16x3 batched head views")
+
+
+def test_gemm_shared_a_and_auto_dispatch(backend):
+    """b200ad_gemm_shared_a (one operand split for several products: the Q / K / V projections) equals separate calls
+    bit for bit, and the AUTO dispatch (F16X3 for tall row-major-A products, b200ad_gemm_set_f16x3_auto) stays inside the
+    default tolerance with the switch on and off."""
+    D = _D()
+    rng = np.random.default_rng(5)
+    M, N, K = 16384 + 200, 512, 512
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Ws = [rng.standard_normal((K, N)).astype(np.float32) / np.sqrt(K) for _ in range(3)]
+    a, ws = D.asarray(A), [D.asarray(w) for w in Ws]
+    refs = [A.astype(np.float64) @ w.astype(np.float64) for w in Ws]
+    outs = D.matmul_shared_a(a, ws, precision="f16x3")
+    for o, w, r in zip(outs, ws, refs):
+        assert_close(o, r, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="shared-A product")
+        np.testing.assert_array_equal(np.asarray(o), np.asarray(D.matmul(a, w, precision="f16x3")))
+    prev = D.set_f16x3_auto(True)
+    try:
+        on = [np.asarray(o) for o in D.matmul_shared_a(a, ws)] + [np.asarray(D.matmul(a, ws[0]))]
+        D.set_f16x3_auto(False)
+        off = [np.asarray(o) for o in D.matmul_shared_a(a, ws)] + [np.asarray(D.matmul(a, ws[0]))]
+    finally:
+        D.set_f16x3_auto(prev)
+    for o, f, r in zip(on, off, refs + [refs[0]]):
+        assert_close(o, r, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="auto, f16x3 on")
+        assert_close(f, r, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="auto, f16x3 off")
+    # different geometries fall back to a loop
+    outs = D.matmul_shared_a(a[:100], [ws[0], D.asarray(Ws[1][:, :64].copy())])
+    assert_close(outs[1], A[:100].astype(np.float64) @ Ws[1][:, :64].astype(np.float64), rtol=2e-5, atol=2e-6 * np.sqrt(K), what="fallback loop")
+
+
 @pytest.mark.parametrize("M,N,K,tb,act,beta", [(64, 1024, 1024, False, 1, 1.0), (64, 1024, 1024, True, 0, 0.0), (17, 2048, 1024, False, 0, 1.0),
                                                (1, 256, 256, True, 2, 0.0), (64, 512, 2048, False, 3, 0.5), (64, 1024, 4096, True, 0, 0.0),
                                                (64, 264, 1024, False, 1, 1.0), (40, 328, 992, True, 0, 0.0)])
@@ -318,7 +411,8 @@ def test_gemm_skinny_recurrent_step(backend, M, N, K, tb, act, beta):
 
 
 @pytest.mark.parametrize("M,N,K,prec", [(300, 260, 96, None), (300, 260, 96, "bf16"), (130, 520, 40, None), (100, 100, 64, None),
-                                        (33, 512, 256, None), (513, 300, 4128, None)])
+                                        (33, 512, 256, None), (513, 300, 4128, None), (300, 260, 96, "f16x3"),
+                                        (513, 300, 4128, "f16x3"), (2304, 264, 72, None)])
 @pytest.mark.parametrize("col_off", [4, 3])
 def test_gemm_output_guards(backend, M, N, K, prec, col_off):
     """C is a window of a larger buffer filled with a sentinel: rows above / below and columns left / right of the window
