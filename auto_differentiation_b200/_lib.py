@@ -91,6 +91,7 @@ SIGNATURES = {
     "b200ad_gemm_set_recurrent_dispatch": (c_int, [c_int]),
     "b200ad_gemm_reload_env": (c_int, []),
     "b200ad_gemm_set_f16x3_auto": (c_int, [c_int]),
+    "b200ad_gemm_shared_a_workspace_bytes": (c_int64, [POINTER(GemmDesc), c_int32]),
     "b200ad_gemm_shared_a": (c_int, [POINTER(GemmDesc), P, c_int32, POINTER(c_void_p), POINTER(c_void_p),
                                      POINTER(c_void_p), P, I64, P]),
     "b200ad_attn_supported": (c_int, [POINTER(AttnDesc)]),

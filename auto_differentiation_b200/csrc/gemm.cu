@@ -35,35 +35,43 @@ static int fill_args(const b200ad_gemm_desc* d, const float* a, const float* b, 
 // 0 = by capture state (default), 1 = device time decides (the captured behaviour), 2 = single launch (the eager behaviour)
 static std::atomic<int> g_recurrent_dispatch{0};
 
-// AUTO -> F16X3 (gemm_h16.cu) where it measures faster than the in-kernel 3xTF32 split: the operand pre-pass must be the
-// fused one-pass row split (row-major op(A), K <= 1024: the activations of a projection) and small against the product.
+// AUTO -> F16X3 (gemm_h16.cu) where a device-time model built from measurements (profiles/r2_gemm_h16_probe.log) says it
+// beats the in-kernel 3xTF32 split by >= 10 %: the F16X3 kernel runs a 256 x 256 tile in max(1536 cycles per 64-deep k-block,
+// ~14 k cycles of output stores), the operand split costs ~2 ps per element (row-major) or ~4 ps (transposing), generation 3
+// sustains ~270 TFLOP/s.  In practice: large tiles with K >= ~2048, or one operand shared by several products.
+// 0 = never, 1 = by the model (default), 2 = whenever the path supports the problem (tests).
 static std::atomic<int> g_f16x3_auto{-1};
-static bool f16x3_auto_enabled() {
+static int f16x3_auto_mode() {
   int v = g_f16x3_auto.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("B200AD_GEMM_F16X3_AUTO");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 2) v = 1;
     g_f16x3_auto.store(v, std::memory_order_relaxed);
   }
-  return v != 0;
+  return v;
 }
-static int64_t f16x3_min_m() {
-  static std::atomic<int64_t> v{-1};
-  int64_t m = v.load(std::memory_order_relaxed);
-  if (m < 0) {
-    const char* e = getenv("B200AD_GEMM_F16X3_MIN_M");
-    m = e ? atoll(e) : 16384;              // below that the launch-bound configs (config 3: M = 8192) measure no gain
-    if (m < 256) m = 256;
-    v.store(m, std::memory_order_relaxed);
-  }
-  return m;
-}
-static bool f16x3_auto_pick(const GemmArgs& g) {
-  if (!f16x3_auto_enabled()) return false;
-  if (g.trans_a || g.m < f16x3_min_m() || g.n < 256 || g.k < 128 || g.k > 1024) return false;
-  if (g.n * g.batch0 * g.batch1 > g.m) return false;           // B (its split is the slow transposing pass) stays small against A
+static bool f16x3_auto_pick(const GemmArgs& g, int count = 1) {
+  const int mode = f16x3_auto_mode();
+  if (mode == 0 || g.m < 1 || g.n < 1 || g.k < 1) return false;
   const char* why = nullptr;
-  return gemm_h16_supported(g, &why);
+  if (!gemm_h16_supported(g, &why)) return false;
+  if (mode == 2) return true;
+  if (g.m < 512 || g.n < 256 || g.k < 128) return false;
+  const double batches = (double)(g.batch0 * g.batch1);
+  const double tiles = (double)(ceil_div(g.m, 256) * ceil_div(g.n, 256)) * batches;
+  const double pairs = sm_count() / 2;
+  const double waves = (double)ceil_div((int64_t)tiles, (int64_t)pairs);
+  const double kb = (double)ceil_div(g.k, 64);
+  double cyc = kb * 1536.0;
+  if (cyc < 14000.0) cyc = 14000.0;
+  if (tiles < pairs && kb >= 16) cyc = cyc * tiles / pairs + 14000.0;      // split-K spreads the k-blocks over the idle pairs
+  const double t_kernel = waves * cyc / 1.7e9 + 2e-6;
+  const double t_a = (double)g.m * g.k * batches * (g.trans_a ? 4e-12 : 2e-12) + 3e-6;
+  const double t_b = (double)g.n * g.k * batches * (g.trans_b ? 2e-12 : 4e-12) + 3e-6;
+  const double t_h16 = t_a + count * (t_b + t_kernel);
+  const double t_tc = count * (2.0 * g.m * g.n * g.k * batches / 2.7e14 + 3e-6);
+  return t_h16 < 0.9 * t_tc;
 }
 // what AUTO resolves to for the tensor-core shapes (the skinny recurrent kernels are decided at launch time)
 static int auto_precision(const GemmArgs& g) {
@@ -84,10 +92,18 @@ int b200ad_gemm_set_recurrent_dispatch(int mode) {
   return g_recurrent_dispatch.exchange(mode);
 }
 
-int b200ad_gemm_set_f16x3_auto(int enabled) {
-  const int prev = f16x3_auto_enabled() ? 1 : 0;
-  g_f16x3_auto.store(enabled ? 1 : 0, std::memory_order_relaxed);
+int b200ad_gemm_set_f16x3_auto(int mode) {
+  const int prev = f16x3_auto_mode();
+  if (mode < 0 || mode > 2) return set_error(B200AD_ERR_INVALID, "gemm_set_f16x3_auto: mode %d not in 0..2", mode);
+  g_f16x3_auto.store(mode, std::memory_order_relaxed);
   return prev;
+}
+
+int64_t b200ad_gemm_shared_a_workspace_bytes(const b200ad_gemm_desc* d, int32_t count) {
+  GemmArgs g;
+  if (fill_args(d, nullptr, nullptr, nullptr, nullptr, &g)) return 0;
+  if (d->precision == B200AD_GEMM_AUTO && count > 1 && f16x3_auto_pick(g, count)) return gemm_h16_workspace_bytes(g);
+  return b200ad_gemm_workspace_bytes(d);
 }
 
 int b200ad_gemm_supported(const b200ad_gemm_desc* d, const float* a, const float* b, const float* c) {
@@ -166,7 +182,7 @@ int b200ad_gemm_shared_a(const b200ad_gemm_desc* d, const float* a, int32_t coun
   int rc = fill_args(d, a, count ? bs[0] : nullptr, count ? cs[0] : nullptr, nullptr, &g);
   if (rc) return rc;
   int prec = d->precision;
-  if (prec == B200AD_GEMM_AUTO && g.m > 0 && g.n > 0 && g.k > 0 && f16x3_auto_pick(g)) prec = B200AD_GEMM_F16X3;
+  if (prec == B200AD_GEMM_AUTO && count > 0 && f16x3_auto_pick(g, count)) prec = B200AD_GEMM_F16X3;
   if (prec == B200AD_GEMM_F16X3 && g.m > 0 && g.n > 0 && g.k > 0 && workspace && workspace_bytes >= gemm_h16_workspace_bytes(g)) {
     const char* why = "unsupported";
     if (!gemm_h16_supported(g, &why)) return set_error(B200AD_ERR_UNSUPPORTED, "gemm_shared_a(f16x3): %s", why);

@@ -16,7 +16,7 @@
 //   fold it into a register-resident running total with round-to-nearest adds (TMEM accumulation truncates)
 //   while the next chunk's MMAs fill the other buffer; the finished tile is scaled by invA[row] invB[col] (exact: powers
 //   of two) and leaves through per-warp swizzled staging tiles + cp.async.bulk.tensor stores.
-//   warp 0 TMA (both CTAs)   warp 1 MMA (leader CTA)   warps 2-3 idle   warps 4-11 fold + epilogue
+//   warp 0 TMA (both CTAs)   warp 1 MMA (leader CTA)   warps 2-7 idle   warps 8-15 fold + epilogue (setmaxnreg 56 / 24 / 208)
 // Split-K (deterministic two-pass) covers the skinny shapes.  b200ad_gemm_shared_a converts ONE A operand for several
 // B / C pairs (the Q / K / V projections of self-attention share their input, layers.py:1347-1349).
 #include "common.cuh"
@@ -28,7 +28,7 @@
 
 namespace b200ad {
 
-constexpr int H_THREADS = 384;
+constexpr int H_THREADS = 512;                                 // 4 warpgroups; setmaxnreg moves registers to the fold warps
 constexpr int H_STAGES = 3;
 constexpr int H_BK = 64;                                       // fp16 elements per k-block (128 B)
 constexpr int H_CHUNK_KB = 2;                                  // accumulation chain: 128 K-elements
@@ -132,6 +132,10 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int total_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
+  // register budget: 512 x 128 at launch >= 128 x 56 + 128 x 24 + 256 x 208; an .inc beyond what the .decs release
+  // would block forever, so the arithmetic is part of the kernel
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
     if (elect_one()) {
@@ -212,10 +216,14 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         printf("[h16] MMA warp: total %lld cycles, %u k-blocks, %u chunks, wait full (TMA) %lld, wait tmem_empty (fold) %lld\n",
                clock64() - t_start, it, uit, w_full, w_empty);
     }
-  } else if (warp >= 4) {
+  }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+  } else {
     // ===================================== fold + epilogue (both CTAs, own 128 rows) =====================================
-    const int q = warp & 3, hf = (warp - 4) >> 2;              // TMEM lane quarter, 128-column half of the tile
-    const uint32_t stg = smem_u32(smem + (size_t)R * H_STAGE_BYTES) + (uint32_t)(warp - 4) * 4096u;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int q = warp & 3, hf = (warp - 8) >> 2;              // TMEM lane quarter, 128-column half of the tile
+    const uint32_t stg = smem_u32(smem + (size_t)R * H_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
     const int sub_row = lane >> 3, chunk = lane & 7;
     const uint32_t x_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hf * 128u;
     uint32_t uit = 0;
@@ -227,18 +235,35 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int kb1 = kb0 + p.kblocks_per_split;
       if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
       const int nchunks = (kb1 - kb0 + H_CHUNK_KB - 1) / H_CHUNK_KB;
+      // the scales this thread applies at the end are fetched now: their L2 latency hides behind the folds
+      const int m_row0 = m_tile * 256 + (int)rank * 128 + q * 32;  // first row of this warp
+      const float ra = (m_row0 + lane < p.m) ? __ldg(p.inv_a + (int64_t)batch * p.m + m_row0 + lane) : 0.f;
+      float cbl[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = n_tile * BN + hf * 128 + g * 32 + lane;
+        cbl[g] = (col < p.n) ? __ldg(p.inv_b + (int64_t)batch * p.n + col) : 0.f;
+      }
       float y[128];                                            // running total: this thread's row, 128 columns
       for (int ch = 0; ch < nchunks; ++ch, ++uit) {
         const uint32_t buf = uit & 1;
         mbar_wait(&tmem_full[buf], (uit >> 1) & 1);
         tc_fence_after();
 #pragma unroll
+        uint32_t dep = 0;                                        // see below
+#pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 16) {
           uint32_t x[16];
-          tmem_ld_32x32b_x16(x_addr + buf * BN + (uint32_t)c0, x);
+          tmem_ld_32x32b_x16(x_addr + buf * BN + (uint32_t)c0 + dep, x);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[c0 + j] = (ch == 0) ? __uint_as_float(x[j]) : y[c0 + j] + __uint_as_float(x[j]);
+          // ptxas otherwise hoists all eight loads above the adds (128 live load registers next to the 128 totals: spills);
+          // a zero it cannot prove (this lane's own value shuffled back) makes the next load's address depend on this sum
+          if (c0 & 16) {
+            const uint32_t yb = __float_as_uint(y[c0 + 15]);
+            dep = __shfl_sync(0xffffffffu, yb, lane) ^ yb;
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -249,29 +274,25 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // the 32 inverse column scales of a group are loaded once per warp and broadcast by shuffles.  An identity epilogue
       // then leaves straight through the TMA store; alpha / beta / bias / activation take the rolled loop.
       if (p.probe & 1) continue;                                 // diagnostic: no output (times MMA + fold alone)
-      const int m_row0 = m_tile * 256 + (int)rank * 128 + q * 32;  // first row of this warp
       const int c2 = p.partial ? batch : (int)b1, c3 = p.partial ? split : (int)b0;
       const bool identity = p.partial || (p.alpha == 1.f && p.beta == 0.f && !p.bias && p.act == 0);
       float* cwarp;
       if (p.partial) cwarp = p.partial + (((int64_t)split * p.batches + batch) * p.m + m_row0) * p.n;
       else cwarp = p.c + b0 * p.c_stride0 + b1 * p.c_stride1 + (int64_t)m_row0 * p.ldc;
       const int64_t row_pitch = p.partial ? p.n : p.ldc;
-      const float ra = (m_row0 + lane < p.m) ? __ldg(p.inv_a + (int64_t)batch * p.m + m_row0 + lane) : 0.f;
-      const float* invb = p.inv_b + (int64_t)batch * p.n;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n_col0 = n_tile * BN + hf * 128 + g * 32;
         if (n_col0 < p.n && m_row0 < p.m) {                    // warp-uniform
-          const float cbl = (n_col0 + lane < p.n) ? __ldg(invb + n_col0 + lane) : 0.f;
           if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 v4;                                            // exact: both factors are powers of two
-            v4.x = __float_as_uint(y[g * 32 + 4 * c] * ra * __shfl_sync(0xffffffffu, cbl, 4 * c));
-            v4.y = __float_as_uint(y[g * 32 + 4 * c + 1] * ra * __shfl_sync(0xffffffffu, cbl, 4 * c + 1));
-            v4.z = __float_as_uint(y[g * 32 + 4 * c + 2] * ra * __shfl_sync(0xffffffffu, cbl, 4 * c + 2));
-            v4.w = __float_as_uint(y[g * 32 + 4 * c + 3] * ra * __shfl_sync(0xffffffffu, cbl, 4 * c + 3));
+            v4.x = __float_as_uint(y[g * 32 + 4 * c] * ra * __shfl_sync(0xffffffffu, cbl[g], 4 * c));
+            v4.y = __float_as_uint(y[g * 32 + 4 * c + 1] * ra * __shfl_sync(0xffffffffu, cbl[g], 4 * c + 1));
+            v4.z = __float_as_uint(y[g * 32 + 4 * c + 2] * ra * __shfl_sync(0xffffffffu, cbl[g], 4 * c + 2));
+            v4.w = __float_as_uint(y[g * 32 + 4 * c + 3] * ra * __shfl_sync(0xffffffffu, cbl[g], 4 * c + 3));
             h16_sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), v4);
           }
           __syncwarp();
@@ -364,7 +385,8 @@ __device__ __forceinline__ uint32_t h16_pack(__half a, __half b) {
 }
 
 // Row-major source (element (r, k) at r*ld + k): one warp per row does maximum, scale and split in one pass.
-// VEC: k % 8 == 0 (kpad == k), k <= 1024, 16 B aligned rows — the row stays in registers between the two steps.
+// VEC: k % 8 == 0 (kpad == k), 16 B aligned rows: 128-bit loads, 64-bit stores; up to K = 1024 the row stays in registers
+// between the two steps, longer rows are read a second time (L1 / L2 hits).
 template <bool VEC>
 __global__ void __launch_bounds__(256) h16_split_rows_kernel(const float* __restrict__ src, __half* __restrict__ hi,
                                                              __half* __restrict__ lo, float* __restrict__ inv_scale, int64_t rows,
@@ -376,7 +398,29 @@ __global__ void __launch_bounds__(256) h16_split_rows_kernel(const float* __rest
   const float* row = src + (batch / batch1) * s0 + (batch % batch1) * s1 + r * ld;
   const int64_t orow = (batch * rows + r) * kpad;
   float scale, inv;
-  if constexpr (VEC) {
+  if (VEC && k > 1024) {
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int n4 = (int)(k >> 2);
+    uint32_t m = 0;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = __ldg(row4 + i);
+      uint32_t a = h16_absbits(v.x), b = h16_absbits(v.y), c = h16_absbits(v.z), d = h16_absbits(v.w);
+      a = a > b ? a : b; c = c > d ? c : d; a = a > c ? a : c;
+      m = m > a ? m : a;
+    }
+    m = h16_warp_umax(m);
+    h16_scales(m, scale, inv);
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = __ldg(row4 + i);
+      __half h0, h1, h2, h3, l0, l1, l2, l3;
+      h16_split(v.x, scale, h0, l0); h16_split(v.y, scale, h1, l1);
+      h16_split(v.z, scale, h2, l2); h16_split(v.w, scale, h3, l3);
+      *reinterpret_cast<uint2*>(hi + orow + 4 * i) = make_uint2(h16_pack(h0, h1), h16_pack(h2, h3));
+      *reinterpret_cast<uint2*>(lo + orow + 4 * i) = make_uint2(h16_pack(l0, l1), h16_pack(l2, l3));
+    }
+  } else if constexpr (VEC) {
     float4 v[8];
     uint32_t m = 0;
 #pragma unroll
@@ -629,7 +673,7 @@ static int h16_prepare(const float* src, int64_t rows, int64_t k, int64_t kpad, 
   __half* lo = planes + (int64_t)batches * rows * kpad;
   if (h16_probe() & 4) return B200AD_OK;
   if (k_contig) {
-    const bool vec = (k % 8 == 0) && k <= 1024 && aligned16(src) && (ld % 4 == 0) && (batches == 1 || (s0 % 4 == 0 && s1 % 4 == 0));
+    const bool vec = (k % 8 == 0) && aligned16(src) && (ld % 4 == 0) && (batches == 1 || (s0 % 4 == 0 && s1 % 4 == 0));
     dim3 grid((unsigned)ceil_div(rows, 8), (unsigned)batches);
     if (vec) h16_split_rows_kernel<true><<<grid, 256, 0, s>>>(src, hi, lo, inv_scale, rows, k, kpad, ld, batch1, s0, s1);
     else h16_split_rows_kernel<false><<<grid, 256, 0, s>>>(src, hi, lo, inv_scale, rows, k, kpad, ld, batch1, s0, s1);

@@ -729,12 +729,12 @@ def set_gemm_precision(name):
     _default_precision[0] = _GEMM_PRECISION[name]
 
 
-def set_f16x3_auto(flag):
-    """Whether 'auto' may resolve to 'f16x3' for the large row-major-A products (b200ad_gemm_set_f16x3_auto).
-    Returns the previous setting."""
+def set_f16x3_auto(mode):
+    """When 'auto' resolves to 'f16x3' (b200ad_gemm_set_f16x3_auto): 0 never, 1 by the library's device-time model
+    (default), 2 whenever the path supports the problem.  Returns the previous mode."""
     _matmul_plans.clear()                  # cached plans carry the workspace size of the path they were planned for
     _shared_a_plans.clear()
-    return bool(_lib().b200ad_gemm_set_f16x3_auto(1 if flag else 0))
+    return L.check(_lib().b200ad_gemm_set_f16x3_auto(int(mode)))
 
 
 def get_gemm_precision():
@@ -936,7 +936,7 @@ def matmul_shared_a(a, bs, precision=None):
         d.lda, d.ldb, d.ldc = la[1], lb[1], N
         d.batch0 = d.batch1 = 1
         d.alpha, d.beta = 1.0, 0.0
-        ws_bytes = int(_lib().b200ad_gemm_workspace_bytes(ctypes.byref(d)))
+        ws_bytes = int(_lib().b200ad_gemm_shared_a_workspace_bytes(ctypes.byref(d), len(tbs)))
         if len(_shared_a_plans) > 256:
             _shared_a_plans.clear()
         hit = _shared_a_plans[key] = (d, ws_bytes, (M, N), (M, N, K, 1, la[0], lb[0], d.precision), 2.0 * M * N * K)

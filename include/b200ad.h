@@ -245,14 +245,17 @@ int64_t b200ad_gemm_workspace_bytes(const b200ad_gemm_desc* d);
 int b200ad_gemm_set_recurrent_dispatch(int mode);
 /* The B200AD_TC_* tuning / debugging environment knobs of the tcgen05 GEMM are read once; this re-reads them. */
 int b200ad_gemm_reload_env(void);
-/* Whether B200AD_GEMM_AUTO may pick F16X3 (1, default; environment B200AD_GEMM_F16X3_AUTO=0 starts with 0) for the
- * shapes where it measures faster than TF32X3: op(A) row-major with K <= 1024 (one fused split pass), M >= 16384
- * (environment B200AD_GEMM_F16X3_MIN_M), N >= 256, K >= 128, B no larger than A.  Returns the previous setting. */
-int b200ad_gemm_set_f16x3_auto(int enabled);
+/* When B200AD_GEMM_AUTO resolves to F16X3: 0 = never, 1 (default; environment B200AD_GEMM_F16X3_AUTO) = where a device-time
+ * model built from measurements says it beats TF32X3 by >= 10 % (the operand split pre-pass must pay for itself: large tiles
+ * with K >= ~2048, or one operand shared by several products), 2 = whenever F16X3 supports the problem.  Returns the
+ * previous mode. */
+int b200ad_gemm_set_f16x3_auto(int mode);
 /* C_i = alpha * op(A) @ op(B_i) + beta * C_i (+ bias_i, activation) for i < count with ONE shared A operand: the
  * Q / K / V projections of self-attention multiply the same input (layers/layers.py:1347-1349).  With precision
  * F16X3 (or AUTO resolving to it) A is split once for all products; any other precision loops b200ad_gemm.
- * All B_i / C_i share the descriptor's geometry; `biases` may be NULL.  Workspace: b200ad_gemm_workspace_bytes(d). */
+ * All B_i / C_i share the descriptor's geometry; `biases` may be NULL.  Workspace: b200ad_gemm_shared_a_workspace_bytes
+ * (AUTO decides with the shared split amortised over `count` products). */
+int64_t b200ad_gemm_shared_a_workspace_bytes(const b200ad_gemm_desc* d, int32_t count);
 int b200ad_gemm_shared_a(const b200ad_gemm_desc* d, const float* a, int32_t count, const float* const* bs,
                          float* const* cs, const float* const* biases, void* workspace, int64_t workspace_bytes,
                          void* stream);

@@ -341,8 +341,11 @@ class Emulator:
     def b200ad_gemm_set_recurrent_dispatch(self, mode):
         return 0
 
-    def b200ad_gemm_set_f16x3_auto(self, enabled):
+    def b200ad_gemm_set_f16x3_auto(self, mode):
         return 1
+
+    def b200ad_gemm_shared_a_workspace_bytes(self, d, count):
+        return 0
 
     def b200ad_gemm_shared_a(self, dref, a, count, bs, cs, biases, ws, ws_bytes, s):
         for i in range(count):

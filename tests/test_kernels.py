@@ -357,8 +357,8 @@ def test_gemm_f16x3_row_scales_and_dynamic_range(backend):
 
 def test_gemm_shared_a_and_auto_dispatch(backend):
     """b200ad_gemm_shared_a (one operand split for several products: the Q / K / V projections) equals separate calls
-    bit for bit, and the AUTO dispatch (F16X3 for tall row-major-A products, b200ad_gemm_set_f16x3_auto) stays inside the
-    default tolerance with the switch on and off."""
+    bit for bit, and the AUTO dispatch (b200ad_gemm_set_f16x3_auto: never / by the device-time model / always) stays inside
+    the default tolerance with F16X3 forced on and off."""
     D = _D()
     rng = np.random.default_rng(5)
     M, N, K = 16384 + 200, 512, 512
@@ -370,10 +370,10 @@ def test_gemm_shared_a_and_auto_dispatch(backend):
     for o, w, r in zip(outs, ws, refs):
         assert_close(o, r, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="shared-A product")
         np.testing.assert_array_equal(np.asarray(o), np.asarray(D.matmul(a, w, precision="f16x3")))
-    prev = D.set_f16x3_auto(True)
+    prev = D.set_f16x3_auto(2)
     try:
         on = [np.asarray(o) for o in D.matmul_shared_a(a, ws)] + [np.asarray(D.matmul(a, ws[0]))]
-        D.set_f16x3_auto(False)
+        D.set_f16x3_auto(0)
         off = [np.asarray(o) for o in D.matmul_shared_a(a, ws)] + [np.asarray(D.matmul(a, ws[0]))]
     finally:
         D.set_f16x3_auto(prev)
