@@ -37,7 +37,7 @@ static std::atomic<int> g_recurrent_dispatch{0};
 
 // AUTO -> F16X3 (gemm_h16.cu) where a device-time model built from measurements (profiles/r2_gemm_h16_probe.log) says it
 // beats the in-kernel 3xTF32 split by >= 10 %: the F16X3 kernel runs a 256 x 256 tile in max(1536 cycles per 64-deep k-block,
-// ~14 k cycles of output stores), the operand split costs ~2 ps per element (row-major) or ~4 ps (transposing), generation 3
+// ~11 k cycles of output stores), the operand split costs ~2 ps per element (row-major) or ~4 ps (transposing), generation 3
 // sustains ~270 TFLOP/s.  In practice: large tiles with K >= ~2048, or one operand shared by several products.
 // 0 = never, 1 = by the model (default), 2 = whenever the path supports the problem (tests).
 static std::atomic<int> g_f16x3_auto{-1};
@@ -64,8 +64,8 @@ static bool f16x3_auto_pick(const GemmArgs& g, int count = 1) {
   const double waves = (double)ceil_div((int64_t)tiles, (int64_t)pairs);
   const double kb = (double)ceil_div(g.k, 64);
   double cyc = kb * 1536.0;
-  if (cyc < 14000.0) cyc = 14000.0;
-  if (tiles < pairs && kb >= 16) cyc = cyc * tiles / pairs + 14000.0;      // split-K spreads the k-blocks over the idle pairs
+  if (cyc < 11000.0) cyc = 11000.0;
+  if (tiles < pairs && kb >= 16) cyc = cyc * tiles / pairs + 11000.0;      // split-K spreads the k-blocks over the idle pairs
   const double t_kernel = waves * cyc / 1.7e9 + 2e-6;
   const double t_a = (double)g.m * g.k * batches * (g.trans_a ? 4e-12 : 2e-12) + 3e-6;
   const double t_b = (double)g.n * g.k * batches * (g.trans_b ? 2e-12 : 4e-12) + 3e-6;

@@ -464,6 +464,50 @@ __global__ void __launch_bounds__(256) h16_split_rows_kernel(const float* __rest
   if (lane == 0) inv_scale[batch * rows + r] = inv;
 }
 
+// Long rows (1024 < K <= 8192, K % 8 == 0, 16 B aligned): one 256-thread block per row, the row in registers (a warp per row
+// walking a 32 KB row twice measured 4x slower than the short-row kernel per element).
+__global__ void __launch_bounds__(256) h16_split_rows_block_kernel(const float* __restrict__ src, __half* __restrict__ hi,
+                                                                   __half* __restrict__ lo, float* __restrict__ inv_scale,
+                                                                   int64_t rows, int64_t k, int64_t ld, int64_t batch1, int64_t s0,
+                                                                   int64_t s1) {
+  __shared__ uint32_t red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = blockIdx.x, batch = blockIdx.y;
+  const float* row = src + (batch / batch1) * s0 + (batch % batch1) * s1 + r * ld;
+  const int64_t orow = (batch * rows + r) * k;
+  float4 v[8];
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = (i * 256 + (int)threadIdx.x) * 4;
+    if (idx < k) {
+      v[i] = ldg_stream(reinterpret_cast<const float4*>(row + idx));
+      uint32_t a = h16_absbits(v[i].x), b = h16_absbits(v[i].y), c = h16_absbits(v[i].z), d = h16_absbits(v[i].w);
+      a = a > b ? a : b; c = c > d ? c : d; a = a > c ? a : c;
+      m = m > a ? m : a;
+    }
+  }
+  m = h16_warp_umax(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m = red[i] > m ? red[i] : m;
+  float scale, inv;
+  h16_scales(m, scale, inv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = (i * 256 + (int)threadIdx.x) * 4;
+    if (idx < k) {
+      __half h0, h1, h2, h3, l0, l1, l2, l3;
+      h16_split(v[i].x, scale, h0, l0); h16_split(v[i].y, scale, h1, l1);
+      h16_split(v[i].z, scale, h2, l2); h16_split(v[i].w, scale, h3, l3);
+      *reinterpret_cast<uint2*>(hi + orow + idx) = make_uint2(h16_pack(h0, h1), h16_pack(h2, h3));
+      *reinterpret_cast<uint2*>(lo + orow + idx) = make_uint2(h16_pack(l0, l1), h16_pack(l2, l3));
+    }
+  }
+  if (threadIdx.x == 0) inv_scale[batch * rows + r] = inv;
+}
+
 // Column-major source (element (r, k) at k*ld + r): maximum per r over k (atomicMax on the bits of |x|: order-independent,
 // hence deterministic), then a transposing split through a shared-memory tile.
 __global__ void __launch_bounds__(256) h16_colmax_kernel(const float* __restrict__ src, uint32_t* __restrict__ amax, int64_t rows,
@@ -675,7 +719,9 @@ static int h16_prepare(const float* src, int64_t rows, int64_t k, int64_t kpad, 
   if (k_contig) {
     const bool vec = (k % 8 == 0) && aligned16(src) && (ld % 4 == 0) && (batches == 1 || (s0 % 4 == 0 && s1 % 4 == 0));
     dim3 grid((unsigned)ceil_div(rows, 8), (unsigned)batches);
-    if (vec) h16_split_rows_kernel<true><<<grid, 256, 0, s>>>(src, hi, lo, inv_scale, rows, k, kpad, ld, batch1, s0, s1);
+    if (vec && k > 1024 && k <= 8192)
+      h16_split_rows_block_kernel<<<dim3((unsigned)rows, (unsigned)batches), 256, 0, s>>>(src, hi, lo, inv_scale, rows, k, ld, batch1, s0, s1);
+    else if (vec) h16_split_rows_kernel<true><<<grid, 256, 0, s>>>(src, hi, lo, inv_scale, rows, k, kpad, ld, batch1, s0, s1);
     else h16_split_rows_kernel<false><<<grid, 256, 0, s>>>(src, hi, lo, inv_scale, rows, k, kpad, ld, batch1, s0, s1);
     count_launch();
   } else if (rows * k <= (1 << 20) && k <= 4096) {
