@@ -205,7 +205,9 @@ template <> struct AhOps<AH_DQ>  { static constexpr int A1 = 0, A2 = 3, B1 = 1, 
 template <> struct AhOps<AH_DKM> { static constexpr int A1 = 1, A2 = 2, B1 = 0, B2 = 3, B3 = 0, B4 = 0; };
 template <> struct AhOps<AH_DKV> { static constexpr int A1 = 1, A2 = 2, B1 = 0, B2 = 3, B3 = 0, B4 = 3; };
 
-template <int MODE, bool CP>
+// SINGLE (the looser-tolerance variant) is a template parameter: as a runtime flag inside the converter / row-owner / issue
+// loops it cost the default variant ~20 % of the backward (config-5 micro-batch, 5.45 against 4.5 ms per 512 sequences).
+template <int MODE, bool CP, bool SINGLE>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
@@ -424,14 +426,14 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       const uint32_t sb = smem_u32(smem + (size_t)s * AH_SLOT);
       const uint64_t dh = make_smem_desc(sb + AH_HI, 16, 1024, 2), dl = make_smem_desc(sb + AH_LO, 16, 1024, 2);
       const uint32_t dst = tmem_base + d_col, a_hi = tmem_base + a_col, a_lo = a_hi + 32u;
-      if (!p.single) {     // the two cross terms first (small), the dominant hi . hi term last
+      if (!SINGLE) {     // the two cross terms first (small), the dominant hi . hi term last
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_lo + kk * 8, dh + (uint64_t)(kk * 2), IDESC, kk ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dl + (uint64_t)(kk * 2), IDESC, 1u);
       }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dh + (uint64_t)(kk * 2), IDESC, (kk || !p.single) ? 1u : 0u);
+      for (int kk = 0; kk < 4; ++kk) mma_ts(dst, a_hi + kk * 8, dh + (uint64_t)(kk * 2), IDESC, (kk || !SINGLE) ? 1u : 0u);
       mma_commit(&empty[s]);
       mma_commit(done);
       if (a_done) mma_commit(a_done);
@@ -517,7 +519,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             return FUSED ? zb + 32u * (kk >> 1) + 16u * (kk & 1) : zb + 32u * (kk >> 1) + 8u * (kk & 1);
           };
           auto zlo = [&](int kk) -> uint32_t { return zhi(kk) + (FUSED ? 8u : 16u); };
-          if (!p.single) {
+          if (!SINGLE) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) mma_ts(dst, zlo(kk), dh + (uint64_t)(kk * 2), IDESC, (kk || !first) ? 1u : 0u);
 #pragma unroll
@@ -525,7 +527,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_ts(dst, zhi(kk), dh + (uint64_t)(kk * 2), IDESC, (p.single && kk == 0 && first) ? 0u : 1u);
+            mma_ts(dst, zhi(kk), dh + (uint64_t)(kk * 2), IDESC, (SINGLE && kk == 0 && first) ? 0u : 1u);
           mma_commit(&empty[slot]);
         };
         if (elect_one()) {
@@ -636,8 +638,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 #pragma unroll
         for (int c = 0; c < 8; ++c) {     // SWIZZLE_128B: 16 B chunk c of row r sits at chunk c ^ (r & 7)
           const uint4 t4 = ah_lds128(row + ((c ^ (r & 7)) << 4));
-          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * c], lo[2 * c], p.single);
-          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * c + 1], lo[2 * c + 1], p.single);
+          ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * c], lo[2 * c], SINGLE);
+          ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * c + 1], lo[2 * c + 1], SINGLE);
         }
         ah_tmem_st_x16(lane_base + col + hh * 16, hi);
         ah_tmem_st_x16(lane_base + col + 32 + hh * 16, lo);
@@ -668,8 +670,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       for (int i = 0; i < NV; ++i) {
         const int f = f0 + i, half = f >> 3, c = f & 7;
         const uint4 t4 = ah_lds128(slot + half * (ROWS * 128) + row * 128 + ((c ^ (row & 7)) << 4));
-        ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * i], lo[2 * i], p.single);
-        ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * i + 1], lo[2 * i + 1], p.single);
+        ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * i], lo[2 * i], SINGLE);
+        ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * i + 1], lo[2 * i + 1], SINGLE);
       }
       // fp16 tile: row = 128 B = 8 chunks of 8 elements; this thread's 8*NV/8... elements [8 f0 / 2 ...]: 4 floats -> 8 B,
       // so NV float4 -> NV/2 chunks starting at chunk f0 / 2
@@ -705,7 +707,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       for (int i = 0; i < NK / 2; ++i) {
         const float v0 = __uint_as_float(ah_lds32(src + (2 * i) * 128)) * sc;
         const float v1 = __uint_as_float(ah_lds32(src + (2 * i + 1) * 128)) * sc;
-        ah_split2(v0, v1, hi[i], lo[i], p.single);
+        ah_split2(v0, v1, hi[i], lo[i], SINGLE);
       }
 #pragma unroll
       for (int i = 0; i < NK / 8; ++i) {                     // 8 kv elements = one 16 B chunk
@@ -756,8 +758,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const uint4 t4 = t ? tb[2 * i + u] : ta[2 * i + u];
-            ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * u], lo[2 * u], p.single);
-            ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * u + 1], lo[2 * u + 1], p.single);
+            ah_split2(__uint_as_float(t4.x) * sc, __uint_as_float(t4.y) * sc, hi[2 * u], lo[2 * u], SINGLE);
+            ah_split2(__uint_as_float(t4.z) * sc, __uint_as_float(t4.w) * sc, hi[2 * u + 1], lo[2 * u + 1], SINGLE);
           }
           const int ch = f0 / 2 + i;
           const uint32_t dst = row * 128 + ((ch ^ (row & 7)) << 4);
@@ -795,7 +797,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         for (int i = 0; i < NK / 2; ++i) {
           const float v0 = __uint_as_float(ah_lds32(slot + rel + (2 * i) * 128)) * sc;
           const float v1 = __uint_as_float(ah_lds32(slot + rel + (2 * i + 1) * 128)) * sc;
-          ah_split2(v0, v1, hi[i], lo[i], p.single);
+          ah_split2(v0, v1, hi[i], lo[i], SINGLE);
         }
 #pragma unroll
         for (int i = 0; i < NK / 8; ++i) {
@@ -986,7 +988,7 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             const float p1 = ah_exp2(fmaf(__uint_as_float(x[c + 1]), c2e, -mc));
             sm[c & 3] += p0;
             sm[(c + 1) & 3] += p1;
-            ah_split2(p0, p1, zh[c >> 1], zl[c >> 1], p.single);
+            ah_split2(p0, p1, zh[c >> 1], zl[c >> 1], SINGLE);
           }
           ah_tmem_st_x16(xaddr, zh);
           ah_tmem_st_x16(xaddr + 16, zl);
@@ -1017,8 +1019,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                 const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
                 const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
                 const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
-                ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1], p.single);
-                ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1], p.single);
+                ah_split2(p0, p1, zh[c4 >> 1], zl[c4 >> 1], SINGLE);
+                ah_split2(p2, p3, zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1], SINGLE);
               }
               ah_tmem_st_x16(xa, zh);
               ah_tmem_st_x16(xa + 16, zl);
@@ -1040,12 +1042,12 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                   const float p1 = ah_exp2(fmaf(__uint_as_float(x[c4 + 1]), c2e, -l4.y));
                   const float p2 = ah_exp2(fmaf(__uint_as_float(x[c4 + 2]), c2e, -l4.z));
                   const float p3 = ah_exp2(fmaf(__uint_as_float(x[c4 + 3]), c2e, -l4.w));
-                  ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1], p.single);
-                  ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1], p.single);
+                  ah_split2(p0, p1, z2h[c4 >> 1], z2l[c4 >> 1], SINGLE);
+                  ah_split2(p2, p3, z2h[(c4 >> 1) + 1], z2l[(c4 >> 1) + 1], SINGLE);
                   ah_split2(p0 * fmaf(__uint_as_float(y[c4]), ce, -d4.x), p1 * fmaf(__uint_as_float(y[c4 + 1]), ce, -d4.y),
-                            z1h[c4 >> 1], z1l[c4 >> 1], p.single);
+                            z1h[c4 >> 1], z1l[c4 >> 1], SINGLE);
                   ah_split2(p2 * fmaf(__uint_as_float(y[c4 + 2]), ce, -d4.z), p3 * fmaf(__uint_as_float(y[c4 + 3]), ce, -d4.w),
-                            z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1], p.single);
+                            z1h[(c4 >> 1) + 1], z1l[(c4 >> 1) + 1], SINGLE);
                 }
                 ah_tmem_st_x8(xa + 16u * hf, z1h);
                 ah_tmem_st_x8(xa + 16u * hf + 8u, z1l);
@@ -1085,8 +1087,8 @@ attn_h16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
                   const float pv = ah_exp2(fmaf(__uint_as_float(x[c]), c2e, -ls[i]));
                   z[i] = pv * fmaf(__uint_as_float(y[c]), ce, -dd[i]);
                 }
-                ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1], p.single);
-                ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1], p.single);
+                ah_split2(z[0], z[1], zh[c4 >> 1], zl[c4 >> 1], SINGLE);
+                ah_split2(z[2], z[3], zh[(c4 >> 1) + 1], zl[(c4 >> 1) + 1], SINGLE);
               }
               ah_tmem_st_x16(xa, zh);
               ah_tmem_st_x16(xa + 16, zl);
@@ -1272,7 +1274,7 @@ static int ah_encode(CUtensorMap* map, const AttnHTensor& t, int64_t B, int64_t 
   return B200AD_OK;
 }
 
-template <int MODE, bool CP>
+template <int MODE, bool CP, bool SINGLE>
 static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTensor& b1, const AttnHTensor& b2,
                           const AttnHTensor& b3, const AttnHTensor& b4, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
   constexpr bool HAS2 = (MODE == AH_DQ || MODE == AH_DKM || MODE == AH_DKV);
@@ -1301,7 +1303,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_h16_kernel<MODE, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AH_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_h16_kernel<MODE, CP, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AH_SMEM);
     if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1330,7 +1332,7 @@ static int ah_launch_impl(const AttnHTensor& a1, const AttnHTensor& a2, const At
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_h16_kernel<MODE, CP>, m_a1, m_a2, m_b1, m_b2, m_b3, m_b4, m_out, m_out2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_h16_kernel<MODE, CP, SINGLE>, m_a1, m_a2, m_b1, m_b2, m_b3, m_b4, m_out, m_out2, p);
   if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "attention(h16): launch: %s", cudaGetErrorString(e));
   count_launch();
   if (want_prof && prof_dev) {
@@ -1372,8 +1374,12 @@ static int ah_launch(const AttnHTensor& a1, const AttnHTensor& a2, const AttnHTe
                      const AttnHTensor& b3, const AttnHTensor& b4, AttnHParams p, int64_t B, int64_t H, cudaStream_t s) {
   static const char* e = getenv("B200AD_ATTN_PAIR");
   const bool pair = e ? atoi(e) == 1 : (ceil_div(p.R, AH_BM) % 2 == 0);
-  if (pair) return ah_launch_impl<MODE, true>(a1, a2, b1, b2, b3, b4, p, B, H, s);
-  return ah_launch_impl<MODE, false>(a1, a2, b1, b2, b3, b4, p, B, H, s);
+  if (p.single) {
+    if (pair) return ah_launch_impl<MODE, true, true>(a1, a2, b1, b2, b3, b4, p, B, H, s);
+    return ah_launch_impl<MODE, false, true>(a1, a2, b1, b2, b3, b4, p, B, H, s);
+  }
+  if (pair) return ah_launch_impl<MODE, true, false>(a1, a2, b1, b2, b3, b4, p, B, H, s);
+  return ah_launch_impl<MODE, false, false>(a1, a2, b1, b2, b3, b4, p, B, H, s);
 }
 
 static AhAmaxJob ah_job(const float* x, const b200ad_attn_strides& st, int64_t B, int64_t H, int64_t S, int slot,
