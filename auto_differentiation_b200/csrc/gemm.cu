@@ -61,6 +61,9 @@ static bool f16x3_auto_pick(const GemmArgs& g, int count = 1) {
   const double batches = (double)(g.batch0 * g.batch1);
   const double tiles = (double)(ceil_div(g.m, 256) * ceil_div(g.n, 256)) * batches;
   const double pairs = sm_count() / 2;
+  // less than two waves of tiles: launch / ramp costs the model does not carry decide (config 3's M = 8192 projections
+  // measured 39 against 28 us), unless K is long enough for split-K to fill the machine
+  if (tiles < 2 * pairs && g.k < 2048) return false;
   const double waves = (double)ceil_div((int64_t)tiles, (int64_t)pairs);
   const double kb = (double)ceil_div(g.k, 64);
   double cyc = kb * 1536.0;
