@@ -420,7 +420,7 @@ def run_c5(args):
         if isinstance(key[0], str):
             issued = (1.0 if loose_attn else 3.0) * (1.0 if key[0] == "attn_fwd" else attn_bwd_units / 4.0)
         else:
-            issued = 3.0 if int(key[6]) in (1, 3) else 1.0       # b200ad_gemm_precision: TF32X3 / AUTO
+            issued = 3.0 if int(key[6]) in (1, 3, 5) else 1.0    # b200ad_gemm_precision: TF32X3 / AUTO / F16X3
         h16_kernel = isinstance(key[0], str) and h16
         pipe_peak = peak if h16_kernel else peak / 2.0      # kind::f16 issues at the bf16 rate, kind::tf32 at half of it
         # every timed tensor-core kernel family with its share of the step (the dominant one is `kernel`)
@@ -450,7 +450,7 @@ def run_c5(args):
         "metric": "fwd+bwd+update steps/sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": {"auto": "f32", "fp32": "f32", "tf32x3": "f32", "bf16": "bf16", "tf32": "tf32"}[args.precision],
+        "dtype": {"auto": "f32", "fp32": "f32", "tf32x3": "f32", "f16x3": "f32", "bf16": "bf16", "tf32": "tf32"}[args.precision],
         "data": "synthetic", "config": workload_config(world, args.micro_batch), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "loss": loss_val,
         "gemm_precision": args.precision,
@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "bf16", "tf32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "f16x3", "bf16", "tf32"])
     ap.add_argument("--micro-batch", type=int, default=0,
                     help="sequences per micro-batch; 0 = automatic: 512 when a rank holds >= 4096 sequences, else 256 (at least\n"
                          "four host->device chunks per step so the input stream overlaps the compute)")
