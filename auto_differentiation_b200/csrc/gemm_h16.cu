@@ -40,6 +40,7 @@ struct H16Params {
   float* c;
   const float* bias;
   float* partial;
+  const float* scale_a;        // A_RAW only: [m] forward row scales of A (the kernel converts the raw fp32 tile itself)
   const float* inv_a;          // [batches][m] inverse row scales of A (powers of two)
   const float* inv_b;          // [batches][n]
   int64_t m, n, k;
@@ -79,6 +80,33 @@ __device__ __forceinline__ float h16_act(float x, int act) {
   return x;
 }
 
+// scale = 2^(14 - floor(log2 amax)): the largest element of the row lands in [2^14, 2^15); hi = RN16(x s),
+// lo = RN16(x s - hi) (the difference is exact in fp32).  Elements below 2^-18 of the row maximum lose relative precision
+// to fp16's subnormal floor (absolute error <= 2^-40 of the row maximum).  amax_bits: bits of the non-negative maximum.
+__device__ __forceinline__ void h16_scales(uint32_t amax_bits, float& scale, float& inv) {
+  int se = 268 - (int)((amax_bits >> 23) & 0xffu);
+  se = se < 1 ? 1 : (se > 253 ? 253 : se);
+  scale = __uint_as_float((uint32_t)se << 23);
+  inv = __uint_as_float((uint32_t)(254 - se) << 23);
+}
+__device__ __forceinline__ void h16_split(float x, float scale, __half& hi, __half& lo) {
+  const float xs = x * scale;
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t h16_absbits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+__device__ __forceinline__ uint32_t h16_warp_umax(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t h16_pack(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
 // Tile order: groups of 8 m-tiles, n fastest inside a group (the tiles in flight share L2-resident panels).
 __device__ __forceinline__ void h16_decode_tile(int tile, const H16Params& p, int& m_tile, int& n_tile, int& split, int& batch) {
   const int per_mat = p.m_tiles * p.n_tiles;
@@ -94,15 +122,24 @@ __device__ __forceinline__ void h16_decode_tile(int tile, const H16Params& p, in
   n_tile = rr / gm;
 }
 
+// A_RAW: op(A) is row-major fp32 in HBM and is converted INSIDE the kernel (no plane pre-pass, only the row scales): TMA
+// delivers the raw 128 x 64 fp32 tile as two 128 B-wide halves (k 0..31 | k 32..63, SWIZZLE_128B) into the 32 KB the hi and lo
+// tiles will occupy; converter thread r (warps 4-7) owns row r of BOTH halves and rewrites them IN PLACE as row r of the hi tile
+// (where half 0 was) and of the lo tile (where half 1 was) — same swizzle phase (r & 7), no other thread touches those 256
+// bytes, so no barrier inside the conversion.  Loads then signal the CTA's own barrier, the converter warps of both CTAs
+// arrive on the leader's conv_full (8 arrivals) and the MMA warp waits for that instead.
+template <bool A_RAW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H_THREADS, 1)
 gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_c, const H16Params p) {
   constexpr int BN = 256, R = H_STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bars[2 * R + 4];
+  __shared__ uint64_t bars[3 * R + 4];
   __shared__ uint32_t tmem_base_smem;
+  uint64_t* conv_full = bars + 2 * R + 4;  // [R] A_RAW: converter warps of BOTH CTAs (8 arrivals) -> leader's MMA warp
   uint64_t* full = bars;                 // [R] (leader's copy is the live one) TMA of BOTH CTAs -> leader's MMA warp
+                                         //     A_RAW: every CTA's own copy, its TMA -> its converter warps
   uint64_t* empty = bars + R;            // [R] MMA commit (multicast) -> TMA of both CTAs
   uint64_t* tmem_full = bars + 2 * R;    // [2] MMA commit (multicast) -> fold warps of both CTAs: a chunk sum is complete
   uint64_t* tmem_empty = tmem_full + 2;  // [2] fold warps of both CTAs (16 arrivals) -> leader's MMA warp
@@ -117,6 +154,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int s = 0; s < R; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&conv_full[s], 2 * 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -153,13 +191,22 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const int s = it % R;
           mbar_wait(&empty[s], ((it / R) & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + (size_t)s * H_STAGE_BYTES);
-          if (rank == 0) mbar_expect_tx(&full[s], 2 * H_STAGE_BYTES);
-          const uint32_t bar = leader_full0 + (uint32_t)s * 8u;
           const int k0 = kb * H_BK;
-          h16_tma_load_pair(&map_a, bar, sa, k0, m0, batch, 0);                          // A hi
-          h16_tma_load_pair(&map_a, bar, sa + H_TILE_BYTES, k0, m0, batch, 1);           // A lo
-          h16_tma_load_pair(&map_b, bar, sa + 2 * H_TILE_BYTES, k0, n0, batch, 0);       // B hi (this CTA's 128 columns)
-          h16_tma_load_pair(&map_b, bar, sa + 3 * H_TILE_BYTES, k0, n0, batch, 1);       // B lo
+          if constexpr (A_RAW) {
+            uint8_t* st = smem + (size_t)s * H_STAGE_BYTES;
+            mbar_expect_tx(&full[s], H_STAGE_BYTES);
+            tma_load_4d(&map_a, &full[s], st, k0, m0, 0, 0);                             // raw fp32, k0 .. k0+31
+            tma_load_4d(&map_a, &full[s], st + H_TILE_BYTES, k0 + 32, m0, 0, 0);         // raw fp32, k0+32 .. k0+63
+            tma_load_4d(&map_b, &full[s], st + 2 * H_TILE_BYTES, k0, n0, batch, 0);      // B hi (this CTA's 128 columns)
+            tma_load_4d(&map_b, &full[s], st + 3 * H_TILE_BYTES, k0, n0, batch, 1);      // B lo
+          } else {
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * H_STAGE_BYTES);
+            const uint32_t bar = leader_full0 + (uint32_t)s * 8u;
+            h16_tma_load_pair(&map_a, bar, sa, k0, m0, batch, 0);                        // A hi
+            h16_tma_load_pair(&map_a, bar, sa + H_TILE_BYTES, k0, m0, batch, 1);         // A lo
+            h16_tma_load_pair(&map_b, bar, sa + 2 * H_TILE_BYTES, k0, n0, batch, 0);     // B hi (this CTA's 128 columns)
+            h16_tma_load_pair(&map_b, bar, sa + 3 * H_TILE_BYTES, k0, n0, batch, 1);     // B lo
+          }
         }
       }
     }
@@ -188,7 +235,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int kb = cb0; kb < cb1; ++kb, ++it) {
             const int s = it % R;
             q0 = prof ? clock64() : 0;
-            mbar_wait(&full[s], (it / R) & 1);                   // both CTAs' four tiles of this stage have landed
+            mbar_wait(A_RAW ? &conv_full[s] : &full[s], (it / R) & 1);   // both CTAs' four tiles of this stage are ready
             if (prof) w_full += clock64() - q0;
             tc_fence_after();
             if (elect_one()) {
@@ -218,10 +265,63 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   }
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if constexpr (!A_RAW) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    } else {
+      // ===================================== converter (both CTAs): raw fp32 A tile -> hi / lo fp16 tiles, in place =====
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      const int r = (int)threadIdx.x - 128;                    // row of this CTA's 128-row A tile
+      const uint32_t sw = (uint32_t)(r & 7);
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+        int m_tile, n_tile, split, batch;
+        h16_decode_tile(tile, p, m_tile, n_tile, split, batch);
+        const int kb0 = split * p.kblocks_per_split;
+        int kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+        const int64_t gm = (int64_t)m_tile * 256 + (int64_t)rank * 128 + r;
+        const float sc = gm < p.m ? __ldg(p.scale_a + gm) : 1.f;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % R;
+          mbar_wait(&full[s], (it / R) & 1);                   // this CTA's raw A halves (and its B planes) have landed
+          const uint32_t row0 = smem_u32(smem + (size_t)s * H_STAGE_BYTES) + (uint32_t)r * 128u, row1 = row0 + H_TILE_BYTES;
+          // half 1 (k 32..63) goes to registers first: its bytes receive the lo chunks of half 0
+          uint4 h1v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) h1v[c] = h16_lds128(row1 + (((uint32_t)c ^ sw) << 4));
+          // half 0 progressively in place: output chunk j (8 elements) needs raw chunks 2j, 2j+1 and overwrites position j <= 2j
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 a = h16_lds128(row0 + (((uint32_t)(2 * j) ^ sw) << 4)), b = h16_lds128(row0 + (((uint32_t)(2 * j + 1) ^ sw) << 4));
+            __half h[8], l[8];
+            h16_split(__uint_as_float(a.x), sc, h[0], l[0]); h16_split(__uint_as_float(a.y), sc, h[1], l[1]);
+            h16_split(__uint_as_float(a.z), sc, h[2], l[2]); h16_split(__uint_as_float(a.w), sc, h[3], l[3]);
+            h16_split(__uint_as_float(b.x), sc, h[4], l[4]); h16_split(__uint_as_float(b.y), sc, h[5], l[5]);
+            h16_split(__uint_as_float(b.z), sc, h[6], l[6]); h16_split(__uint_as_float(b.w), sc, h[7], l[7]);
+            h16_sts128(row0 + (((uint32_t)j ^ sw) << 4), make_uint4(h16_pack(h[0], h[1]), h16_pack(h[2], h[3]), h16_pack(h[4], h[5]), h16_pack(h[6], h[7])));
+            h16_sts128(row1 + (((uint32_t)j ^ sw) << 4), make_uint4(h16_pack(l[0], l[1]), h16_pack(l[2], l[3]), h16_pack(l[4], l[5]), h16_pack(l[6], l[7])));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                          // half 1 from registers -> chunks 4..7 of both tiles
+            const uint4 a = h1v[2 * j], b = h1v[2 * j + 1];
+            __half h[8], l[8];
+            h16_split(__uint_as_float(a.x), sc, h[0], l[0]); h16_split(__uint_as_float(a.y), sc, h[1], l[1]);
+            h16_split(__uint_as_float(a.z), sc, h[2], l[2]); h16_split(__uint_as_float(a.w), sc, h[3], l[3]);
+            h16_split(__uint_as_float(b.x), sc, h[4], l[4]); h16_split(__uint_as_float(b.y), sc, h[5], l[5]);
+            h16_split(__uint_as_float(b.z), sc, h[6], l[6]); h16_split(__uint_as_float(b.w), sc, h[7], l[7]);
+            h16_sts128(row0 + (((uint32_t)(4 + j) ^ sw) << 4), make_uint4(h16_pack(h[0], h[1]), h16_pack(h[2], h[3]), h16_pack(h[4], h[5]), h16_pack(h[6], h[7])));
+            h16_sts128(row1 + (((uint32_t)(4 + j) ^ sw) << 4), make_uint4(h16_pack(l[0], l[1]), h16_pack(l[2], l[3]), h16_pack(l[4], l[5]), h16_pack(l[6], l[7])));
+          }
+          fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA's shared-memory reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&conv_full[s], 0);  // one (cumulative) release per warp; the leader counts both CTAs
+        }
+      }
+    }
   } else {
     // ===================================== fold + epilogue (both CTAs, own 128 rows) =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if constexpr (A_RAW) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");   // 128 x 56 + 128 x 72 + 256 x 200 = 65536
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int q = warp & 3, hf = (warp - 8) >> 2;              // TMEM lane quarter, 128-column half of the tile
     const uint32_t stg = smem_u32(smem + (size_t)R * H_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
     const int sub_row = lane >> 3, chunk = lane & 7;
@@ -357,33 +457,6 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // operand pre-pass: fp32 -> (hi, lo) fp16 planes, K-major [plane][batch][rows][kpad], one power-of-two scale per row
 // ---------------------------------------------------------------------------------------------------------
-// scale = 2^(14 - floor(log2 amax)): the largest element of the row lands in [2^14, 2^15); hi = RN16(x s),
-// lo = RN16(x s - hi) (the difference is exact in fp32).  Elements below 2^-18 of the row maximum lose relative precision
-// to fp16's subnormal floor (absolute error <= 2^-40 of the row maximum).  amax_bits: bits of the non-negative maximum.
-__device__ __forceinline__ void h16_scales(uint32_t amax_bits, float& scale, float& inv) {
-  int se = 268 - (int)((amax_bits >> 23) & 0xffu);
-  se = se < 1 ? 1 : (se > 253 ? 253 : se);
-  scale = __uint_as_float((uint32_t)se << 23);
-  inv = __uint_as_float((uint32_t)(254 - se) << 23);
-}
-__device__ __forceinline__ void h16_split(float x, float scale, __half& hi, __half& lo) {
-  const float xs = x * scale;
-  hi = __float2half_rn(xs);
-  lo = __float2half_rn(xs - __half2float(hi));
-}
-__device__ __forceinline__ uint32_t h16_absbits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
-__device__ __forceinline__ uint32_t h16_warp_umax(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = w > v ? w : v;
-  }
-  return v;
-}
-__device__ __forceinline__ uint32_t h16_pack(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-
 // Row-major source (element (r, k) at r*ld + k): one warp per row does maximum, scale and split in one pass.
 // VEC: k % 8 == 0 (kpad == k), 16 B aligned rows: 128-bit loads, 64-bit stores; up to K = 1024 the row stays in registers
 // between the two steps, longer rows are read a second time (L1 / L2 hits).
@@ -462,6 +535,39 @@ __global__ void __launch_bounds__(256) h16_split_rows_kernel(const float* __rest
     }
   }
   if (lane == 0) inv_scale[batch * rows + r] = inv;
+}
+
+// A_RAW path: only the row scales are computed ahead of the GEMM (read-only pass; a warp per row)
+__global__ void __launch_bounds__(256) h16_rowscale_kernel(const float* __restrict__ src, float* __restrict__ scale_out,
+                                                           float* __restrict__ inv_out, int64_t rows, int64_t k, int64_t ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const float* row = src + r * ld;
+  uint32_t m = 0;
+  if ((k & 3) == 0) {                                         // callers guarantee 16 B aligned rows
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int n4 = (int)(k >> 2);
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = ldg_stream(row4 + i);
+      uint32_t a = h16_absbits(v.x), b = h16_absbits(v.y), c = h16_absbits(v.z), d = h16_absbits(v.w);
+      a = a > b ? a : b; c = c > d ? c : d; a = a > c ? a : c;
+      m = m > a ? m : a;
+    }
+  } else {
+    for (int64_t kk = lane; kk < k; kk += 32) {
+      const uint32_t a = h16_absbits(row[kk]);
+      m = m > a ? m : a;
+    }
+  }
+  m = h16_warp_umax(m);
+  float scale, inv;
+  h16_scales(m, scale, inv);
+  if (lane == 0) {
+    scale_out[r] = scale;
+    inv_out[r] = inv;
+  }
 }
 
 // Long rows (1024 < K <= 8192, K % 8 == 0, 16 B aligned): one 256-thread block per row, the row in registers (a warp per row
@@ -637,7 +743,7 @@ __global__ void __launch_bounds__(256) h16_splitk_reduce_kernel(const float* __r
 // host side
 // ---------------------------------------------------------------------------------------------------------
 // B200AD_H16_PROBE (diagnostic, read once): 1 = no output stores, 4 = skip the operand split (times the GEMM kernel alone on
-// whatever the workspace holds), 8 = print the MMA warp's wait cycles
+// whatever the workspace holds), 8 = print the MMA warp's wait cycles, 16 = no in-kernel conversion of A (plane path)
 static int h16_probe() {
   static int v = -1;
   if (v < 0) {
@@ -740,19 +846,42 @@ static int h16_prepare(const float* src, int64_t rows, int64_t k, int64_t kpad, 
   return check_launch("gemm(f16x3) operand split");
 }
 
-// GEMM proper on prepared planes
-static int h16_run(const GemmArgs& g, H16Plan pl, const __half* a_planes, const float* inv_a, const __half* b_planes,
-                   const float* inv_b, float* part, cudaStream_t s) {
+// op(A) row-major, one matrix, rows 16 B aligned: the kernel converts the raw tiles itself (A_RAW), the pre-pass only finds the
+// row scales.  B200AD_H16_PROBE bit 16 forces the plane path (A/B measurements).
+static bool h16_a_raw_ok(const GemmArgs& g) {
+  return !g.trans_a && g.batch0 * g.batch1 == 1 && (g.lda % 4) == 0 && aligned16(g.a) && !(h16_probe() & 16);
+}
+static int h16_prepare_raw_a(const GemmArgs& g, float* scale_a, float* inv_a, cudaStream_t s) {
+  if (h16_probe() & 4) return B200AD_OK;
+  h16_rowscale_kernel<<<(unsigned)ceil_div(g.m, 8), 256, 0, s>>>(g.a, scale_a, inv_a, g.m, g.k, g.lda);
+  count_launch();
+  return check_launch("gemm(f16x3) row scales");
+}
+
+// GEMM proper on prepared planes (a_planes == nullptr: A_RAW, the raw fp32 A of `g` + scale_a)
+static int h16_run(const GemmArgs& g, H16Plan pl, const __half* a_planes, const float* scale_a, const float* inv_a,
+                   const __half* b_planes, const float* inv_b, float* part, cudaStream_t s) {
   CUtensorMap map_a, map_b, map_c;
   int rc;
-  if ((rc = encode_h16_planes(&map_a, a_planes, g.m, pl.kpad, pl.batches))) return rc;
+  const bool a_raw = a_planes == nullptr;
+  if (a_raw) {
+    EncodeTiledFn enc = get_encode_fn();
+    cuuint64_t dims[4] = {(cuuint64_t)g.k, (cuuint64_t)g.m, 1, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)g.lda * 4, (cuuint64_t)g.lda * 4 * (cuuint64_t)g.m, (cuuint64_t)g.lda * 4 * (cuuint64_t)g.m};
+    cuuint32_t box[4] = {32u, 128u, 1u, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(g.a), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(B200AD_ERR_CUDA, "gemm(f16x3): cuTensorMapEncodeTiled (raw A) failed (%d)", (int)r);
+  } else if ((rc = encode_h16_planes(&map_a, a_planes, g.m, pl.kpad, pl.batches))) return rc;
   if ((rc = encode_h16_planes(&map_b, b_planes, g.n, pl.kpad, pl.batches))) return rc;
   if (!part) {
     pl.splits = 1;
     pl.kblocks_per_split = pl.kblocks;
   }
   H16Params p{};
-  p.c = g.c; p.bias = g.bias; p.partial = part; p.inv_a = inv_a; p.inv_b = inv_b;
+  p.c = g.c; p.bias = g.bias; p.partial = part; p.scale_a = scale_a; p.inv_a = inv_a; p.inv_b = inv_b;
   p.m = g.m; p.n = g.n; p.k = g.k;
   p.ldc = g.ldc; p.c_stride0 = g.c_stride0; p.c_stride1 = g.c_stride1;
   p.batch1 = g.batch1;                   // C addressing keeps the caller's two batch levels: batch = b0 * batch1 + b1
@@ -783,14 +912,16 @@ static int h16_run(const GemmArgs& g, H16Plan pl, const __half* a_planes, const 
   }
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_h16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_h16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
     if (e != cudaSuccess) return set_error(B200AD_ERR_CUDA, "gemm(f16x3): smem attribute: %s", cudaGetErrorString(e));
     attr = true;
   }
   const int64_t total_tiles = (int64_t)pl.batches * pl.splits * pl.m_tiles * pl.n_tiles;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (int)(total_tiles < pairs ? total_tiles : pairs);
-  gemm_h16_kernel<<<grid, H_THREADS, H_SMEM, s>>>(map_a, map_b, map_c, p);
+  if (a_raw) gemm_h16_kernel<true><<<grid, H_THREADS, H_SMEM, s>>>(map_a, map_b, map_c, p);
+  else gemm_h16_kernel<false><<<grid, H_THREADS, H_SMEM, s>>>(map_a, map_b, map_c, p);
   count_launch();
   rc = check_launch("gemm(f16x3)");
   if (rc) return rc;
@@ -829,13 +960,16 @@ int gemm_h16_launch(const GemmArgs& g, void* ws, int64_t ws_bytes, cudaStream_t 
   const H16Workspace w = h16_carve(pl, ws, ws_bytes);
   int rc;
   // A: (m x k), row-major unless trans_a; B: (k x n) row-major, i.e. K-contiguous only when trans_b
-  if ((rc = h16_prepare(g.a, g.m, g.k, pl.kpad, g.lda, !g.trans_a, pl.batches, g.batch1, g.a_stride0, g.a_stride1, w.a_planes,
-                        w.inv_a, w.amax_a, s)))
-    return rc;
+  const bool a_raw = h16_a_raw_ok(g);
+  float* scale_a = reinterpret_cast<float*>(w.amax_a);         // the maxima scratch doubles as the forward scales of a raw A
+  if (a_raw) rc = h16_prepare_raw_a(g, scale_a, w.inv_a, s);
+  else rc = h16_prepare(g.a, g.m, g.k, pl.kpad, g.lda, !g.trans_a, pl.batches, g.batch1, g.a_stride0, g.a_stride1, w.a_planes,
+                        w.inv_a, w.amax_a, s);
+  if (rc) return rc;
   if ((rc = h16_prepare(g.b, g.n, g.k, pl.kpad, g.ldb, g.trans_b != 0, pl.batches, g.batch1, g.b_stride0, g.b_stride1, w.b_planes,
                         w.inv_b, w.amax_b, s)))
     return rc;
-  return h16_run(g, pl, w.a_planes, w.inv_a, w.b_planes, w.inv_b, w.part, s);
+  return h16_run(g, pl, a_raw ? nullptr : w.a_planes, scale_a, w.inv_a, w.b_planes, w.inv_b, w.part, s);
 }
 
 // One A operand, `count` (B, C, bias) triples: A is split once.  Workspace: gemm_h16_workspace_bytes of the descriptor.
@@ -846,16 +980,19 @@ int gemm_h16_shared_a_launch(const GemmArgs& g0, int count, const float* const* 
     return set_error(B200AD_ERR_INVALID, "gemm_shared_a(f16x3): workspace of %lld bytes required", (long long)pl.total());
   const H16Workspace w = h16_carve(pl, ws, ws_bytes);
   int rc;
-  if ((rc = h16_prepare(g0.a, g0.m, g0.k, pl.kpad, g0.lda, !g0.trans_a, pl.batches, g0.batch1, g0.a_stride0, g0.a_stride1,
-                        w.a_planes, w.inv_a, w.amax_a, s)))
-    return rc;
+  const bool a_raw = h16_a_raw_ok(g0);
+  float* scale_a = reinterpret_cast<float*>(w.amax_a);
+  if (a_raw) rc = h16_prepare_raw_a(g0, scale_a, w.inv_a, s);
+  else rc = h16_prepare(g0.a, g0.m, g0.k, pl.kpad, g0.lda, !g0.trans_a, pl.batches, g0.batch1, g0.a_stride0, g0.a_stride1,
+                        w.a_planes, w.inv_a, w.amax_a, s);
+  if (rc) return rc;
   for (int i = 0; i < count; ++i) {
     GemmArgs g = g0;
     g.b = bs[i]; g.c = cs[i]; g.bias = biases ? biases[i] : nullptr;
     if ((rc = h16_prepare(g.b, g.n, g.k, pl.kpad, g.ldb, g.trans_b != 0, pl.batches, g.batch1, g.b_stride0, g.b_stride1,
                           w.b_planes, w.inv_b, w.amax_b, s)))
       return rc;
-    if ((rc = h16_run(g, pl, w.a_planes, w.inv_a, w.b_planes, w.inv_b, w.part, s))) return rc;
+    if ((rc = h16_run(g, pl, a_raw ? nullptr : w.a_planes, scale_a, w.inv_a, w.b_planes, w.inv_b, w.part, s))) return rc;
   }
   return B200AD_OK;
 }

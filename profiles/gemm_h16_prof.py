@@ -1,5 +1,6 @@
 """Diagnostic: where the fp16-split GEMM (csrc/gemm_h16.cu) spends its time.  Runs the config-5 projection and 8192^3 under the
-B200AD_H16_PROBE bits (1 = no output stores, 4 = no operand split: kernel alone, 8 = MMA-warp wait counters), each setting in
+B200AD_H16_PROBE bits (1 = no output stores, 4 = no operand split: kernel alone, 8 = MMA-warp wait counters, 16 = plane
+path instead of the in-kernel conversion of A), each setting in
 its own process (the library reads the variable once).
     python profiles/gemm_h16_prof.py            # all settings
     python profiles/gemm_h16_prof.py run        # one setting (B200AD_H16_PROBE from the environment)
@@ -32,6 +33,6 @@ def run():
 if len(sys.argv) > 1 and sys.argv[1] == "run":
     run()
 else:
-    for probe in ("0", "4", "5", "12"):
+    for probe in ("0", "16", "4", "5", "12"):
         env = dict(os.environ, B200AD_H16_PROBE=probe)
         subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=env, timeout=300)
