@@ -170,10 +170,11 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int total_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
-  // register budget: 512 x 128 at launch >= 128 x 56 + 128 x 24 + 256 x 208; an .inc beyond what the .decs release
+  // register budget: 512 x 128 = 65536 at launch must cover the three setmaxnreg values; an .inc beyond what the .decs release
   // would block forever, so the arithmetic is part of the kernel
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (A_RAW) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");    // A_RAW: 128 x 48 + 128 x 72 + 256 x 192 = 64512
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");                    // else:  128 x 56 + 128 x 24 + 256 x 208 = 63488
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
     if (elect_one()) {
@@ -320,7 +321,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else {
     // ===================================== fold + epilogue (both CTAs, own 128 rows) =====================================
-    if constexpr (A_RAW) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");   // 128 x 56 + 128 x 72 + 256 x 200 = 65536
+    if constexpr (A_RAW) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int q = warp & 3, hf = (warp - 8) >> 2;              // TMEM lane quarter, 128-column half of the tile
     const uint32_t stg = smem_u32(smem + (size_t)R * H_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
