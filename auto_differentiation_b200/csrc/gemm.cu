@@ -71,7 +71,7 @@ static bool f16x3_auto_pick(const GemmArgs& g, int count = 1) {
   if (tiles < pairs && kb >= 16) cyc = cyc * tiles / pairs + 11000.0;      // split-K spreads the k-blocks over the idle pairs
   const double t_kernel = waves * cyc / 1.7e9 + 2e-6;
   // row-major single-matrix A: converted inside the kernel, the pre-pass only reads it once for the row scales
-  const bool a_raw = !g.trans_a && batches == 1 && (g.lda % 4) == 0;
+  const bool a_raw = !g.trans_a && batches == 1 && (g.lda % 4) == 0 && g.n <= 2048;
   const double t_a = (double)g.m * g.k * batches * (g.trans_a ? 4e-12 : (a_raw ? 0.7e-12 : 2e-12)) + 3e-6;
   const double t_b = (double)g.n * g.k * batches * (g.trans_b ? 2e-12 : 4e-12) + 3e-6;
   const double t_h16 = t_a + count * (t_b + t_kernel);

@@ -94,6 +94,17 @@ __device__ __forceinline__ void h16_split(float x, float scale, __half& hi, __ha
   hi = __float2half_rn(xs);
   lo = __float2half_rn(xs - __half2float(hi));
 }
+// The in-kernel converter's split of a pair (same scheme as attn_h16.cu's ah_split2): hi = x s TRUNCATED to 11 significant bits
+// (a mask; exactly an fp16 value, so the packed conversion is exact), lo = RN16(x s - hi).  One bit less in lo than the
+// round-to-nearest split of the pre-pass, a third of its instruction cost (scalar F2F conversions issue at a quarter rate).
+__device__ __forceinline__ void h16_split_pair_trunc(float x0, float x1, float scale, uint32_t& hi, uint32_t& lo) {
+  const float v0 = x0 * scale, v1 = x1 * scale;
+  const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
+  const __half2 hh = __floats2half2_rn(h0, h1);
+  const __half2 ll = __floats2half2_rn(v0 - h0, v1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
 __device__ __forceinline__ uint32_t h16_absbits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
 __device__ __forceinline__ uint32_t h16_warp_umax(uint32_t v) {
 #pragma unroll
@@ -294,24 +305,24 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 a = h16_lds128(row0 + (((uint32_t)(2 * j) ^ sw) << 4)), b = h16_lds128(row0 + (((uint32_t)(2 * j + 1) ^ sw) << 4));
-            __half h[8], l[8];
-            h16_split(__uint_as_float(a.x), sc, h[0], l[0]); h16_split(__uint_as_float(a.y), sc, h[1], l[1]);
-            h16_split(__uint_as_float(a.z), sc, h[2], l[2]); h16_split(__uint_as_float(a.w), sc, h[3], l[3]);
-            h16_split(__uint_as_float(b.x), sc, h[4], l[4]); h16_split(__uint_as_float(b.y), sc, h[5], l[5]);
-            h16_split(__uint_as_float(b.z), sc, h[6], l[6]); h16_split(__uint_as_float(b.w), sc, h[7], l[7]);
-            h16_sts128(row0 + (((uint32_t)j ^ sw) << 4), make_uint4(h16_pack(h[0], h[1]), h16_pack(h[2], h[3]), h16_pack(h[4], h[5]), h16_pack(h[6], h[7])));
-            h16_sts128(row1 + (((uint32_t)j ^ sw) << 4), make_uint4(h16_pack(l[0], l[1]), h16_pack(l[2], l[3]), h16_pack(l[4], l[5]), h16_pack(l[6], l[7])));
+            uint4 h, l;
+            h16_split_pair_trunc(__uint_as_float(a.x), __uint_as_float(a.y), sc, h.x, l.x);
+            h16_split_pair_trunc(__uint_as_float(a.z), __uint_as_float(a.w), sc, h.y, l.y);
+            h16_split_pair_trunc(__uint_as_float(b.x), __uint_as_float(b.y), sc, h.z, l.z);
+            h16_split_pair_trunc(__uint_as_float(b.z), __uint_as_float(b.w), sc, h.w, l.w);
+            h16_sts128(row0 + (((uint32_t)j ^ sw) << 4), h);
+            h16_sts128(row1 + (((uint32_t)j ^ sw) << 4), l);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                          // half 1 from registers -> chunks 4..7 of both tiles
             const uint4 a = h1v[2 * j], b = h1v[2 * j + 1];
-            __half h[8], l[8];
-            h16_split(__uint_as_float(a.x), sc, h[0], l[0]); h16_split(__uint_as_float(a.y), sc, h[1], l[1]);
-            h16_split(__uint_as_float(a.z), sc, h[2], l[2]); h16_split(__uint_as_float(a.w), sc, h[3], l[3]);
-            h16_split(__uint_as_float(b.x), sc, h[4], l[4]); h16_split(__uint_as_float(b.y), sc, h[5], l[5]);
-            h16_split(__uint_as_float(b.z), sc, h[6], l[6]); h16_split(__uint_as_float(b.w), sc, h[7], l[7]);
-            h16_sts128(row0 + (((uint32_t)(4 + j) ^ sw) << 4), make_uint4(h16_pack(h[0], h[1]), h16_pack(h[2], h[3]), h16_pack(h[4], h[5]), h16_pack(h[6], h[7])));
-            h16_sts128(row1 + (((uint32_t)(4 + j) ^ sw) << 4), make_uint4(h16_pack(l[0], l[1]), h16_pack(l[2], l[3]), h16_pack(l[4], l[5]), h16_pack(l[6], l[7])));
+            uint4 h, l;
+            h16_split_pair_trunc(__uint_as_float(a.x), __uint_as_float(a.y), sc, h.x, l.x);
+            h16_split_pair_trunc(__uint_as_float(a.z), __uint_as_float(a.w), sc, h.y, l.y);
+            h16_split_pair_trunc(__uint_as_float(b.x), __uint_as_float(b.y), sc, h.z, l.z);
+            h16_split_pair_trunc(__uint_as_float(b.z), __uint_as_float(b.w), sc, h.w, l.w);
+            h16_sts128(row0 + (((uint32_t)(4 + j) ^ sw) << 4), h);
+            h16_sts128(row1 + (((uint32_t)(4 + j) ^ sw) << 4), l);
           }
           fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA's shared-memory reads
           __syncwarp();
@@ -850,7 +861,8 @@ static int h16_prepare(const float* src, int64_t rows, int64_t k, int64_t kpad, 
 // op(A) row-major, one matrix, rows 16 B aligned: the kernel converts the raw tiles itself (A_RAW), the pre-pass only finds the
 // row scales.  B200AD_H16_PROBE bit 16 forces the plane path (A/B measurements).
 static bool h16_a_raw_ok(const GemmArgs& g) {
-  return !g.trans_a && g.batch0 * g.batch1 == 1 && (g.lda % 4) == 0 && aligned16(g.a) && !(h16_probe() & 16);
+  // (each of the N / 256 column tiles of a row panel converts the panel again: beyond N = 2048 the one-time plane split is cheaper)
+  return !g.trans_a && g.batch0 * g.batch1 == 1 && (g.lda % 4) == 0 && aligned16(g.a) && g.n <= 2048 && !(h16_probe() & 16);
 }
 static int h16_prepare_raw_a(const GemmArgs& g, float* scale_a, float* inv_a, cudaStream_t s) {
   if (h16_probe() & 4) return B200AD_OK;
