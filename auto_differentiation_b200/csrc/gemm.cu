@@ -66,12 +66,13 @@ static bool f16x3_auto_pick(const GemmArgs& g, int count = 1) {
   if (tiles < 2 * pairs && g.k < 2048) return false;
   const double waves = (double)ceil_div((int64_t)tiles, (int64_t)pairs);
   const double kb = (double)ceil_div(g.k, 64);
-  double cyc = kb * 1536.0;
+  // row-major single-matrix A: converted inside the kernel (measured ~2300 cycles per k-block instead of the 1536 of pure MMA
+  // time), the pre-pass only reads it once for the row scales
+  const bool a_raw = !g.trans_a && batches == 1 && (g.lda % 4) == 0 && g.n <= 2048;
+  double cyc = kb * (a_raw ? 2300.0 : 1536.0);
   if (cyc < 11000.0) cyc = 11000.0;
   if (tiles < pairs && kb >= 16) cyc = cyc * tiles / pairs + 11000.0;      // split-K spreads the k-blocks over the idle pairs
   const double t_kernel = waves * cyc / 1.7e9 + 2e-6;
-  // row-major single-matrix A: converted inside the kernel, the pre-pass only reads it once for the row scales
-  const bool a_raw = !g.trans_a && batches == 1 && (g.lda % 4) == 0 && g.n <= 2048;
   const double t_a = (double)g.m * g.k * batches * (g.trans_a ? 4e-12 : (a_raw ? 0.7e-12 : 2e-12)) + 3e-6;
   const double t_b = (double)g.n * g.k * batches * (g.trans_b ? 2e-12 : 4e-12) + 3e-6;
   const double t_h16 = t_a + count * (t_b + t_kernel);
