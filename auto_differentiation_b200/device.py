@@ -62,6 +62,26 @@ def raw_bytes(n):
     return torch.empty(max(int(n), 1), dtype=torch.uint8, device=_DEVICE)
 
 
+# GEMM workspaces: launches of one stream are ordered, so consecutive products of a stream share ONE grow-only buffer instead
+# of a torch.empty per call (~4 us of host time each on the launch-bound paths).  Outgrown buffers stay referenced (a CUDA
+# graph may have baked their address in; sizes grow geometrically, so the total stays below twice the largest).  While a
+# stream is being captured the allocation goes through torch (the graph's private pool), as before.
+_ws_cache = {}
+_ws_keep = []
+
+
+def _workspace(nbytes, stream):
+    if _DEVICE != "cpu" and torch.cuda.is_current_stream_capturing():
+        return raw_bytes(nbytes)
+    t = _ws_cache.get(stream)
+    if t is None or t.numel() < nbytes:
+        if t is not None:
+            _ws_keep.append(t)
+        size = 1 << max(int(nbytes) - 1, 1).bit_length()
+        t = _ws_cache[stream] = torch.empty(size, dtype=torch.uint8, device=_DEVICE)
+    return t
+
+
 def _lib():
     return L.load()
 
@@ -809,15 +829,16 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
     if hit is not None:
         d, ws_bytes, out_shape, tkey, flops = hit
         if out is None:
-            out = empty(out_shape)
-        ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
+            out = DeviceArray(torch.empty(out_shape, dtype=_F32, device=_DEVICE))
+        sp = stream_ptr()
+        ws = _workspace(ws_bytes, sp) if ws_bytes > 0 else None
         timer = _gemm_timer[0]
         if timer is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         L.check(_lib().b200ad_gemm(ctypes.byref(d), ta.data_ptr(), tb.data_ptr(), out.t.data_ptr(),
                                    bias.ptr if bias is not None else None, ws.data_ptr() if ws is not None else None,
-                                   ws_bytes, stream_ptr()))
+                                   ws_bytes, sp))
         if timer is not None:
             e1.record()
             timer.records.append((tkey, flops, e0, e1))
@@ -881,7 +902,7 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, preci
     d.a_stride0, d.b_stride0, d.c_stride0 = dims[0][1]
     d.a_stride1, d.b_stride1, d.c_stride1 = dims[1][1]
     ws_bytes = int(lib.b200ad_gemm_workspace_bytes(ctypes.byref(d)))
-    ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
+    ws = _workspace(ws_bytes, s) if ws_bytes > 0 else None
     wptr = ws.data_ptr() if ws is not None else None
     pa, pb, pc = ta.data_ptr(), tb.data_ptr(), tc.data_ptr()
     if cacheable and not outer and a.t.dim() >= 2 and b.t.dim() >= 2:
@@ -941,17 +962,18 @@ def matmul_shared_a(a, bs, precision=None):
             _shared_a_plans.clear()
         hit = _shared_a_plans[key] = (d, ws_bytes, (M, N), (M, N, K, 1, la[0], lb[0], d.precision), 2.0 * M * N * K)
     d, ws_bytes, out_shape, tkey, flops = hit
-    outs = [empty(out_shape) for _ in tbs]
+    outs = [DeviceArray(torch.empty(out_shape, dtype=_F32, device=_DEVICE)) for _ in tbs]
     n = len(tbs)
     arr = ctypes.c_void_p * n
-    ws = raw_bytes(ws_bytes) if ws_bytes > 0 else None
+    sp = stream_ptr()
+    ws = _workspace(ws_bytes, sp) if ws_bytes > 0 else None
     timer = _gemm_timer[0]
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     L.check(_lib().b200ad_gemm_shared_a(ctypes.byref(d), ta.data_ptr(), n, arr(*[t.data_ptr() for t in tbs]),
                                         arr(*[o.t.data_ptr() for o in outs]), None,
-                                        ws.data_ptr() if ws is not None else None, ws_bytes, stream_ptr()))
+                                        ws.data_ptr() if ws is not None else None, ws_bytes, sp))
     if timer is not None:
         e1.record()
         # one record per product so that launch counts and per-launch flops stay comparable with `matmul` records
