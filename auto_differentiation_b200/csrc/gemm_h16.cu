@@ -6,19 +6,22 @@
 // exponent bits).  Reference calls replaced: the same np.matmul / np.dot sites as gemm_tc.cu (Matmul tgrad.py:523-551,
 // TimeAffine layers.py:280-308, MultiHeadAttention projections :1347-1349,:1360).
 //
-// Unlike gemm_tc3_kernel the split is NOT done inside the GEMM (its splitter warps would bound the kernel at ~1.35x,
-// DESIGN section 8 item 2): a pre-pass writes K-major fp16 hi / lo planes + the inverse row scales into the caller's
-// workspace (one fused pass for row-major operands: row maximum, scale, split; column maximum + transposing split for
-// the others), and the GEMM itself is pure TMA + MMA:
-//   CTA pair (cta_group::2), 256 x 256 tiles, BK = 64 (128 B rows, SWIZZLE_128B), 3-stage ring of {A hi, A lo, B hi, B lo}
-//   tiles (64 KB per stage and CTA) whose loads of BOTH CTAs signal the leader's mbarrier, 12 MMAs per k-block,
-//   chunked accumulation: a chain covers 128 K-elements in one of TWO TMEM accumulator buffers, the eight epilogue warps
-//   fold it into a register-resident running total with round-to-nearest adds (TMEM accumulation truncates)
-//   while the next chunk's MMAs fill the other buffer; the finished tile is scaled by invA[row] invB[col] (exact: powers
-//   of two) and leaves through per-warp swizzled staging tiles + cp.async.bulk.tensor stores.
-//   warp 0 TMA (both CTAs)   warp 1 MMA (leader CTA)   warps 2-7 idle   warps 8-15 fold + epilogue (setmaxnreg 56 / 24 / 208)
-// Split-K (deterministic two-pass) covers the skinny shapes.  b200ad_gemm_shared_a converts ONE A operand for several
-// B / C pairs (the Q / K / V projections of self-attention share their input, layers.py:1347-1349).
+// Two variants of one kernel (gemm_h16_kernel<A_RAW>), both a CTA pair (cta_group::2) on 256 x 256 tiles, BK = 64 (128 B rows,
+// SWIZZLE_128B), a 3-stage ring of {A hi, A lo, B hi, B lo} tiles (64 KB per stage and CTA), 12 MMAs per k-block, chunked
+// accumulation (a chain covers 128 K-elements in one of TWO TMEM accumulator buffers; eight fold warps add it into a
+// register-resident running total with round-to-nearest adds — TMEM accumulation truncates, DESIGN 3.1 — while the next chain
+// fills the other buffer), the finished tile scaled by invA[row] invB[col] (exact: powers of two) on its way through two 2 KB
+// swizzled staging tiles per warp + cp.async.bulk.tensor stores:
+//   * planes (A_RAW = false): a pre-pass writes K-major fp16 hi / lo planes + the inverse row scales of BOTH operands into the
+//     caller's workspace (one fused pass for row-major operands: row maximum, scale, split; column maximum + transposing split
+//     for the others); the kernel is pure TMA + MMA, the loads of both CTAs signal the leader's mbarrier.
+//   * in-kernel conversion (A_RAW = true; op(A) one row-major matrix, N <= 2048): only A's row scales are computed ahead
+//     (read-only pass); TMA delivers the raw fp32 tile and four converter warps rewrite it IN PLACE as the hi / lo tiles (see
+//     the kernel).  B always comes as planes (weights: small).
+//   warp 0 TMA (both CTAs)   warp 1 MMA (leader CTA)   warps 2-3 idle   warps 4-7 converter (A_RAW) / idle   warps 8-15 fold +
+//   epilogue; setmaxnreg 56 / 24 / 208 (planes), 48 / 72 / 192 (A_RAW) of the 512 x 128 registers launched.
+// Split-K (deterministic two-pass) covers the skinny shapes.  b200ad_gemm_shared_a prepares ONE A operand for several
+// B / C pairs (the Q / K / V projections of self-attention share their input, layers.py:1347-1349).  Measurements: DESIGN 3.5.
 #include "common.cuh"
 #include "gemm_internal.cuh"
 #include "tcgen05.cuh"

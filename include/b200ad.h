@@ -212,7 +212,8 @@ int b200ad_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, void* 
  *                                 (looser tolerance: rtol 2e-2 of |A||B| row-norm bound)
  *              B200AD_GEMM_F16X3  tcgen05 kind::f16 on fp16 hi/lo pairs with one power-of-two scale per operand
  *                                 row, 3-term split (fp32-faithful like TF32X3 at twice its MMA rate; the operands
- *                                 are split by a pre-pass into the workspace, csrc/gemm_h16.cu)
+ *                                 are split by a pre-pass into the workspace, or — a row-major op(A) — converted inside
+ *                                 the kernel after a read-only row-scale pass, csrc/gemm_h16.cu)
  *              B200AD_GEMM_AUTO   fp32-faithful: F16X3 for the large row-major-A products where it measures faster
  *                                 (b200ad_gemm_set_f16x3_auto), TF32X3 when the shape/alignment allows the TMA
  *                                 path, else FP32
