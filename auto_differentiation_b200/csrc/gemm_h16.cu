@@ -340,7 +340,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int q = warp & 3, hf = (warp - 8) >> 2;              // TMEM lane quarter, 128-column half of the tile
     const uint32_t stg = smem_u32(smem + (size_t)R * H_STAGE_BYTES) + (uint32_t)(warp - 8) * 4096u;
     const uint32_t x_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hf * 128u;
-    uint32_t uit = 0;
+    uint32_t uit = 0, stc = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
       int m_tile, n_tile, split, batch;
       h16_decode_tile(tile, p, m_tile, n_tile, split, batch);
@@ -401,8 +401,11 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int g = 0; g < 8; ++g) {
         const int n_col0 = n_tile * BN + hf * 128 + g * 16;
         if (n_col0 < p.n && m_row0 < p.m) {                    // warp-uniform
-          const uint32_t stgb = stg + (uint32_t)(g & 1) * 2048u;
-          // the store issued two groups ago read this tile; the most recent one (other tile) may still be in flight
+          // staging tiles alternate by a RUNNING count of issued stores, not by g: with partial column tiles (N % 32 != 0) a
+          // tile may issue a single group, and two consecutive stores of this warp must never share a staging tile
+          const uint32_t stgb = stg + (stc & 1u) * 2048u;
+          ++stc;
+          // the store issued two stores ago read this tile; the most recent one (other tile) may still be in flight
           if (p.tma_store && elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
 #pragma unroll
