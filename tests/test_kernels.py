@@ -355,6 +355,27 @@ def test_gemm_f16x3_row_scales_and_dynamic_range(backend):
     assert_close(got, xr @ yr.transpose(0, 1, 3, 2), rtol=2e-5, atol=2e-6 * np.sqrt(dk), what="f16x3 batched head views")
 
 
+def test_gemm_f16x3_partial_column_tiles_repeatable(backend):
+    """Partial column tiles (N % 32 != 0) make a fold warp issue a single output group per tile: consecutive stores of a warp
+    must still alternate between its two staging tiles (a version that picked the tile by the group index let the next fill
+    overwrite a tile the TMA engine was still reading — an intermittent wrong block).  Many row tiles per CTA, repeated."""
+    D = _D()
+    rng = np.random.default_rng(91)
+    for (M, N, K) in ((6000, 260, 128), (5000, 530, 96)):
+        A = rng.standard_normal((M, K)).astype(np.float32)
+        B = rng.standard_normal((K, N)).astype(np.float32)
+        ref = A.astype(np.float64) @ B.astype(np.float64)
+        a, b = D.asarray(A), D.asarray(B)
+        first = None
+        for rep in range(6):
+            got = np.asarray(D.matmul(a, b, precision="f16x3"))
+            if first is None:
+                first = got
+                assert_close(got, ref, rtol=2e-5, atol=2e-6 * np.sqrt(K), what="M=%d N=%d K=%d" % (M, N, K))
+            else:
+                np.testing.assert_array_equal(got, first)
+
+
 def test_gemm_shared_a_and_auto_dispatch(backend):
     """b200ad_gemm_shared_a (one operand split for several products: the Q / K / V projections) equals separate calls
     bit for bit, and the AUTO dispatch (b200ad_gemm_set_f16x3_auto: never / by the device-time model / always) stays inside
